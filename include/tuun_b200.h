@@ -1,0 +1,174 @@
+/*
+ * tuun_b200.h — C ABI of the B200-native renderer for Tuun's waveform-generation hot path.
+ *
+ * This is the drop-in boundary for the reference path
+ *     generator::initialize_state            (src/lib/generator.rs:39)
+ *     Generator::new / generate / length     (src/lib/generator.rs:68, :86, :620)
+ *     waveform::set_state(.., Initial)       (src/lib/waveform.rs:322)
+ *     tracker mix loop  out[j] += tmp[j]     (src/lib/tracker.rs:597-642)
+ * The reference has no FFI for this path (it is a Rust method on a value type), so the
+ * entry points below are what a Rust `extern "C"` block would bind (see INTEGRATION.md and
+ * rust/tuun-b200-sys/src/lib.rs).  Plain pointers and sizes only; no C++/torch types.
+ *
+ * A `Waveform<MarkId, State>` tree (src/lib/waveform.rs:23-100) crosses the ABI as a flat
+ * array of `tb_node` in topological order (children before parents, root = last node) —
+ * one node per enum variant instance, one-for-one, nothing re-associated or folded.
+ *
+ * All entry points return 0 (TB_OK) or a negative tb_status; they never unwind and never
+ * fall back to a CPU implementation: without a usable CUDA device every compute call
+ * fails with TB_ERR_CUDA.
+ */
+#ifndef TUUN_B200_H
+#define TUUN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TB_ABI_VERSION 1u
+
+/* enum Waveform variants, src/lib/waveform.rs:23-100 (same order). */
+typedef enum tb_kind {
+    TB_CONST = 0,    /* Const(f32)                                   waveform.rs:25 */
+    TB_TIME = 1,     /* Time(State)                                  waveform.rs:27 */
+    TB_NOISE = 2,    /* Noise                                        waveform.rs:29 */
+    TB_FIXED = 3,    /* Fixed(Vec<f32>, State)                       waveform.rs:31 */
+    TB_FIN = 4,      /* Fin{length=a, waveform=b}                    waveform.rs:35 */
+    TB_APPEND = 5,   /* Append(a, b, State)                          waveform.rs:41 */
+    TB_SINE = 6,     /* Sine{frequency=a, phase=b, state}            waveform.rs:51 */
+    TB_FILTER = 7,   /* Filter{waveform=a, feed_forward, feedback}   waveform.rs:59 */
+    TB_BINARY = 8,   /* BinaryPointOp(op, a, b)                      waveform.rs:67 */
+    TB_RESET = 9,    /* Reset{trigger=a, waveform=b, state}          waveform.rs:74 */
+    TB_ALT = 10,     /* Alt{trigger=a, positive=b, negative=c}       waveform.rs:81 */
+    TB_MARKED = 11,  /* Marked{id=mark_id, waveform=a}               waveform.rs:90 */
+    TB_CAPTURED = 12 /* Captured{file_stem=#mark_id, waveform=a}     waveform.rs:96 */
+} tb_kind;
+
+/* enum Operator, src/lib/waveform.rs:5-19 (same order). */
+typedef enum tb_operator {
+    TB_ADD = 0,
+    TB_SUBTRACT = 1,
+    TB_MULTIPLY = 2,
+    TB_DIVIDE = 3, /* b == 0 yields 0                                generator.rs:266 */
+    TB_MERGE = 4,  /* Add with zero-extension to the longer input    generator.rs:263 */
+    TB_POWER = 5   /* f32::powf                                      generator.rs:269 */
+} tb_operator;
+
+/*
+ * One node of the op list.  `a`, `b`, `c` are indices of child nodes (or -1).  For TB_FILTER
+ * the coefficient waveforms are listed in the program's `lists` array:
+ *   feed_forward[i] = lists[list_off + i]                 for i in 0..ff_count   (b_0, b_1, ...)
+ *   feedback[j]     = lists[list_off + ff_count + j]      for j in 0..fb_count   (a_1, a_2, ...)
+ * For TB_FIXED the samples are fixed_pool[fixed_off .. fixed_off + fixed_len].
+ * For TB_CONST, `param_slot >= 0` makes the constant a per-voice parameter: voice v renders
+ * with value params[v * n_params + param_slot] (a batch of identically shaped trees that
+ * differ only in their constants); `value` is then the default used when no table is given.
+ */
+typedef struct tb_node {
+    uint32_t kind;       /* tb_kind */
+    uint32_t op;         /* tb_operator, TB_BINARY only */
+    int32_t a, b, c;     /* children, -1 when unused */
+    float value;         /* TB_CONST */
+    int32_t param_slot;  /* TB_CONST: -1, or column of the parameter table */
+    uint32_t list_off;   /* TB_FILTER */
+    uint32_t ff_count;   /* TB_FILTER, >= 1 (generator.rs:233) */
+    uint32_t fb_count;   /* TB_FILTER */
+    uint32_t mark_id;    /* TB_MARKED / TB_CAPTURED */
+    uint32_t reserved;   /* must be 0 */
+    uint64_t fixed_off;  /* TB_FIXED */
+    uint64_t fixed_len;  /* TB_FIXED */
+} tb_node;
+
+typedef enum tb_status {
+    TB_OK = 0,
+    TB_ERR_INVALID = -1,     /* malformed op list / bad argument (the reference would panic) */
+    TB_ERR_UNSUPPORTED = -2, /* well-formed but outside what the device path implements */
+    TB_ERR_CUDA = -3,        /* no device, kernel image missing, or a CUDA call failed */
+    TB_ERR_NOMEM = -4,
+    TB_ERR_STATE = -5        /* call sequence error (e.g. voice count changed mid-stream) */
+} tb_status;
+
+/* tb_render flags */
+#define TB_OUT_DEVICE 1u   /* `out`/`mix` are device pointers (default: host, copied back) */
+#define TB_PARAMS_DEVICE 2u /* `params` is a device pointer */
+#define TB_NO_VOICE_OUT 4u /* tb_render_mix only: do not materialise per-voice rows */
+
+typedef struct tb_program tb_program;
+
+/*
+ * initialize_state + ownership of the tree (generator.rs:39, waveform.rs:179).
+ * Validates and lowers the op list to the device byte-code; all persistent render state
+ * (the reference's per-node `State`, generator.rs:12-35) lives behind the handle.
+ * `device` is the CUDA ordinal (-1 = current device).
+ */
+int tb_program_create(const tb_node* nodes, uint32_t n_nodes,
+                      const int32_t* lists, uint32_t n_lists,
+                      const float* fixed_pool, uint64_t fixed_len,
+                      uint32_t sample_rate, int device, tb_program** out_program);
+
+void tb_program_destroy(tb_program* p);
+
+/*
+ * Generator::generate over a batch of voices (generator.rs:86).
+ * Renders the next `n_samples` samples of every voice into out[v * out_stride + i].
+ * out_len[v] (may be NULL) receives the number of samples generated; a value smaller than
+ * n_samples means voice v has finished, and out[v][out_len[v]..] is undefined, exactly as
+ * the reference states (generator.rs:79-81).  State is carried, so successive calls continue
+ * where the previous one stopped ("pick up where this one left off", generator.rs:76-78).
+ * `params` may be NULL (use the constants in the tree); n_voices must stay the same for the
+ * life of the stream (until tb_reset).
+ */
+int tb_render(tb_program* p, const float* params, uint32_t n_params, uint32_t n_voices,
+              uint64_t n_samples, float* out, uint64_t out_stride, uint64_t* out_len,
+              uint32_t flags);
+
+/*
+ * tb_render plus the tracker's mix loop (tracker.rs:597-642): mix[i] = sum over voices of
+ * out[v][i] for i < out_len[v]  (voices summed in index order per 32-voice group, groups
+ * combined in f32 — see DESIGN.md "mixdown").  `out` may be NULL with TB_NO_VOICE_OUT.
+ * `mix` holds n_samples floats and is overwritten.
+ */
+int tb_render_mix(tb_program* p, const float* params, uint32_t n_params, uint32_t n_voices,
+                  uint64_t n_samples, float* out, uint64_t out_stride, uint64_t* out_len,
+                  float* mix, uint32_t flags);
+
+/*
+ * Generator::length (generator.rs:620): advance every voice by `max` samples without
+ * producing output; len[v] = number of samples the voice would have generated.
+ */
+int tb_length(tb_program* p, const float* params, uint32_t n_params, uint32_t n_voices,
+              uint64_t max, uint64_t* len, uint32_t flags);
+
+/* waveform::set_state(root, State::Initial) for every voice (waveform.rs:322). */
+int tb_reset(tb_program* p);
+
+/* Stream the render is enqueued on (a cudaStream_t), for callers that time with events. */
+void* tb_stream(tb_program* p);
+/* Run subsequent renders of this program on a caller-owned cudaStream_t. */
+int tb_set_stream(tb_program* p, void* cuda_stream);
+
+/* Introspection used by tests, bench.py and DESIGN.md numbers. */
+typedef struct tb_program_info {
+    uint32_t n_nodes;
+    uint32_t n_code_words;    /* device byte-code length */
+    uint32_t n_slots;         /* shared-memory tile slots per CTA */
+    uint32_t state_words;     /* 32-bit words of carried state per voice */
+    uint32_t tile;            /* samples per tile */
+    uint32_t threads;         /* threads per CTA */
+    uint32_t smem_bytes;      /* dynamic shared memory per CTA */
+    uint32_t n_params;        /* highest param_slot + 1 */
+    uint64_t kernel_launches; /* cumulative launches of this library's kernels */
+} tb_program_info;
+int tb_program_get_info(const tb_program* p, tb_program_info* info);
+
+/* Human-readable text of the last error on the calling thread (never NULL). */
+const char* tb_last_error(void);
+uint32_t tb_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TUUN_B200_H */
