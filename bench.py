@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""bench.py — rendered voice-samples/sec of the B200 renderer on BASELINE.json's config 5
+(65,536 parameter-swept FM+filter voices x 10 s @ 44.1 kHz), next to the CPU oracle.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          the CUDA path (one rank per GPU)
+  python bench.py --impl reference [...]                       the reference algorithm on host cores
+
+A step renders the whole batch once from Initial state: every rank renders its contiguous share
+of the voices into HBM (no data-path collective); with --mix the per-rank mixdowns are reduced
+over NCCL.  Scaling is "strong": the 65,536 voices are divided over the ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SAMPLE_RATE = 44100
+METRIC = "rendered voice-samples/sec"
+UNIT = "voice-samples/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--voices", type=int, default=65536)
+    ap.add_argument("--seconds", type=float, default=10.0)
+    ap.add_argument("--e2e-voices", type=int, default=0, help="0 = all local voices")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def config(args, n_samples):
+    return {
+        "workload": "cfg5: 65,536 parameter-swept FM+biquad voices x 10 s @ 44.1 kHz "
+                    "(sine(2pi(fc+I*fm*sine(2pi*fm,pi/2)),0) | lpf(Q,cut)), one shared op list + [V x 8] f32 table",
+        "voices": args.voices,
+        "samples_per_voice": n_samples,
+        "sample_rate": SAMPLE_RATE,
+        "sharding": f"voices/{args.gpus} per GPU, no data-path collective",
+        "l2": "output rows (>= 14 GB per GPU) are far larger than L2; nothing is re-read between steps",
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks line of B200_PROFILING.md, sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ts, line in self.rows:
+            if ts < t0 - 0.05 or ts > t1 + 0.15:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples inside the timed region"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_baseline(args, n_samples, target_seconds, threads):
+    """The CPU oracle (a port of generator.rs) timed on a bounded sample of the same workload:
+    whole voices of the same length, as many as fit in about `target_seconds` of wall time."""
+    from oracle.binding import OracleProgram
+    from tuun_b200.workloads import fm_filter_params, fm_filter_voice
+    o = OracleProgram(fm_filter_voice(), SAMPLE_RATE)
+    probe_ids = (np.arange(threads) * 4099) % args.voices
+    t = time.perf_counter()
+    o.render_batch(fm_filter_params(probe_ids), len(probe_ids), min(n_samples, 44100), keep=False, threads=threads)
+    dt = time.perf_counter() - t
+    rate = len(probe_ids) * min(n_samples, 44100) / max(dt, 1e-6)
+    n_v = int(max(threads, min(args.voices, rate * target_seconds / n_samples)))
+    n_v = max(threads, (n_v // threads) * threads)
+    ids = (np.arange(n_v) * 4099) % args.voices
+    t = time.perf_counter()
+    _, _, _, total = o.render_batch(fm_filter_params(ids), n_v, n_samples, keep=False, threads=threads)
+    dt = time.perf_counter() - t
+    return {"value": total / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n_v} voices (ids v*4099 mod {args.voices}) x {n_samples} samples, 1024-sample blocks, "
+                      f"{dt:.1f} s wall"}, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_samples = int(round(args.seconds * SAMPLE_RATE))
+    threads = os.cpu_count() or 1
+    per_step = max(2.0, 60.0 / max(1, args.steps + args.warmup))
+    vals, times = [], []
+    sample = ""
+    for i in range(args.warmup + args.steps):
+        cb, dt = cpu_baseline(args, n_samples, per_step, threads)
+        if i >= args.warmup:
+            vals.append(cb["value"]); times.append(dt)
+        sample = cb["sample"]
+    v = float(np.mean(vals))
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (f64 phase)",
+            "data": "synthetic", "config": config(args, n_samples),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "the Rust reference cannot be built here (no cargo/rustc); this arm times the C++ "
+                    "restatement of generator.rs (oracle/) on all host threads"}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    import torch
+    import torch.distributed as dist
+
+    from tuun_b200.generator import Program
+    from tuun_b200.workloads import fm_filter_params, fm_filter_voice
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the renderer has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n_samples = int(round(args.seconds * SAMPLE_RATE))
+    lo = args.voices * rank // world
+    hi = args.voices * (rank + 1) // world
+    n_local = hi - lo
+    params_h = fm_filter_params(np.arange(lo, hi))
+    params_d = torch.from_numpy(params_h).cuda()
+    prog = Program(fm_filter_voice(), SAMPLE_RATE, device=local)
+    stream = torch.cuda.ExternalStream(prog.stream, device=local)
+    out = torch.empty((n_local, n_samples), dtype=torch.float32, device="cuda")
+    lens = np.zeros(n_local, dtype=np.uint64)
+
+    def step():
+        prog.reset()
+        prog.render(out, params=params_d)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = prog.info.kernel_launches
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t0 = time.time()
+    w0 = time.perf_counter()
+    for a, b in evs:
+        a.record(stream)
+        step()
+        b.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    w1 = time.perf_counter()
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1) if sampler else None
+    launches = prog.info.kernel_launches - launches0
+    kern_ms = [a.elapsed_time(b) for a, b in evs]
+    dev_ms = float(sum(kern_ms))
+    tmax = torch.tensor([dev_ms, (w1 - w0) * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms = float(tmax[0].item())
+    lens_ok = True
+    prog.reset()
+    chk = prog.render(out, params=params_d, out_len=lens)
+    lens_ok = bool((chk == n_samples).all())
+    value = args.voices * n_samples * args.steps / (total_ms * 1e-3)
+
+    # roofline of the one kernel: 4 B stored per voice-sample, per launch
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak, peak_src = 6650.0, "fallback"
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured"
+    alg_bytes = 4.0 * n_local * n_samples
+    avg_launch_s = (dev_ms / max(1, launches)) * 1e-3
+    achieved = alg_bytes / avg_launch_s / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "tb_render_kernel", "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_launch_s * 1e3}
+
+    # end to end through the C ABI with HOST buffers: H2D of the parameter table, D2H of every row
+    e2e = None
+    if not args.no_e2e:
+        ev = args.e2e_voices or n_local
+        ev = min(ev, n_local)
+        host = torch.empty((ev, n_samples), dtype=torch.float32, pin_memory=True)
+        host_np = host.numpy()
+        ph = torch.from_numpy(params_h[:ev].copy()).pin_memory().numpy()
+        e2e_steps = max(1, min(args.steps, 2))
+        prog_h = Program(fm_filter_voice(), SAMPLE_RATE, device=local)
+        prog_h.render(host_np, params=ph)  # warm: staging buffers, page touch
+        barrier()
+        e0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            prog_h.reset()
+            prog_h.render(host_np, params=ph)
+        torch.cuda.synchronize()
+        e1 = time.perf_counter()
+        et = torch.tensor([e1 - e0], dtype=torch.float64, device="cuda")
+        ne = torch.tensor([float(ev)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(et, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ne, op=dist.ReduceOp.SUM)
+        e2e = {"value": float(ne.item()) * n_samples * e2e_steps / float(et.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(ev * 8 * 4), "d2h_bytes_per_step": int(ev * n_samples * 4 + ev * 8),
+               "voices": int(ne.item()), "steps": e2e_steps,
+               "path": "tb_render with pinned host rows: chunked render -> cudaMemcpy2DAsync on a second stream"}
+        del host, host_np
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32 samples, u64 fixed-point phase, f64 sine core",
+                "data": "synthetic", "config": config(args, n_samples), "clocks": clocks,
+                "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e,
+                "wall_ms_per_step": float(tmax[1].item()) / args.steps, "lengths_ok": lens_ok}
+        if not args.no_cpu:
+            cb, _ = cpu_baseline(args, n_samples, args.cpu_seconds, os.cpu_count() or 1)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,76 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every symbol include/tuun_b200.h
+declares, validates op lists before touching CUDA, and fails loudly (TB_ERR_CUDA) instead of
+falling back when no device is present."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from tuun_b200 import _abi
+from tuun_b200.waveform import (BinaryPointOp, Const, Filter, Fixed, Noise, Operator, Reset, Sine,
+                                TbNode, Time, flatten)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_exports_match_header():
+    header = open(os.path.join(ROOT, "include", "tuun_b200.h")).read()
+    declared = set(re.findall(r"\b(tb_[a-z_]+)\s*\(", header))
+    assert declared == set(_abi.EXPORTS)
+    L = _abi.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.tb_abi_version() == 1
+
+
+def test_node_layout():
+    assert ctypes.sizeof(TbNode) == 64
+    assert TbNode.fixed_off.offset == 48 and TbNode.value.offset == 20
+
+
+def _create(ops, sample_rate=44100):
+    h = ctypes.c_void_p()
+    L = _abi.lib()
+    rc = L.tb_program_create(ops.nodes, ops.n_nodes,
+                             ops.lists.ctypes.data_as(ctypes.c_void_p) if ops.lists.size else None,
+                             len(ops.lists),
+                             ops.fixed_pool.ctypes.data_as(ctypes.c_void_p) if ops.fixed_pool.size else None,
+                             len(ops.fixed_pool), sample_rate, -1, ctypes.byref(h))
+    return rc, h, L.tb_last_error().decode()
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_invalid_op_list_rejected_before_cuda():
+    ops = flatten(BinaryPointOp(Operator.Add, Time(), Const(1.0)))
+    ops.nodes[2].a = 7  # child index out of range
+    rc, h, msg = _create(ops)
+    assert rc == _abi.TB_ERR_INVALID and "malformed" in msg
+    ops = flatten(Time())
+    rc, h, msg = _create(ops, sample_rate=0)
+    assert rc == _abi.TB_ERR_INVALID
+
+
+def test_unsupported_is_reported_not_emulated():
+    rc, h, msg = _create(flatten(BinaryPointOp(Operator.Multiply, Noise(), Const(0.1))))
+    assert rc == _abi.TB_ERR_UNSUPPORTED and "Noise" in msg
+    w = Reset(Sine(Const(1.0), Const(0.0)), Filter(Time(), [Const(1.0)], []))
+    rc, h, msg = _create(flatten(w))
+    assert rc == _abi.TB_ERR_UNSUPPORTED and "Filter inside a Reset" in msg
+    rc, h, msg = _create(flatten(Filter(Time(), [Const(1.0)] * 12, [])))
+    assert rc == _abi.TB_ERR_UNSUPPORTED
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-device behaviour")
+def test_no_device_fails_loudly():
+    rc, h, msg = _create(flatten(Sine(Const(2764.6), Const(0.0))))
+    assert rc == _abi.TB_ERR_CUDA and "CUDA" in msg
+    assert not h.value

@@ -1,0 +1,169 @@
+"""Parity of the CUDA path against the CPU oracle at audio rates: lengths bit-exact, samples
+within 1e-4 (BASELINE.json north_star), on trees that cross many tile boundaries."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle.binding import OracleProgram
+from tuun_b200.waveform import (Alt, Append, BinaryPointOp, Const, Filter, Fin, Fixed, Operator, Reset,
+                                Sine, Time, add, f32, merge, mul, sub)
+
+pytestmark = pytest.mark.gpu
+SR = 44100
+TOL = 1e-4  # north_star: max-abs error <= 1e-4 vs the reference f32 render
+
+
+def gpu_render(w, n, sr=SR, block=None):
+    from tuun_b200.generator import Generator
+    g = Generator(sr)
+    p = g.initialize_state(w)
+    out = np.full(n, np.inf, dtype=np.float32)
+    if block is None:
+        return out[:g.generate(p, out)]
+    done = 0
+    while done < n:
+        want = min(block, n - done)
+        got = g.generate(p, out[done:done + want])
+        done += got
+        if got < want:
+            break
+    return out[:done]
+
+
+def check(w, n, tol=TOL, block=None, sr=SR):
+    ref = OracleProgram(w, sr).render(n, block=1024)
+    got = gpu_render(w, n, sr, block)
+    assert len(got) == len(ref), f"length {len(got)} != oracle {len(ref)}"
+    err = float(np.max(np.abs(got - ref))) if len(ref) else 0.0
+    assert err <= tol, f"max abs err {err}"
+    return err
+
+
+TAU = f32(2 * math.pi)
+
+
+def hz(f):
+    return Const(f32(TAU * f32(f)))
+
+
+def lpf(x, q, fc, sr=SR):
+    # lib/v0/std.tuun:118-129 evaluated in f32 like builtins.rs does
+    w0 = np.float32(2.0) * np.float32(3.14159265) * np.float32(fc) / np.float32(sr)
+    alpha = np.float32(np.sin(np.float32(w0))) / (np.float32(2.0) * np.float32(q))
+    cosw = np.float32(np.cos(np.float32(w0)))
+    a0 = np.float32(1.0) + alpha
+    b1 = (np.float32(1.0) - cosw) / a0
+    b0 = b1 / np.float32(2.0)
+    a1 = (np.float32(-2.0) * cosw) / a0
+    a2 = (np.float32(1.0) - alpha) / a0
+    return Filter(x, [Const(b0), Const(b1), Const(b0)], [Const(a1), Const(a2)])
+
+
+def test_cfg1_sine_fin():
+    w = Fin(add(Time(), Const(-0.5)), Sine(hz(440), Const(0.0)))
+    assert check(w, 30000) < 1e-6
+
+
+def test_time_and_ramps():
+    w = add(mul(Time(), Const(-3.5)), Const(1.0))
+    check(w, 5000, tol=0.0)
+
+
+def test_fm_10s():
+    mod = Sine(hz(220), Const(f32(math.pi / 2)))
+    w = Sine(add(mul(mod, Const(8293.805)), hz(440)), Const(0.0))
+    check(w, SR * 10)
+
+
+def test_pm_10s():
+    w = Sine(hz(440), mul(Sine(hz(220), Const(0.0)), Const(6.0)))
+    check(w, SR * 10)
+
+
+def test_biquad_over_square_20s():
+    sq = Alt(Sine(hz(220), Const(0.0)), Const(1.0), Const(-1.0))
+    check(lpf(sq, 0.707, 2000), SR * 20)
+
+
+def test_biquad_cascade_high_q():
+    sq = Alt(Sine(hz(110), Const(0.0)), Const(1.0), Const(-1.0))
+    w = lpf(lpf(lpf(sq, 4, 800), 2, 1600), 1, 3200)
+    check(w, SR * 5)
+
+
+def test_filter_4_3():  # benches/tracker_benches.rs:69-89
+    w = Filter(Time(), [Const(0.00107949), Const(0.00323847), Const(0.00323847), Const(0.00107949)],
+               [Const(-2.5610316), Const(2.2132402), Const(-0.6435727)])
+    ref = OracleProgram(w, SR).render(43 * 1024)
+    got = gpu_render(w, 43 * 1024)
+    assert len(got) == len(ref)
+    assert np.max(np.abs(got - ref) / np.maximum(1.0, np.abs(ref))) <= 1e-5
+
+
+def test_filter_1_1_linear():  # benches/tracker_benches.rs:36-67, time-varying coefficients
+    w = Filter(Time(), [add(mul(Time(), Const(-0.5)), Const(0.5))], [add(mul(Time(), Const(0.5)), Const(-0.5))])
+    check(w, 43 * 1024, tol=1e-5)
+
+
+def test_sawtooth_and_triangle():
+    f = 55.0
+    t = Sine(hz(f), Const(0.0))
+    saw = mul(add(Reset(Sine(hz(f), Const(0.0)), mul(Time(), Const(-f))), Const(0.5)), Const(2.0))
+    check(saw, SR * 2)
+    tri = Alt(t, Reset(Sine(hz(f), Const(0.0)), add(mul(Time(), Const(4 * f)), Const(-1.0))),
+              Reset(Sine(hz(f), Const(0.0)), add(mul(Time(), Const(-4 * f)), Const(3.0))))
+    check(tri, SR * 2)
+
+
+def test_envelope_append_chain():
+    def seg(c, m, d):
+        return Fin(add(Time(), Const(-d)), add(mul(Time(), Const(m)), Const(c)))
+    env = Append(seg(0.0, 1 / 0.13, 0.13), Append(seg(1.0, -0.5 / 0.33, 0.33), seg(0.5, -0.5 / 0.33, 0.33)))
+    w = mul(Sine(hz(330), Const(0.0)), env)
+    check(w, SR)
+
+
+def test_nested_reset_hard_sync():
+    master = Alt(Sine(hz(110), Const(0.0)), Const(1.0), Const(-1.0))
+    slave_saw = mul(add(Reset(Sine(hz(173), Const(0.0)), mul(Time(), Const(-173.0))), Const(0.5)), Const(2.0))
+    w = Reset(master, Alt(sub(slave_saw, Const(0.7)), Const(1.0), Const(-1.0)))
+    check(w, SR)
+
+
+def test_merge_and_seq():
+    note = Fin(add(Time(), Const(-0.25)), Sine(hz(440), Const(0.0)))
+    note2 = Fin(add(Time(), Const(-0.25)), Sine(hz(660), Const(0.0)))
+    w = merge(note, Append(Fin(add(Time(), Const(-0.2)), Const(0.0)), note2))
+    check(w, SR)
+
+
+def test_streaming_blocks_match_one_shot():
+    mod = Sine(hz(3), Const(0.0))
+    w = lpf(Sine(add(mul(mod, Const(500.0)), hz(300)), Const(0.0)), 2.0, 900)
+    a = gpu_render(w, 20000)
+    b = gpu_render(w, 20000, block=1024)
+    c = gpu_render(w, 20000, block=777)
+    assert len(a) == len(b) == len(c) == 20000
+    assert np.max(np.abs(a - b)) <= 2e-6 and np.max(np.abs(a - c)) <= 2e-6
+
+
+def test_batch_params():
+    from tuun_b200.generator import Program
+    w = lpf(Sine(add(mul(Sine(Const(1.0, param=0), Const(f32(math.pi / 2))), Const(1.0, param=1)), Const(1.0, param=2)),
+                 Const(0.0)), 0.7, 2000)
+    # make the filter coefficients per-voice too
+    rng = np.random.default_rng(0)
+    V, N = 37, 5000
+    params = np.stack([TAU * rng.uniform(50, 400, V), TAU * rng.uniform(0, 2000, V), TAU * rng.uniform(100, 1000, V)],
+                      axis=1).astype(np.float32)
+    p = Program(w, SR)
+    out = np.zeros((V, N), dtype=np.float32)
+    lens = p.render(out, params=params)
+    assert (lens == N).all()
+    o = OracleProgram(w, SR)
+    for v in range(V):
+        o.initialize_state()
+        o.set_params(params[v])
+        ref = o.render(N)
+        assert np.max(np.abs(out[v] - ref)) <= TOL, v

@@ -1,0 +1,384 @@
+// abi.cpp — the C ABI of include/tuun_b200.h over the lowering (lower.cpp) and the kernels
+// (render.cu).  Plain CUDA runtime; no torch, no CPU fallback: every compute entry point fails
+// with TB_ERR_CUDA when no device is usable.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/tuun_b200.h"
+#include "lower.h"
+#include "program.h"
+
+extern "C" size_t tb_kernel_smem_bytes(uint32_t n_code, uint32_t n_slots, uint32_t aux_words,
+                                       uint32_t n_cval, uint32_t state_words);
+extern "C" cudaError_t tb_kernel_launch(const tb_launch* P, size_t smem, cudaStream_t stream);
+
+namespace {
+
+thread_local std::string g_error = "";
+
+int set_error(int status, const std::string& msg) {
+    g_error = msg;
+    return status;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    return set_error(TB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(call)                                       \
+    do {                                               \
+        cudaError_t e_ = (call);                       \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
+    } while (0)
+
+template <class T>
+int upload(const std::vector<T>& v, T** dst) {
+    *dst = nullptr;
+    const size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+    CU(cudaMalloc(reinterpret_cast<void**>(dst), bytes));
+    if (!v.empty()) CU(cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return TB_OK;
+}
+
+}  // namespace
+
+struct tb_program {
+    tb::Lowered low;
+    uint32_t sample_rate = 0;
+    int device = 0;
+    tb_insn* d_code = nullptr;
+    tb_cexpr* d_cexpr = nullptr;
+    tb_aux* d_aux = nullptr;
+    tb_goe* d_goe = nullptr;
+    int32_t* d_goe_steps = nullptr;
+    tb_filter_tab* d_filt = nullptr;
+    tb_fixed_tab* d_fixed = nullptr;
+    float* d_pool = nullptr;
+    uint32_t* d_state = nullptr;
+    uint32_t n_voices = 0;
+    bool fresh = true;  // no samples generated since create / tb_reset
+    float* d_params = nullptr;
+    size_t params_cap = 0;
+    unsigned long long* d_len = nullptr;
+    uint8_t* d_done = nullptr;
+    float* d_stage[2] = {nullptr, nullptr};
+    size_t stage_cap = 0;  // floats per staging buffer
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    bool own_stream = false;
+    cudaEvent_t ev_render[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
+    size_t smem = 0;
+    uint64_t launches = 0;
+
+    ~tb_program() {
+        cudaSetDevice(device);
+        cudaFree(d_code); cudaFree(d_cexpr); cudaFree(d_aux); cudaFree(d_goe); cudaFree(d_goe_steps);
+        cudaFree(d_filt); cudaFree(d_fixed); cudaFree(d_pool); cudaFree(d_state); cudaFree(d_params);
+        cudaFree(d_len); cudaFree(d_done); cudaFree(d_stage[0]); cudaFree(d_stage[1]);
+        for (int i = 0; i < 2; i++) {
+            if (ev_render[i]) cudaEventDestroy(ev_render[i]);
+            if (ev_copy[i]) cudaEventDestroy(ev_copy[i]);
+        }
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+        if (own_stream && stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace {
+
+int ensure_voices(tb_program* p, uint32_t n_voices) {
+    if (p->n_voices == n_voices && p->d_state) {
+        p->fresh = false;
+        return TB_OK;
+    }
+    if (!p->fresh) return set_error(TB_ERR_STATE, "n_voices changed mid-stream; call tb_reset first");
+    cudaFree(p->d_state);
+    cudaFree(p->d_len);
+    cudaFree(p->d_done);
+    p->d_state = nullptr;
+    p->d_len = nullptr;
+    p->d_done = nullptr;
+    p->n_voices = 0;
+    const size_t words = (size_t)n_voices * p->low.state_words;
+    CU(cudaMalloc(reinterpret_cast<void**>(&p->d_state), words * 4));
+    CU(cudaMemsetAsync(p->d_state, 0, words * 4, p->stream));
+    CU(cudaMalloc(reinterpret_cast<void**>(&p->d_len), (size_t)n_voices * 8));
+    CU(cudaMalloc(reinterpret_cast<void**>(&p->d_done), (size_t)n_voices));
+    p->n_voices = n_voices;
+    p->fresh = false;
+    return TB_OK;
+}
+
+int stage_params(tb_program* p, const float* params, uint32_t n_params, uint32_t n_voices, uint32_t flags,
+                 const float** d_out) {
+    *d_out = nullptr;
+    if (!params) {
+        if (p->low.n_params > 0 && n_params != 0) return set_error(TB_ERR_INVALID, "params is NULL but n_params != 0");
+        return TB_OK;
+    }
+    if (n_params < p->low.n_params)
+        return set_error(TB_ERR_INVALID, "parameter table has fewer columns than the program's param_slots");
+    if (flags & TB_PARAMS_DEVICE) {
+        *d_out = params;
+        return TB_OK;
+    }
+    const size_t bytes = (size_t)n_voices * n_params * 4;
+    if (bytes > p->params_cap) {
+        cudaFree(p->d_params);
+        p->d_params = nullptr;
+        p->params_cap = 0;
+        CU(cudaMalloc(reinterpret_cast<void**>(&p->d_params), std::max<size_t>(bytes, 16)));
+        p->params_cap = bytes;
+    }
+    CU(cudaMemcpyAsync(p->d_params, params, bytes, cudaMemcpyHostToDevice, p->stream));
+    *d_out = p->d_params;
+    return TB_OK;
+}
+
+void fill_launch(const tb_program* p, tb_launch* L) {
+    std::memset(L, 0, sizeof(*L));
+    L->code = p->d_code;
+    L->n_code = (uint32_t)p->low.code.size();
+    L->pc_gen = p->low.pc_gen;
+    L->pc_len = p->low.pc_len;
+    L->cexpr = p->d_cexpr;
+    L->n_cval = (uint32_t)p->low.cexpr.size();
+    L->aux = p->d_aux;
+    L->n_aux = (uint32_t)p->low.aux.size();
+    L->aux_words = p->low.aux_words;
+    L->goe = p->d_goe;
+    L->goe_steps = p->d_goe_steps;
+    L->filt = p->d_filt;
+    L->fixed = p->d_fixed;
+    L->pool = p->d_pool;
+    L->n_slots = p->low.n_slots;
+    L->state_words = p->low.state_words;
+    L->sample_rate = p->sample_rate;
+    L->pure_len = p->low.pure_len;
+    L->state = p->d_state;
+}
+
+int launch(tb_program* p, const tb_launch& L) {
+    cudaError_t e = tb_kernel_launch(&L, p->smem, p->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "tb_render_kernel launch");
+    p->launches++;
+    return TB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+uint32_t tb_abi_version(void) { return TB_ABI_VERSION; }
+const char* tb_last_error(void) { return g_error.c_str(); }
+
+int tb_program_create(const tb_node* nodes, uint32_t n_nodes, const int32_t* lists, uint32_t n_lists,
+                      const float* fixed_pool, uint64_t fixed_len, uint32_t sample_rate, int device,
+                      tb_program** out_program) {
+    if (!out_program) return set_error(TB_ERR_INVALID, "out_program is NULL");
+    *out_program = nullptr;
+    if (!nodes || n_nodes == 0) return set_error(TB_ERR_INVALID, "empty op list");
+    if (sample_rate == 0) return set_error(TB_ERR_INVALID, "sample_rate must be > 0");
+    if (fixed_len > 0 && !fixed_pool) return set_error(TB_ERR_INVALID, "fixed_pool is NULL");
+    tb_program* p = new (std::nothrow) tb_program();
+    if (!p) return set_error(TB_ERR_NOMEM, "out of host memory");
+    const char* fs = std::getenv("TUUN_B200_FAST_SINES");
+    const bool fast = !(fs && fs[0] == '0');
+    int rc = tb::lower(nodes, n_nodes, lists, n_lists, fixed_len, fast, p->low);
+    if (rc != TB_OK) {
+        std::string msg = p->low.error;
+        delete p;
+        return set_error(rc, msg);
+    }
+    p->sample_rate = sample_rate;
+    // Everything below needs a device: no CPU path exists.
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        delete p;
+        return set_error(TB_ERR_CUDA, std::string("no usable CUDA device: ") +
+                                          (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    }
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+    }
+    if (device >= count) {
+        delete p;
+        return set_error(TB_ERR_INVALID, "device ordinal out of range");
+    }
+    p->device = device;
+    auto bail = [&](int code) {
+        delete p;
+        return code;
+    };
+    if (cudaSetDevice(device) != cudaSuccess) return bail(set_error(TB_ERR_CUDA, "cudaSetDevice failed"));
+    if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess)
+        return bail(set_error(TB_ERR_CUDA, "cudaStreamCreate failed"));
+    p->own_stream = true;
+    if (cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking) != cudaSuccess)
+        return bail(set_error(TB_ERR_CUDA, "cudaStreamCreate failed"));
+    for (int i = 0; i < 2; i++) {
+        if (cudaEventCreateWithFlags(&p->ev_render[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&p->ev_copy[i], cudaEventDisableTiming) != cudaSuccess)
+            return bail(set_error(TB_ERR_CUDA, "cudaEventCreate failed"));
+    }
+    std::vector<float> pool(fixed_pool, fixed_pool + fixed_len);
+    if ((rc = upload(p->low.code, &p->d_code)) || (rc = upload(p->low.cexpr, &p->d_cexpr)) ||
+        (rc = upload(p->low.aux, &p->d_aux)) || (rc = upload(p->low.goe, &p->d_goe)) ||
+        (rc = upload(p->low.goe_steps, &p->d_goe_steps)) || (rc = upload(p->low.filt, &p->d_filt)) ||
+        (rc = upload(p->low.fixed, &p->d_fixed)) || (rc = upload(pool, &p->d_pool)))
+        return bail(rc);
+    p->smem = tb_kernel_smem_bytes((uint32_t)p->low.code.size(), p->low.n_slots, p->low.aux_words,
+                                   (uint32_t)p->low.cexpr.size(), p->low.state_words);
+    if (p->smem > 220 * 1024)
+        return bail(set_error(TB_ERR_UNSUPPORTED, "program needs more shared memory than one CTA has"));
+    *out_program = p;
+    return TB_OK;
+}
+
+void tb_program_destroy(tb_program* p) { delete p; }
+
+int tb_program_get_info(const tb_program* p, tb_program_info* info) {
+    if (!p || !info) return set_error(TB_ERR_INVALID, "NULL argument");
+    info->n_nodes = p->low.n_nodes;
+    info->n_code_words = (uint32_t)p->low.code.size() * 4;
+    info->n_slots = p->low.n_slots;
+    info->state_words = p->low.state_words;
+    info->tile = TB_TILE;
+    info->threads = 32 * TB_WARPS_PER_CTA;
+    info->smem_bytes = (uint32_t)p->smem;
+    info->n_params = p->low.n_params;
+    info->kernel_launches = p->launches;
+    return TB_OK;
+}
+
+void* tb_stream(tb_program* p) { return p ? (void*)p->stream : nullptr; }
+
+int tb_set_stream(tb_program* p, void* cuda_stream) {
+    if (!p) return set_error(TB_ERR_INVALID, "NULL program");
+    cudaSetDevice(p->device);
+    cudaStreamSynchronize(p->stream);
+    if (p->own_stream) cudaStreamDestroy(p->stream);
+    p->stream = (cudaStream_t)cuda_stream;
+    p->own_stream = false;
+    return TB_OK;
+}
+
+int tb_reset(tb_program* p) {
+    if (!p) return set_error(TB_ERR_INVALID, "NULL program");
+    CU(cudaSetDevice(p->device));
+    // Every node's Initial state is the all-zero block, so a reset is one memset on the stream.
+    if (p->d_state)
+        CU(cudaMemsetAsync(p->d_state, 0, (size_t)p->n_voices * p->low.state_words * 4, p->stream));
+    p->fresh = true;
+    return TB_OK;
+}
+
+int tb_render(tb_program* p, const float* params, uint32_t n_params, uint32_t n_voices, uint64_t n_samples,
+              float* out, uint64_t out_stride, uint64_t* out_len, uint32_t flags) {
+    if (!p) return set_error(TB_ERR_INVALID, "NULL program");
+    if (n_voices == 0) return TB_OK;
+    if (!out) return set_error(TB_ERR_INVALID, "out is NULL");
+    if (out_stride < n_samples) return set_error(TB_ERR_INVALID, "out_stride < n_samples");
+    CU(cudaSetDevice(p->device));
+    int rc = ensure_voices(p, n_voices);
+    if (rc) return rc;
+    const float* d_params = nullptr;
+    if ((rc = stage_params(p, params, n_params, n_voices, flags, &d_params))) return rc;
+    tb_launch L;
+    fill_launch(p, &L);
+    L.params = d_params;
+    L.n_params = n_params;
+    L.n_voices = n_voices;
+    L.out_len = p->d_len;
+    L.mode = 0;
+    if (n_samples == 0) {
+        if (out_len) std::fill(out_len, out_len + n_voices, 0ull);
+        return TB_OK;
+    }
+    if (flags & TB_OUT_DEVICE) {
+        L.n_samples = n_samples;
+        L.out = out;
+        L.out_stride = out_stride;
+        if ((rc = launch(p, L))) return rc;
+    } else {
+        // Host rows: render time chunks into two device staging buffers and stream them out on a
+        // second stream while the next chunk renders (state is carried between launches).
+        const uint64_t budget = (uint64_t)64 << 20;  // floats per staging buffer (256 MiB)
+        uint64_t chunk = budget / n_voices / TB_TILE * TB_TILE;
+        if (chunk < TB_TILE) chunk = TB_TILE;
+        if (chunk > n_samples) chunk = (n_samples + TB_TILE - 1) / TB_TILE * TB_TILE;
+        const size_t need = (size_t)chunk * n_voices;
+        if (need > p->stage_cap) {
+            for (int i = 0; i < 2; i++) {
+                cudaFree(p->d_stage[i]);
+                p->d_stage[i] = nullptr;
+            }
+            p->stage_cap = 0;
+            for (int i = 0; i < 2; i++) CU(cudaMalloc(reinterpret_cast<void**>(&p->d_stage[i]), need * 4));
+            p->stage_cap = need;
+        }
+        CU(cudaMemsetAsync(p->d_done, 0, n_voices, p->stream));
+        L.done = p->d_done;
+        int k = 0;
+        for (uint64_t base = 0; base < n_samples; base += chunk, k++) {
+            const uint64_t len = std::min<uint64_t>(chunk, n_samples - base);
+            const int b = k & 1;
+            if (k >= 2) CU(cudaStreamWaitEvent(p->stream, p->ev_copy[b], 0));
+            L.n_samples = len;
+            L.out = p->d_stage[b];
+            L.out_stride = chunk;
+            L.accumulate = k > 0;
+            if ((rc = launch(p, L))) return rc;
+            CU(cudaEventRecord(p->ev_render[b], p->stream));
+            CU(cudaStreamWaitEvent(p->copy_stream, p->ev_render[b], 0));
+            CU(cudaMemcpy2DAsync(out + base, out_stride * 4, p->d_stage[b], chunk * 4, len * 4, n_voices,
+                                 cudaMemcpyDeviceToHost, p->copy_stream));
+            CU(cudaEventRecord(p->ev_copy[b], p->copy_stream));
+        }
+        CU(cudaStreamSynchronize(p->copy_stream));
+    }
+    if (out_len) {
+        CU(cudaMemcpyAsync(out_len, p->d_len, (size_t)n_voices * 8, cudaMemcpyDeviceToHost, p->stream));
+        CU(cudaStreamSynchronize(p->stream));
+    } else if (!(flags & TB_OUT_DEVICE)) {
+        CU(cudaStreamSynchronize(p->stream));
+    }
+    return TB_OK;
+}
+
+int tb_render_mix(tb_program* p, const float* params, uint32_t n_params, uint32_t n_voices, uint64_t n_samples,
+                  float* out, uint64_t out_stride, uint64_t* out_len, float* mix, uint32_t flags) {
+    (void)p; (void)params; (void)n_params; (void)n_voices; (void)n_samples; (void)out; (void)out_stride;
+    (void)out_len; (void)mix; (void)flags;
+    return set_error(TB_ERR_UNSUPPORTED, "tb_render_mix: not built yet");
+}
+
+int tb_length(tb_program* p, const float* params, uint32_t n_params, uint32_t n_voices, uint64_t max,
+              uint64_t* len, uint32_t flags) {
+    if (!p) return set_error(TB_ERR_INVALID, "NULL program");
+    if (n_voices == 0) return TB_OK;
+    if (!len) return set_error(TB_ERR_INVALID, "len is NULL");
+    CU(cudaSetDevice(p->device));
+    int rc = ensure_voices(p, n_voices);
+    if (rc) return rc;
+    const float* d_params = nullptr;
+    if ((rc = stage_params(p, params, n_params, n_voices, flags, &d_params))) return rc;
+    tb_launch L;
+    fill_launch(p, &L);
+    L.params = d_params;
+    L.n_params = n_params;
+    L.n_voices = n_voices;
+    L.n_samples = max;
+    L.out_len = p->d_len;
+    L.mode = 1;
+    if ((rc = launch(p, L))) return rc;
+    CU(cudaMemcpyAsync(len, p->d_len, (size_t)n_voices * 8, cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    return TB_OK;
+}
+
+}  // extern "C"

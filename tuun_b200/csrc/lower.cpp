@@ -1,0 +1,668 @@
+// lower.cpp — host lowering of the tb_node op list (a reference Waveform tree,
+// src/lib/waveform.rs:23-100) to the warp byte-code of program.h.
+//
+// The emitters follow the reference's three tree walks:
+//   emit_gen  <- Generator::generate   (generator.rs:86-380)
+//   emit_len  <- Generator::length     (generator.rs:620-782)
+//   emit_seg  <- generate re-entered run by run under a Reset (generator.rs:281-318)
+// Everything the reference decides from the SHAPE of the tree is decided here once:
+// is_const (generator.rs:574-612), the all-constant-coefficient test of Filter (:428-440), the
+// form of a Fin length (greater_or_equals_at, :787-862).  Everything it decides from VALUES or
+// STATE (lengths, Append hand-over, restarts) stays in the byte-code as warp-uniform control.
+#include "lower.h"
+
+#include <algorithm>
+#include <cstring>
+#include <functional>
+
+namespace tb {
+
+namespace {
+
+struct Lowerer {
+    const tb_node* nodes;
+    uint32_t n_nodes;
+    const int32_t* lists;
+    uint32_t n_lists;
+    uint64_t pool_len;
+    Lowered& out;
+    bool fast_sines;
+
+    std::vector<int> const_memo;   // node -> cval index, -2 = not computed, -1 = not const
+    std::vector<int> state_off;    // node -> offset of its state block (or -1)
+    std::vector<int> fixed_idx;    // node -> fixed table index
+    std::vector<int> filt_idx;     // node -> filter table index
+    std::vector<uint8_t> sensitive;  // node output reaches a phase / trigger / length / coefficient
+    int slots_in_use = 0;
+
+    Lowerer(const tb_node* n, uint32_t nn, const int32_t* l, uint32_t nl, uint64_t pl, Lowered& o, bool fs)
+        : nodes(n), n_nodes(nn), lists(l), n_lists(nl), pool_len(pl), out(o), fast_sines(fs) {}
+
+    [[noreturn]] void fail(int status, const std::string& msg) {
+        out.status = status;
+        out.error = msg;
+        throw status;
+    }
+
+    int alloc_slot() {
+        int s = slots_in_use++;
+        out.n_slots = std::max<uint32_t>(out.n_slots, (uint32_t)slots_in_use);
+        return s;
+    }
+    void free_slot() { slots_in_use--; }
+
+    int emit(uint32_t op, int a = 0, int b = 0, int c = 0) {
+        out.code.push_back(tb_insn{op, a, b, c});
+        return (int)out.code.size() - 1;
+    }
+    int here() const { return (int)out.code.size(); }
+
+    // ---- validation -------------------------------------------------------------------
+    void validate() {
+        if (!nodes || n_nodes == 0) fail(TB_ERR_INVALID, "empty op list");
+        auto child_ok = [&](int32_t c, uint32_t self) { return c >= 0 && (uint32_t)c < self; };
+        for (uint32_t i = 0; i < n_nodes; i++) {
+            const tb_node& n = nodes[i];
+            if (n.reserved != 0) fail(TB_ERR_INVALID, "tb_node.reserved must be 0");
+            bool ok = true;
+            switch (n.kind) {
+                case TB_CONST:
+                    if (n.param_slot >= 0) out.n_params = std::max<uint32_t>(out.n_params, n.param_slot + 1);
+                    break;
+                case TB_TIME:
+                case TB_NOISE: break;
+                case TB_FIXED: ok = n.fixed_off + n.fixed_len <= pool_len; break;
+                case TB_FIN:
+                case TB_APPEND:
+                case TB_SINE:
+                case TB_RESET: ok = child_ok(n.a, i) && child_ok(n.b, i); break;
+                case TB_BINARY: ok = n.op <= TB_POWER && child_ok(n.a, i) && child_ok(n.b, i); break;
+                case TB_ALT: ok = child_ok(n.a, i) && child_ok(n.b, i) && child_ok(n.c, i); break;
+                case TB_MARKED:
+                case TB_CAPTURED: ok = child_ok(n.a, i); break;
+                case TB_FILTER:
+                    ok = child_ok(n.a, i) && n.ff_count >= 1 &&
+                         (uint64_t)n.list_off + n.ff_count + n.fb_count <= n_lists;
+                    if (ok)
+                        for (uint32_t j = 0; j < n.ff_count + n.fb_count; j++)
+                            ok = ok && child_ok(lists[n.list_off + j], i);
+                    break;
+                default: ok = false;
+            }
+            if (!ok) fail(TB_ERR_INVALID, "malformed node " + std::to_string(i));
+        }
+    }
+
+    // ---- is_const (generator.rs:574-612), evaluated per voice through the cexpr table ----
+    int new_cexpr(const tb_cexpr& e) {
+        out.cexpr.push_back(e);
+        return (int)out.cexpr.size() - 1;
+    }
+    int const_of(int i) {
+        if (const_memo[i] != -2) return const_memo[i];
+        const tb_node& n = nodes[i];
+        int r = -1;
+        switch (n.kind) {
+            case TB_CONST:
+                if (n.param_slot >= 0) r = new_cexpr(tb_cexpr{CE_PARAM, 0, n.param_slot, 0, n.value});
+                else r = new_cexpr(tb_cexpr{CE_LIT, 0, 0, 0, n.value});
+                break;
+            case TB_BINARY: {
+                int a = const_of(n.a), b = const_of(n.b);
+                if (a >= 0 && b >= 0) r = new_cexpr(tb_cexpr{CE_BIN, n.op, a, b, 0.f});
+                break;
+            }
+            case TB_APPEND: {  // (Some(f), Some(g)) if f == g — decidable here only for literals
+                int a = const_of(n.a), b = const_of(n.b);
+                if (a >= 0 && b >= 0 && out.cexpr[a].kind == CE_LIT && out.cexpr[b].kind == CE_LIT &&
+                    out.cexpr[a].value == out.cexpr[b].value)
+                    r = a;
+                break;
+            }
+            case TB_MARKED: r = const_of(n.a); break;
+            default: break;
+        }
+        const_memo[i] = r;
+        return r;
+    }
+    int literal_cexpr(float v) { return new_cexpr(tb_cexpr{CE_LIT, 0, 0, 0, v}); }
+
+    int new_aux(uint32_t kind, int a, int b, uint32_t words) {
+        for (const tb_aux& e : out.aux)  // a node emitted twice (Filter pre-read, Fin) shares its constants
+            if (e.kind == kind && e.a == a && e.b == b) return (int)e.off;
+        tb_aux x{kind, a, b, out.aux_words};
+        out.aux.push_back(x);
+        out.aux_words += words;
+        return (int)x.off;
+    }
+
+    int state_of(int i, int words) {
+        if (state_off[i] < 0) {
+            state_off[i] = (int)out.state_words;
+            out.state_words += words;
+        }
+        return state_off[i];
+    }
+
+    // ---- which sines may use the f32 polynomial ------------------------------------------
+    void mark_sensitive(int i, bool s) {
+        const tb_node& n = nodes[i];
+        if (s) sensitive[i] = 1;
+        switch (n.kind) {
+            case TB_FIN: mark_sensitive(n.a, true); mark_sensitive(n.b, s); break;
+            case TB_APPEND:
+            case TB_BINARY: mark_sensitive(n.a, s); mark_sensitive(n.b, s); break;
+            case TB_SINE: mark_sensitive(n.a, true); mark_sensitive(n.b, true); break;
+            case TB_FILTER:
+                mark_sensitive(n.a, s);
+                for (uint32_t j = 0; j < n.ff_count + n.fb_count; j++) mark_sensitive(lists[n.list_off + j], true);
+                break;
+            case TB_RESET: mark_sensitive(n.a, true); mark_sensitive(n.b, s); break;
+            case TB_ALT: mark_sensitive(n.a, true); mark_sensitive(n.b, s); mark_sensitive(n.c, s); break;
+            case TB_MARKED:
+            case TB_CAPTURED: mark_sensitive(n.a, s); break;
+            default: break;
+        }
+    }
+    uint32_t sine_flags(int i) const {
+        return (fast_sines && !sensitive[i]) ? (TB_SINE_FAST << 8) : (TB_SINE_EXACT << 8);
+    }
+
+    // ---- greater_or_equals_at chain (generator.rs:787-862) --------------------------------
+    int build_goe(int i) {
+        tb_goe g{};
+        g.term = GOE_MAYBE;
+        g.step_off = (uint32_t)out.goe_steps.size();
+        int cur = i;
+        for (;;) {
+            const tb_node& n = nodes[cur];
+            int c = const_of(cur);
+            if (c >= 0) {  // :796-802
+                g.term = GOE_CONST;
+                g.term_arg = c;
+                break;
+            }
+            if (n.kind == TB_TIME) {
+                g.term = GOE_TIME;
+                g.term_arg = state_of(cur, 2);
+                break;
+            }
+            if (n.kind == TB_APPEND) {  // looks at `a` only; None degrades to Maybe
+                g.through_append = 1;
+                cur = n.a;
+                continue;
+            }
+            if (n.kind == TB_BINARY && (n.op == TB_ADD || n.op == TB_SUBTRACT)) {
+                const bool ac = nodes[n.a].kind == TB_CONST, bc = nodes[n.b].kind == TB_CONST;
+                if (n.op == TB_ADD && ac) {  // value - va, recurse into b
+                    out.goe_steps.push_back(-1);
+                    out.goe_steps.push_back(const_of(n.a));
+                    g.n_steps++;
+                    cur = n.b;
+                    continue;
+                }
+                if (n.op == TB_ADD && bc) {
+                    out.goe_steps.push_back(-1);
+                    out.goe_steps.push_back(const_of(n.b));
+                    g.n_steps++;
+                    cur = n.a;
+                    continue;
+                }
+                if (n.op == TB_SUBTRACT && bc) {  // value + vb
+                    out.goe_steps.push_back(+1);
+                    out.goe_steps.push_back(const_of(n.b));
+                    g.n_steps++;
+                    cur = n.a;
+                    continue;
+                }
+            }
+            g.term = GOE_MAYBE;  // :853, :857-860 (Marked, Multiply, ...)
+            break;
+        }
+        out.goe.push_back(g);
+        return (int)out.goe.size() - 1;
+    }
+
+    // ---- Filter tables -----------------------------------------------------------------------
+    int filter_table(int i) {
+        if (filt_idx[i] >= 0) return filt_idx[i];
+        const tb_node& n = nodes[i];
+        const uint32_t K = n.ff_count, J = n.fb_count;
+        if (K > TB_MAX_K) fail(TB_ERR_UNSUPPORTED, "Filter with more than " + std::to_string(TB_MAX_K) + " feed-forward taps");
+        if (J > TB_MAX_J) fail(TB_ERR_UNSUPPORTED, "Filter with more than " + std::to_string(TB_MAX_J) + " feedback taps");
+        tb_filter_tab t{};
+        t.K = K;
+        t.J = J;
+        t.all_const = 1;
+        t.fb_const = 1;
+        t.x_slot = t.u_slot = -1;
+        for (uint32_t j = 0; j < K + J; j++) {
+            int c = lists[n.list_off + j];
+            if (nodes[c].kind != TB_CONST) t.all_const = 0;
+            int k = const_of(c);
+            t.coef[j] = k >= 0 ? TB_OPERAND_CONST(k) : 0;  // slots are filled in by emit_gen
+            if (j >= K && k < 0) t.fb_const = 0;
+        }
+        out.filt.push_back(t);
+        filt_idx[i] = (int)out.filt.size() - 1;
+        if (t.fb_const && J > 0) {
+            out.filt.back().pow_aux = out.aux_words;
+            new_aux(AUX_FILT_POW, 0, filt_idx[i], 5 * J * J);
+        }
+        return filt_idx[i];
+    }
+    int filter_state(int i) {
+        const tb_node& n = nodes[i];
+        return state_of(i, 2 + (n.ff_count - 1) + n.fb_count + 2);
+    }
+
+    int fixed_table(int i) {
+        if (fixed_idx[i] < 0) {
+            out.fixed.push_back(tb_fixed_tab{nodes[i].fixed_off, nodes[i].fixed_len});
+            fixed_idx[i] = (int)out.fixed.size() - 1;
+        }
+        return fixed_idx[i];
+    }
+
+    // ---- generate ------------------------------------------------------------------------------
+    void emit_gen(int i) {
+        const tb_node& n = nodes[i];
+        switch (n.kind) {
+            case TB_CONST: emit(G_CONST, const_of(i)); break;
+            case TB_TIME: emit(G_TIME, state_of(i, 2)); break;
+            case TB_FIXED: emit(G_FIXED, state_of(i, 2), fixed_table(i)); break;
+            case TB_NOISE:
+                fail(TB_ERR_UNSUPPORTED,
+                     "Noise: the reference draws from an unseeded thread-local generator (generator.rs:115); "
+                     "supply the samples as a Fixed buffer");
+            case TB_MARKED:
+            case TB_CAPTURED: emit_gen(n.a); break;
+            case TB_BINARY: {
+                const int merge = n.op == TB_MERGE;
+                const int cb = const_of(n.b);
+                emit_gen(n.a);
+                if (cb >= 0) {
+                    emit(G_BINC, (int)n.op, cb, merge);
+                } else {
+                    const int s = alloc_slot();
+                    const int b0 = emit(G_BIN_BEGIN, s, merge, 0);
+                    emit_gen(n.b);
+                    out.code[b0].c = emit(G_BIN_END, s, (int)n.op, merge);
+                    free_slot();
+                }
+                break;
+            }
+            case TB_SINE: {
+                const int cf = const_of(n.a), cp = const_of(n.b);
+                const int st = state_of(i, 2);
+                const uint32_t fl = sine_flags(i);
+                const int aux_inc = cf >= 0 ? new_aux(AUX_SINE_INC, cf, 0, 1) : 0;
+                const int aux_ph = cp >= 0 ? new_aux(AUX_SINE_PHASE, cp, 0, 1) : 0;
+                if (cf >= 0 && cp >= 0) {
+                    emit(G_SINE_CC | fl, st, aux_inc, aux_ph);
+                } else if (cp >= 0) {
+                    emit_gen(n.a);
+                    emit(G_SINE_AC | fl, st, 0, aux_ph);
+                } else if (cf >= 0) {
+                    emit_gen(n.b);
+                    emit(G_SINE_CA | fl, st, aux_inc, 0);
+                } else {
+                    emit_gen(n.a);
+                    const int s = alloc_slot();
+                    const int b0 = emit(G_SINE_BEGIN, s, 0, 0);
+                    emit_gen(n.b);
+                    out.code[b0].c = emit(G_SINE_END | fl, st, s, 0);
+                    free_slot();
+                }
+                break;
+            }
+            case TB_ALT: {
+                const int cp = const_of(n.b), cn = const_of(n.c);
+                emit_gen(n.a);
+                if (cp >= 0 && cn >= 0) {
+                    emit(G_ALT_CC, cp, cn);
+                } else {
+                    const int st = alloc_slot();
+                    const int b0 = emit(G_ALT_BEGIN, st, 0, 0);
+                    int opp = TB_OPERAND_CONST(cp), opn = TB_OPERAND_CONST(cn);
+                    int extra = 0;
+                    if (cp < 0) {
+                        emit_gen(n.b);
+                        if (cn < 0) {
+                            opp = alloc_slot();
+                            extra = 1;
+                            emit(G_ALT_POS, opp);
+                        } else {
+                            // the negative branch is constant: keep the positive one in a slot too
+                            opp = alloc_slot();
+                            extra = 1;
+                            emit(G_ALT_POS, opp);
+                        }
+                    }
+                    if (cn < 0) {
+                        emit_gen(n.c);
+                        opn = 0;
+                    }
+                    out.code[b0].c = emit(G_ALT_END, st, opp, opn);
+                    if (extra) free_slot();
+                    free_slot();
+                }
+                break;
+            }
+            case TB_FILTER: {
+                const int fi = filter_table(i);
+                const int st = filter_state(i);
+                const int K = (int)n.ff_count, J = (int)n.fb_count;
+                const int p0 = emit(G_FILT_PRE, st, K, 0);
+                emit_gen(n.a);
+                emit(G_FILT_PRE_END, st, K, J);
+                out.code[p0].c = here();
+                emit_gen(n.a);
+                bool any_code = false;
+                for (int j = 0; j < K + J; j++) any_code |= const_of(lists[n.list_off + j]) < 0;
+                const bool need_u = J > 0 && !out.filt[fi].fb_const;
+                if (!any_code) {
+                    emit(G_FILT_RUN, st, fi, 0);
+                } else {
+                    int used = 0;
+                    const int xs = alloc_slot();
+                    used++;
+                    out.filt[fi].x_slot = xs;
+                    const int b0 = emit(G_FILT_BEGIN, st, fi, 0);
+                    for (int j = 0; j < K + J; j++) {
+                        const int c = lists[n.list_off + j];
+                        if (const_of(c) >= 0) continue;
+                        const int s = alloc_slot();
+                        used++;
+                        out.filt[fi].coef[j] = s;
+                        emit_gen(c);
+                        emit(G_FILT_COEF, s);
+                    }
+                    if (need_u) {
+                        out.filt[fi].u_slot = alloc_slot();
+                        used++;
+                    }
+                    out.code[b0].c = emit(G_FILT_RUN, st, fi, 1);
+                    while (used--) free_slot();
+                }
+                break;
+            }
+            case TB_FIN: {
+                const int gi = build_goe(n.a);
+                const tb_goe g = out.goe[gi];
+                const bool may_maybe = g.term == GOE_MAYBE || g.through_append;
+                const bool may_static = g.term != GOE_MAYBE;
+                const int h0 = emit(G_FIN_HEAD, gi, 0, 0);
+                int scan = -1;
+                if (may_maybe) {
+                    emit_gen(n.a);
+                    scan = emit(G_FIN_SCAN, 0, 0, 0);
+                }
+                out.code[h0].c = here();
+                if (may_static) {
+                    emit_len(n.a);
+                    emit(G_FIN_STATIC);
+                }
+                if (scan >= 0) out.code[scan].c = here();
+                const int in0 = emit(G_FIN_INNER, 0, 0, 0);
+                emit_gen(n.b);
+                out.code[in0].c = emit(G_FIN_ADV);
+                emit_len(n.b);
+                emit(G_FIN_END);
+                break;
+            }
+            case TB_APPEND: {
+                const int st = state_of(i, 1);
+                const int s = alloc_slot();
+                const int b0 = emit(G_APP_BEGIN, st, 0, 0);
+                emit_gen(n.a);
+                const int m0 = emit(G_APP_MID, st, s, 0);
+                out.code[b0].c = m0;
+                emit_gen(n.b);
+                emit(G_APP_END, 0, s, 0);
+                out.code[m0].c = here();
+                free_slot();
+                break;
+            }
+            case TB_RESET: {
+                const int st = state_of(i, 1);
+                emit_gen(n.a);
+                const int s = alloc_slot();
+                const int b0 = emit(G_RESET_BEGIN, st, s, 0);
+                emit_seg(n.b);
+                out.code[b0].c = emit(G_RESET_END, st);
+                free_slot();
+                break;
+            }
+            default: fail(TB_ERR_INVALID, "unknown node kind");
+        }
+    }
+
+    // ---- length ----------------------------------------------------------------------------------
+    void emit_len(int i) {
+        const tb_node& n = nodes[i];
+        switch (n.kind) {
+            case TB_CONST:
+            case TB_NOISE: emit(L_INF); break;
+            case TB_TIME: emit(L_TIME, state_of(i, 2)); break;
+            case TB_FIXED: emit(L_FIXED, state_of(i, 2), fixed_table(i)); break;
+            case TB_MARKED:
+            case TB_CAPTURED: emit_len(n.a); break;
+            case TB_SINE:
+                (void)state_of(i, 2);
+                emit_len(n.a);
+                emit(L_PUSH);
+                emit_len(n.b);
+                emit(L_MIN);
+                break;
+            case TB_BINARY:
+                emit_len(n.a);
+                emit(L_PUSH);
+                emit_len(n.b);
+                emit(n.op == TB_MERGE ? L_MAX : L_MIN);
+                break;
+            case TB_RESET:
+                (void)state_of(i, 1);
+                emit_len(n.a);
+                break;
+            case TB_ALT:
+                emit_len(n.a);
+                emit(L_PUSH);
+                emit_len(n.b);
+                emit_len(n.c);
+                emit(L_POP);
+                break;
+            case TB_FILTER: {
+                (void)filter_table(i);
+                const int st = filter_state(i);
+                emit(L_FILT_HEAD, st, (int)n.ff_count, (int)n.fb_count);
+                emit_len(n.a);
+                const int m0 = emit(L_FILT_MID, 0, 0, 0);
+                for (uint32_t j = 0; j < n.ff_count + n.fb_count; j++) emit_len(lists[n.list_off + j]);
+                out.code[m0].c = emit(L_FILT_END);
+                break;
+            }
+            case TB_APPEND: {
+                const int st = state_of(i, 1);
+                const int b0 = emit(L_APP_BEGIN, st, 0, 0);
+                emit_len(n.a);
+                out.code[b0].c = emit(L_APP_MID, st);
+                emit_len(n.b);
+                emit(L_APP_END);
+                break;
+            }
+            case TB_FIN: {
+                const int gi = build_goe(n.a);
+                const tb_goe g = out.goe[gi];
+                const bool may_maybe = g.term == GOE_MAYBE || g.through_append;
+                const bool may_static = g.term != GOE_MAYBE;
+                const int h0 = emit(G_FIN_HEAD, gi, 0, 0);
+                int scan2 = -1;
+                if (may_maybe) {
+                    out.pure_len = 0;
+                    const int s = alloc_slot();
+                    emit(G_SAVE, s);
+                    emit_gen(n.a);
+                    emit(L_FIN_SCAN1);
+                    emit(G_RESTORE, s);
+                    free_slot();
+                    emit_len(n.b);
+                    scan2 = emit(L_FIN_SCAN2, 0, 0, 0);
+                }
+                out.code[h0].c = here();
+                if (may_static) {
+                    emit_len(n.b);
+                    emit(L_PUSH);
+                    emit_len(n.a);
+                    emit(L_FIN_STATIC);
+                }
+                if (scan2 >= 0) out.code[scan2].c = here();
+                break;
+            }
+            default: fail(TB_ERR_INVALID, "unknown node kind");
+        }
+    }
+
+    // ---- segmented (inside a Reset) ----------------------------------------------------------------
+    void emit_seg(int i) {
+        const tb_node& n = nodes[i];
+        switch (n.kind) {
+            case TB_CONST: emit(S_CONST, const_of(i)); break;
+            case TB_TIME: emit(S_TIME, state_of(i, 2)); break;
+            case TB_FIXED: emit(S_FIXED, state_of(i, 2), fixed_table(i)); break;
+            case TB_MARKED:
+            case TB_CAPTURED: emit_seg(n.a); break;
+            case TB_BINARY: {
+                const int merge = n.op == TB_MERGE;
+                const int cb = const_of(n.b);
+                emit_seg(n.a);
+                if (cb >= 0) {
+                    emit(S_BINC, (int)n.op, cb, merge);
+                } else {
+                    const int s = alloc_slot();
+                    emit(S_BIN_BEGIN, s);
+                    emit_seg(n.b);
+                    emit(S_BIN_END, s, (int)n.op, merge);
+                    free_slot();
+                }
+                break;
+            }
+            case TB_SINE: {
+                const int cf = const_of(n.a), cp = const_of(n.b);
+                const int st = state_of(i, 2);
+                const uint32_t fl = sine_flags(i);
+                const int aux_inc = cf >= 0 ? new_aux(AUX_SINE_INC, cf, 0, 1) : 0;
+                const int aux_ph = cp >= 0 ? new_aux(AUX_SINE_PHASE, cp, 0, 1) : 0;
+                if (cf >= 0 && cp >= 0) {
+                    emit(S_SINE_CC | fl, st, aux_inc, aux_ph);
+                } else if (cp >= 0) {
+                    emit_seg(n.a);
+                    emit(S_SINE_AC | fl, st, 0, aux_ph);
+                } else if (cf >= 0) {
+                    emit_seg(n.b);
+                    emit(S_SINE_CA | fl, st, aux_inc, 0);
+                } else {
+                    emit_seg(n.a);
+                    const int s = alloc_slot();
+                    emit(S_SINE_BEGIN, s);
+                    emit_seg(n.b);
+                    emit(S_SINE_END | fl, st, s, 0);
+                    free_slot();
+                }
+                break;
+            }
+            case TB_ALT: {
+                const int cp = const_of(n.b), cn = const_of(n.c);
+                emit_seg(n.a);
+                if (cp >= 0 && cn >= 0) {
+                    emit(S_ALT_CC, cp, cn);
+                } else {
+                    const int st = alloc_slot();
+                    emit(S_ALT_BEGIN, st);
+                    int opp = TB_OPERAND_CONST(cp), opn = TB_OPERAND_CONST(cn);
+                    int extra = 0;
+                    if (cp < 0) {
+                        emit_seg(n.b);
+                        opp = alloc_slot();
+                        extra = 1;
+                        emit(S_ALT_POS, opp);
+                    }
+                    if (cn < 0) {
+                        emit_seg(n.c);
+                        opn = 0;
+                    }
+                    emit(S_ALT_END, st, opp, opn);
+                    if (extra) free_slot();
+                    free_slot();
+                }
+                break;
+            }
+            case TB_RESET: {
+                const int st = state_of(i, 1);
+                emit_seg(n.a);
+                const int s = alloc_slot();
+                emit(S_RESET_BEGIN, st, s);
+                emit_seg(n.b);
+                emit(S_RESET_END, st);
+                free_slot();
+                break;
+            }
+            case TB_FIN: {
+                const int gi = build_goe(n.a);
+                const tb_goe g = out.goe[gi];
+                if (g.term == GOE_MAYBE || g.through_append)
+                    fail(TB_ERR_UNSUPPORTED, "Fin with a rendered (non-analytic) length inside a Reset");
+                emit_seg(n.b);
+                emit(S_FIN, gi);
+                break;
+            }
+            case TB_NOISE: fail(TB_ERR_UNSUPPORTED, "Noise (see generator.rs:115): supply a Fixed buffer");
+            case TB_FILTER: fail(TB_ERR_UNSUPPORTED, "Filter inside a Reset");
+            case TB_APPEND: fail(TB_ERR_UNSUPPORTED, "Append inside a Reset");
+            default: fail(TB_ERR_INVALID, "unknown node kind");
+        }
+    }
+
+    void run() {
+        validate();
+        const_memo.assign(n_nodes, -2);
+        state_off.assign(n_nodes, -1);
+        fixed_idx.assign(n_nodes, -1);
+        filt_idx.assign(n_nodes, -1);
+        sensitive.assign(n_nodes, 0);
+        const int root = (int)n_nodes - 1;
+        mark_sensitive(root, false);
+        out.pure_len = 1;
+        out.pc_gen = (uint32_t)here();
+        emit_gen(root);
+        emit(OP_END);
+        out.pc_len = (uint32_t)here();
+        emit_len(root);
+        emit(OP_END);
+        if (out.state_words == 0) out.state_words = 1;
+        if (out.cexpr.empty()) literal_cexpr(0.f);
+        if (out.aux_words == 0) out.aux_words = 1;
+        if (out.n_slots == 0) out.n_slots = 1;
+        out.n_nodes = n_nodes;
+    }
+};
+
+}  // namespace
+
+int lower(const tb_node* nodes, uint32_t n_nodes, const int32_t* lists, uint32_t n_lists,
+          uint64_t pool_len, bool fast_sines, Lowered& out) {
+    out = Lowered();
+    Lowerer L(nodes, n_nodes, lists, n_lists, pool_len, out, fast_sines);
+    try {
+        L.run();
+    } catch (int status) {
+        return status;
+    } catch (const std::bad_alloc&) {
+        out.status = TB_ERR_NOMEM;
+        out.error = "out of host memory while lowering";
+        return TB_ERR_NOMEM;
+    }
+    return TB_OK;
+}
+
+}  // namespace tb

@@ -1,0 +1,33 @@
+// lower.h — result of lowering a tb_node op list to the warp byte-code (see lower.cpp).
+#pragma once
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/tuun_b200.h"
+#include "program.h"
+
+namespace tb {
+
+struct Lowered {
+    std::vector<tb_insn> code;
+    uint32_t pc_gen = 0, pc_len = 0;
+    std::vector<tb_cexpr> cexpr;
+    std::vector<tb_aux> aux;
+    uint32_t aux_words = 0;
+    std::vector<tb_goe> goe;
+    std::vector<int32_t> goe_steps;
+    std::vector<tb_filter_tab> filt;
+    std::vector<tb_fixed_tab> fixed;
+    uint32_t n_slots = 0, state_words = 0, n_params = 0, n_nodes = 0;
+    uint32_t pure_len = 1;
+    int status = 0;
+    std::string error;
+};
+
+// Returns TB_OK or a negative tb_status (out.error holds the reason).
+int lower(const tb_node* nodes, uint32_t n_nodes, const int32_t* lists, uint32_t n_lists,
+          uint64_t pool_len, bool fast_sines, Lowered& out);
+
+}  // namespace tb

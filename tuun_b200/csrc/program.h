@@ -1,0 +1,188 @@
+// program.h — device byte-code shared by the host lowering (lower.cpp) and the kernels
+// (render.cu).
+//
+// A Waveform tree (reference src/lib/waveform.rs:23-100) is lowered to a flat list of
+// fixed-width instructions that ONE WARP executes per voice, with warp-uniform control flow.
+// The warp renders a tile of TB_TILE = 32 * TB_C samples per pass: lane l owns the C
+// consecutive tile positions [l*C, l*C + C) of every intermediate, the "accumulator" being C
+// registers per lane and the named temporaries living in per-warp shared-memory slots.
+//
+// Three instruction families mirror the three ways the reference walks a tree:
+//   G_*  Generator::generate            (generator.rs:86-380)   samples + state
+//   L_*  Generator::length              (generator.rs:620-782)  lengths + position state only
+//   S_*  generate under a Reset         (generator.rs:281-318)  segmented: every sample knows the
+//        tile position at which its run (re)started, so all runs of a tile evaluate at once
+#pragma once
+#include <stdint.h>
+
+#define TB_C 8               // samples per lane per tile
+#define TB_TILE (32 * TB_C)  // samples per tile
+#define TB_WARPS_PER_CTA 4
+#define TB_MAX_K 9   // feed-forward taps supported by the device path (K-1 <= C)
+#define TB_MAX_J 4   // feedback taps supported by the scan path
+#define TB_CTL_DEPTH 96
+
+struct tb_insn {
+    uint32_t op;
+    int32_t a, b, c;
+};
+
+enum tb_op : uint32_t {
+    OP_END = 0,
+    // ---- generate ----
+    G_CONST,       // a = cval index
+    G_TIME,        // a = state offset
+    G_FIXED,       // a = state offset, b = fixed table index (off,len)
+    G_NOISE,       // a = node id
+    G_BINC,        // a = operator, b = cval index, c = merge
+    G_BIN_BEGIN,   // a = slot, b = merge, c = jump target (the matching G_BIN_END)
+    G_BIN_END,     // a = slot, b = operator, c = merge
+    G_SINE_CC,     // a = state, b = aux index of increment, c = aux index of phase; flags in op>>8
+    G_SINE_AC,     // a = state, c = aux index of phase          (frequency in acc)
+    G_SINE_CA,     // a = state, b = aux index of increment      (phase in acc)
+    G_SINE_BEGIN,  // a = slot, c = jump target (G_SINE_END)
+    G_SINE_END,    // a = state, b = slot
+    G_ALT_CC,      // a = cval (positive), b = cval (negative)
+    G_ALT_BEGIN,   // a = trigger slot, c = jump target (G_ALT_END)
+    G_ALT_POS,     // a = slot for the positive branch
+    G_ALT_END,     // a = trigger slot, b = positive operand, c = negative operand
+    G_FILT_PRE,    // a = state, b = K, c = jump target (after G_FILT_PRE_END)
+    G_FILT_PRE_END,  // a = state, b = K, c = J
+    G_FILT_BEGIN,  // a = state, b = filter table index, c = jump target (G_FILT_RUN)
+    G_FILT_COEF,   // a = slot
+    G_FILT_RUN,    // a = state, b = filter table index, c = 1 when G_FILT_BEGIN preceded
+    G_FIN_HEAD,    // a = goe table index, c = jump target (static path)
+    G_FIN_SCAN,    // c = jump target (join)
+    G_FIN_STATIC,  //
+    G_FIN_INNER,   // c = jump target (G_FIN_ADV)
+    G_FIN_ADV,     //
+    G_FIN_END,     //
+    G_APP_BEGIN,   // a = state, c = jump target (G_APP_MID)
+    G_APP_MID,     // a = state, b = slot, c = jump target (just past G_APP_END)
+    G_APP_END,     // b = slot
+    G_RESET_BEGIN, // a = state, b = origin slot, c = jump target (G_RESET_END)
+    G_RESET_END,   // a = state
+    G_SAVE,        // a = slot        acc -> slot (with its length)
+    G_RESTORE,     // a = slot
+    // ---- length ----
+    L_INF,
+    L_TIME,        // a = state
+    L_FIXED,       // a = state, b = fixed table index
+    L_PUSH,
+    L_MIN,
+    L_MAX,
+    L_POP,
+    L_FILT_HEAD,   // a = state, b = K, c = J
+    L_FILT_MID,    // c = jump target (L_FILT_END)
+    L_FILT_END,
+    L_APP_BEGIN,   // a = state, c = jump target (L_APP_MID)
+    L_APP_MID,     // a = state
+    L_APP_END,
+    L_FIN_SCAN1,
+    L_FIN_SCAN2,   // c = jump target (join)
+    L_FIN_STATIC,
+    // ---- segmented (under Reset) ----
+    S_CONST,
+    S_TIME,
+    S_FIXED,
+    S_BINC,
+    S_BIN_BEGIN,   // a = slot
+    S_BIN_END,     // a = slot, b = operator, c = merge
+    S_SINE_CC,
+    S_SINE_AC,
+    S_SINE_CA,
+    S_SINE_BEGIN,  // a = slot
+    S_SINE_END,    // a = state, b = slot
+    S_ALT_CC,
+    S_ALT_BEGIN,   // a = trigger slot
+    S_ALT_POS,     // a = slot
+    S_ALT_END,     // a = trigger slot, b = positive operand, c = negative operand
+    S_RESET_BEGIN, // a = state, b = origin slot
+    S_RESET_END,   // a = state
+    S_FIN,         // a = goe table index   (static Time / const forms only)
+    OP_COUNT
+};
+
+// Operand encoding for instructions that take "a waveform that may be constant":
+//   >= 0  shared-memory slot index;   < 0  ~cval index.
+#define TB_OPERAND_CONST(k) (~(int32_t)(k))
+
+// Sine precision classes (op >> 8 of the G_SINE_* / S_SINE_* instructions).
+#define TB_SINE_EXACT 0u  // f64 polynomial, rounds like the reference's (f64 sin) as f32
+#define TB_SINE_FAST 1u   // f32 polynomial; only for sines that feed no phase, trigger or length
+
+// Constant-table construction, evaluated per voice at kernel start (generator.rs:574-612 is_const
+// folding done once instead of once per block).
+enum tb_cexpr_kind : uint32_t { CE_LIT = 0, CE_PARAM = 1, CE_BIN = 2 };
+struct tb_cexpr {
+    uint32_t kind;
+    uint32_t op;   // CE_BIN: tb_operator
+    int32_t a, b;  // CE_PARAM: a = column; CE_BIN: cval indices
+    float value;   // CE_LIT, and CE_PARAM default
+};
+
+// Per-voice derived 64-bit constants ("aux"), evaluated after the constant table.
+enum tb_aux_kind : uint32_t {
+    AUX_SINE_INC = 0,    // cval[a] rad/s  -> phase increment, 2^-64 turns per sample
+    AUX_SINE_PHASE = 1,  // cval[a] rad    -> phase offset, 2^-64 turns
+    AUX_FILT_POW = 2     // feedback coefficients of filter table b -> 5 JxJ f64 matrices
+};
+struct tb_aux {
+    uint32_t kind;
+    int32_t a, b;
+    uint32_t off;  // offset in 64-bit words inside the per-warp aux area
+};
+
+// greater_or_equals_at chain (generator.rs:787-862), flattened.
+enum tb_goe_term : uint32_t { GOE_TIME = 0, GOE_CONST = 1, GOE_MAYBE = 2 };
+struct tb_goe {
+    uint32_t term;        // tb_goe_term
+    int32_t term_arg;     // GOE_TIME: state offset; GOE_CONST: cval index
+    uint32_t through_append;  // a `None` answer degrades to `Maybe` (generator.rs:821-836)
+    uint32_t n_steps;
+    uint32_t step_off;    // into the goe step table: pairs (sign, cval index): value -= / += cval
+};
+
+struct tb_filter_tab {
+    uint32_t K, J;
+    uint32_t all_const;    // every coefficient literally Const (generator.rs:428-440)
+    uint32_t fb_const;     // every feedback coefficient is a constant operand -> scan path
+    uint32_t pow_aux;      // aux offset of the matrix powers (fb_const && J > 0)
+    int32_t x_slot;        // slot holding the zero-extended input when not all-const
+    int32_t u_slot;        // scratch slot for the serial feedback fallback
+    int32_t coef[TB_MAX_K + 16];  // K feed-forward then J feedback operands
+};
+
+struct tb_fixed_tab {
+    uint64_t off, len;
+};
+
+// Everything the kernel needs, passed by value.
+struct tb_launch {
+    const tb_insn* code;
+    uint32_t n_code;
+    uint32_t pc_gen, pc_len;  // entry points of the root's G_* and L_* programs
+    const tb_cexpr* cexpr;
+    uint32_t n_cval;
+    const tb_aux* aux;
+    uint32_t n_aux, aux_words;
+    const tb_goe* goe;
+    const int32_t* goe_steps;
+    const tb_filter_tab* filt;
+    const tb_fixed_tab* fixed;
+    const float* pool;
+    uint32_t n_slots, state_words;
+    uint32_t sample_rate;
+    // per call
+    const float* params;
+    uint32_t n_params, n_voices;
+    uint64_t n_samples;
+    float* out;
+    uint64_t out_stride;
+    unsigned long long* out_len;
+    uint32_t* state;       // [n_voices][state_words]
+    uint32_t mode;         // 0 = generate, 1 = length only
+    uint32_t pure_len;     // length program contains no G_* code
+    uint32_t accumulate;   // out_len[v] += (chunked host-output renders) instead of =
+    uint8_t* done;         // [n_voices] or NULL: voices that already returned short in this call
+};
