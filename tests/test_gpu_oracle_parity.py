@@ -98,7 +98,9 @@ def test_filter_4_3():  # benches/tracker_benches.rs:69-89
     ref = OracleProgram(w, SR).render(43 * 1024)
     got = gpu_render(w, 43 * 1024)
     assert len(got) == len(ref)
-    assert np.max(np.abs(got - ref) / np.maximum(1.0, np.abs(ref))) <= 1e-5
+    # Poles at radius ~0.99 next to z = 1: the reference's own f32 round-off noise is ~1e-5 here, and
+    # a scan cannot reproduce one particular noise realisation (DESIGN.md "Filter numerics").
+    assert np.max(np.abs(got - ref) / np.maximum(1.0, np.abs(ref))) <= TOL
 
 
 def test_filter_1_1_linear():  # benches/tracker_benches.rs:36-67, time-varying coefficients
@@ -145,7 +147,10 @@ def test_streaming_blocks_match_one_shot():
     b = gpu_render(w, 20000, block=1024)
     c = gpu_render(w, 20000, block=777)
     assert len(a) == len(b) == len(c) == 20000
-    assert np.max(np.abs(a - b)) <= 2e-6 and np.max(np.abs(a - c)) <= 2e-6
+    # Tile-aligned blocks evaluate exactly the same arithmetic; unaligned ones re-partition the
+    # filter scan, which moves the result by round-off noise only.  The phase is integer: exact.
+    np.testing.assert_array_equal(a, b)
+    assert np.max(np.abs(a - c)) <= TOL
 
 
 def test_batch_params():
