@@ -35,10 +35,11 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--voices", type=int, default=65536)
     ap.add_argument("--seconds", type=float, default=10.0)
-    ap.add_argument("--e2e-voices", type=int, default=0, help="0 = all local voices")
+    ap.add_argument("--e2e-voices", type=int, default=0, help="rows of the reused pinned host window (default 8192)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-mix", action="store_true")
     return ap.parse_args()
 
 
@@ -236,41 +237,80 @@ def main():
                 "traffic": None, "kernel": "tb_render_kernel", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_launch_s * 1e3}
 
-    # end to end through the C ABI with HOST buffers: H2D of the parameter table, D2H of every row
+    # end to end through the C ABI with HOST buffers: H2D of the parameter table, D2H of every row.
+    # All local voices are rendered; the pinned host window (e2e_group rows) is reused group after
+    # group, the way a consumer draining the rows would.
     e2e = None
     if not args.no_e2e:
-        ev = args.e2e_voices or n_local
-        ev = min(ev, n_local)
-        host = torch.empty((ev, n_samples), dtype=torch.float32, pin_memory=True)
+        grp = min(n_local, args.e2e_voices or 8192)
+        host = torch.empty((grp, n_samples), dtype=torch.float32, pin_memory=True)
         host_np = host.numpy()
-        ph = torch.from_numpy(params_h[:ev].copy()).pin_memory().numpy()
+        ph = params_h
         e2e_steps = max(1, min(args.steps, 2))
         prog_h = Program(fm_filter_voice(), SAMPLE_RATE, device=local)
-        prog_h.render(host_np, params=ph)  # warm: staging buffers, page touch
+
+        def e2e_step():
+            for a in range(0, n_local, grp):
+                b = min(n_local, a + grp)
+                prog_h.reset()
+                prog_h.render(host_np[: b - a], params=ph[a:b])
+
+        prog_h.render(host_np, params=ph[:grp])  # warm: staging buffers, page touch
         barrier()
         e0 = time.perf_counter()
         for _ in range(e2e_steps):
-            prog_h.reset()
-            prog_h.render(host_np, params=ph)
+            e2e_step()
         torch.cuda.synchronize()
         e1 = time.perf_counter()
         et = torch.tensor([e1 - e0], dtype=torch.float64, device="cuda")
-        ne = torch.tensor([float(ev)], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(et, op=dist.ReduceOp.MAX)
-            dist.all_reduce(ne, op=dist.ReduceOp.SUM)
-        e2e = {"value": float(ne.item()) * n_samples * e2e_steps / float(et.item()), "unit": UNIT,
-               "h2d_bytes_per_step": int(ev * 8 * 4), "d2h_bytes_per_step": int(ev * n_samples * 4 + ev * 8),
-               "voices": int(ne.item()), "steps": e2e_steps,
-               "path": "tb_render with pinned host rows: chunked render -> cudaMemcpy2DAsync on a second stream"}
-        del host, host_np
+        e2e = {"value": args.voices * n_samples * e2e_steps / float(et.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(n_local * 8 * 4), "d2h_bytes_per_step": int(n_local * n_samples * 4 + n_local * 8),
+               "voices": args.voices, "steps": e2e_steps, "host_window_rows": grp,
+               "path": "tb_render with pinned host rows: voice groups rendered into 2 device staging buffers, "
+                       "each group leaves with one cudaMemcpyAsync on a second stream while the next renders"}
+        del host, host_np, prog_h
+
+    # optional mixdown: per-GPU mix on the device, NCCL reduce of the [n_samples] partials over NVLink
+    mixdown = None
+    if not args.no_mix:
+        mix_d = torch.empty(n_samples, dtype=torch.float32, device="cuda")
+        prog_m = Program(fm_filter_voice(), SAMPLE_RATE, device=local)
+        mstream = torch.cuda.ExternalStream(prog_m.stream, device=local)
+        done_ev = torch.cuda.Event()
+
+        def mix_step():
+            prog_m.reset()
+            prog_m.render_mix(mix_d, n_local, params=params_d)
+            if world > 1:
+                done_ev.record(mstream)
+                torch.cuda.current_stream().wait_event(done_ev)
+                dist.reduce(mix_d, dst=0, op=dist.ReduceOp.SUM)
+
+        mix_step()
+        barrier()
+        m0 = time.perf_counter()
+        msteps = max(1, min(args.steps, 2))
+        for _ in range(msteps):
+            mix_step()
+        torch.cuda.synchronize()
+        barrier()
+        m1 = time.perf_counter()
+        mt = torch.tensor([m1 - m0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(mt, op=dist.ReduceOp.MAX)
+        mixdown = {"value": args.voices * n_samples * msteps / float(mt.item()), "unit": UNIT,
+                   "ms_per_step": 1e3 * float(mt.item()) / msteps, "nccl_reduce_bytes": int(n_samples * 4) if world > 1 else 0,
+                   "mode": "tb_render_mix(TB_NO_VOICE_OUT | TB_OUT_DEVICE) per rank, then ncclReduce(sum,f32) to rank 0"}
+        del prog_m
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32 samples, u64 fixed-point phase, f64 sine core",
                 "data": "synthetic", "config": config(args, n_samples), "clocks": clocks,
-                "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e,
+                "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e, "mixdown": mixdown,
                 "wall_ms_per_step": float(tmax[1].item()) / args.steps, "lengths_ok": lens_ok}
         if not args.no_cpu:
             cb, _ = cpu_baseline(args, n_samples, args.cpu_seconds, os.cpu_count() or 1)

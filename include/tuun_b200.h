@@ -127,9 +127,9 @@ int tb_render(tb_program* p, const float* params, uint32_t n_params, uint32_t n_
 
 /*
  * tb_render plus the tracker's mix loop (tracker.rs:597-642): mix[i] = sum over voices of
- * out[v][i] for i < out_len[v]  (voices summed in index order per 32-voice group, groups
- * combined in f32 — see DESIGN.md "mixdown").  `out` may be NULL with TB_NO_VOICE_OUT.
- * `mix` holds n_samples floats and is overwritten.
+ * out[v][i] for i < out_len[v], added in f32 in voice index order exactly like the tracker's
+ * serial `out[j] += tmp[j]` (tracker.rs:617-619).  `out` may be NULL with TB_NO_VOICE_OUT.
+ * `mix` holds n_samples floats, is overwritten, and lives where `out` lives (TB_OUT_DEVICE).
  */
 int tb_render_mix(tb_program* p, const float* params, uint32_t n_params, uint32_t n_voices,
                   uint64_t n_samples, float* out, uint64_t out_stride, uint64_t* out_len,

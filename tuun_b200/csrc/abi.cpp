@@ -17,6 +17,9 @@
 extern "C" size_t tb_kernel_smem_bytes(uint32_t n_code, uint32_t n_slots, uint32_t aux_words,
                                        uint32_t n_cval, uint32_t state_words);
 extern "C" cudaError_t tb_kernel_launch(const tb_launch* P, size_t smem, cudaStream_t stream);
+extern "C" cudaError_t tb_mix_launch(const float* rows, uint64_t stride, const unsigned long long* lens,
+                                     uint32_t n_voices, uint64_t n_samples, uint64_t t0, float* mix,
+                                     int accumulate, cudaStream_t stream);
 
 namespace {
 
@@ -65,6 +68,8 @@ struct tb_program {
     size_t params_cap = 0;
     unsigned long long* d_len = nullptr;
     uint8_t* d_done = nullptr;
+    float* d_mix = nullptr;
+    size_t mix_cap = 0;
     float* d_stage[2] = {nullptr, nullptr};
     size_t stage_cap = 0;  // floats per staging buffer
     cudaStream_t stream = nullptr, copy_stream = nullptr;
@@ -77,7 +82,7 @@ struct tb_program {
         cudaSetDevice(device);
         cudaFree(d_code); cudaFree(d_cexpr); cudaFree(d_aux); cudaFree(d_goe); cudaFree(d_goe_steps);
         cudaFree(d_filt); cudaFree(d_fixed); cudaFree(d_pool); cudaFree(d_state); cudaFree(d_params);
-        cudaFree(d_len); cudaFree(d_done); cudaFree(d_stage[0]); cudaFree(d_stage[1]);
+        cudaFree(d_len); cudaFree(d_done); cudaFree(d_mix); cudaFree(d_stage[0]); cudaFree(d_stage[1]);
         for (int i = 0; i < 2; i++) {
             if (ev_render[i]) cudaEventDestroy(ev_render[i]);
             if (ev_copy[i]) cudaEventDestroy(ev_copy[i]);
@@ -277,41 +282,77 @@ int tb_reset(tb_program* p) {
     return TB_OK;
 }
 
-int tb_render(tb_program* p, const float* params, uint32_t n_params, uint32_t n_voices, uint64_t n_samples,
-              float* out, uint64_t out_stride, uint64_t* out_len, uint32_t flags) {
+}  // extern "C"
+
+namespace {
+
+// Shared body of tb_render / tb_render_mix.
+//  * device rows:   one launch over all voices straight into `out`.
+//  * host rows / no rows: voices are rendered group by group into two device staging buffers;
+//    a group's rows are contiguous, so each group leaves with ONE cudaMemcpyAsync on a second
+//    stream (2-D copies run at a few GB/s on this platform, 1-D ones at ~56 GB/s) while the next
+//    group renders.  Very long renders are additionally cut in time; state carries over.
+//  * mix: after a group (or the whole batch) is rendered, tb_mix_kernel adds its rows in voice
+//    order — the tracker's serial `out[j] += tmp[j]` (tracker.rs:617-619).
+int render_impl(tb_program* p, const float* params, uint32_t n_params, uint32_t n_voices, uint64_t n_samples,
+                float* out, uint64_t out_stride, uint64_t* out_len, float* mix, bool want_mix, uint32_t flags) {
     if (!p) return set_error(TB_ERR_INVALID, "NULL program");
     if (n_voices == 0) return TB_OK;
-    if (!out) return set_error(TB_ERR_INVALID, "out is NULL");
-    if (out_stride < n_samples) return set_error(TB_ERR_INVALID, "out_stride < n_samples");
+    const bool dev_out = (flags & TB_OUT_DEVICE) != 0;
+    const bool no_rows = want_mix && (flags & TB_NO_VOICE_OUT);
+    if (!no_rows && !out) return set_error(TB_ERR_INVALID, "out is NULL");
+    if (!no_rows && out_stride < n_samples) return set_error(TB_ERR_INVALID, "out_stride < n_samples");
+    if (want_mix && !mix) return set_error(TB_ERR_INVALID, "mix is NULL");
     CU(cudaSetDevice(p->device));
     int rc = ensure_voices(p, n_voices);
     if (rc) return rc;
     const float* d_params = nullptr;
     if ((rc = stage_params(p, params, n_params, n_voices, flags, &d_params))) return rc;
-    tb_launch L;
-    fill_launch(p, &L);
-    L.params = d_params;
-    L.n_params = n_params;
-    L.n_voices = n_voices;
-    L.out_len = p->d_len;
-    L.mode = 0;
     if (n_samples == 0) {
         if (out_len) std::fill(out_len, out_len + n_voices, 0ull);
         return TB_OK;
     }
-    if (flags & TB_OUT_DEVICE) {
+    tb_launch L;
+    fill_launch(p, &L);
+    L.n_params = n_params;
+    L.mode = 0;
+    float* d_mix = nullptr;
+    if (want_mix) {
+        if (dev_out) d_mix = mix;
+        else {
+            if (n_samples > p->mix_cap) {
+                cudaFree(p->d_mix);
+                p->d_mix = nullptr;
+                p->mix_cap = 0;
+                CU(cudaMalloc(reinterpret_cast<void**>(&p->d_mix), n_samples * 4));
+                p->mix_cap = n_samples;
+            }
+            d_mix = p->d_mix;
+        }
+    }
+    if (dev_out && !no_rows) {
+        L.params = d_params;
+        L.n_voices = n_voices;
         L.n_samples = n_samples;
         L.out = out;
         L.out_stride = out_stride;
+        L.out_len = p->d_len;
         if ((rc = launch(p, L))) return rc;
+        if (want_mix) {
+            cudaError_t e = tb_mix_launch(out, out_stride, p->d_len, n_voices, n_samples, 0, d_mix, 0, p->stream);
+            if (e != cudaSuccess) return cuda_fail(e, "tb_mix_kernel launch");
+            p->launches++;
+        }
     } else {
-        // Host rows: render time chunks into two device staging buffers and stream them out on a
-        // second stream while the next chunk renders (state is carried between launches).
-        const uint64_t budget = (uint64_t)64 << 20;  // floats per staging buffer (256 MiB)
-        uint64_t chunk = budget / n_voices / TB_TILE * TB_TILE;
-        if (chunk < TB_TILE) chunk = TB_TILE;
-        if (chunk > n_samples) chunk = (n_samples + TB_TILE - 1) / TB_TILE * TB_TILE;
-        const size_t need = (size_t)chunk * n_voices;
+        const char* env = std::getenv("TUUN_B200_STAGE_MB");
+        uint64_t budget = (env ? std::strtoull(env, nullptr, 10) : 2048ull) << 18;  // floats per buffer
+        if (budget < (uint64_t)TB_TILE) budget = TB_TILE;
+        uint64_t t_chunk = n_samples;
+        if (t_chunk > budget) t_chunk = budget / TB_TILE * TB_TILE;
+        uint64_t G = budget / t_chunk;
+        if (G < 1) G = 1;
+        if (G > n_voices) G = n_voices;
+        const size_t need = (size_t)G * t_chunk;
         if (need > p->stage_cap) {
             for (int i = 0; i < 2; i++) {
                 cudaFree(p->d_stage[i]);
@@ -321,40 +362,74 @@ int tb_render(tb_program* p, const float* params, uint32_t n_params, uint32_t n_
             for (int i = 0; i < 2; i++) CU(cudaMalloc(reinterpret_cast<void**>(&p->d_stage[i]), need * 4));
             p->stage_cap = need;
         }
-        CU(cudaMemsetAsync(p->d_done, 0, n_voices, p->stream));
-        L.done = p->d_done;
+        const bool cut_time = t_chunk < n_samples;
+        if (cut_time) CU(cudaMemsetAsync(p->d_done, 0, n_voices, p->stream));
         int k = 0;
-        for (uint64_t base = 0; base < n_samples; base += chunk, k++) {
-            const uint64_t len = std::min<uint64_t>(chunk, n_samples - base);
-            const int b = k & 1;
-            if (k >= 2) CU(cudaStreamWaitEvent(p->stream, p->ev_copy[b], 0));
-            L.n_samples = len;
-            L.out = p->d_stage[b];
-            L.out_stride = chunk;
-            L.accumulate = k > 0;
-            if ((rc = launch(p, L))) return rc;
-            CU(cudaEventRecord(p->ev_render[b], p->stream));
-            CU(cudaStreamWaitEvent(p->copy_stream, p->ev_render[b], 0));
-            CU(cudaMemcpy2DAsync(out + base, out_stride * 4, p->d_stage[b], chunk * 4, len * 4, n_voices,
-                                 cudaMemcpyDeviceToHost, p->copy_stream));
-            CU(cudaEventRecord(p->ev_copy[b], p->copy_stream));
+        for (uint64_t v0 = 0; v0 < n_voices; v0 += G) {
+            const uint32_t g = (uint32_t)std::min<uint64_t>(G, n_voices - v0);
+            for (uint64_t t0 = 0; t0 < n_samples; t0 += t_chunk, k++) {
+                const uint64_t len = std::min<uint64_t>(t_chunk, n_samples - t0);
+                const int b = k & 1;
+                if (k >= 2) CU(cudaStreamWaitEvent(p->stream, p->ev_copy[b], 0));
+                L.params = d_params ? d_params + (size_t)v0 * n_params : nullptr;
+                L.state = p->d_state + (size_t)v0 * p->low.state_words;
+                L.out_len = p->d_len + v0;
+                L.done = cut_time ? p->d_done + v0 : nullptr;
+                L.accumulate = t0 > 0;
+                L.n_voices = g;
+                L.n_samples = len;
+                L.out = p->d_stage[b];
+                L.out_stride = len;
+                if ((rc = launch(p, L))) return rc;
+                if (want_mix) {
+                    cudaError_t e = tb_mix_launch(p->d_stage[b], len, p->d_len + v0, g, len, t0, d_mix + t0,
+                                                  v0 > 0 ? 1 : 0, p->stream);
+                    if (e != cudaSuccess) return cuda_fail(e, "tb_mix_kernel launch");
+                    p->launches++;
+                }
+                CU(cudaEventRecord(p->ev_render[b], p->stream));
+                if (!no_rows) {
+                    CU(cudaStreamWaitEvent(p->copy_stream, p->ev_render[b], 0));
+                    if (!cut_time && out_stride == n_samples) {
+                        CU(cudaMemcpyAsync(out + (size_t)v0 * out_stride, p->d_stage[b], (size_t)g * len * 4,
+                                           cudaMemcpyDeviceToHost, p->copy_stream));
+                    } else {
+                        for (uint32_t r = 0; r < g; r++)
+                            CU(cudaMemcpyAsync(out + (size_t)(v0 + r) * out_stride + t0, p->d_stage[b] + (size_t)r * len,
+                                               len * 4, cudaMemcpyDeviceToHost, p->copy_stream));
+                    }
+                    CU(cudaEventRecord(p->ev_copy[b], p->copy_stream));
+                } else {
+                    CU(cudaEventRecord(p->ev_copy[b], p->stream));
+                }
+            }
         }
-        CU(cudaStreamSynchronize(p->copy_stream));
+        if (!no_rows) CU(cudaStreamSynchronize(p->copy_stream));
     }
+    if (want_mix && !dev_out)
+        CU(cudaMemcpyAsync(mix, d_mix, n_samples * 4, cudaMemcpyDeviceToHost, p->stream));
     if (out_len) {
         CU(cudaMemcpyAsync(out_len, p->d_len, (size_t)n_voices * 8, cudaMemcpyDeviceToHost, p->stream));
         CU(cudaStreamSynchronize(p->stream));
-    } else if (!(flags & TB_OUT_DEVICE)) {
+    } else if (!dev_out) {
         CU(cudaStreamSynchronize(p->stream));
     }
     return TB_OK;
 }
 
+}  // namespace
+
+extern "C" {
+
+int tb_render(tb_program* p, const float* params, uint32_t n_params, uint32_t n_voices, uint64_t n_samples,
+              float* out, uint64_t out_stride, uint64_t* out_len, uint32_t flags) {
+    return render_impl(p, params, n_params, n_voices, n_samples, out, out_stride, out_len, nullptr, false,
+                       flags & ~TB_NO_VOICE_OUT);
+}
+
 int tb_render_mix(tb_program* p, const float* params, uint32_t n_params, uint32_t n_voices, uint64_t n_samples,
                   float* out, uint64_t out_stride, uint64_t* out_len, float* mix, uint32_t flags) {
-    (void)p; (void)params; (void)n_params; (void)n_voices; (void)n_samples; (void)out; (void)out_stride;
-    (void)out_len; (void)mix; (void)flags;
-    return set_error(TB_ERR_UNSUPPORTED, "tb_render_mix: not built yet");
+    return render_impl(p, params, n_params, n_voices, n_samples, out, out_stride, out_len, mix, true, flags);
 }
 
 int tb_length(tb_program* p, const float* params, uint32_t n_params, uint32_t n_voices, uint64_t max,

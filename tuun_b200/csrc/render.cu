@@ -1369,3 +1369,29 @@ extern "C" cudaError_t tb_kernel_launch(const tb_launch* P, size_t smem, cudaStr
     tb_render_kernel<<<grid, 32 * TB_WARPS_PER_CTA, smem, stream>>>(*P);
     return cudaGetLastError();
 }
+
+// ------------------------------------------------------------------------------------------
+// Mixdown: mix[i] (+)= sum over voices, in voice index order, of rows[v][i] for i < lens[v] —
+// the tracker's serial `out[filled + j] += tmp[j]` (tracker.rs:617-619).  One thread per sample,
+// rows read coalesced; `t0` is the time offset of this chunk inside the voices' streams.
+// ------------------------------------------------------------------------------------------
+extern "C" __global__ void __launch_bounds__(256)
+tb_mix_kernel(const float* __restrict__ rows, uint64_t stride, const unsigned long long* __restrict__ lens,
+              uint32_t n_voices, uint64_t n_samples, uint64_t t0, float* __restrict__ mix, int accumulate) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_samples) return;
+    float s = accumulate ? mix[i] : 0.0f;
+    for (uint32_t v = 0; v < n_voices; v++) {
+        const unsigned long long len = lens[v];  // total generated so far, including this chunk
+        if (t0 + i < len) s = __fadd_rn(s, rows[(size_t)v * stride + i]);
+    }
+    mix[i] = s;
+}
+
+extern "C" cudaError_t tb_mix_launch(const float* rows, uint64_t stride, const unsigned long long* lens,
+                                     uint32_t n_voices, uint64_t n_samples, uint64_t t0, float* mix,
+                                     int accumulate, cudaStream_t stream) {
+    const uint32_t grid = (uint32_t)((n_samples + 255) / 256);
+    tb_mix_kernel<<<grid, 256, 0, stream>>>(rows, stride, lens, n_voices, n_samples, t0, mix, accumulate);
+    return cudaGetLastError();
+}

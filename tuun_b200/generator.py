@@ -104,6 +104,43 @@ class Program:
                                         _np_ptr(out_len) if want_len else None, flags))
         return out_len
 
+    def render_mix(self, mix, n_voices: int, params=None, out=None, out_len: Optional[np.ndarray] = None):
+        """tb_render_mix: the tracker's mix loop (tracker.rs:597-642) over a batch.  `mix` is a 1-D
+        float32 array (numpy, or torch.cuda when `out`/`params` are device tensors too); with
+        out=None the per-voice rows are never materialised for the caller (TB_NO_VOICE_OUT)."""
+        flags = 0
+        dev = hasattr(mix, "data_ptr")
+        n = mix.shape[0]
+        if dev:
+            assert mix.is_cuda and mix.is_contiguous() and mix.element_size() == 4
+            mptr = ctypes.c_void_p(mix.data_ptr())
+            flags |= _abi.TB_OUT_DEVICE
+        else:
+            assert mix.dtype == np.float32 and mix.flags.c_contiguous
+            mptr = mix.ctypes.data_as(ctypes.c_void_p)
+        optr, stride = None, 0
+        if out is None:
+            flags |= _abi.TB_NO_VOICE_OUT
+        else:
+            assert hasattr(out, "data_ptr") == dev, "out and mix must live on the same side"
+            if dev:
+                optr, stride = ctypes.c_void_p(out.data_ptr()), out.stride(0)
+            else:
+                optr, stride = out.ctypes.data_as(ctypes.c_void_p), out.strides[0] // 4
+        pptr, n_params = None, 0
+        if params is not None:
+            if hasattr(params, "data_ptr"):
+                pptr, n_params = ctypes.c_void_p(params.data_ptr()), params.shape[1]
+                flags |= _abi.TB_PARAMS_DEVICE
+            else:
+                params = np.ascontiguousarray(params, dtype=np.float32)
+                pptr, n_params = params.ctypes.data_as(ctypes.c_void_p), params.shape[1]
+        if out_len is None and not dev:
+            out_len = np.zeros(n_voices, dtype=np.uint64)
+        _abi.check(_abi.lib().tb_render_mix(self._h, pptr, n_params, n_voices, n, optr, stride,
+                                            _np_ptr(out_len) if out_len is not None else None, mptr, flags))
+        return out_len
+
     def lengths(self, n_voices: int, max_: int, params=None) -> np.ndarray:
         pptr, n_params = None, 0
         if params is not None:
