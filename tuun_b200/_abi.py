@@ -11,7 +11,7 @@ import os
 from .waveform import TbNode
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtuun_b200.so")
+LIB_PATH = os.environ.get("TUUN_B200_LIB") or os.path.join(_HERE, "libtuun_b200.so")
 
 TB_OK = 0
 TB_ERR_INVALID = -1

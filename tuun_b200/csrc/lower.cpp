@@ -56,6 +56,28 @@ struct Lowerer {
         return (int)out.code.size() - 1;
     }
     int here() const { return (int)out.code.size(); }
+    // A jump lands on the next instruction to be emitted: nothing emitted from now on may be fused
+    // backwards into what precedes the label.
+    int label_at = -1;
+    int last_producer = -1;  // index of the last instruction that leaves a fresh accumulator
+    int label() {
+        label_at = here();
+        return label_at;
+    }
+    void produced(int idx) { last_producer = idx; }
+    // acc = acc (op) const as a post-op of the producing instruction when that is legal.
+    void emit_binc(int op, int cidx) {
+        const int h = here();
+        if (last_producer >= 0 && label_at != h) {
+            const int npost = (int)(out.code[last_producer].op >> 16);
+            if (last_producer + 1 + npost == h && npost < 15) {
+                out.code[last_producer].op += 1u << 16;
+                out.code.push_back(tb_insn{(uint32_t)G_BINC, op, cidx, 0});
+                return;
+            }
+        }
+        produced(emit(G_BINC, op, cidx, 0));
+    }
 
     // ---- validation -------------------------------------------------------------------
     void validate() {
@@ -268,9 +290,9 @@ struct Lowerer {
     void emit_gen(int i) {
         const tb_node& n = nodes[i];
         switch (n.kind) {
-            case TB_CONST: emit(G_CONST, const_of(i)); break;
-            case TB_TIME: emit(G_TIME, state_of(i, 2)); break;
-            case TB_FIXED: emit(G_FIXED, state_of(i, 2), fixed_table(i)); break;
+            case TB_CONST: produced(emit(G_CONST, const_of(i))); break;
+            case TB_TIME: produced(emit(G_TIME, state_of(i, 2))); break;
+            case TB_FIXED: produced(emit(G_FIXED, state_of(i, 2), fixed_table(i))); break;
             case TB_NOISE:
                 fail(TB_ERR_UNSUPPORTED,
                      "Noise: the reference draws from an unseeded thread-local generator (generator.rs:115); "
@@ -282,12 +304,14 @@ struct Lowerer {
                 const int cb = const_of(n.b);
                 emit_gen(n.a);
                 if (cb >= 0) {
-                    emit(G_BINC, (int)n.op, cb, merge);
+                    if (merge) emit(G_BINC, (int)n.op, cb, merge);
+                    else emit_binc((int)n.op, cb);
                 } else {
                     const int s = alloc_slot();
                     const int b0 = emit(G_BIN_BEGIN, s, merge, 0);
                     emit_gen(n.b);
                     out.code[b0].c = emit(G_BIN_END, s, (int)n.op, merge);
+                    produced(out.code[b0].c);
                     free_slot();
                 }
                 break;
@@ -299,19 +323,20 @@ struct Lowerer {
                 const int aux_inc = cf >= 0 ? new_aux(AUX_SINE_INC, cf, 0, 1) : 0;
                 const int aux_ph = cp >= 0 ? new_aux(AUX_SINE_PHASE, cp, 0, 1) : 0;
                 if (cf >= 0 && cp >= 0) {
-                    emit(G_SINE_CC | fl, st, aux_inc, aux_ph);
+                    produced(emit(G_SINE_CC | fl, st, aux_inc, aux_ph));
                 } else if (cp >= 0) {
                     emit_gen(n.a);
-                    emit(G_SINE_AC | fl, st, 0, aux_ph);
+                    produced(emit(G_SINE_AC | fl, st, 0, aux_ph));
                 } else if (cf >= 0) {
                     emit_gen(n.b);
-                    emit(G_SINE_CA | fl, st, aux_inc, 0);
+                    produced(emit(G_SINE_CA | fl, st, aux_inc, 0));
                 } else {
                     emit_gen(n.a);
                     const int s = alloc_slot();
                     const int b0 = emit(G_SINE_BEGIN, s, 0, 0);
                     emit_gen(n.b);
                     out.code[b0].c = emit(G_SINE_END | fl, st, s, 0);
+                    produced(out.code[b0].c);
                     free_slot();
                 }
                 break;
@@ -320,7 +345,7 @@ struct Lowerer {
                 const int cp = const_of(n.b), cn = const_of(n.c);
                 emit_gen(n.a);
                 if (cp >= 0 && cn >= 0) {
-                    emit(G_ALT_CC, cp, cn);
+                    produced(emit(G_ALT_CC, cp, cn));
                 } else {
                     const int st = alloc_slot();
                     const int b0 = emit(G_ALT_BEGIN, st, 0, 0);
@@ -344,6 +369,7 @@ struct Lowerer {
                         opn = 0;
                     }
                     out.code[b0].c = emit(G_ALT_END, st, opp, opn);
+                    produced(out.code[b0].c);
                     if (extra) free_slot();
                     free_slot();
                 }
@@ -356,13 +382,13 @@ struct Lowerer {
                 const int p0 = emit(G_FILT_PRE, st, K, 0);
                 emit_gen(n.a);
                 emit(G_FILT_PRE_END, st, K, J);
-                out.code[p0].c = here();
+                out.code[p0].c = label();
                 emit_gen(n.a);
                 bool any_code = false;
                 for (int j = 0; j < K + J; j++) any_code |= const_of(lists[n.list_off + j]) < 0;
                 const bool need_u = J > 0 && !out.filt[fi].fb_const;
                 if (!any_code) {
-                    emit(G_FILT_RUN, st, fi, 0);
+                    produced(emit(G_FILT_RUN, st, fi, 0));
                 } else {
                     int used = 0;
                     const int xs = alloc_slot();
@@ -383,6 +409,7 @@ struct Lowerer {
                         used++;
                     }
                     out.code[b0].c = emit(G_FILT_RUN, st, fi, 1);
+                    produced(out.code[b0].c);
                     while (used--) free_slot();
                 }
                 break;
@@ -398,12 +425,12 @@ struct Lowerer {
                     emit_gen(n.a);
                     scan = emit(G_FIN_SCAN, 0, 0, 0);
                 }
-                out.code[h0].c = here();
+                out.code[h0].c = label();
                 if (may_static) {
                     emit_len(n.a);
                     emit(G_FIN_STATIC);
                 }
-                if (scan >= 0) out.code[scan].c = here();
+                if (scan >= 0) out.code[scan].c = label();
                 const int in0 = emit(G_FIN_INNER, 0, 0, 0);
                 emit_gen(n.b);
                 out.code[in0].c = emit(G_FIN_ADV);
@@ -420,7 +447,7 @@ struct Lowerer {
                 out.code[b0].c = m0;
                 emit_gen(n.b);
                 emit(G_APP_END, 0, s, 0);
-                out.code[m0].c = here();
+                out.code[m0].c = label();
                 free_slot();
                 break;
             }
@@ -431,6 +458,7 @@ struct Lowerer {
                 const int b0 = emit(G_RESET_BEGIN, st, s, 0);
                 emit_seg(n.b);
                 out.code[b0].c = emit(G_RESET_END, st);
+                produced(out.code[b0].c);
                 free_slot();
                 break;
             }
@@ -509,14 +537,14 @@ struct Lowerer {
                     emit_len(n.b);
                     scan2 = emit(L_FIN_SCAN2, 0, 0, 0);
                 }
-                out.code[h0].c = here();
+                out.code[h0].c = label();
                 if (may_static) {
                     emit_len(n.b);
                     emit(L_PUSH);
                     emit_len(n.a);
                     emit(L_FIN_STATIC);
                 }
-                if (scan2 >= 0) out.code[scan2].c = here();
+                if (scan2 >= 0) out.code[scan2].c = label();
                 break;
             }
             default: fail(TB_ERR_INVALID, "unknown node kind");

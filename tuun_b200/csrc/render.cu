@@ -107,30 +107,69 @@ __device__ __forceinline__ u64 phase_to_fx(float p, const SineK& k) {
     if (fabsf(p) < k.plimit) return magic_to_fx(fma((double)p, k.pscale, 6755399441055744.0));
     return turns_to_fx_slow((double)p * (1.0 / TB_TAU));
 }
+// Vector forms: the magic-number conversion for all C samples, then ONE warp vote decides whether
+// any input was outside its exact range (|f| >= 100*TAU*sr: never for audio) and redoes those.
+__device__ __forceinline__ void freq_to_inc_vec(u64 (&inc)[C], const float (&f)[C], const SineK& k) {
+    float big = 0.0f;
+    UNROLL for (int j = 0; j < C; j++) {
+        inc[j] = magic_to_fx(fma((double)f[j], k.kscale, 6755399441055744.0));
+        big = fmaxf(big, fabsf(f[j]));
+    }
+    if (__any_sync(FULL, !(big < k.flimit))) {
+        UNROLL for (int j = 0; j < C; j++)
+            if (!(fabsf(f[j]) < k.flimit)) inc[j] = turns_to_fx_slow((double)f[j] * k.inv_turn);
+    }
+}
+__device__ __forceinline__ void phase_to_fx_vec(u64 (&ph)[C], const float (&p)[C], const SineK& k) {
+    float big = 0.0f;
+    UNROLL for (int j = 0; j < C; j++) {
+        ph[j] = magic_to_fx(fma((double)p[j], k.pscale, 6755399441055744.0));
+        big = fmaxf(big, fabsf(p[j]));
+    }
+    if (__any_sync(FULL, !(big < k.plimit))) {
+        UNROLL for (int j = 0; j < C; j++)
+            if (!(fabsf(p[j]) < k.plimit)) ph[j] = turns_to_fx_slow((double)p[j] * (1.0 / TB_TAU));
+    }
+}
 
-// sin(2*pi * ph / 2^64).  Fold to [-1/4, 1/4] turn with integer ops (exact), then
+// sin(2*pi * ph / 2^64).  Fold to [-1/4, 1/4] turn with integer ops (exact, branch-free), then
 // sin(pi/2 x) = x P(x^2) on x in [-1, 1]; coefficients from tools/fit_sine.py.
+__device__ __forceinline__ u64 fold_quarter(u64 ph) {
+    const u64 m = (u64)((i64)(ph ^ (ph << 1)) >> 63);  // all ones in the 2nd and 3rd quarter turn
+    return ((ph ^ m) - m) ^ (m & 0x8000000000000000ull);  // there: 2^63 - ph
+}
 // EXACT: f64, 7 coefficients, |err| < 8e-14, rounded once to f32: the same f32 as the
 // reference's `(acc + ph).sin() as f32` except where the f64 values straddle an f32 rounding
-// boundary (about 1e-6 of the samples, by one ulp, sign-symmetric).
+// boundary (measured: 0.02 % of the samples, by one ulp, sign-symmetric).  The coefficients carry
+// the 2^-62 scaling of the integer phase (c_k * 2^(-62 - 124 k)), so no extra multiply is needed.
+// The fold is done on the converted double: |x| > 2^62  ->  x = copysign(2^63, x) - x (exact).
+__constant__ double c_sin_exact[7] = {0x1.921fb54442bb4p-62,  -0x1.4abbce624ad99p-187, 0x1.466bc66ed3d1cp-314,
+                                      -0x1.32d2c9b2d1df5p-442, 0x1.50770f6a5a66bp-571,  -0x1.e29b82ab98ea9p-701,
+                                      0x1.d53abdeb199c1p-831};
 __device__ __forceinline__ float sin_turns_exact(u64 ph) {
-    if ((ph ^ (ph << 1)) >> 63) ph = 0x8000000000000000ull - ph;
-    const double x = (double)(i64)ph * 2.16840434497100886801e-19;  // 2^-62
+    double x = (double)(i64)ph;  // signed turns * 2^64, in [-2^63, 2^63]
+    const int hi = __double2hiint(x);
+    const double half = __hiloint2double((hi & 0x80000000) | 0x43e00000, 0);  // copysign(2^63, x)
+    const double folded = half - x;
+    x = ((hi & 0x7fffffff) > 0x43d00000) ? folded : x;  // |x| > 2^62 (the = case folds to itself)
     const double z = x * x;
-    double p = 0x1.d53abdeb199c1p-25;
-    p = fma(p, z, -0x1.e29b82ab98ea9p-19);
-    p = fma(p, z, 0x1.50770f6a5a66bp-13);
-    p = fma(p, z, -0x1.32d2c9b2d1df5p-8);
-    p = fma(p, z, 0x1.466bc66ed3d1cp-4);
-    p = fma(p, z, -0x1.4abbce624ad99p-1);
-    p = fma(p, z, 0x1.921fb54442bb4p+0);
+    double p = c_sin_exact[6];
+    p = fma(p, z, c_sin_exact[5]);
+    p = fma(p, z, c_sin_exact[4]);
+    p = fma(p, z, c_sin_exact[3]);
+    p = fma(p, z, c_sin_exact[2]);
+    p = fma(p, z, c_sin_exact[1]);
+    p = fma(p, z, c_sin_exact[0]);
     return (float)(x * p);
 }
 // FAST: f32, 5 coefficients, |err| < 2e-7 — for sines whose output reaches only the sample
-// stream (never a frequency, phase, trigger, length or filter coefficient).
+// stream (never a frequency, phase, trigger, length or filter coefficient).  Only the top 32
+// phase bits matter here, so the fold is 32-bit.
 __device__ __forceinline__ float sin_turns_fast(u64 ph) {
-    if ((ph ^ (ph << 1)) >> 63) ph = 0x8000000000000000ull - ph;
-    const float x = (float)(int)(ph >> 32) * 9.31322574615478515625e-10f;  // 2^-30
+    const int h = (int)(ph >> 32);
+    const int m = (h ^ (h << 1)) >> 31;
+    const int f = ((h ^ m) - m) ^ (m & (int)0x80000000);
+    const float x = (float)f * 9.31322574615478515625e-10f;  // 2^-30
     const float z = x * x;
     float p = 0.00015167170204222202f;
     p = fmaf(p, z, -0.004674143623560667f);
@@ -141,6 +180,10 @@ __device__ __forceinline__ float sin_turns_fast(u64 ph) {
 }
 __device__ __forceinline__ float sin_turns(u64 ph, bool fast) {
     return fast ? sin_turns_fast(ph) : sin_turns_exact(ph);
+}
+__device__ __forceinline__ void sin_turns_vec(float (&out)[C], const u64 (&ph)[C], bool fast) {
+    if (fast) { UNROLL for (int j = 0; j < C; j++) out[j] = sin_turns_fast(ph[j]); }
+    else      { UNROLL for (int j = 0; j < C; j++) out[j] = sin_turns_exact(ph[j]); }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -236,34 +279,47 @@ __device__ void goe_eval(const tb_launch& P, const WarpMem& M, const Ctx& cx, in
 // Sine kernels (window mode)
 // ------------------------------------------------------------------------------------------
 // Frequencies in `f` (valid for positions [w0, w0+f_len)), phase offsets already in fixed point.
-__device__ __forceinline__ void sine_window(float (&acc)[C], const float (&f)[C], const u64 (&phfx)[C],
+template <bool UNIFORM_PH>
+__device__ __forceinline__ void sine_window(float (&acc)[C], const float (&f)[C], const u64 (&phfx)[C], u64 ph0,
                                             int w0, int f_len, uint32_t* state, int st,
                                             const SineK& sk, bool fast) {
     const int l = lane_id();
     const u64 acc0 = ld_state64(state, st);
-    u64 ex[C];
+    u64 inc[C];
+    freq_to_inc_vec(inc, f, sk);
+    if (!(w0 == 0 && f_len == TILE)) {  // partial window: samples outside it do not advance the phase
+        UNROLL for (int j = 0; j < C; j++) {
+            const int i = l * C + j;
+            inc[j] = (i >= w0 && i < w0 + f_len) ? inc[j] : 0ull;
+        }
+    }
+    u64 ph[C];
     u64 run = 0;
     UNROLL for (int j = 0; j < C; j++) {
-        const int i = l * C + j;
-        ex[j] = run;
-        if (i >= w0 && i < w0 + f_len) run += freq_to_inc(f[j], sk);
+        ph[j] = UNIFORM_PH ? run : run + phfx[j];
+        run += inc[j];
     }
     const u64 incl = warp_incl_sum(run);
-    const u64 base = acc0 + (incl - run);
+    const u64 base = acc0 + (incl - run) + (UNIFORM_PH ? ph0 : 0ull);
     const u64 total = __shfl_sync(FULL, incl, 31);
-    UNROLL for (int j = 0; j < C; j++) acc[j] = sin_turns(base + ex[j] + phfx[j], fast);
+    UNROLL for (int j = 0; j < C; j++) ph[j] += base;
+    sin_turns_vec(acc, ph, fast);
     __syncwarp();
     st_state64(state, st, acc0 + total);
 }
 // Constant frequency: phase(i) = acc0 + (i - w0) * inc, no scan.
-__device__ __forceinline__ void sine_window_cf(float (&acc)[C], u64 inc, const u64 (&phfx)[C], int w0,
+template <bool UNIFORM_PH>
+__device__ __forceinline__ void sine_window_cf(float (&acc)[C], u64 inc, const u64 (&phfx)[C], u64 ph0, int w0,
                                                int f_len, uint32_t* state, int st, bool fast) {
     const int l = lane_id();
     const u64 acc0 = ld_state64(state, st);
+    u64 ph[C];
+    u64 p = acc0 + inc * (u64)(i64)(l * C - w0) + (UNIFORM_PH ? ph0 : 0ull);
     UNROLL for (int j = 0; j < C; j++) {
-        const int i = l * C + j;
-        acc[j] = sin_turns(acc0 + inc * (u64)(i - w0) + phfx[j], fast);
+        ph[j] = UNIFORM_PH ? p : p + phfx[j];
+        p += inc;
     }
+    sin_turns_vec(acc, ph, fast);
     __syncwarp();
     st_state64(state, st, acc0 + inc * (u64)f_len);
 }
@@ -325,6 +381,85 @@ __device__ __forceinline__ void iir_scan_const(float (&acc)[C], const float (&u)
     }
 }
 
+// Full-tile fast path of the constant-coefficient filter: window = whole tile, history complete,
+// nothing finishing.  Same arithmetic as filter_run below without any per-sample window test.
+template <int J>
+__device__ __forceinline__ void filter_full_tile(const WarpMem& M, const tb_filter_tab* ft, float (&acc)[C],
+                                                 float* hx, float* hy) {
+    const int l = lane_id();
+    const int K = ft->K;
+    float u[C];
+    {
+        const float b0 = M.cval[~ft->coef[0]];
+        UNROLL for (int j = 0; j < C; j++) u[j] = __fmul_rn(acc[j], b0);
+    }
+    UNROLL for (int k = 1; k < TB_MAX_K; k++) {
+        if (k < K) {
+            const float bk = M.cval[~ft->coef[k]];
+            float pv[C];
+            UNROLL for (int j = 0; j < C; j++) {
+                if (j < k) {
+                    float t = __shfl_up_sync(FULL, acc[C - k + j], 1);
+                    if (l == 0) t = hx[K - 1 - k + j];
+                    pv[j] = t;
+                }
+            }
+            UNROLL for (int j = 0; j < C; j++) u[j] = __fadd_rn(u[j], __fmul_rn(bk, (j >= k) ? acc[j - k] : pv[j]));
+        }
+    }
+    float xin[C];
+    UNROLL for (int j = 0; j < C; j++) xin[j] = acc[j];
+    if (J > 0) {
+        float a[J > 0 ? J : 1];
+        UNROLL for (int jj = 0; jj < J; jj++) a[jj] = M.cval[~ft->coef[K + jj]];
+        const double* mpow = reinterpret_cast<const double*>(M.aux + ft->pow_aux);
+        float s[J > 0 ? J : 1];
+        UNROLL for (int jj = 0; jj < J; jj++) s[jj] = (l == 0) ? hy[J - 1 - jj] : 0.0f;
+        UNROLL for (int j = 0; j < C; j++) {  // pass 1: chunk response (zero state except lane 0)
+            float y = u[j];
+            UNROLL for (int jj = 0; jj < J; jj++) y = fmaf(-a[jj], s[jj], y);
+            UNROLL for (int jj = J - 1; jj > 0; jj--) s[jj] = s[jj - 1];
+            s[0] = y;
+        }
+        double v[J > 0 ? J : 1];
+        UNROLL for (int jj = 0; jj < J; jj++) v[jj] = (double)s[jj];
+        UNROLL for (int k = 0; k < 5; k++) {  // scan with A^(8*2^k)
+            const int d = 1 << k;
+            double t[J > 0 ? J : 1];
+            UNROLL for (int jj = 0; jj < J; jj++) t[jj] = __shfl_up_sync(FULL, v[jj], d);
+            if (l >= d) {
+                UNROLL for (int r = 0; r < J; r++) {
+                    double accv = v[r];
+                    UNROLL for (int c = 0; c < J; c++) accv = fma(mpow[(k * J + r) * J + c], t[c], accv);
+                    v[r] = accv;
+                }
+            }
+        }
+        UNROLL for (int jj = 0; jj < J; jj++) {
+            const double up = __shfl_up_sync(FULL, v[jj], 1);
+            s[jj] = (l == 0) ? hy[J - 1 - jj] : (float)up;
+        }
+        UNROLL for (int j = 0; j < C; j++) {  // pass 2: the reference's exact f32 order (generator.rs:500-502)
+            float y = u[j];
+            UNROLL for (int jj = 0; jj < J; jj++) y = __fsub_rn(y, __fmul_rn(a[jj], s[jj]));
+            UNROLL for (int jj = J - 1; jj > 0; jj--) s[jj] = s[jj - 1];
+            s[0] = y;
+            acc[j] = y;
+        }
+    } else {
+        UNROLL for (int j = 0; j < C; j++) acc[j] = u[j];
+    }
+    __syncwarp();
+    if (l == 31) {  // the deques keep the last K-1 inputs and J outputs of the tile
+        UNROLL for (int j = 0; j < C; j++) {
+            const int ex = j - (C - (K - 1));
+            if (ex >= 0) hx[ex] = xin[j];
+            const int ey = j - (C - J);
+            if (ey >= 0) hy[ey] = acc[j];
+        }
+    }
+}
+
 __device__ void filter_run(const tb_launch& P, const WarpMem& M, Ctx& cx, float (&acc)[C], int st,
                            int fi, bool had_begin) {
     const tb_filter_tab* ft = &P.filt[fi];
@@ -335,6 +470,18 @@ __device__ void filter_run(const tb_launch& P, const WarpMem& M, Ctx& cx, float 
     float* hy = hx + (K - 1);
     int n, inner_len, out_len, h;
     int w0 = cx.w0;
+    if (!had_begin && S[0] != 0u && cx.w0 == 0 && cx.w1 == TILE && cx.L == TILE && (int)S[1] == K - 1 &&
+        (J == 0 || ft->fb_const)) {
+        switch (J) {
+            case 0: filter_full_tile<0>(M, ft, acc, hx, hy); break;
+            case 1: filter_full_tile<1>(M, ft, acc, hx, hy); break;
+            case 2: filter_full_tile<2>(M, ft, acc, hx, hy); break;
+            case 3: filter_full_tile<3>(M, ft, acc, hx, hy); break;
+            default: filter_full_tile<4>(M, ft, acc, hx, hy); break;
+        }
+        cx.L = TILE;
+        return;
+    }
     if (had_begin) {
         // G_FILT_BEGIN already narrowed the window to out_len and stored the zero-extended input.
         out_len = cx.w1 - cx.w0;
@@ -632,28 +779,25 @@ __device__ void run_program(const tb_launch& P, const tb_insn* code, const WarpM
             }
             case G_SINE_CC: {  // constant frequency and phase
                 u64 ph[C];
-                const u64 p0 = M.aux[in.c];
-                UNROLL for (int j = 0; j < C; j++) ph[j] = p0;
-                sine_window_cf(acc, M.aux[in.b], ph, cx.w0, n, M.state, in.a, fast);
+                sine_window_cf<true>(acc, M.aux[in.b], ph, M.aux[in.c], cx.w0, n, M.state, in.a, fast);
                 cx.L = n;
                 break;
             }
             case G_SINE_AC: {  // frequency in acc (length L), constant phase
                 u64 ph[C];
-                const u64 p0 = M.aux[in.c];
-                UNROLL for (int j = 0; j < C; j++) ph[j] = p0;
                 float f[C];
                 UNROLL for (int j = 0; j < C; j++) f[j] = acc[j];
-                sine_window(acc, f, ph, cx.w0, cx.L, M.state, in.a, sk, fast);
+                sine_window<true>(acc, f, ph, M.aux[in.c], cx.w0, cx.L, M.state, in.a, sk, fast);
                 break;
             }
             case G_SINE_CA: {  // constant frequency, phase in acc (length L, zeros beyond)
                 u64 ph[C];
+                phase_to_fx_vec(ph, acc, sk);
                 UNROLL for (int j = 0; j < C; j++) {
                     const int i = l * C + j;
-                    ph[j] = i < cx.w0 + cx.L ? phase_to_fx(acc[j], sk) : 0ull;
+                    ph[j] = i < cx.w0 + cx.L ? ph[j] : 0ull;
                 }
-                sine_window_cf(acc, M.aux[in.b], ph, cx.w0, n, M.state, in.a, fast);
+                sine_window_cf<false>(acc, M.aux[in.b], ph, 0ull, cx.w0, n, M.state, in.a, fast);
                 break;
             }
             case G_SINE_BEGIN: {  // generator.rs:206-210
@@ -670,11 +814,12 @@ __device__ void run_program(const tb_launch& P, const tb_insn* code, const WarpM
                 float f[C];
                 slot_load(M.slots, in.b, f);
                 u64 ph[C];
+                phase_to_fx_vec(ph, acc, sk);
                 UNROLL for (int j = 0; j < C; j++) {
                     const int i = l * C + j;
-                    ph[j] = i < cx.w0 + cx.L ? phase_to_fx(acc[j], sk) : 0ull;
+                    ph[j] = i < cx.w0 + cx.L ? ph[j] : 0ull;
                 }
-                sine_window(acc, f, ph, cx.w0, f_len, M.state, in.a, sk, fast);
+                sine_window<false>(acc, f, ph, 0ull, cx.w0, f_len, M.state, in.a, sk, fast);
                 break;
             }
             case G_ALT_CC: {  // generator.rs:335-341 with constant branches
@@ -1197,6 +1342,13 @@ __device__ void run_program(const tb_launch& P, const tb_insn* code, const WarpM
             }
             default: return;
         }
+        // Post-ops: `npost` constant-operand point ops (generator.rs:541-548) fused behind the
+        // instruction that produced the accumulator; each is one extra code word.
+        for (uint32_t np = in.op >> 16; np > 0; np--) {
+            const tb_insn po = code[pc++];
+            const float c = M.cval[po.b];
+            APPLY_OP((uint32_t)po.a, acc, acc[j], c)
+        }
     }
 #undef PUSH
 #undef POP
@@ -1255,7 +1407,10 @@ __device__ void setup_voice(const tb_launch& P, const WarpMem& M, const float* p
 // ------------------------------------------------------------------------------------------
 // Kernel: grid = ceil(n_voices / TB_WARPS_PER_CTA), block = 32 * TB_WARPS_PER_CTA.
 // ------------------------------------------------------------------------------------------
-extern "C" __global__ void __launch_bounds__(32 * TB_WARPS_PER_CTA)
+#ifndef TB_MIN_BLOCKS
+#define TB_MIN_BLOCKS 4
+#endif
+extern "C" __global__ void __launch_bounds__(32 * TB_WARPS_PER_CTA, TB_MIN_BLOCKS)
 tb_render_kernel(const tb_launch P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, l = threadIdx.x & 31;
