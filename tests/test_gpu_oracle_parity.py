@@ -147,10 +147,24 @@ def test_streaming_blocks_match_one_shot():
     b = gpu_render(w, 20000, block=1024)
     c = gpu_render(w, 20000, block=777)
     assert len(a) == len(b) == len(c) == 20000
-    # Tile-aligned blocks evaluate exactly the same arithmetic; unaligned ones re-partition the
-    # filter scan, which moves the result by round-off noise only.  The phase is integer: exact.
-    np.testing.assert_array_equal(a, b)
+    # Different block sizes re-partition the filter scan (general 256-sample tiles at stream
+    # start and in tails, 512-sample steady tiles in between), which moves the result by
+    # round-off noise only.  The phase is integer: exact, whatever the partition.
+    assert np.max(np.abs(a - b)) <= TOL
     assert np.max(np.abs(a - c)) <= TOL
+
+
+def test_streaming_phase_is_partition_invariant():
+    # No filter: the carrier phase is a 64-bit integer prefix sum, so block size cannot move it.
+    # The constant-rate modulator is evaluated by two f64 routes (polynomial in general tiles,
+    # angle addition in steady tiles) that agree to ~1e-15 before the f32 rounding.
+    mod = Sine(hz(3), Const(0.0))
+    w = Sine(add(mul(mod, Const(500.0)), hz(300)), Const(0.0))
+    a = gpu_render(w, 20000)
+    b = gpu_render(w, 20000, block=1024)
+    c = gpu_render(w, 20000, block=777)
+    assert np.max(np.abs(a - b)) <= 2.5e-7 and np.max(np.abs(a - c)) <= 2.5e-7
+    assert np.count_nonzero(a != b) <= 20 and np.count_nonzero(a != c) <= 20
 
 
 def test_batch_params():

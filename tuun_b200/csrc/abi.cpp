@@ -15,7 +15,7 @@
 #include "program.h"
 
 extern "C" size_t tb_kernel_smem_bytes(uint32_t n_code, uint32_t n_slots, uint32_t aux_words,
-                                       uint32_t n_cval, uint32_t state_words);
+                                       uint32_t n_cval, uint32_t state_words, uint32_t steady_ok);
 extern "C" cudaError_t tb_kernel_launch(const tb_launch* P, size_t smem, cudaStream_t stream);
 extern "C" cudaError_t tb_mix_launch(const float* rows, uint64_t stride, const unsigned long long* lens,
                                      uint32_t n_voices, uint64_t n_samples, uint64_t t0, float* mix,
@@ -77,6 +77,7 @@ struct tb_program {
     cudaEvent_t ev_render[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
     size_t smem = 0;
     uint64_t launches = 0;
+    uint32_t fast_mode = 1;  // FAST-class sines: 1 = f32 polynomial, 2 = MUFU (TUUN_B200_FAST_SINES)
 
     ~tb_program() {
         cudaSetDevice(device);
@@ -163,6 +164,9 @@ void fill_launch(const tb_program* p, tb_launch* L) {
     L->state_words = p->low.state_words;
     L->sample_rate = p->sample_rate;
     L->pure_len = p->low.pure_len;
+    L->n_filt = (uint32_t)p->low.filt.size();
+    L->steady_ok = p->low.steady_ok;
+    L->fast_mode = p->fast_mode;
     L->state = p->d_state;
 }
 
@@ -199,6 +203,9 @@ int tb_program_create(const tb_node* nodes, uint32_t n_nodes, const int32_t* lis
         return set_error(rc, msg);
     }
     p->sample_rate = sample_rate;
+    p->fast_mode = (fs && fs[0] == '2') ? 2u : 1u;
+    if (const char* se = std::getenv("TUUN_B200_STEADY"))
+        if (se[0] == '0') p->low.steady_ok = 0;  // diagnostics: force the general interpreter
     // Everything below needs a device: no CPU path exists.
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
@@ -237,7 +244,7 @@ int tb_program_create(const tb_node* nodes, uint32_t n_nodes, const int32_t* lis
         (rc = upload(p->low.fixed, &p->d_fixed)) || (rc = upload(pool, &p->d_pool)))
         return bail(rc);
     p->smem = tb_kernel_smem_bytes((uint32_t)p->low.code.size(), p->low.n_slots, p->low.aux_words,
-                                   (uint32_t)p->low.cexpr.size(), p->low.state_words);
+                                   (uint32_t)p->low.cexpr.size(), p->low.state_words, p->low.steady_ok);
     if (p->smem > 220 * 1024)
         return bail(set_error(TB_ERR_UNSUPPORTED, "program needs more shared memory than one CTA has"));
     *out_program = p;

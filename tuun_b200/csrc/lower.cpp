@@ -154,7 +154,7 @@ struct Lowerer {
             if (e.kind == kind && e.a == a && e.b == b) return (int)e.off;
         tb_aux x{kind, a, b, out.aux_words};
         out.aux.push_back(x);
-        out.aux_words += words;
+        out.aux_words += (words + 1u) & ~1u;  // blocks stay 16-byte aligned (double2 loads)
         return (int)x.off;
     }
 
@@ -269,13 +269,15 @@ struct Lowerer {
         filt_idx[i] = (int)out.filt.size() - 1;
         if (t.fb_const && J > 0) {
             out.filt.back().pow_aux = out.aux_words;
-            new_aux(AUX_FILT_POW, 0, filt_idx[i], 5 * J * J);
+            new_aux(AUX_FILT_POW, 0, filt_idx[i], 6 * J * J);
         }
         return filt_idx[i];
     }
     int filter_state(int i) {
         const tb_node& n = nodes[i];
-        return state_of(i, 2 + (n.ff_count - 1) + n.fb_count + 2);
+        const int st = state_of(i, 2 + (n.ff_count - 1) + n.fb_count + 2);
+        if (filt_idx[i] >= 0) out.filt[filt_idx[i]].state_off = (uint32_t)st;
+        return st;
     }
 
     int fixed_table(int i) {
@@ -320,7 +322,7 @@ struct Lowerer {
                 const int cf = const_of(n.a), cp = const_of(n.b);
                 const int st = state_of(i, 2);
                 const uint32_t fl = sine_flags(i);
-                const int aux_inc = cf >= 0 ? new_aux(AUX_SINE_INC, cf, 0, 1) : 0;
+                const int aux_inc = cf >= 0 ? new_aux(AUX_SINE_INC, cf, 0, 2 + 2 * TB_CS) : 0;
                 const int aux_ph = cp >= 0 ? new_aux(AUX_SINE_PHASE, cp, 0, 1) : 0;
                 if (cf >= 0 && cp >= 0) {
                     produced(emit(G_SINE_CC | fl, st, aux_inc, aux_ph));
@@ -579,7 +581,7 @@ struct Lowerer {
                 const int cf = const_of(n.a), cp = const_of(n.b);
                 const int st = state_of(i, 2);
                 const uint32_t fl = sine_flags(i);
-                const int aux_inc = cf >= 0 ? new_aux(AUX_SINE_INC, cf, 0, 1) : 0;
+                const int aux_inc = cf >= 0 ? new_aux(AUX_SINE_INC, cf, 0, 2 + 2 * TB_CS) : 0;
                 const int aux_ph = cp >= 0 ? new_aux(AUX_SINE_PHASE, cp, 0, 1) : 0;
                 if (cf >= 0 && cp >= 0) {
                     emit(S_SINE_CC | fl, st, aux_inc, aux_ph);
@@ -651,6 +653,39 @@ struct Lowerer {
         }
     }
 
+    // The steady-state interpreter (steady.cuh) takes programs made only of infinite, window-free
+    // nodes: constants, clocks, sines, point operators, Alt and constant-coefficient filters.
+    bool steady_eligible(uint32_t begin, uint32_t end) const {
+        for (uint32_t pc = begin; pc < end; pc++) {
+            const tb_insn& in = out.code[pc];
+            switch (in.op & 0xffu) {
+                case OP_END:
+                case G_CONST:
+                case G_TIME:
+                case G_BIN_BEGIN:
+                case G_BIN_END:
+                case G_SINE_CC:
+                case G_SINE_AC:
+                case G_SINE_CA:
+                case G_SINE_BEGIN:
+                case G_SINE_END:
+                case G_ALT_CC:
+                case G_ALT_BEGIN:
+                case G_ALT_POS:
+                case G_ALT_END:
+                case G_FILT_PRE:
+                case G_FILT_PRE_END: break;
+                case G_BINC: break;
+                case G_FILT_RUN:
+                    if (in.c != 0) return false;  // coefficient waveforms
+                    break;
+                default: return false;
+            }
+            pc += in.op >> 16;  // fused post-ops
+        }
+        return true;
+    }
+
     void run() {
         validate();
         const_memo.assign(n_nodes, -2);
@@ -664,6 +699,7 @@ struct Lowerer {
         out.pc_gen = (uint32_t)here();
         emit_gen(root);
         emit(OP_END);
+        out.steady_ok = steady_eligible(out.pc_gen, (uint32_t)here());
         out.pc_len = (uint32_t)here();
         emit_len(root);
         emit(OP_END);

@@ -22,6 +22,7 @@ struct Lowered {
     std::vector<tb_fixed_tab> fixed;
     uint32_t n_slots = 0, state_words = 0, n_params = 0, n_nodes = 0;
     uint32_t pure_len = 1;
+    uint32_t steady_ok = 0;  // the generate program runs through the steady-state interpreter too
     int status = 0;
     std::string error;
 };

@@ -18,6 +18,8 @@
 #define TB_C 8               // samples per lane per tile
 #define TB_TILE (32 * TB_C)  // samples per tile
 #define TB_WARPS_PER_CTA 4
+#define TB_CS 16                 // samples per lane per tile of the steady-state interpreter (steady.cuh)
+#define TB_TILE_S (32 * TB_CS)
 #define TB_MAX_K 9   // feed-forward taps supported by the device path (K-1 <= C)
 #define TB_MAX_J 4   // feedback taps supported by the scan path
 #define TB_CTL_DEPTH 96
@@ -109,7 +111,8 @@ enum tb_op : uint32_t {
 
 // Sine precision classes (op >> 8 of the G_SINE_* / S_SINE_* instructions).
 #define TB_SINE_EXACT 0u  // f64 polynomial, rounds like the reference's (f64 sin) as f32
-#define TB_SINE_FAST 1u   // f32 polynomial; only for sines that feed no phase, trigger or length
+#define TB_SINE_FAST 1u   // f32 polynomial (or MUFU, tb_launch::fast_mode == 2); only for sines that
+                          // feed no phase, trigger or length
 
 // Constant-table construction, evaluated per voice at kernel start (generator.rs:574-612 is_const
 // folding done once instead of once per block).
@@ -123,9 +126,10 @@ struct tb_cexpr {
 
 // Per-voice derived 64-bit constants ("aux"), evaluated after the constant table.
 enum tb_aux_kind : uint32_t {
-    AUX_SINE_INC = 0,    // cval[a] rad/s  -> phase increment, 2^-64 turns per sample
+    AUX_SINE_INC = 0,    // cval[a] rad/s  -> [0] phase increment, 2^-64 turns per sample; [2..2+2*TB_CS)
+                         // the rotations (cos, sin)(2 pi j inc / 2^64), j < TB_CS, as doubles
     AUX_SINE_PHASE = 1,  // cval[a] rad    -> phase offset, 2^-64 turns
-    AUX_FILT_POW = 2     // feedback coefficients of filter table b -> 5 JxJ f64 matrices
+    AUX_FILT_POW = 2     // feedback coefficients of filter table b -> 6 JxJ f64 matrices A^(8 * 2^k)
 };
 struct tb_aux {
     uint32_t kind;
@@ -148,6 +152,7 @@ struct tb_filter_tab {
     uint32_t all_const;    // every coefficient literally Const (generator.rs:428-440)
     uint32_t fb_const;     // every feedback coefficient is a constant operand -> scan path
     uint32_t pow_aux;      // aux offset of the matrix powers (fb_const && J > 0)
+    uint32_t state_off;    // the node's state block
     int32_t x_slot;        // slot holding the zero-extended input when not all-const
     int32_t u_slot;        // scratch slot for the serial feedback fallback
     int32_t coef[TB_MAX_K + 16];  // K feed-forward then J feedback operands
@@ -173,6 +178,9 @@ struct tb_launch {
     const float* pool;
     uint32_t n_slots, state_words;
     uint32_t sample_rate;
+    uint32_t n_filt;
+    uint32_t steady_ok;    // the generate program may run through the steady-state interpreter
+    uint32_t fast_mode;    // FAST-class sine evaluation: 1 = f32 polynomial, 2 = MUFU
     // per call
     const float* params;
     uint32_t n_params, n_voices;

@@ -1354,6 +1354,8 @@ __device__ void run_program(const tb_launch& P, const tb_insn* code, const WarpM
 #undef POP
 }
 
+#include "steady.cuh"
+
 // ------------------------------------------------------------------------------------------
 // Per-voice setup: constant table (is_const folding, generator.rs:574-612) and derived constants.
 // ------------------------------------------------------------------------------------------
@@ -1370,13 +1372,21 @@ __device__ void setup_voice(const tb_launch& P, const WarpMem& M, const float* p
         }
     }
     __syncwarp();
-    for (uint32_t t = l; t < P.n_aux; t += 32) {
+    for (uint32_t t = 0; t < P.n_aux; t++) {  // warp-uniform walk; lanes share the work of one entry
         const tb_aux a = P.aux[t];
         if (a.kind == AUX_SINE_INC) {
-            M.aux[a.off] = turns_to_fx_slow((double)M.cval[a.a] / (TB_TAU * (double)P.sample_rate));
+            const u64 inc = turns_to_fx_slow((double)M.cval[a.a] / (TB_TAU * (double)P.sample_rate));
+            if (l == 0) M.aux[a.off] = inc;
+            if (l < TB_CS) {  // rotation table of the steady-state interpreter: (cos, sin)(j * inc)
+                const u64 ang = inc * (u64)l;
+                double2 r;
+                r.x = l == 0 ? 1.0 : sin_turns_d8(ang + 0x4000000000000000ull);
+                r.y = l == 0 ? 0.0 : sin_turns_d8(ang);
+                reinterpret_cast<double2*>(M.aux + a.off + 2)[l] = r;
+            }
         } else if (a.kind == AUX_SINE_PHASE) {
-            M.aux[a.off] = turns_to_fx_slow((double)M.cval[a.a] / TB_TAU);
-        } else {  // AUX_FILT_POW: A^(C*2^k), k = 0..4, A the companion matrix of the feedback taps
+            if (l == 0) M.aux[a.off] = turns_to_fx_slow((double)M.cval[a.a] / TB_TAU);
+        } else if (l == 0) {  // AUX_FILT_POW: A^(8*2^k), k = 0..5, A the companion matrix of the feedback taps
             const tb_filter_tab* ft = &P.filt[a.b];
             const int J = ft->J, K = ft->K;
             double A[TB_MAX_J * TB_MAX_J], B[TB_MAX_J * TB_MAX_J];
@@ -1384,10 +1394,10 @@ __device__ void setup_voice(const tb_launch& P, const WarpMem& M, const float* p
                 for (int c = 0; c < J; c++)
                     A[r * J + c] = r == 0 ? -(double)M.cval[~ft->coef[K + c]] : (c == r - 1 ? 1.0 : 0.0);
             double* out = reinterpret_cast<double*>(M.aux + a.off);
-            for (int step = 0; step < 3 + 5; step++) {  // C = 2^3
+            for (int step = 0; step < 3 + 6; step++) {
                 if (step >= 3) {
                     for (int e = 0; e < J * J; e++) out[(step - 3) * J * J + e] = A[e];
-                    if (step == 7) break;
+                    if (step == 8) break;
                 }
                 for (int r = 0; r < J; r++)
                     for (int c = 0; c < J; c++) {
@@ -1426,7 +1436,7 @@ tb_render_kernel(const tb_launch P) {
     }
 
     size_t off = ((size_t)P.n_code * sizeof(tb_insn) + 15) & ~(size_t)15;
-    const size_t per_warp_slots = (size_t)P.n_slots * TILE * sizeof(float);
+    const size_t per_warp_slots = (size_t)P.n_slots * (P.steady_ok ? TILE_S : TILE) * sizeof(float);
     const size_t aux_b = ((size_t)P.aux_words * 8 + 15) & ~(size_t)15;
     const size_t cval_b = ((size_t)P.n_cval * 4 + 15) & ~(size_t)15;
     const size_t state_b = ((size_t)P.state_words * 4 + 15) & ~(size_t)15;
@@ -1463,8 +1473,40 @@ tb_render_kernel(const tb_launch P) {
     if (P.mode == 0) {
         float* row = P.out ? P.out + (size_t)voice * P.out_stride : nullptr;
         const bool vec_ok = row && ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
-        for (u64 tbase = 0; tbase < P.n_samples; tbase += TILE) {
+        const uint32_t code_s = (uint32_t)__cvta_generic_to_shared(code);
+        // Whole tiles take the steady path once every filter holds its full history
+        // (generator.rs:234-252): normally after the first general tile of a stream.
+        auto filters_ready = [&]() {
+            bool ready = true;
+            for (uint32_t fi = 0; fi < P.n_filt; fi++) {
+                const uint32_t* S = M.state + P.filt[fi].state_off;
+                ready = ready && S[0] != 0u && S[1] == P.filt[fi].K - 1u;
+            }
+            return ready;
+        };
+        bool steady = P.steady_ok && filters_ready();
+        u64 tbase = 0;
+        while (tbase < P.n_samples) {
             const u64 left = P.n_samples - tbase;
+            if (steady && left >= (u64)TILE_S) {
+                // Whole tile, every node infinite, histories complete: the steady-state interpreter.
+                float sacc[CS];
+                if (P.fast_mode == 2) run_steady<2>(P, code_s, M, sacc, (int)P.pc_gen, sk);
+                else run_steady<1>(P, code_s, M, sacc, (int)P.pc_gen, sk);
+                if (row) {
+                    float* dst = row + tbase + l * CS;
+                    if (vec_ok) {
+                        UNROLL for (int q = 0; q < CS / 4; q++)
+                            reinterpret_cast<float4*>(dst)[q] =
+                                make_float4(sacc[4 * q], sacc[4 * q + 1], sacc[4 * q + 2], sacc[4 * q + 3]);
+                    } else {
+                        UNROLL for (int j = 0; j < CS; j++) dst[j] = sacc[j];
+                    }
+                }
+                total += (u64)TILE_S;
+                tbase += (u64)TILE_S;
+                continue;
+            }
             cx.w0 = 0;
             cx.w1 = left < (u64)TILE ? (int)left : TILE;
             cx.L = 0;
@@ -1482,6 +1524,11 @@ tb_render_kernel(const tb_launch P) {
             }
             total += (u64)L;
             if (L < cx.w1) break;
+            tbase += (u64)TILE;
+            if (P.steady_ok && !steady) {
+                __syncwarp();
+                steady = filters_ready();
+            }
         }
     } else {
         const u64 step = P.pure_len ? (u64)(1 << 30) : (u64)TILE;
@@ -1505,9 +1552,9 @@ tb_render_kernel(const tb_launch P) {
 }
 
 extern "C" size_t tb_kernel_smem_bytes(uint32_t n_code, uint32_t n_slots, uint32_t aux_words,
-                                       uint32_t n_cval, uint32_t state_words) {
+                                       uint32_t n_cval, uint32_t state_words, uint32_t steady_ok) {
     size_t off = ((size_t)n_code * sizeof(tb_insn) + 15) & ~(size_t)15;
-    const size_t per_warp = (size_t)n_slots * TILE * sizeof(float) + (((size_t)aux_words * 8 + 15) & ~(size_t)15) +
+    const size_t per_warp = (size_t)n_slots * (steady_ok ? TILE_S : TILE) * sizeof(float) + (((size_t)aux_words * 8 + 15) & ~(size_t)15) +
                             (((size_t)n_cval * 4 + 15) & ~(size_t)15) + (((size_t)state_words * 4 + 15) & ~(size_t)15) +
                             (((size_t)n_slots * 4 + 15) & ~(size_t)15) + (((size_t)n_slots * 32 + 15) & ~(size_t)15);
     return off + per_warp * TB_WARPS_PER_CTA;
