@@ -150,6 +150,7 @@ void fill_launch(const tb_program* p, tb_launch* L) {
     L->n_code = (uint32_t)p->low.code.size();
     L->pc_gen = p->low.pc_gen;
     L->pc_len = p->low.pc_len;
+    L->pc_steady = p->low.pc_steady;
     L->cexpr = p->d_cexpr;
     L->n_cval = (uint32_t)p->low.cexpr.size();
     L->aux = p->d_aux;

@@ -653,37 +653,133 @@ struct Lowerer {
         }
     }
 
-    // The steady-state interpreter (steady.cuh) takes programs made only of infinite, window-free
-    // nodes: constants, clocks, sines, point operators, Alt and constant-coefficient filters.
-    bool steady_eligible(uint32_t begin, uint32_t end) const {
-        for (uint32_t pc = begin; pc < end; pc++) {
-            const tb_insn& in = out.code[pc];
-            switch (in.op & 0xffu) {
-                case OP_END:
-                case G_CONST:
-                case G_TIME:
-                case G_BIN_BEGIN:
-                case G_BIN_END:
-                case G_SINE_CC:
-                case G_SINE_AC:
-                case G_SINE_CA:
-                case G_SINE_BEGIN:
-                case G_SINE_END:
-                case G_ALT_CC:
-                case G_ALT_BEGIN:
-                case G_ALT_POS:
-                case G_ALT_END:
-                case G_FILT_PRE:
-                case G_FILT_PRE_END: break;
-                case G_BINC: break;
-                case G_FILT_RUN:
-                    if (in.c != 0) return false;  // coefficient waveforms
-                    break;
-                default: return false;
-            }
-            pc += in.op >> 16;  // fused post-ops
+    // ---- steady-state stream (steady.cuh) ---------------------------------------------------------
+    // A second, straight-line rendering of the generate walk for trees made only of infinite,
+    // window-free nodes (constants, clocks, sines, point operators, Alt, constant-coefficient
+    // filters).  Returns false when the tree holds anything else; the caller then discards it.
+    // Point operators with a constant right-hand side (generator.rs:538-549) become post-op words
+    // of the instruction that produced the accumulator; `* c` followed by `+ c'` or `- c'` shares
+    // one word (both operations still round separately, like the reference's two nodes).
+    int s_slots = 0;
+    int s_last = -1;  // last instruction that left a fresh accumulator
+    int one_idx = -1, negzero_idx = -1;
+    int s_alloc() {
+        int s = s_slots++;
+        out.n_slots = std::max<uint32_t>(out.n_slots, (uint32_t)s_slots);
+        return s;
+    }
+    void s_produced(int idx) { s_last = idx; }
+    void s_postop(uint32_t op, int cidx) {
+        if (one_idx < 0) {
+            one_idx = literal_cexpr(1.0f);
+            negzero_idx = literal_cexpr(-0.0f);
         }
-        return true;
+        tb_insn& prod = out.code[s_last];
+        const int npost = (int)(prod.op >> 16);
+        if (op == TB_MERGE) op = TB_ADD;  // infinite operands: Merge is Add (generator.rs:263)
+        if (op == TB_ADD || op == TB_SUBTRACT) {
+            const int addend = op == TB_ADD ? cidx : new_cexpr(tb_cexpr{CE_NEG, 0, cidx, 0, 0.f});
+            if (npost > 0) {
+                tb_insn& prev = out.code[s_last + npost];
+                if ((prev.op & 0xffu) == ST_AFFINE && prev.c == negzero_idx) {  // completes a multiply
+                    prev.c = addend;
+                    return;
+                }
+            }
+            out.code[s_last].op += 1u << 16;
+            emit(ST_AFFINE, 0, one_idx, addend);
+        } else if (op == TB_MULTIPLY) {
+            out.code[s_last].op += 1u << 16;
+            emit(ST_AFFINE, 0, cidx, negzero_idx);
+        } else {
+            out.code[s_last].op += 1u << 16;
+            emit(ST_OPC, (int)op, cidx, 0);
+        }
+    }
+    bool emit_steady(int i) {
+        const tb_node& n = nodes[i];
+        switch (n.kind) {
+            case TB_CONST: s_produced(emit(ST_CONST, const_of(i))); return true;
+            case TB_TIME: s_produced(emit(ST_TIME, state_of(i, 2))); return true;
+            case TB_MARKED:
+            case TB_CAPTURED: return emit_steady(n.a);
+            case TB_BINARY: {
+                const int cb = const_of(n.b);
+                if (!emit_steady(n.a)) return false;
+                if (cb >= 0) {
+                    if ((out.code[s_last].op >> 16) >= 15) return false;
+                    s_postop(n.op, cb);
+                } else {
+                    const int s = s_alloc();
+                    emit(ST_SAVE, s);
+                    if (!emit_steady(n.b)) return false;
+                    s_produced(emit(ST_BIN, s, n.op == TB_MERGE ? (int)TB_ADD : (int)n.op));
+                    s_slots--;
+                }
+                return true;
+            }
+            case TB_SINE: {
+                const int cf = const_of(n.a), cp = const_of(n.b);
+                const int st = state_of(i, 2);
+                const uint32_t fl = sine_flags(i);
+                const int aux_inc = cf >= 0 ? new_aux(AUX_SINE_INC, cf, 0, 2 + 2 * TB_CS) : 0;
+                const int aux_ph = cp >= 0 ? new_aux(AUX_SINE_PHASE, cp, 0, 1) : 0;
+                if (cf >= 0 && cp >= 0) {
+                    s_produced(emit(ST_SINE_CC, st, aux_inc, aux_ph));
+                } else if (cp >= 0) {
+                    if (!emit_steady(n.a)) return false;
+                    s_produced(emit(ST_SINE_AC | fl, st, 0, aux_ph));
+                } else if (cf >= 0) {
+                    if (!emit_steady(n.b)) return false;
+                    s_produced(emit(ST_SINE_CA | fl, st, aux_inc, 0));
+                } else {
+                    if (!emit_steady(n.a)) return false;
+                    const int s = s_alloc();
+                    emit(ST_SAVE, s);
+                    if (!emit_steady(n.b)) return false;
+                    s_produced(emit(ST_SINE_AA | fl, st, s, 0));
+                    s_slots--;
+                }
+                return true;
+            }
+            case TB_ALT: {
+                const int cp = const_of(n.b), cn = const_of(n.c);
+                if (!emit_steady(n.a)) return false;
+                if (cp >= 0 && cn >= 0) {
+                    s_produced(emit(ST_ALT_CC, cp, cn));
+                    return true;
+                }
+                const int st = s_alloc();
+                emit(ST_SAVE, st);
+                int opp = TB_OPERAND_CONST(cp), opn = TB_OPERAND_CONST(cn);
+                int extra = 0;
+                if (cp < 0) {
+                    if (!emit_steady(n.b)) return false;
+                    opp = s_alloc();
+                    extra = 1;
+                    emit(ST_SAVE, opp);
+                }
+                if (cn < 0) {
+                    if (!emit_steady(n.c)) return false;
+                    opn = 0;
+                }
+                s_produced(emit(ST_ALT, st, opp, opn));
+                s_slots -= 1 + extra;
+                return true;
+            }
+            case TB_FILTER: {
+                const int fi = filter_table(i);
+                const int st = filter_state(i);
+                const uint32_t K = n.ff_count, J = n.fb_count;
+                for (uint32_t j = 0; j < K + J; j++)
+                    if (const_of(lists[n.list_off + j]) < 0) return false;  // coefficient waveforms
+                if (!emit_steady(n.a)) return false;
+                const int coef = new_aux(AUX_FILT_COEF, 0, fi, (K + J + 1) / 2);
+                s_produced(emit(ST_FILT | (K << 8) | (J << 12), st, coef, J > 0 ? (int)out.filt[fi].pow_aux : 0));
+                return true;
+            }
+            default: return false;
+        }
     }
 
     void run() {
@@ -699,10 +795,29 @@ struct Lowerer {
         out.pc_gen = (uint32_t)here();
         emit_gen(root);
         emit(OP_END);
-        out.steady_ok = steady_eligible(out.pc_gen, (uint32_t)here());
         out.pc_len = (uint32_t)here();
         emit_len(root);
         emit(OP_END);
+        {   // the steady-state stream, when the whole tree qualifies
+            const size_t code0 = out.code.size(), cexpr0 = out.cexpr.size(), aux0 = out.aux.size();
+            const uint32_t aux_words0 = out.aux_words, slots0 = out.n_slots;
+            out.pc_steady = (uint32_t)here();
+            if (emit_steady(root)) {
+                emit(ST_END);
+                out.steady_ok = 1;
+            } else {
+                out.code.resize(code0);
+                out.cexpr.resize(cexpr0);
+                for (int& m : const_memo)
+                    if (m >= (int)cexpr0) m = -2;
+                one_idx = negzero_idx = -1;
+                out.aux.resize(aux0);
+                out.aux_words = aux_words0;
+                out.n_slots = slots0;
+                out.pc_steady = 0;
+                out.steady_ok = 0;
+            }
+        }
         if (out.state_words == 0) out.state_words = 1;
         if (out.cexpr.empty()) literal_cexpr(0.f);
         if (out.aux_words == 0) out.aux_words = 1;

@@ -12,7 +12,7 @@ namespace tb {
 
 struct Lowered {
     std::vector<tb_insn> code;
-    uint32_t pc_gen = 0, pc_len = 0;
+    uint32_t pc_gen = 0, pc_len = 0, pc_steady = 0;
     std::vector<tb_cexpr> cexpr;
     std::vector<tb_aux> aux;
     uint32_t aux_words = 0;

@@ -102,6 +102,22 @@ enum tb_op : uint32_t {
     S_RESET_BEGIN, // a = state, b = origin slot
     S_RESET_END,   // a = state
     S_FIN,         // a = goe table index   (static Time / const forms only)
+    // ---- steady-state stream (steady.cuh): straight-line, every operand infinite ----
+    ST_END,
+    ST_CONST,      // a = cval index
+    ST_TIME,       // a = state
+    ST_SAVE,       // a = slot                      acc -> slot
+    ST_BIN,        // a = slot, b = operator        acc = slot (op) acc
+    ST_SINE_CC,    // a = state, b = aux of increment (+ rotation table), c = aux of phase
+    ST_SINE_AC,    // a = state, c = aux of phase           (frequency in acc); class in op>>8
+    ST_SINE_CA,    // a = state, b = aux of increment       (phase in acc)
+    ST_SINE_AA,    // a = state, b = slot of the frequency  (phase in acc)
+    ST_ALT_CC,     // a = cval (positive), b = cval (negative)
+    ST_ALT,        // a = trigger slot, b = positive operand, c = negative operand (>= 0: in acc)
+    ST_FILT,       // a = state, b = aux of the coefficient values, c = aux of the matrix powers;
+                   // K in op bits 8-11, J in bits 12-14
+    ST_AFFINE,     // post-op word: acc = (acc * cval[b]) + cval[c], both operations rounded
+    ST_OPC,        // post-op word: acc = acc (operator a) cval[b]
     OP_COUNT
 };
 
@@ -116,7 +132,7 @@ enum tb_op : uint32_t {
 
 // Constant-table construction, evaluated per voice at kernel start (generator.rs:574-612 is_const
 // folding done once instead of once per block).
-enum tb_cexpr_kind : uint32_t { CE_LIT = 0, CE_PARAM = 1, CE_BIN = 2 };
+enum tb_cexpr_kind : uint32_t { CE_LIT = 0, CE_PARAM = 1, CE_BIN = 2, CE_NEG = 3 /* -cval[a] */ };
 struct tb_cexpr {
     uint32_t kind;
     uint32_t op;   // CE_BIN: tb_operator
@@ -129,7 +145,8 @@ enum tb_aux_kind : uint32_t {
     AUX_SINE_INC = 0,    // cval[a] rad/s  -> [0] phase increment, 2^-64 turns per sample; [2..2+2*TB_CS)
                          // the rotations (cos, sin)(2 pi j inc / 2^64), j < TB_CS, as doubles
     AUX_SINE_PHASE = 1,  // cval[a] rad    -> phase offset, 2^-64 turns
-    AUX_FILT_POW = 2     // feedback coefficients of filter table b -> 6 JxJ f64 matrices A^(8 * 2^k)
+    AUX_FILT_POW = 2,    // feedback coefficients of filter table b -> 6 JxJ f64 matrices A^(8 * 2^k)
+    AUX_FILT_COEF = 3    // constant coefficients of filter table b as K + J floats (steady stream)
 };
 struct tb_aux {
     uint32_t kind;
@@ -167,6 +184,7 @@ struct tb_launch {
     const tb_insn* code;
     uint32_t n_code;
     uint32_t pc_gen, pc_len;  // entry points of the root's G_* and L_* programs
+    uint32_t pc_steady;       // entry point of the ST_* stream (valid when steady_ok)
     const tb_cexpr* cexpr;
     uint32_t n_cval;
     const tb_aux* aux;

@@ -1367,6 +1367,7 @@ __device__ void setup_voice(const tb_launch& P, const WarpMem& M, const float* p
             float v;
             if (e.kind == CE_LIT) v = e.value;
             else if (e.kind == CE_PARAM) v = prow ? prow[e.a] : e.value;
+            else if (e.kind == CE_NEG) v = -M.cval[e.a];
             else v = apply1(e.op, M.cval[e.a], M.cval[e.b]);
             M.cval[k] = v;
         }
@@ -1386,6 +1387,10 @@ __device__ void setup_voice(const tb_launch& P, const WarpMem& M, const float* p
             }
         } else if (a.kind == AUX_SINE_PHASE) {
             if (l == 0) M.aux[a.off] = turns_to_fx_slow((double)M.cval[a.a] / TB_TAU);
+        } else if (a.kind == AUX_FILT_COEF) {  // coefficient values of a constant filter: b_0.., a_1..
+            const tb_filter_tab* ft = &P.filt[a.b];
+            float* cf = reinterpret_cast<float*>(M.aux + a.off);
+            for (uint32_t e = l; e < ft->K + ft->J; e += 32) cf[e] = M.cval[~ft->coef[e]];
         } else if (l == 0) {  // AUX_FILT_POW: A^(8*2^k), k = 0..5, A the companion matrix of the feedback taps
             const tb_filter_tab* ft = &P.filt[a.b];
             const int J = ft->J, K = ft->K;
@@ -1491,8 +1496,8 @@ tb_render_kernel(const tb_launch P) {
             if (steady && left >= (u64)TILE_S) {
                 // Whole tile, every node infinite, histories complete: the steady-state interpreter.
                 float sacc[CS];
-                if (P.fast_mode == 2) run_steady<2>(P, code_s, M, sacc, (int)P.pc_gen, sk);
-                else run_steady<1>(P, code_s, M, sacc, (int)P.pc_gen, sk);
+                if (P.fast_mode == 2) run_steady<2>(P, code_s, M, sacc, sk);
+                else run_steady<1>(P, code_s, M, sacc, sk);
                 if (row) {
                     float* dst = row + tbase + l * CS;
                     if (vec_ok) {

@@ -3,17 +3,20 @@
 //
 // Most of a render is spent far from any boundary: every node of the program is an infinite
 // waveform, the window is a whole tile, all filter histories are complete and nothing finishes.
-// For programs whose generate code contains only such nodes (lower.cpp: `steady_ok`) the kernel
-// runs the SAME byte-code through this second interpreter, which
-//   * walks tiles of 32 x CS = 512 samples (lane l owns [16 l, 16 l + 16)): half the dispatches
-//     and half the warp scans per sample of the general path,
-//   * carries no window / length / validity bookkeeping at all,
-//   * evaluates constant-rate sines (generator.rs:206-219 with Const frequency and phase) by
-//     angle addition in f64: one sin/cos pair per lane per tile, then
-//     sin(a + j d) = sin a cos(j d) + cos a sin(j d) against a per-voice table of the 16 rotations,
-//   * prefetches the next instruction word while the current one executes.
-// State blocks, constants and the carried semantics are those of the general interpreter, so the
-// two can alternate tile by tile (the first tile of a launch and the tail always run there).
+// For trees made only of such nodes lower.cpp emits, next to the general byte-code, a second
+// straight-line stream of ST_* words (program.h) that this interpreter runs:
+//   * tiles of 32 x CS = 512 samples (lane l owns [16 l, 16 l + 16)): half the dispatches and
+//     half the warp scans per sample of the general path,
+//   * no window / length / validity bookkeeping, no jumps, every operand pre-resolved
+//     (filter coefficients as values, K and J in the instruction word),
+//   * constant-rate sines (generator.rs:206-219 with Const frequency and phase) by angle
+//     addition in f64: one sin/cos pair per lane per tile, then
+//     sin(a + j d) = sin a cos(j d) + cos a sin(j d) against a per-voice table of 16 rotations,
+//   * constant point operators as branch-free `acc * m + a` post-op words (two roundings),
+//   * FAST-class sines from the top 32 phase bits only (the 2^-32-turn carry is dropped),
+//   * the next instruction word prefetched while the current one executes.
+// State blocks, constants and carried semantics are those of the general interpreter, so the two
+// alternate tile by tile (the first tile of a stream and the tail of a launch always run there).
 #pragma once
 
 constexpr int CS = TB_CS;
@@ -59,20 +62,37 @@ __device__ __forceinline__ double sin_turns_d8(u64 ph) {
     return x * p;
 }
 
-// FAST class through the special-function unit: the top 32 phase bits as radians in [-pi, pi),
-// sin.approx (range reduction multiply + MUFU.SIN), |err| <= 2^-21.4 (CUDA math API, __sinf on
-// [-pi, pi]).  Selected by tb_launch::fast_mode == 2.
-__device__ __forceinline__ float sin_turns_mufu(u64 ph) {
-    return __sinf((float)(int)(ph >> 32) * 1.4629180792671596e-09f);  // 2 pi / 2^32
+// FAST class from the top 32 phase bits h (2^-32 turns, two's complement = [-1/2, 1/2) turn).
+//   MODE 1: the f32 polynomial of the general path (|err| < 2e-7);
+//   MODE 2: the special-function unit — radians in [-pi, pi), sin.approx = range-reduction
+//           multiply + MUFU.SIN, |err| <= 2^-21.4 (CUDA math API, __sinf on [-pi, pi]).
+template <int MODE>
+__device__ __forceinline__ float sin_hi(int h) {
+    if (MODE == 2) return __sinf((float)h * 1.4629180792671596e-09f);  // 2 pi / 2^32
+    const int m = (h ^ (h << 1)) >> 31;
+    const int f = ((h ^ m) - m) ^ (m & (int)0x80000000);
+    const float x = (float)f * 9.31322574615478515625e-10f;  // 2^-30
+    const float z = x * x;
+    float p = 0.00015167170204222202f;
+    p = fmaf(p, z, -0.004674143623560667f);
+    p = fmaf(p, z, 0.07968991994857788f);
+    p = fmaf(p, z, -0.6459637880325317f);
+    p = fmaf(p, z, 1.5707963705062866f);
+    return x * p;
 }
 
-template <int MODE>  // 0 exact, 1 f32 polynomial, 2 MUFU
-__device__ __forceinline__ float sin_turns_m(u64 ph) {
-    return MODE == 0 ? sin_turns_exact(ph) : (MODE == 1 ? sin_turns_fast(ph) : sin_turns_mufu(ph));
+// Bits of (f * scale + 1.5 * 2^52): the low mantissa bits hold rint(f * scale) in 2^-44 turns.
+// Shifted left by 20 they are 2^-64 turns and the exponent / magic bits fall off the top, so
+// sums of raw words can be shifted once at the end:  (sum raw) << 20 == sum (q << 20) mod 2^64.
+__device__ __forceinline__ u64 magic_raw(float f, double scale) {
+    return (u64)__double_as_longlong(fma((double)f, scale, 6755399441055744.0));
+}
+__device__ __forceinline__ int raw_hi(u64 raw) {  // top 32 bits of raw << 20
+    return (int)__funnelshift_l((uint32_t)raw, (uint32_t)(raw >> 32), 20);
 }
 
 // Constant frequency and phase: angle addition against the per-voice rotation table
-// rot[j] = (cos, sin)(2 pi j inc / 2^64), j < CS  (setup_voice, AUX_SINE_ROT).
+// rot[j] = (cos, sin)(2 pi j inc / 2^64), j < CS  (setup_voice, AUX_SINE_INC).
 __device__ __forceinline__ void steady_sine_cc(float (&acc)[CS], u64 inc, u64 ph0, const double2* rot,
                                                uint32_t* state, int st) {
     const u64 acc0 = ld_state64(state, st);
@@ -102,13 +122,32 @@ __device__ __forceinline__ void steady_sine_scan(float (&acc)[CS], const float (
         if (!UNIFORM_PH) bigp = fmaxf(bigp, fabsf(p[j]));
     }
     const bool slow = __any_sync(FULL, !(big < sk.flimit) || !(bigp < sk.plimit));
+    if (MODE != 0 && !slow) {
+        // FAST: only the top 32 bits of each sample's phase are formed; the running sum of the
+        // lane stays 64-bit (it feeds the carried accumulator, which must stay exact).
+        int h[CS];
+        u64 raw = 0;
+        UNROLL for (int j = 0; j < CS; j++) {
+            h[j] = raw_hi(raw);
+            if (!UNIFORM_PH) h[j] += raw_hi(magic_raw(p[j], sk.pscale));
+            raw += magic_raw(f[j], sk.kscale);
+        }
+        const u64 run = raw << 20;
+        const u64 incl = warp_incl_sum(run);
+        const u64 base = acc0 + (incl - run) + (UNIFORM_PH ? ph0 : 0ull);
+        const u64 total = __shfl_sync(FULL, incl, 31);
+        const int bh = (int)(base >> 32);
+        UNROLL for (int j = 0; j < CS; j++) acc[j] = sin_hi<MODE>(h[j] + bh);
+        __syncwarp();
+        st_state64(state, st, acc0 + total);
+        return;
+    }
     u64 ph[CS];
     u64 run = 0;
     if (!slow) {
         UNROLL for (int j = 0; j < CS; j++) {
-            const u64 inc = magic_to_fx(fma((double)f[j], sk.kscale, 6755399441055744.0));
-            ph[j] = UNIFORM_PH ? run : run + magic_to_fx(fma((double)p[j], sk.pscale, 6755399441055744.0));
-            run += inc;
+            ph[j] = UNIFORM_PH ? run : run + (magic_raw(p[j], sk.pscale) << 20);
+            run += magic_raw(f[j], sk.kscale) << 20;
         }
     } else {
         UNROLL for (int j = 0; j < CS; j++) {
@@ -119,7 +158,10 @@ __device__ __forceinline__ void steady_sine_scan(float (&acc)[CS], const float (
     const u64 incl = warp_incl_sum(run);
     const u64 base = acc0 + (incl - run) + (UNIFORM_PH ? ph0 : 0ull);
     const u64 total = __shfl_sync(FULL, incl, 31);
-    UNROLL for (int j = 0; j < CS; j++) acc[j] = sin_turns_m<MODE>(ph[j] + base);
+    UNROLL for (int j = 0; j < CS; j++) {
+        const u64 a = ph[j] + base;
+        acc[j] = MODE == 0 ? sin_turns_exact(a) : sin_hi<MODE>((int)(a >> 32));
+    }
     __syncwarp();
     st_state64(state, st, acc0 + total);
 }
@@ -134,12 +176,18 @@ __device__ __forceinline__ void steady_sine_ca(float (&acc)[CS], u64 inc, const 
     UNROLL for (int j = 0; j < CS; j++) bigp = fmaxf(bigp, fabsf(p[j]));
     if (__any_sync(FULL, !(bigp < sk.plimit))) {
         UNROLL for (int j = 0; j < CS; j++) {
-            acc[j] = sin_turns_m<MODE>(b + phase_to_fx(p[j], sk));
+            const u64 a = b + phase_to_fx(p[j], sk);
+            acc[j] = MODE == 0 ? sin_turns_exact(a) : sin_hi<MODE>((int)(a >> 32));
+            b += inc;
+        }
+    } else if (MODE == 0) {
+        UNROLL for (int j = 0; j < CS; j++) {
+            acc[j] = sin_turns_exact(b + (magic_raw(p[j], sk.pscale) << 20));
             b += inc;
         }
     } else {
         UNROLL for (int j = 0; j < CS; j++) {
-            acc[j] = sin_turns_m<MODE>(b + magic_to_fx(fma((double)p[j], sk.pscale, 6755399441055744.0)));
+            acc[j] = sin_hi<MODE>((int)(b >> 32) + raw_hi(magic_raw(p[j], sk.pscale)));
             b += inc;
         }
     }
@@ -147,82 +195,105 @@ __device__ __forceinline__ void steady_sine_ca(float (&acc)[CS], u64 inc, const 
     st_state64(state, st, acc0 + inc * (u64)TILE_S);
 }
 
-// Constant-coefficient filter over a whole tile with complete history (generator.rs:382-515).
+// ---- constant-coefficient filter over a whole tile with complete history (generator.rs:382-515) ----
 // Same arithmetic, operation order and carried deques as filter_full_tile of the general path.
-template <int J>
-__device__ __forceinline__ void steady_filter(const WarpMem& M, const tb_filter_tab* ft, float (&acc)[CS],
-                                              uint32_t* S) {
+// Feed-forward part: u[j] = x[j] b0 + b1 x[j-1] + ... (each product and sum rounded, :496-499).
+// KT > 0: K known at compile time (1, 2, 3 cover every filter of lib/v0/std.tuun); KT == 0: any K.
+template <int KT>
+__device__ __forceinline__ void steady_fir(float (&u)[CS], const float (&x)[CS], const float* b, int K, float* hx) {
     const int l = lane_id();
-    const int K = ft->K;
-    float* hx = reinterpret_cast<float*>(S + 2);
-    float* hy = hx + (K - 1);
+    constexpr int NP = KT > 0 ? (KT > 1 ? KT - 1 : 1) : TB_MAX_K - 1;
     // pe[m] = x[-1 - m]: the sample m + 1 places before this lane's chunk.
-    // (All TB_MAX_K - 1 are fetched unconditionally: eight shuffles per 16 samples cost less than
-    // keeping conditionally defined registers alive across the tap loop.)
-    float pe[TB_MAX_K - 1];
-    UNROLL for (int m = 0; m < TB_MAX_K - 1; m++) {
-        const float t = __shfl_up_sync(FULL, acc[CS - 1 - m], 1);
-        pe[m] = (l == 0) ? ((m < K - 1) ? hx[K - 2 - m] : 0.0f) : t;
+    float pe[NP];
+    UNROLL for (int m = 0; m < NP; m++) {
+        pe[m] = 0.0f;
+        if (KT == 0 || m < KT - 1) {
+            const float t = __shfl_up_sync(FULL, x[CS - 1 - m], 1);
+            pe[m] = (l == 0) ? ((m < K - 1) ? hx[K - 2 - m] : 0.0f) : t;
+        }
     }
-    float u[CS];
     {
-        const float b0 = M.cval[~ft->coef[0]];
-        UNROLL for (int j = 0; j < CS; j++) u[j] = __fmul_rn(acc[j], b0);
+        const float b0 = b[0];
+        UNROLL for (int j = 0; j < CS; j++) u[j] = __fmul_rn(x[j], b0);
     }
-    UNROLL for (int k = 1; k < TB_MAX_K; k++) {
-        if (k < K) {
-            const float bk = M.cval[~ft->coef[k]];
-            UNROLL for (int j = 0; j < CS; j++) u[j] = __fadd_rn(u[j], __fmul_rn(bk, (j >= k) ? acc[j - k] : pe[k - j - 1]));
+    UNROLL for (int k = 1; k < (KT > 0 ? KT : TB_MAX_K); k++) {
+        if (KT > 0 || k < K) {
+            const float bk = b[k];
+            UNROLL for (int j = 0; j < CS; j++) u[j] = __fadd_rn(u[j], __fmul_rn(bk, (j >= k) ? x[j - k] : pe[k - j - 1]));
         }
     }
     __syncwarp();
     if (l == 31) {  // the input deque keeps the last K-1 inputs of the tile (oldest first)
-        UNROLL for (int m = 0; m < TB_MAX_K - 1; m++)
-            if (m < K - 1) hx[K - 2 - m] = acc[CS - 1 - m];
+        UNROLL for (int m = 0; m < NP; m++)
+            if (KT > 0 ? (m < KT - 1) : (m < K - 1)) hx[K - 2 - m] = x[CS - 1 - m];
     }
-    if (J > 0) {
-        float a[J > 0 ? J : 1];
-        UNROLL for (int jj = 0; jj < J; jj++) a[jj] = M.cval[~ft->coef[K + jj]];
-        const double* mpow = reinterpret_cast<const double*>(M.aux + ft->pow_aux) + J * J;  // A^(16*2^k)
-        float s[J > 0 ? J : 1];
-        UNROLL for (int jj = 0; jj < J; jj++) s[jj] = (l == 0) ? hy[J - 1 - jj] : 0.0f;
-        UNROLL for (int j = 0; j < CS; j++) {  // pass 1: chunk response from a zero state
-            float y = u[j];
-            UNROLL for (int jj = 0; jj < J; jj++) y = fmaf(-a[jj], s[jj], y);
-            UNROLL for (int jj = J - 1; jj > 0; jj--) s[jj] = s[jj - 1];
-            s[0] = y;
-        }
-        double v[J > 0 ? J : 1];
-        UNROLL for (int jj = 0; jj < J; jj++) v[jj] = (double)s[jj];
-        UNROLL for (int k = 0; k < 5; k++) {
-            const int d = 1 << k;
-            double t[J > 0 ? J : 1];
-            UNROLL for (int jj = 0; jj < J; jj++) t[jj] = __shfl_up_sync(FULL, v[jj], d);
-            if (l >= d) {
-                UNROLL for (int r = 0; r < J; r++) {
-                    double accv = v[r];
-                    UNROLL for (int c = 0; c < J; c++) accv = fma(mpow[(k * J + r) * J + c], t[c], accv);
-                    v[r] = accv;
-                }
+}
+
+// Feedback part: scan of affine state transitions (see iir_scan_const in render.cu); mpow holds
+// A^(16 * 2^k), k = 0..4.
+template <int J>
+__device__ __forceinline__ void steady_iir(float (&acc)[CS], const float (&u)[CS], const float* af,
+                                           const double* mpow, float* hy) {
+    const int l = lane_id();
+    float a[J];
+    UNROLL for (int jj = 0; jj < J; jj++) a[jj] = af[jj];
+    float s[J];
+    UNROLL for (int jj = 0; jj < J; jj++) s[jj] = (l == 0) ? hy[J - 1 - jj] : 0.0f;
+    UNROLL for (int j = 0; j < CS; j++) {  // pass 1: chunk response from a zero state
+        float y = u[j];
+        UNROLL for (int jj = 0; jj < J; jj++) y = fmaf(-a[jj], s[jj], y);
+        UNROLL for (int jj = J - 1; jj > 0; jj--) s[jj] = s[jj - 1];
+        s[0] = y;
+    }
+    double v[J];
+    UNROLL for (int jj = 0; jj < J; jj++) v[jj] = (double)s[jj];
+    UNROLL for (int k = 0; k < 5; k++) {
+        const int d = 1 << k;
+        double t[J];
+        UNROLL for (int jj = 0; jj < J; jj++) t[jj] = __shfl_up_sync(FULL, v[jj], d);
+        if (l >= d) {
+            UNROLL for (int r = 0; r < J; r++) {
+                double accv = v[r];
+                UNROLL for (int c = 0; c < J; c++) accv = fma(mpow[(k * J + r) * J + c], t[c], accv);
+                v[r] = accv;
             }
         }
-        UNROLL for (int jj = 0; jj < J; jj++) {
-            const double up = __shfl_up_sync(FULL, v[jj], 1);
-            s[jj] = (l == 0) ? hy[J - 1 - jj] : (float)up;
-        }
-        UNROLL for (int j = 0; j < CS; j++) {  // pass 2: the reference's f32 operation order (generator.rs:500-502)
-            float y = u[j];
-            UNROLL for (int jj = 0; jj < J; jj++) y = __fsub_rn(y, __fmul_rn(a[jj], s[jj]));
-            UNROLL for (int jj = J - 1; jj > 0; jj--) s[jj] = s[jj - 1];
-            s[0] = y;
-            acc[j] = y;
-        }
-        __syncwarp();
-        if (l == 31) {
-            UNROLL for (int jj = 0; jj < J; jj++) hy[J - 1 - jj] = acc[CS - 1 - jj];
-        }
-    } else {
-        UNROLL for (int j = 0; j < CS; j++) acc[j] = u[j];
+    }
+    UNROLL for (int jj = 0; jj < J; jj++) {
+        const double up = __shfl_up_sync(FULL, v[jj], 1);
+        s[jj] = (l == 0) ? hy[J - 1 - jj] : (float)up;
+    }
+    UNROLL for (int j = 0; j < CS; j++) {  // pass 2: the reference's f32 operation order (generator.rs:500-502)
+        float y = u[j];
+        UNROLL for (int jj = 0; jj < J; jj++) y = __fsub_rn(y, __fmul_rn(a[jj], s[jj]));
+        UNROLL for (int jj = J - 1; jj > 0; jj--) s[jj] = s[jj - 1];
+        s[0] = y;
+        acc[j] = y;
+    }
+    __syncwarp();
+    if (l == 31) {
+        UNROLL for (int jj = 0; jj < J; jj++) hy[J - 1 - jj] = acc[CS - 1 - jj];
+    }
+}
+
+__device__ __forceinline__ void steady_filter(float (&acc)[CS], uint32_t* S, int K, int J, const float* coef,
+                                              const double* pow8) {
+    float* hx = reinterpret_cast<float*>(S + 2);
+    float* hy = hx + (K - 1);
+    float u[CS];
+    switch (K) {
+        case 1: steady_fir<1>(u, acc, coef, K, hx); break;
+        case 2: steady_fir<2>(u, acc, coef, K, hx); break;
+        case 3: steady_fir<3>(u, acc, coef, K, hx); break;
+        default: steady_fir<0>(u, acc, coef, K, hx); break;
+    }
+    const double* mpow = pow8 + J * J;  // skip A^8: the steady chunk is 16 samples
+    switch (J) {
+        case 0: { UNROLL for (int j = 0; j < CS; j++) acc[j] = u[j]; break; }
+        case 1: steady_iir<1>(acc, u, coef + K, mpow, hy); break;
+        case 2: steady_iir<2>(acc, u, coef + K, mpow, hy); break;
+        case 3: steady_iir<3>(acc, u, coef + K, mpow, hy); break;
+        default: steady_iir<4>(acc, u, coef + K, mpow, hy); break;
     }
 }
 
@@ -241,13 +312,13 @@ __device__ __forceinline__ void steady_filter(const WarpMem& M, const tb_filter_
         default: UNROLL for (int j = 0; j < CS; j++) DST[j] = powf(A, B); break;      \
     }
 
-// One steady tile.  `code_s` is the shared-memory address of the program, `pc` its entry point.
+// One steady tile.  `code_s` is the shared-memory address of the program.
 template <int FASTMODE>
 __device__ __forceinline__ void run_steady(const tb_launch& P, uint32_t code_s, const WarpMem& M, float (&acc)[CS],
-                                           int pc, const SineK& sk) {
+                                           const SineK& sk) {
     const int l = lane_id();
     const float srf = (float)P.sample_rate;
-    uint32_t ip = code_s + (uint32_t)pc * (uint32_t)sizeof(tb_insn);
+    uint32_t ip = code_s + P.pc_steady * (uint32_t)sizeof(tb_insn);
     tb_insn nxt = lds_insn(ip);
     for (;;) {
         const tb_insn in = nxt;
@@ -256,53 +327,46 @@ __device__ __forceinline__ void run_steady(const tb_launch& P, uint32_t code_s, 
         const uint32_t op = in.op & 0xffu;
         const bool fast = ((in.op >> 8) & 0xffu) == TB_SINE_FAST;
         switch (op) {
-            case OP_END: return;
-            case G_CONST: {
+            case ST_END: return;
+            case ST_CONST: {
                 const float c = M.cval[in.a];
                 UNROLL for (int j = 0; j < CS; j++) acc[j] = c;
                 break;
             }
-            case G_TIME: {  // generator.rs:101-111
-                const u64 pos = ld_state64(M.state, in.a) + (u64)(l * CS);
+            case ST_TIME: {  // generator.rs:101-111
+                const u64 pos0 = ld_state64(M.state, in.a);
+                const u64 pos = pos0 + (u64)(l * CS);
                 UNROLL for (int j = 0; j < CS; j++) acc[j] = __fdiv_rn(__ull2float_rn(pos + (u64)j), srf);
                 __syncwarp();
-                st_state64(M.state, in.a, pos - (u64)(l * CS) + (u64)TILE_S);
+                st_state64(M.state, in.a, pos0 + (u64)TILE_S);
                 break;
             }
-            case G_BINC: {  // generator.rs:538-549; every operand is infinite here, so Merge is Add
-                const float c = M.cval[in.b];
-                APPLY_OP_S((uint32_t)in.a, acc, acc[j], c)
-                break;
-            }
-            case G_BIN_BEGIN:
-            case G_SINE_BEGIN:
-            case G_ALT_BEGIN:
-            case G_ALT_POS: sslot_store(M.slots, in.a, acc); break;
-            case G_BIN_END: {
+            case ST_SAVE: sslot_store(M.slots, in.a, acc); break;
+            case ST_BIN: {  // generator.rs:555-567 with both sides infinite
                 float av[CS];
                 sslot_load(M.slots, in.a, av);
                 APPLY_OP_S((uint32_t)in.b, acc, av[j], acc[j])
                 break;
             }
-            case G_SINE_CC:
+            case ST_SINE_CC:
                 steady_sine_cc(acc, M.aux[in.b], M.aux[in.c], reinterpret_cast<const double2*>(M.aux + in.b + 2),
                                M.state, in.a);
                 break;
-            case G_SINE_AC: {
+            case ST_SINE_AC: {
                 float f[CS];
                 UNROLL for (int j = 0; j < CS; j++) f[j] = acc[j];
                 if (!fast) steady_sine_scan<true, 0>(acc, f, f, M.aux[in.c], M.state, in.a, sk);
                 else steady_sine_scan<true, FASTMODE>(acc, f, f, M.aux[in.c], M.state, in.a, sk);
                 break;
             }
-            case G_SINE_CA: {
+            case ST_SINE_CA: {
                 float p[CS];
                 UNROLL for (int j = 0; j < CS; j++) p[j] = acc[j];
                 if (!fast) steady_sine_ca<0>(acc, M.aux[in.b], p, M.state, in.a, sk);
                 else steady_sine_ca<FASTMODE>(acc, M.aux[in.b], p, M.state, in.a, sk);
                 break;
             }
-            case G_SINE_END: {
+            case ST_SINE_AA: {
                 float f[CS], p[CS];
                 sslot_load(M.slots, in.b, f);
                 UNROLL for (int j = 0; j < CS; j++) p[j] = acc[j];
@@ -310,12 +374,12 @@ __device__ __forceinline__ void run_steady(const tb_launch& P, uint32_t code_s, 
                 else steady_sine_scan<false, FASTMODE>(acc, f, p, 0ull, M.state, in.a, sk);
                 break;
             }
-            case G_ALT_CC: {  // generator.rs:335-341
+            case ST_ALT_CC: {  // generator.rs:335-341
                 const float cp = M.cval[in.a], cn = M.cval[in.b];
                 UNROLL for (int j = 0; j < CS; j++) acc[j] = acc[j] >= 0.0f ? cp : cn;
                 break;
             }
-            case G_ALT_END: {
+            case ST_ALT: {
                 float t[CS];
                 sslot_load(M.slots, in.a, t);
                 if (in.c < 0) { const float c = M.cval[~in.c]; UNROLL for (int j = 0; j < CS; j++) acc[j] = c; }
@@ -329,30 +393,24 @@ __device__ __forceinline__ void run_steady(const tb_launch& P, uint32_t code_s, 
                 }
                 break;
             }
-            case G_FILT_PRE:  // history is complete: skip the pre-read block
-                ip = code_s + (uint32_t)in.c * (uint32_t)sizeof(tb_insn);
-                nxt = lds_insn(ip);
+            case ST_FILT:
+                steady_filter(acc, M.state + in.a, (int)((in.op >> 8) & 0xfu), (int)((in.op >> 12) & 0x7u),
+                              reinterpret_cast<const float*>(M.aux + in.b),
+                              reinterpret_cast<const double*>(M.aux + in.c));
                 break;
-            case G_FILT_RUN: {
-                const tb_filter_tab* ft = &P.filt[in.b];
-                uint32_t* S = M.state + in.a;
-                switch (ft->J) {
-                    case 0: steady_filter<0>(M, ft, acc, S); break;
-                    case 1: steady_filter<1>(M, ft, acc, S); break;
-                    case 2: steady_filter<2>(M, ft, acc, S); break;
-                    case 3: steady_filter<3>(M, ft, acc, S); break;
-                    default: steady_filter<4>(M, ft, acc, S); break;
-                }
-                break;
-            }
-            default: return;  // unreachable: lower.cpp admits only the ops above
+            default: return;  // unreachable: lower.cpp emits only the words above
         }
-        for (uint32_t np = in.op >> 16; np > 0; np--) {  // fused constant post-ops
+        for (uint32_t np = in.op >> 16; np > 0; np--) {  // constant point operators (generator.rs:541-548)
             const tb_insn po = nxt;
             ip += sizeof(tb_insn);
             nxt = lds_insn(ip);
-            const float c = M.cval[po.b];
-            APPLY_OP_S((uint32_t)po.a, acc, acc[j], c)
+            if ((po.op & 0xffu) == ST_AFFINE) {
+                const float m = M.cval[po.b], a = M.cval[po.c];
+                UNROLL for (int j = 0; j < CS; j++) acc[j] = __fadd_rn(__fmul_rn(acc[j], m), a);
+            } else {
+                const float c = M.cval[po.b];
+                APPLY_OP_S((uint32_t)po.a, acc, acc[j], c)
+            }
         }
         __syncwarp();
     }
