@@ -5,9 +5,11 @@
   python bench.py [--gpus N] [--steps K] [--warmup W]          the CUDA path (one rank per GPU)
   python bench.py --impl reference [...]                       the reference algorithm on host cores
 
-A step renders the whole batch once from Initial state: every rank renders its contiguous share
-of the voices into HBM (no data-path collective); with --mix the per-rank mixdowns are reduced
-over NCCL.  Scaling is "strong": the 65,536 voices are divided over the ranks.
+A step renders the whole batch once from Initial state: every rank renders its own contiguous
+range of voices into HBM (no data-path collective); the optional mixdown reduces the per-rank
+partial mixes over NCCL.  Scaling is "weak" by default: every GPU renders --voices voices (voice
+ids continue the parameter sweep, rank r takes [r*V, (r+1)*V)); --scaling strong divides the
+--voices voices over the ranks instead.
 """
 import argparse
 import json
@@ -35,6 +37,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--voices", type=int, default=65536)
     ap.add_argument("--seconds", type=float, default=10.0)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--e2e-voices", type=int, default=0, help="rows of the reused pinned host window (default 8192)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
@@ -43,14 +46,21 @@ def parse():
     return ap.parse_args()
 
 
-def config(args, n_samples):
+def total_voices(args, world):
+    return args.voices * world if args.scaling == "weak" else args.voices
+
+
+def config(args, n_samples, world=None):
+    world = world or args.gpus
     return {
         "workload": "cfg5: 65,536 parameter-swept FM+biquad voices x 10 s @ 44.1 kHz "
                     "(sine(2pi(fc+I*fm*sine(2pi*fm,pi/2)),0) | lpf(Q,cut)), one shared op list + [V x 8] f32 table",
-        "voices": args.voices,
+        "voices": total_voices(args, world),
+        "voices_per_gpu": total_voices(args, world) // world,
         "samples_per_voice": n_samples,
         "sample_rate": SAMPLE_RATE,
-        "sharding": f"voices/{args.gpus} per GPU, no data-path collective",
+        "sharding": "contiguous voice ranges per GPU, no data-path collective"
+                    + (" (weak: every GPU renders the full 65,536-voice sweep shape)" if args.scaling == "weak" else ""),
         "l2": "output rows (>= 14 GB per GPU) are far larger than L2; nothing is re-read between steps",
     }
 
@@ -144,7 +154,7 @@ def run_reference(args):
     v = float(np.mean(vals))
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)),
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (f64 phase)",
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32 (f64 phase)",
             "data": "synthetic", "config": config(args, n_samples),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -172,8 +182,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_samples = int(round(args.seconds * SAMPLE_RATE))
-    lo = args.voices * rank // world
-    hi = args.voices * (rank + 1) // world
+    n_total = total_voices(args, world)
+    lo = n_total * rank // world
+    hi = n_total * (rank + 1) // world
     n_local = hi - lo
     params_h = fm_filter_params(np.arange(lo, hi))
     params_d = torch.from_numpy(params_h).cuda()
@@ -223,7 +234,7 @@ def main():
     prog.reset()
     chk = prog.render(out, params=params_d, out_len=lens)
     lens_ok = bool((chk == n_samples).all())
-    value = args.voices * n_samples * args.steps / (total_ms * 1e-3)
+    value = n_total * n_samples * args.steps / (total_ms * 1e-3)
 
     # roofline of the one kernel: 4 B stored per voice-sample, per launch
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -233,9 +244,20 @@ def main():
     alg_bytes = 4.0 * n_local * n_samples
     avg_launch_s = (dev_ms / max(1, launches)) * 1e-3
     achieved = alg_bytes / avg_launch_s / 1e9
+    # DRAM traffic of the kernel from the committed ncu --set full capture (profiles/), which ran
+    # the same kernel and per-voice work on a smaller launch: bytes per voice-sample x this launch.
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        traffic = float(tj["dram_bytes_per_voice_sample"]) * n_local * n_samples
+        traffic_src = tj["source"]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "tb_render_kernel", "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_launch_s * 1e3}
+                "traffic": traffic, "traffic_source": traffic_src, "kernel": "tb_render_kernel",
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                "avg_launch_ms": avg_launch_s * 1e3,
+                "note": "instruction-issue bound, not HBM bound: see profiles/README.md (issue-active %, "
+                        "thread-instructions per voice-sample)"}
 
     # end to end through the C ABI with HOST buffers: H2D of the parameter table, D2H of every row.
     # All local voices are rendered; the pinned host window (e2e_group rows) is reused group after
@@ -265,9 +287,9 @@ def main():
         et = torch.tensor([e1 - e0], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(et, op=dist.ReduceOp.MAX)
-        e2e = {"value": args.voices * n_samples * e2e_steps / float(et.item()), "unit": UNIT,
+        e2e = {"value": n_total * n_samples * e2e_steps / float(et.item()), "unit": UNIT,
                "h2d_bytes_per_step": int(n_local * 8 * 4), "d2h_bytes_per_step": int(n_local * n_samples * 4 + n_local * 8),
-               "voices": args.voices, "steps": e2e_steps, "host_window_rows": grp,
+               "voices": n_total, "steps": e2e_steps, "host_window_rows": grp,
                "path": "tb_render with pinned host rows: voice groups rendered into 2 device staging buffers, "
                        "each group leaves with one cudaMemcpyAsync on a second stream while the next renders"}
         del host, host_np, prog_h
@@ -300,7 +322,7 @@ def main():
         mt = torch.tensor([m1 - m0], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(mt, op=dist.ReduceOp.MAX)
-        mixdown = {"value": args.voices * n_samples * msteps / float(mt.item()), "unit": UNIT,
+        mixdown = {"value": n_total * n_samples * msteps / float(mt.item()), "unit": UNIT,
                    "ms_per_step": 1e3 * float(mt.item()) / msteps, "nccl_reduce_bytes": int(n_samples * 4) if world > 1 else 0,
                    "mode": "tb_render_mix(TB_NO_VOICE_OUT | TB_OUT_DEVICE) per rank, then ncclReduce(sum,f32) to rank 0"}
         del prog_m
@@ -308,8 +330,9 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f32 samples, u64 fixed-point phase, f64 sine core",
-                "data": "synthetic", "config": config(args, n_samples), "clocks": clocks,
+                "scaling": args.scaling, "vs_baseline": None,
+                "dtype": "f32 samples, u64 fixed-point phase, f64 sine core (EXACT class), MUFU sine (FAST class)",
+                "data": "synthetic", "config": config(args, n_samples, world), "clocks": clocks,
                 "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e, "mixdown": mixdown,
                 "wall_ms_per_step": float(tmax[1].item()) / args.steps, "lengths_ok": lens_ok}
         if not args.no_cpu:

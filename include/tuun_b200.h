@@ -164,6 +164,17 @@ typedef struct tb_program_info {
 } tb_program_info;
 int tb_program_get_info(const tb_program* p, tb_program_info* info);
 
+/*
+ * Validate and lower an op list WITHOUT touching a device: the status a tb_program_create of the
+ * same tree would return from its host half (TB_ERR_INVALID / TB_ERR_UNSUPPORTED with
+ * tb_last_error(), else TB_OK), and the launch geometry it would use.  The reference's analogue is
+ * the panics of initialize_state / generate on a malformed tree (generator.rs:112,132,189,...),
+ * surfaced before any sample is produced.  `tile` reports 512 when the tree qualifies for the
+ * steady-state interpreter, else 256.
+ */
+int tb_lower_check(const tb_node* nodes, uint32_t n_nodes, const int32_t* lists, uint32_t n_lists,
+                   uint64_t fixed_len, tb_program_info* info);
+
 /* Human-readable text of the last error on the calling thread (never NULL). */
 const char* tb_last_error(void);
 uint32_t tb_abi_version(void);

@@ -164,9 +164,11 @@ def test_streaming_phase_is_partition_invariant():
     a = gpu_render(w, 20000)
     b = gpu_render(w, 20000, block=1024)
     c = gpu_render(w, 20000, block=777)
-    assert np.max(np.abs(a - b)) <= 2.5e-7 and np.max(np.abs(a - c)) <= 2.5e-7
+    # (MUFU.SIN is not monotone at its own 2^-21.4 resolution: a phase one unit of 2^-32 turn away
+    # can move the result by a few 1e-7.)
+    assert np.max(np.abs(a - b)) <= 1e-6 and np.max(np.abs(a - c)) <= 1e-6
     # ... and it does not accumulate: the last block is as close as the first.
-    assert np.max(np.abs(a[-777:] - c[-777:])) <= 2.5e-7
+    assert np.max(np.abs(a[-777:] - c[-777:])) <= 1e-6
 
 
 def test_batch_params():

@@ -27,7 +27,7 @@ TB_NO_VOICE_OUT = 4
 # every symbol include/tuun_b200.h declares
 EXPORTS = [
     "tb_program_create", "tb_program_destroy", "tb_render", "tb_render_mix", "tb_length", "tb_reset",
-    "tb_stream", "tb_set_stream", "tb_program_get_info", "tb_last_error", "tb_abi_version",
+    "tb_stream", "tb_set_stream", "tb_program_get_info", "tb_lower_check", "tb_last_error", "tb_abi_version",
 ]
 
 
@@ -85,6 +85,8 @@ def lib():
     L.tb_set_stream.argtypes = [P, P]
     L.tb_program_get_info.restype = ctypes.c_int
     L.tb_program_get_info.argtypes = [P, ctypes.POINTER(TbProgramInfo)]
+    L.tb_lower_check.restype = ctypes.c_int
+    L.tb_lower_check.argtypes = [ctypes.POINTER(TbNode), u32, P, u32, u64, ctypes.POINTER(TbProgramInfo)]
     L.tb_last_error.restype = ctypes.c_char_p
     L.tb_last_error.argtypes = []
     L.tb_abi_version.restype = u32

@@ -15,8 +15,9 @@
 #include "program.h"
 
 extern "C" size_t tb_kernel_smem_bytes(uint32_t n_code, uint32_t n_slots, uint32_t aux_words,
-                                       uint32_t n_cval, uint32_t state_words, uint32_t steady_ok);
-extern "C" cudaError_t tb_kernel_launch(const tb_launch* P, size_t smem, cudaStream_t stream);
+                                       uint32_t n_cval, uint32_t state_words, uint32_t steady_ok,
+                                       uint32_t warps);
+extern "C" cudaError_t tb_kernel_launch(const tb_launch* P, size_t smem, uint32_t warps, cudaStream_t stream);
 extern "C" cudaError_t tb_mix_launch(const float* rows, uint64_t stride, const unsigned long long* lens,
                                      uint32_t n_voices, uint64_t n_samples, uint64_t t0, float* mix,
                                      int accumulate, cudaStream_t stream);
@@ -76,8 +77,9 @@ struct tb_program {
     bool own_stream = false;
     cudaEvent_t ev_render[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
     size_t smem = 0;
+    uint32_t warps = TB_WARPS_PER_CTA;  // voices per CTA; fewer when one voice needs a lot of shared memory
     uint64_t launches = 0;
-    uint32_t fast_mode = 1;  // FAST-class sines: 1 = f32 polynomial, 2 = MUFU (TUUN_B200_FAST_SINES)
+    uint32_t fast_mode = 2;  // FAST-class sines: 1 = f32 polynomial, 2 = MUFU (TUUN_B200_FAST_SINES)
 
     ~tb_program() {
         cudaSetDevice(device);
@@ -94,6 +96,21 @@ struct tb_program {
 };
 
 namespace {
+
+// Voices (warps) per CTA and the CTA's dynamic shared memory: as many warps as fit, up to
+// TB_WARPS_PER_CTA.
+bool size_cta(const tb::Lowered& low, uint32_t* warps, size_t* smem) {
+    for (uint32_t w = TB_WARPS_PER_CTA; w >= 1; w >>= 1) {
+        const size_t s = tb_kernel_smem_bytes((uint32_t)low.code.size(), low.n_slots, low.aux_words,
+                                              (uint32_t)low.cexpr.size(), low.state_words, low.steady_ok, w);
+        if (s <= 220 * 1024) {
+            *warps = w;
+            *smem = s;
+            return true;
+        }
+    }
+    return false;
+}
 
 int ensure_voices(tb_program* p, uint32_t n_voices) {
     if (p->n_voices == n_voices && p->d_state) {
@@ -172,7 +189,7 @@ void fill_launch(const tb_program* p, tb_launch* L) {
 }
 
 int launch(tb_program* p, const tb_launch& L) {
-    cudaError_t e = tb_kernel_launch(&L, p->smem, p->stream);
+    cudaError_t e = tb_kernel_launch(&L, p->smem, p->warps, p->stream);
     if (e != cudaSuccess) return cuda_fail(e, "tb_render_kernel launch");
     p->launches++;
     return TB_OK;
@@ -204,7 +221,7 @@ int tb_program_create(const tb_node* nodes, uint32_t n_nodes, const int32_t* lis
         return set_error(rc, msg);
     }
     p->sample_rate = sample_rate;
-    p->fast_mode = (fs && fs[0] == '2') ? 2u : 1u;
+    p->fast_mode = (fs && fs[0] == '1') ? 1u : 2u;  // "0" all exact, "1" f32 polynomial, default MUFU
     if (const char* se = std::getenv("TUUN_B200_STEADY"))
         if (se[0] == '0') p->low.steady_ok = 0;  // diagnostics: force the general interpreter
     // Everything below needs a device: no CPU path exists.
@@ -244,9 +261,7 @@ int tb_program_create(const tb_node* nodes, uint32_t n_nodes, const int32_t* lis
         (rc = upload(p->low.goe_steps, &p->d_goe_steps)) || (rc = upload(p->low.filt, &p->d_filt)) ||
         (rc = upload(p->low.fixed, &p->d_fixed)) || (rc = upload(pool, &p->d_pool)))
         return bail(rc);
-    p->smem = tb_kernel_smem_bytes((uint32_t)p->low.code.size(), p->low.n_slots, p->low.aux_words,
-                                   (uint32_t)p->low.cexpr.size(), p->low.state_words, p->low.steady_ok);
-    if (p->smem > 220 * 1024)
+    if (!size_cta(p->low, &p->warps, &p->smem))
         return bail(set_error(TB_ERR_UNSUPPORTED, "program needs more shared memory than one CTA has"));
     *out_program = p;
     return TB_OK;
@@ -254,14 +269,39 @@ int tb_program_create(const tb_node* nodes, uint32_t n_nodes, const int32_t* lis
 
 void tb_program_destroy(tb_program* p) { delete p; }
 
+int tb_lower_check(const tb_node* nodes, uint32_t n_nodes, const int32_t* lists, uint32_t n_lists,
+                   uint64_t fixed_len, tb_program_info* info) {
+    if (!nodes || n_nodes == 0) return set_error(TB_ERR_INVALID, "empty op list");
+    tb::Lowered low;
+    const char* fs = std::getenv("TUUN_B200_FAST_SINES");
+    int rc = tb::lower(nodes, n_nodes, lists, n_lists, fixed_len, !(fs && fs[0] == '0'), low);
+    if (rc != TB_OK) return set_error(rc, low.error);
+    uint32_t warps = 0;
+    size_t smem = 0;
+    if (!size_cta(low, &warps, &smem))
+        return set_error(TB_ERR_UNSUPPORTED, "program needs more shared memory than one CTA has");
+    if (info) {
+        info->n_nodes = low.n_nodes;
+        info->n_code_words = (uint32_t)low.code.size() * 4;
+        info->n_slots = low.n_slots;
+        info->state_words = low.state_words;
+        info->tile = low.steady_ok ? TB_TILE_S : TB_TILE;
+        info->threads = 32 * warps;
+        info->smem_bytes = (uint32_t)smem;
+        info->n_params = low.n_params;
+        info->kernel_launches = 0;
+    }
+    return TB_OK;
+}
+
 int tb_program_get_info(const tb_program* p, tb_program_info* info) {
     if (!p || !info) return set_error(TB_ERR_INVALID, "NULL argument");
     info->n_nodes = p->low.n_nodes;
     info->n_code_words = (uint32_t)p->low.code.size() * 4;
     info->n_slots = p->low.n_slots;
     info->state_words = p->low.state_words;
-    info->tile = TB_TILE;
-    info->threads = 32 * TB_WARPS_PER_CTA;
+    info->tile = p->low.steady_ok ? TB_TILE_S : TB_TILE;
+    info->threads = 32 * p->warps;
     info->smem_bytes = (uint32_t)p->smem;
     info->n_params = p->low.n_params;
     info->kernel_launches = p->launches;

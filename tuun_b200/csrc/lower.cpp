@@ -322,7 +322,7 @@ struct Lowerer {
                 const int cf = const_of(n.a), cp = const_of(n.b);
                 const int st = state_of(i, 2);
                 const uint32_t fl = sine_flags(i);
-                const int aux_inc = cf >= 0 ? new_aux(AUX_SINE_INC, cf, 0, 2 + 2 * TB_CS) : 0;
+                const int aux_inc = cf >= 0 ? new_aux(AUX_SINE_INC, cf, 0, 1) : 0;
                 const int aux_ph = cp >= 0 ? new_aux(AUX_SINE_PHASE, cp, 0, 1) : 0;
                 if (cf >= 0 && cp >= 0) {
                     produced(emit(G_SINE_CC | fl, st, aux_inc, aux_ph));
@@ -581,7 +581,7 @@ struct Lowerer {
                 const int cf = const_of(n.a), cp = const_of(n.b);
                 const int st = state_of(i, 2);
                 const uint32_t fl = sine_flags(i);
-                const int aux_inc = cf >= 0 ? new_aux(AUX_SINE_INC, cf, 0, 2 + 2 * TB_CS) : 0;
+                const int aux_inc = cf >= 0 ? new_aux(AUX_SINE_INC, cf, 0, 1) : 0;
                 const int aux_ph = cp >= 0 ? new_aux(AUX_SINE_PHASE, cp, 0, 1) : 0;
                 if (cf >= 0 && cp >= 0) {
                     emit(S_SINE_CC | fl, st, aux_inc, aux_ph);
@@ -722,10 +722,10 @@ struct Lowerer {
                 const int cf = const_of(n.a), cp = const_of(n.b);
                 const int st = state_of(i, 2);
                 const uint32_t fl = sine_flags(i);
-                const int aux_inc = cf >= 0 ? new_aux(AUX_SINE_INC, cf, 0, 2 + 2 * TB_CS) : 0;
+                const int aux_inc = cf >= 0 ? new_aux(AUX_SINE_INC, cf, 0, 1) : 0;
                 const int aux_ph = cp >= 0 ? new_aux(AUX_SINE_PHASE, cp, 0, 1) : 0;
                 if (cf >= 0 && cp >= 0) {
-                    s_produced(emit(ST_SINE_CC, st, aux_inc, aux_ph));
+                    s_produced(emit(ST_SINE_CC, st, new_aux(AUX_SINE_ROT, cf, 0, 2 + 2 * TB_CS), aux_ph));
                 } else if (cp >= 0) {
                     if (!emit_steady(n.a)) return false;
                     s_produced(emit(ST_SINE_AC | fl, st, 0, aux_ph));

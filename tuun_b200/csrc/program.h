@@ -108,7 +108,7 @@ enum tb_op : uint32_t {
     ST_TIME,       // a = state
     ST_SAVE,       // a = slot                      acc -> slot
     ST_BIN,        // a = slot, b = operator        acc = slot (op) acc
-    ST_SINE_CC,    // a = state, b = aux of increment (+ rotation table), c = aux of phase
+    ST_SINE_CC,    // a = state, b = aux of the AUX_SINE_ROT block, c = aux of phase
     ST_SINE_AC,    // a = state, c = aux of phase           (frequency in acc); class in op>>8
     ST_SINE_CA,    // a = state, b = aux of increment       (phase in acc)
     ST_SINE_AA,    // a = state, b = slot of the frequency  (phase in acc)
@@ -142,11 +142,12 @@ struct tb_cexpr {
 
 // Per-voice derived 64-bit constants ("aux"), evaluated after the constant table.
 enum tb_aux_kind : uint32_t {
-    AUX_SINE_INC = 0,    // cval[a] rad/s  -> [0] phase increment, 2^-64 turns per sample; [2..2+2*TB_CS)
-                         // the rotations (cos, sin)(2 pi j inc / 2^64), j < TB_CS, as doubles
+    AUX_SINE_INC = 0,    // cval[a] rad/s  -> phase increment, 2^-64 turns per sample
     AUX_SINE_PHASE = 1,  // cval[a] rad    -> phase offset, 2^-64 turns
     AUX_FILT_POW = 2,    // feedback coefficients of filter table b -> 6 JxJ f64 matrices A^(8 * 2^k)
-    AUX_FILT_COEF = 3    // constant coefficients of filter table b as K + J floats (steady stream)
+    AUX_FILT_COEF = 3,   // constant coefficients of filter table b as K + J floats (steady stream)
+    AUX_SINE_ROT = 4     // cval[a] rad/s  -> [0] phase increment; [2 .. 2 + 2*TB_CS) the rotations
+                         // (cos, sin)(2 pi j inc / 2^64), j < TB_CS, as doubles (steady stream)
 };
 struct tb_aux {
     uint32_t kind;

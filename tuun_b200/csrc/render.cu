@@ -178,11 +178,18 @@ __device__ __forceinline__ float sin_turns_fast(u64 ph) {
     p = fmaf(p, z, 1.5707963705062866f);
     return x * p;
 }
-__device__ __forceinline__ float sin_turns(u64 ph, bool fast) {
-    return fast ? sin_turns_fast(ph) : sin_turns_exact(ph);
+// FAST through the special-function unit (tb_launch::fast_mode == 2): the top 32 phase bits as
+// radians in [-pi, pi), sin.approx = range-reduction multiply + MUFU.SIN, |err| <= 2^-21.4.
+__device__ __forceinline__ float sin_turns_mufu(u64 ph) {
+    return __sinf((float)(int)(ph >> 32) * 1.4629180792671596e-09f);  // 2 pi / 2^32
 }
-__device__ __forceinline__ void sin_turns_vec(float (&out)[C], const u64 (&ph)[C], bool fast) {
-    if (fast) { UNROLL for (int j = 0; j < C; j++) out[j] = sin_turns_fast(ph[j]); }
+// `fast`: 0 = EXACT, 1 = f32 polynomial, 2 = MUFU.
+__device__ __forceinline__ float sin_turns(u64 ph, int fast) {
+    return fast == 0 ? sin_turns_exact(ph) : (fast == 1 ? sin_turns_fast(ph) : sin_turns_mufu(ph));
+}
+__device__ __forceinline__ void sin_turns_vec(float (&out)[C], const u64 (&ph)[C], int fast) {
+    if (fast == 2) { UNROLL for (int j = 0; j < C; j++) out[j] = sin_turns_mufu(ph[j]); }
+    else if (fast == 1) { UNROLL for (int j = 0; j < C; j++) out[j] = sin_turns_fast(ph[j]); }
     else      { UNROLL for (int j = 0; j < C; j++) out[j] = sin_turns_exact(ph[j]); }
 }
 
@@ -282,7 +289,7 @@ __device__ void goe_eval(const tb_launch& P, const WarpMem& M, const Ctx& cx, in
 template <bool UNIFORM_PH>
 __device__ __forceinline__ void sine_window(float (&acc)[C], const float (&f)[C], const u64 (&phfx)[C], u64 ph0,
                                             int w0, int f_len, uint32_t* state, int st,
-                                            const SineK& sk, bool fast) {
+                                            const SineK& sk, int fast) {
     const int l = lane_id();
     const u64 acc0 = ld_state64(state, st);
     u64 inc[C];
@@ -310,7 +317,7 @@ __device__ __forceinline__ void sine_window(float (&acc)[C], const float (&f)[C]
 // Constant frequency: phase(i) = acc0 + (i - w0) * inc, no scan.
 template <bool UNIFORM_PH>
 __device__ __forceinline__ void sine_window_cf(float (&acc)[C], u64 inc, const u64 (&phfx)[C], u64 ph0, int w0,
-                                               int f_len, uint32_t* state, int st, bool fast) {
+                                               int f_len, uint32_t* state, int st, int fast) {
     const int l = lane_id();
     const u64 acc0 = ld_state64(state, st);
     u64 ph[C];
@@ -692,7 +699,7 @@ __device__ void run_program(const tb_launch& P, const tb_insn* code, const WarpM
         __syncwarp();
         const tb_insn in = code[pc++];
         const uint32_t op = in.op & 0xffu;
-        const bool fast = ((in.op >> 8) & 0xffu) == TB_SINE_FAST;
+        const int fast = ((in.op >> 8) & 0xffu) == TB_SINE_FAST ? (int)P.fast_mode : 0;
         const int n = cx.w1 - cx.w0;
         switch (op) {
             case OP_END: return;
@@ -1376,9 +1383,11 @@ __device__ void setup_voice(const tb_launch& P, const WarpMem& M, const float* p
     for (uint32_t t = 0; t < P.n_aux; t++) {  // warp-uniform walk; lanes share the work of one entry
         const tb_aux a = P.aux[t];
         if (a.kind == AUX_SINE_INC) {
+            if (l == 0) M.aux[a.off] = turns_to_fx_slow((double)M.cval[a.a] / (TB_TAU * (double)P.sample_rate));
+        } else if (a.kind == AUX_SINE_ROT) {  // steady stream: increment + the 16 rotations (cos, sin)(j * inc)
             const u64 inc = turns_to_fx_slow((double)M.cval[a.a] / (TB_TAU * (double)P.sample_rate));
             if (l == 0) M.aux[a.off] = inc;
-            if (l < TB_CS) {  // rotation table of the steady-state interpreter: (cos, sin)(j * inc)
+            if (l < TB_CS) {
                 const u64 ang = inc * (u64)l;
                 double2 r;
                 r.x = l == 0 ? 1.0 : sin_turns_d8(ang + 0x4000000000000000ull);
@@ -1420,7 +1429,8 @@ __device__ void setup_voice(const tb_launch& P, const WarpMem& M, const float* p
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
-// Kernel: grid = ceil(n_voices / TB_WARPS_PER_CTA), block = 32 * TB_WARPS_PER_CTA.
+// Kernel: grid = ceil(n_voices / warps), block = 32 * warps; warps = TB_WARPS_PER_CTA unless the
+// program's per-warp shared-memory footprint forces fewer (abi.cpp).
 // ------------------------------------------------------------------------------------------
 #ifndef TB_MIN_BLOCKS
 #define TB_MIN_BLOCKS 4
@@ -1433,7 +1443,7 @@ tb_render_kernel(const tb_launch P) {
     tb_insn* code = reinterpret_cast<tb_insn*>(smem_raw);
     for (uint32_t t = threadIdx.x; t < P.n_code; t += blockDim.x) code[t] = P.code[t];
     __syncthreads();
-    const uint32_t voice = blockIdx.x * TB_WARPS_PER_CTA + warp;
+    const uint32_t voice = blockIdx.x * (blockDim.x >> 5) + warp;
     if (voice >= P.n_voices) return;
     if (P.done && P.done[voice]) {  // already returned short earlier in this (chunked) call
         if (l == 0 && P.out_len && !P.accumulate) P.out_len[voice] = 0ull;
@@ -1490,14 +1500,18 @@ tb_render_kernel(const tb_launch P) {
             return ready;
         };
         bool steady = P.steady_ok && filters_ready();
+        // The lane index held in a register for the steady loop (S2R would otherwise be re-issued,
+        // with its latency, wherever the compiler rematerialises threadIdx).
+        int lane_pinned;
+        asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane_pinned));
         u64 tbase = 0;
         while (tbase < P.n_samples) {
             const u64 left = P.n_samples - tbase;
             if (steady && left >= (u64)TILE_S) {
                 // Whole tile, every node infinite, histories complete: the steady-state interpreter.
                 float sacc[CS];
-                if (P.fast_mode == 2) run_steady<2>(P, code_s, M, sacc, sk);
-                else run_steady<1>(P, code_s, M, sacc, sk);
+                if (P.fast_mode == 2) run_steady<2>(P, code_s, M, sacc, sk, lane_pinned);
+                else run_steady<1>(P, code_s, M, sacc, sk, lane_pinned);
                 if (row) {
                     float* dst = row + tbase + l * CS;
                     if (vec_ok) {
@@ -1557,23 +1571,24 @@ tb_render_kernel(const tb_launch P) {
 }
 
 extern "C" size_t tb_kernel_smem_bytes(uint32_t n_code, uint32_t n_slots, uint32_t aux_words,
-                                       uint32_t n_cval, uint32_t state_words, uint32_t steady_ok) {
+                                       uint32_t n_cval, uint32_t state_words, uint32_t steady_ok,
+                                       uint32_t warps) {
     size_t off = ((size_t)n_code * sizeof(tb_insn) + 15) & ~(size_t)15;
     const size_t per_warp = (size_t)n_slots * (steady_ok ? TILE_S : TILE) * sizeof(float) + (((size_t)aux_words * 8 + 15) & ~(size_t)15) +
                             (((size_t)n_cval * 4 + 15) & ~(size_t)15) + (((size_t)state_words * 4 + 15) & ~(size_t)15) +
                             (((size_t)n_slots * 4 + 15) & ~(size_t)15) + (((size_t)n_slots * 32 + 15) & ~(size_t)15);
-    return off + per_warp * TB_WARPS_PER_CTA;
+    return off + per_warp * warps;
 }
 
-extern "C" cudaError_t tb_kernel_launch(const tb_launch* P, size_t smem, cudaStream_t stream) {
+extern "C" cudaError_t tb_kernel_launch(const tb_launch* P, size_t smem, uint32_t warps, cudaStream_t stream) {
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(tb_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    const uint32_t grid = (P->n_voices + TB_WARPS_PER_CTA - 1) / TB_WARPS_PER_CTA;
-    tb_render_kernel<<<grid, 32 * TB_WARPS_PER_CTA, smem, stream>>>(*P);
+    const uint32_t grid = (P->n_voices + warps - 1) / warps;
+    tb_render_kernel<<<grid, 32 * warps, smem, stream>>>(*P);
     return cudaGetLastError();
 }
 

@@ -32,13 +32,21 @@ __device__ __forceinline__ tb_insn lds_insn(uint32_t saddr) {
     return r;
 }
 
+__device__ __forceinline__ u64 warp_incl_sum_l(u64 x, int l) {
+    UNROLL for (int d = 1; d < 32; d <<= 1) {
+        const u64 t = __shfl_up_sync(FULL, x, d);
+        if (l >= d) x += t;
+    }
+    return x;
+}
+
 // Steady slots: float4 #q (q = 0..3) of lane l at float4 index q*32 + l (conflict free).
-__device__ __forceinline__ void sslot_store(float* slots, int s, const float (&v)[CS]) {
-    float4* p = reinterpret_cast<float4*>(slots + (size_t)s * TILE_S) + lane_id();
+__device__ __forceinline__ void sslot_store(float* slots, int s, const float (&v)[CS], int l) {
+    float4* p = reinterpret_cast<float4*>(slots + (size_t)s * TILE_S) + l;
     UNROLL for (int q = 0; q < CS / 4; q++) p[32 * q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
 }
-__device__ __forceinline__ void sslot_load(const float* slots, int s, float (&v)[CS]) {
-    const float4* p = reinterpret_cast<const float4*>(slots + (size_t)s * TILE_S) + lane_id();
+__device__ __forceinline__ void sslot_load(const float* slots, int s, float (&v)[CS], int l) {
+    const float4* p = reinterpret_cast<const float4*>(slots + (size_t)s * TILE_S) + l;
     UNROLL for (int q = 0; q < CS / 4; q++) {
         const float4 t = p[32 * q];
         v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
@@ -94,9 +102,9 @@ __device__ __forceinline__ int raw_hi(u64 raw) {  // top 32 bits of raw << 20
 // Constant frequency and phase: angle addition against the per-voice rotation table
 // rot[j] = (cos, sin)(2 pi j inc / 2^64), j < CS  (setup_voice, AUX_SINE_INC).
 __device__ __forceinline__ void steady_sine_cc(float (&acc)[CS], u64 inc, u64 ph0, const double2* rot,
-                                               uint32_t* state, int st) {
+                                               uint32_t* state, int st, int l) {
     const u64 acc0 = ld_state64(state, st);
-    const u64 pb = acc0 + inc * (u64)(lane_id() * CS) + ph0;
+    const u64 pb = acc0 + inc * (u64)(l * CS) + ph0;
     const double S = sin_turns_d8(pb);
     const double Cq = sin_turns_d8(pb + 0x4000000000000000ull);  // a quarter turn ahead: the cosine
     UNROLL for (int j = 0; j < CS; j++) {
@@ -114,7 +122,7 @@ __device__ __forceinline__ void steady_sine_cc(float (&acc)[CS], u64 inc, u64 ph
 // magic-number conversion (|f| >= 100 tau sr, |p| >= 600 rad: never for audio).
 template <bool UNIFORM_PH, int MODE>
 __device__ __forceinline__ void steady_sine_scan(float (&acc)[CS], const float (&f)[CS], const float (&p)[CS],
-                                                 u64 ph0, uint32_t* state, int st, const SineK& sk) {
+                                                 u64 ph0, uint32_t* state, int st, const SineK& sk, int l) {
     const u64 acc0 = ld_state64(state, st);
     float big = 0.0f, bigp = 0.0f;
     UNROLL for (int j = 0; j < CS; j++) {
@@ -133,7 +141,7 @@ __device__ __forceinline__ void steady_sine_scan(float (&acc)[CS], const float (
             raw += magic_raw(f[j], sk.kscale);
         }
         const u64 run = raw << 20;
-        const u64 incl = warp_incl_sum(run);
+        const u64 incl = warp_incl_sum_l(run, l);
         const u64 base = acc0 + (incl - run) + (UNIFORM_PH ? ph0 : 0ull);
         const u64 total = __shfl_sync(FULL, incl, 31);
         const int bh = (int)(base >> 32);
@@ -155,7 +163,7 @@ __device__ __forceinline__ void steady_sine_scan(float (&acc)[CS], const float (
             run += freq_to_inc(f[j], sk);
         }
     }
-    const u64 incl = warp_incl_sum(run);
+    const u64 incl = warp_incl_sum_l(run, l);
     const u64 base = acc0 + (incl - run) + (UNIFORM_PH ? ph0 : 0ull);
     const u64 total = __shfl_sync(FULL, incl, 31);
     UNROLL for (int j = 0; j < CS; j++) {
@@ -169,9 +177,9 @@ __device__ __forceinline__ void steady_sine_scan(float (&acc)[CS], const float (
 // Constant frequency, phase offsets in p (phase modulation).
 template <int MODE>
 __device__ __forceinline__ void steady_sine_ca(float (&acc)[CS], u64 inc, const float (&p)[CS], uint32_t* state,
-                                               int st, const SineK& sk) {
+                                               int st, const SineK& sk, int l) {
     const u64 acc0 = ld_state64(state, st);
-    u64 b = acc0 + inc * (u64)(lane_id() * CS);
+    u64 b = acc0 + inc * (u64)(l * CS);
     float bigp = 0.0f;
     UNROLL for (int j = 0; j < CS; j++) bigp = fmaxf(bigp, fabsf(p[j]));
     if (__any_sync(FULL, !(bigp < sk.plimit))) {
@@ -200,8 +208,8 @@ __device__ __forceinline__ void steady_sine_ca(float (&acc)[CS], u64 inc, const 
 // Feed-forward part: u[j] = x[j] b0 + b1 x[j-1] + ... (each product and sum rounded, :496-499).
 // KT > 0: K known at compile time (1, 2, 3 cover every filter of lib/v0/std.tuun); KT == 0: any K.
 template <int KT>
-__device__ __forceinline__ void steady_fir(float (&u)[CS], const float (&x)[CS], const float* b, int K, float* hx) {
-    const int l = lane_id();
+__device__ __forceinline__ void steady_fir(float (&u)[CS], const float (&x)[CS], const float* b, int K, float* hx,
+                                           int l) {
     constexpr int NP = KT > 0 ? (KT > 1 ? KT - 1 : 1) : TB_MAX_K - 1;
     // pe[m] = x[-1 - m]: the sample m + 1 places before this lane's chunk.
     float pe[NP];
@@ -233,8 +241,7 @@ __device__ __forceinline__ void steady_fir(float (&u)[CS], const float (&x)[CS],
 // A^(16 * 2^k), k = 0..4.
 template <int J>
 __device__ __forceinline__ void steady_iir(float (&acc)[CS], const float (&u)[CS], const float* af,
-                                           const double* mpow, float* hy) {
-    const int l = lane_id();
+                                           const double* mpow, float* hy, int l) {
     float a[J];
     UNROLL for (int jj = 0; jj < J; jj++) a[jj] = af[jj];
     float s[J];
@@ -277,23 +284,23 @@ __device__ __forceinline__ void steady_iir(float (&acc)[CS], const float (&u)[CS
 }
 
 __device__ __forceinline__ void steady_filter(float (&acc)[CS], uint32_t* S, int K, int J, const float* coef,
-                                              const double* pow8) {
+                                              const double* pow8, int l) {
     float* hx = reinterpret_cast<float*>(S + 2);
     float* hy = hx + (K - 1);
     float u[CS];
     switch (K) {
-        case 1: steady_fir<1>(u, acc, coef, K, hx); break;
-        case 2: steady_fir<2>(u, acc, coef, K, hx); break;
-        case 3: steady_fir<3>(u, acc, coef, K, hx); break;
-        default: steady_fir<0>(u, acc, coef, K, hx); break;
+        case 1: steady_fir<1>(u, acc, coef, K, hx, l); break;
+        case 2: steady_fir<2>(u, acc, coef, K, hx, l); break;
+        case 3: steady_fir<3>(u, acc, coef, K, hx, l); break;
+        default: steady_fir<0>(u, acc, coef, K, hx, l); break;
     }
     const double* mpow = pow8 + J * J;  // skip A^8: the steady chunk is 16 samples
     switch (J) {
         case 0: { UNROLL for (int j = 0; j < CS; j++) acc[j] = u[j]; break; }
-        case 1: steady_iir<1>(acc, u, coef + K, mpow, hy); break;
-        case 2: steady_iir<2>(acc, u, coef + K, mpow, hy); break;
-        case 3: steady_iir<3>(acc, u, coef + K, mpow, hy); break;
-        default: steady_iir<4>(acc, u, coef + K, mpow, hy); break;
+        case 1: steady_iir<1>(acc, u, coef + K, mpow, hy, l); break;
+        case 2: steady_iir<2>(acc, u, coef + K, mpow, hy, l); break;
+        case 3: steady_iir<3>(acc, u, coef + K, mpow, hy, l); break;
+        default: steady_iir<4>(acc, u, coef + K, mpow, hy, l); break;
     }
 }
 
@@ -315,8 +322,7 @@ __device__ __forceinline__ void steady_filter(float (&acc)[CS], uint32_t* S, int
 // One steady tile.  `code_s` is the shared-memory address of the program.
 template <int FASTMODE>
 __device__ __forceinline__ void run_steady(const tb_launch& P, uint32_t code_s, const WarpMem& M, float (&acc)[CS],
-                                           const SineK& sk) {
-    const int l = lane_id();
+                                           const SineK& sk, const int l) {
     const float srf = (float)P.sample_rate;
     uint32_t ip = code_s + P.pc_steady * (uint32_t)sizeof(tb_insn);
     tb_insn nxt = lds_insn(ip);
@@ -341,37 +347,37 @@ __device__ __forceinline__ void run_steady(const tb_launch& P, uint32_t code_s, 
                 st_state64(M.state, in.a, pos0 + (u64)TILE_S);
                 break;
             }
-            case ST_SAVE: sslot_store(M.slots, in.a, acc); break;
+            case ST_SAVE: sslot_store(M.slots, in.a, acc, l); break;
             case ST_BIN: {  // generator.rs:555-567 with both sides infinite
                 float av[CS];
-                sslot_load(M.slots, in.a, av);
+                sslot_load(M.slots, in.a, av, l);
                 APPLY_OP_S((uint32_t)in.b, acc, av[j], acc[j])
                 break;
             }
             case ST_SINE_CC:
                 steady_sine_cc(acc, M.aux[in.b], M.aux[in.c], reinterpret_cast<const double2*>(M.aux + in.b + 2),
-                               M.state, in.a);
+                               M.state, in.a, l);
                 break;
             case ST_SINE_AC: {
                 float f[CS];
                 UNROLL for (int j = 0; j < CS; j++) f[j] = acc[j];
-                if (!fast) steady_sine_scan<true, 0>(acc, f, f, M.aux[in.c], M.state, in.a, sk);
-                else steady_sine_scan<true, FASTMODE>(acc, f, f, M.aux[in.c], M.state, in.a, sk);
+                if (!fast) steady_sine_scan<true, 0>(acc, f, f, M.aux[in.c], M.state, in.a, sk, l);
+                else steady_sine_scan<true, FASTMODE>(acc, f, f, M.aux[in.c], M.state, in.a, sk, l);
                 break;
             }
             case ST_SINE_CA: {
                 float p[CS];
                 UNROLL for (int j = 0; j < CS; j++) p[j] = acc[j];
-                if (!fast) steady_sine_ca<0>(acc, M.aux[in.b], p, M.state, in.a, sk);
-                else steady_sine_ca<FASTMODE>(acc, M.aux[in.b], p, M.state, in.a, sk);
+                if (!fast) steady_sine_ca<0>(acc, M.aux[in.b], p, M.state, in.a, sk, l);
+                else steady_sine_ca<FASTMODE>(acc, M.aux[in.b], p, M.state, in.a, sk, l);
                 break;
             }
             case ST_SINE_AA: {
                 float f[CS], p[CS];
-                sslot_load(M.slots, in.b, f);
+                sslot_load(M.slots, in.b, f, l);
                 UNROLL for (int j = 0; j < CS; j++) p[j] = acc[j];
-                if (!fast) steady_sine_scan<false, 0>(acc, f, p, 0ull, M.state, in.a, sk);
-                else steady_sine_scan<false, FASTMODE>(acc, f, p, 0ull, M.state, in.a, sk);
+                if (!fast) steady_sine_scan<false, 0>(acc, f, p, 0ull, M.state, in.a, sk, l);
+                else steady_sine_scan<false, FASTMODE>(acc, f, p, 0ull, M.state, in.a, sk, l);
                 break;
             }
             case ST_ALT_CC: {  // generator.rs:335-341
@@ -381,11 +387,11 @@ __device__ __forceinline__ void run_steady(const tb_launch& P, uint32_t code_s, 
             }
             case ST_ALT: {
                 float t[CS];
-                sslot_load(M.slots, in.a, t);
+                sslot_load(M.slots, in.a, t, l);
                 if (in.c < 0) { const float c = M.cval[~in.c]; UNROLL for (int j = 0; j < CS; j++) acc[j] = c; }
                 if (in.b >= 0) {
                     float pv[CS];
-                    sslot_load(M.slots, in.b, pv);
+                    sslot_load(M.slots, in.b, pv, l);
                     UNROLL for (int j = 0; j < CS; j++) acc[j] = t[j] >= 0.0f ? pv[j] : acc[j];
                 } else {
                     const float c = M.cval[~in.b];
@@ -396,7 +402,7 @@ __device__ __forceinline__ void run_steady(const tb_launch& P, uint32_t code_s, 
             case ST_FILT:
                 steady_filter(acc, M.state + in.a, (int)((in.op >> 8) & 0xfu), (int)((in.op >> 12) & 0x7u),
                               reinterpret_cast<const float*>(M.aux + in.b),
-                              reinterpret_cast<const double*>(M.aux + in.c));
+                              reinterpret_cast<const double*>(M.aux + in.c), l);
                 break;
             default: return;  // unreachable: lower.cpp emits only the words above
         }

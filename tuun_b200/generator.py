@@ -21,6 +21,16 @@ def _np_ptr(a: Optional[np.ndarray]):
     return None if a is None or a.size == 0 else a.ctypes.data_as(ctypes.c_void_p)
 
 
+def lower_check(w) -> _abi.TbProgramInfo:
+    """Validate and lower a tree on the host only (tb_lower_check): raises TuunB200Error with the
+    status a render would get, else returns the launch geometry.  Needs no device."""
+    ops: OpList = w if isinstance(w, OpList) else flatten(w)
+    info = _abi.TbProgramInfo()
+    _abi.check(_abi.lib().tb_lower_check(ops.nodes, ops.n_nodes, _np_ptr(ops.lists), len(ops.lists),
+                                         len(ops.fixed_pool), ctypes.byref(info)))
+    return info
+
+
 class Program:
     """A Waveform with its carried state on the device (`Waveform<M, State>`, generator.rs:37)."""
 

@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .waveform import (Alt, BinaryPointOp, Const, Filter, Fin, Operator, Sine, Time, Waveform, add, mul)
+from .waveform import (Alt, BinaryPointOp, Const, Filter, Fin, Fixed, Operator, Sine, Time, Waveform, add, mul)
 
 F = np.float32
 PI = F(3.14159265)  # lib/v0/std.tuun:7
@@ -70,3 +70,90 @@ def fm_filter_params(voice_ids, sample_rate=44100) -> np.ndarray:
 def square(freq_rad: Waveform) -> Waveform:
     """lib/v0/std.tuun:21."""
     return Alt(Sine(freq_rad, Const(0.0)), Const(1.0), Const(-1.0))
+
+
+# ---------------------------------------------------------------------------------------------
+# Configs 1-4 written the way their Tuun source reads (tuun_b200.builder mirrors builtins.rs and
+# lib/v0/std.tuun), then optimized like the reference pipeline does before generating.
+# ---------------------------------------------------------------------------------------------
+def _std(tempo=120.0, sample_rate=44100):
+    from .builder import Std
+    return Std(tempo=tempo, sample_rate=sample_rate)
+
+
+def _finish(value) -> Waveform:
+    from .builder import to_waveform
+    from .optimizer import optimize
+    return optimize(to_waveform(value))
+
+
+def cfg1_from_source(tempo=120.0) -> Waveform:
+    """`$440 * Qw` with `open std` (config 1)."""
+    from .builder import times
+    s = _std(tempo)
+    return _finish(times(s.hz(440), s.note(s.Q)))
+
+
+def cfg2_harmonica(n_notes=4, tempo=120.0, freq=440.0) -> Waveform:
+    """`let h = harmonica(Q, 440) in <[h, h, h, h]>` (config 2): envelopes, seq / time-shift combinators."""
+    from .builder import sequence
+    s = _std(tempo)
+    return _finish(sequence([s.harmonica(s.Q, freq) for _ in range(n_notes)]))
+
+
+def cfg3_fm_variations():
+    """The 12 uncommented programs of fm-variations.tuunp (lines 2,4,6,7,9,10,11,12,15,19,22,24),
+    `capture(..)` stripped.  Returns [(name, optimized waveform)]; each is rendered for 10 s."""
+    from .builder import divide, plus, sine, times
+    s = _std()
+    pi = s.pi
+    fc, I, D = F(440), F(6), F(1)
+    fm = times(divide(D, 2), fc)
+    two_pi = times(2, pi)
+    half_pi = divide(pi, 2)
+    w_fm = times(two_pi, fm)   # 2*pi*fm
+    w_fc = times(two_pi, fc)
+    i_fm = times(I, fm)        # I * fm
+
+    def true_fm(mod):  # sine(2*pi*(fc + (I * fm * mod)), 0)
+        return sine(times(two_pi, plus(fc, times(i_fm, mod))), 0)
+
+    def pm(mod):       # sine(2*pi*fc, I * mod)
+        return sine(w_fc, times(I, mod))
+
+    sweep = times(s.linear(0, 0.25), half_pi)  # linear(0,0.25)*pi/2  ((linear * pi) / 2 by precedence)
+    sweep = divide(times(s.linear(0, 0.25), pi), 2)
+    progs = [
+        ("true-fm", true_fm(sine(w_fm, half_pi))),
+        ("pm", pm(sine(w_fm, 0))),
+        ("true-fm-mod-sweep", true_fm(sine(w_fm, plus(half_pi, sweep)))),
+        ("pm-mod-sweep", pm(sine(w_fm, sweep))),
+        ("true-fm-freq", times(two_pi, plus(fc, times(i_fm, sine(w_fm, half_pi))))),
+        ("true-fm-mod-only", times(two_pi, times(i_fm, sine(w_fm, half_pi)))),
+        ("square-fm", true_fm(s.square(w_fm))),   # passes 2*pi*fm to square as written
+        ("square-pm", pm(s.square(w_fm))),
+        ("cos-fm", true_fm(sine(w_fm, 0))),
+        ("cos-pm", pm(sine(w_fm, half_pi))),
+        ("pulse-fm", true_fm(s.pulse(0.5, fm))),
+        ("pulse-pm", pm(s.pulse(0.5, fm))),
+    ]
+    return [(name, _finish(v)) for name, v in progs]
+
+
+def cfg4_filters(noise_seconds=60.0, sample_rate=44100):
+    """Config 4: resonant IIR chains (docs/filter.md style) over pulse / noise sources, 60 s each.
+    The reference's Noise draws from an unseeded RNG, so the noise source is a Fixed buffer
+    (Philox, seed 0x7475756E) as SURVEY 8(d) prescribes.  Returns [(name, optimized waveform)]."""
+    from .builder import filter_, pipe, times
+    s = _std(sample_rate=sample_rate)
+    n = int(round(noise_seconds * sample_rate))
+    rng = np.random.Generator(np.random.Philox(0x7475756E))
+    noise = Fixed((rng.random(n, dtype=np.float32) * F(2) - F(1)).astype(F))
+    f43 = filter_([0.2, 0.3, 0.2, 0.1], [-0.5, 0.2, -0.1])  # benches/tracker_benches.rs:74-80 shape
+    progs = [
+        ("square220-lpf", pipe(s.square(220), s.lpf(0.707, 2000))),
+        ("noise-lpf", pipe(times(noise, 0.1), s.lpf(0.7, 2000))),
+        ("square-cascade", pipe(s.square(220), s.lpf(4, 800), s.lpf(2, 1600), s.lpf(1, 3200))),
+        ("pulse-filter_4_3", pipe(s.pulse(0.5, 110), f43)),
+    ]
+    return [(name, _finish(v)) for name, v in progs]
