@@ -182,9 +182,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_samples = int(round(args.seconds * SAMPLE_RATE))
+    from tuun_b200.sharding import reduce_mix, voice_range, weak_voice_range
     n_total = total_voices(args, world)
-    lo = n_total * rank // world
-    hi = n_total * (rank + 1) // world
+    lo, hi = weak_voice_range(args.voices, rank) if args.scaling == "weak" else voice_range(n_total, rank, world)
     n_local = hi - lo
     params_h = fm_filter_params(np.arange(lo, hi))
     params_d = torch.from_numpy(params_h).cuda()
@@ -308,7 +308,7 @@ def main():
             if world > 1:
                 done_ev.record(mstream)
                 torch.cuda.current_stream().wait_event(done_ev)
-                dist.reduce(mix_d, dst=0, op=dist.ReduceOp.SUM)
+                reduce_mix(mix_d, dst=0)
 
         mix_step()
         barrier()
