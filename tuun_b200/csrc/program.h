@@ -17,7 +17,9 @@
 
 #define TB_C 8               // samples per lane per tile
 #define TB_TILE (32 * TB_C)  // samples per tile
+#ifndef TB_WARPS_PER_CTA
 #define TB_WARPS_PER_CTA 4
+#endif
 #define TB_CS 16                 // samples per lane per tile of the steady-state interpreter (steady.cuh)
 #define TB_TILE_S (32 * TB_CS)
 #define TB_MAX_K 9   // feed-forward taps supported by the device path (K-1 <= C)

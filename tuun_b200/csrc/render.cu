@@ -1600,20 +1600,53 @@ extern "C" cudaError_t tb_kernel_launch(const tb_launch* P, size_t smem, uint32_
 extern "C" __global__ void __launch_bounds__(256)
 tb_mix_kernel(const float* __restrict__ rows, uint64_t stride, const unsigned long long* __restrict__ lens,
               uint32_t n_voices, uint64_t n_samples, uint64_t t0, float* __restrict__ mix, int accumulate) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // Four consecutive samples per thread (one 128-bit load per voice when the rows allow it), eight
+    // voices in flight; the adds stay in voice index order, each rounded (tracker.rs:617-619).
+    const uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i >= n_samples) return;
-    float s = accumulate ? mix[i] : 0.0f;
-    for (uint32_t v = 0; v < n_voices; v++) {
-        const unsigned long long len = lens[v];  // total generated so far, including this chunk
-        if (t0 + i < len) s = __fadd_rn(s, rows[(size_t)v * stride + i]);
+    const bool vec = ((stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(rows) & 15) == 0) && i + 4 <= n_samples;
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    if (accumulate) {
+        UNROLL for (int k = 0; k < 4; k++) if (i + k < n_samples) s[k] = mix[i + k];
     }
-    mix[i] = s;
+    if (vec) {
+        uint32_t v = 0;
+        for (; v + 8 <= n_voices; v += 8) {
+            float4 x[8];
+            unsigned long long len[8];
+            UNROLL for (int u = 0; u < 8; u++) {
+                len[u] = lens[v + u];
+                x[u] = __ldcs(reinterpret_cast<const float4*>(rows + (size_t)(v + u) * stride + i));
+            }
+            UNROLL for (int u = 0; u < 8; u++) {
+                if (t0 + i + 0 < len[u]) s[0] = __fadd_rn(s[0], x[u].x);
+                if (t0 + i + 1 < len[u]) s[1] = __fadd_rn(s[1], x[u].y);
+                if (t0 + i + 2 < len[u]) s[2] = __fadd_rn(s[2], x[u].z);
+                if (t0 + i + 3 < len[u]) s[3] = __fadd_rn(s[3], x[u].w);
+            }
+        }
+        for (; v < n_voices; v++) {
+            const unsigned long long len = lens[v];
+            const float4 x = __ldcs(reinterpret_cast<const float4*>(rows + (size_t)v * stride + i));
+            if (t0 + i + 0 < len) s[0] = __fadd_rn(s[0], x.x);
+            if (t0 + i + 1 < len) s[1] = __fadd_rn(s[1], x.y);
+            if (t0 + i + 2 < len) s[2] = __fadd_rn(s[2], x.z);
+            if (t0 + i + 3 < len) s[3] = __fadd_rn(s[3], x.w);
+        }
+    } else {
+        for (uint32_t v = 0; v < n_voices; v++) {
+            const unsigned long long len = lens[v];  // total generated so far, including this chunk
+            UNROLL for (int k = 0; k < 4; k++)
+                if (i + k < n_samples && t0 + i + k < len) s[k] = __fadd_rn(s[k], rows[(size_t)v * stride + i + k]);
+        }
+    }
+    UNROLL for (int k = 0; k < 4; k++) if (i + k < n_samples) mix[i + k] = s[k];
 }
 
 extern "C" cudaError_t tb_mix_launch(const float* rows, uint64_t stride, const unsigned long long* lens,
                                      uint32_t n_voices, uint64_t n_samples, uint64_t t0, float* mix,
                                      int accumulate, cudaStream_t stream) {
-    const uint32_t grid = (uint32_t)((n_samples + 255) / 256);
+    const uint32_t grid = (uint32_t)((n_samples + 1023) / 1024);
     tb_mix_kernel<<<grid, 256, 0, stream>>>(rows, stride, lens, n_voices, n_samples, t0, mix, accumulate);
     return cudaGetLastError();
 }

@@ -288,13 +288,20 @@ __device__ __forceinline__ void steady_filter(float (&acc)[CS], uint32_t* S, int
     float* hx = reinterpret_cast<float*>(S + 2);
     float* hy = hx + (K - 1);
     float u[CS];
+    const double* mpow = pow8 + J * J;  // skip A^8: the steady chunk is 16 samples
+    if (K == 3 && J == 2) {
+        // The biquad (every filter of lib/v0/std.tuun): feed-forward and feedback in one basic
+        // block, so the independent FIR arithmetic fills the latency of the serial recurrences.
+        steady_fir<3>(u, acc, coef, 3, hx, l);
+        steady_iir<2>(acc, u, coef + 3, mpow, hy, l);
+        return;
+    }
     switch (K) {
         case 1: steady_fir<1>(u, acc, coef, K, hx, l); break;
         case 2: steady_fir<2>(u, acc, coef, K, hx, l); break;
         case 3: steady_fir<3>(u, acc, coef, K, hx, l); break;
         default: steady_fir<0>(u, acc, coef, K, hx, l); break;
     }
-    const double* mpow = pow8 + J * J;  // skip A^8: the steady chunk is 16 samples
     switch (J) {
         case 0: { UNROLL for (int j = 0; j < CS; j++) acc[j] = u[j]; break; }
         case 1: steady_iir<1>(acc, u, coef + K, mpow, hy, l); break;
