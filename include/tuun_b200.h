@@ -142,6 +142,17 @@ int tb_render_mix(tb_program* p, const float* params, uint32_t n_params, uint32_
 int tb_length(tb_program* p, const float* params, uint32_t n_params, uint32_t n_voices,
               uint64_t max, uint64_t* len, uint32_t flags);
 
+/*
+ * Noise (generator.rs:113-118) draws `fastrand::f32() * 2 - 1` from the reference's unseeded
+ * thread-local generator, so the reference itself never produces the same noise twice.  Here
+ * every Noise node of every voice owns a seeded stream of the same generator (fastrand 2.3.0 =
+ * wyrand), a pure function of (seed, node index, voice index, sample count): renders are
+ * reproducible, tb_reset replays them, and a batch split over several programs / GPUs draws what
+ * the unsplit batch would when each part passes the index of its first voice.  Defaults: a fixed
+ * seed, first_voice 0.
+ */
+int tb_seed_noise(tb_program* p, uint64_t seed, uint64_t first_voice);
+
 /* waveform::set_state(root, State::Initial) for every voice (waveform.rs:322). */
 int tb_reset(tb_program* p);
 

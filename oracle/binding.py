@@ -48,6 +48,7 @@ def lib():
         L.tbo_allocations.restype = ctypes.c_uint64
         L.tbo_allocations.argtypes = [P]
         L.tbo_seed_noise.argtypes = [P, ctypes.c_uint64]
+        L.tbo_set_voice.argtypes = [P, ctypes.c_uint64]
         L.tbo_render_batch.restype = ctypes.c_uint64
         L.tbo_render_batch.argtypes = [P, P, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64,
                                        ctypes.c_uint32, P, ctypes.c_uint64, P, P, ctypes.c_uint32]
@@ -93,6 +94,11 @@ class OracleProgram:
 
     def initialize_state(self):
         lib().tbo_initialize_state(self._h)
+
+    def seed_noise(self, seed: int, voice: int = 0):
+        """Seed and voice index of the Noise streams (same convention as tb_seed_noise)."""
+        lib().tbo_seed_noise(self._h, ctypes.c_uint64(seed))
+        lib().tbo_set_voice(self._h, ctypes.c_uint64(voice))
 
     def substitute_const(self, mark_id: int, value: float) -> int:
         return lib().tbo_substitute_const(self._h, mark_id, value)

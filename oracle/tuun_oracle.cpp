@@ -36,6 +36,9 @@ struct Node {
     std::deque<float> input, output;
     double accumulator = 0.0;
     float signum = 0.f;
+    // Noise: index of this node in the op list and the number of samples drawn so far
+    uint32_t index = 0;
+    uint64_t noise_drawn = 0;
 };
 
 enum class MO { Some, None, Maybe };  // generator.rs:58-63
@@ -44,13 +47,28 @@ struct MaybeOption {
     size_t v;
 };
 
-struct Rng {  // stand-in for fastrand (parity unpinned)
-    uint64_t s = 0x7475756E2545F491ull;
-    float next_f32() {
-        s ^= s << 13;
-        s ^= s >> 7;
-        s ^= s << 17;
-        return (float)(s >> 40) * (1.0f / 16777216.0f);
+// fastrand 2.3.0 (Cargo.lock:372-373; not vendored under /root/reference) — its published
+// generator is wyrand: state += C0; t = state * (state ^ C1) as u128; out = lo(t) ^ hi(t);
+// f32() = from_bits(0x3F800000 | (u32 >> 9)) - 1.0 in [0, 1).  The reference calls the UNSEEDED
+// thread-local instance (generator.rs:115), so no sequence of it is reproducible: parity unpinned.
+// Here every Noise node of every voice owns a stream of that generator (state advances by a
+// constant, so sample k is a pure function of the stream's seed and k):
+//     state_k = seed + NODE_K * (node_index + 1) + VOICE_K * voice + C0 * (k + 1)
+struct Rng {
+    static constexpr uint64_t C0 = 0x2d358dccaa6c78a5ull, C1 = 0x8bb84b93962eacc9ull;
+    static constexpr uint64_t NODE_K = 0x9e3779b97f4a7c15ull, VOICE_K = 0xd6e8feb86659fd93ull;
+    uint64_t seed = 0x7475756E2545F491ull;
+    uint64_t voice = 0;
+    static float f32_at(uint64_t state) {
+        const unsigned __int128 t = (unsigned __int128)state * (unsigned __int128)(state ^ C1);
+        const uint64_t r = (uint64_t)t ^ (uint64_t)(t >> 64);
+        const uint32_t bits = 0x3F800000u | ((uint32_t)r >> 9);
+        float f;
+        memcpy(&f, &bits, 4);
+        return f - 1.0f;
+    }
+    float sample(uint32_t node_index, uint64_t k) const {
+        return f32_at(seed + NODE_K * (uint64_t)(node_index + 1) + VOICE_K * voice + C0 * (k + 1));
     }
 };
 
@@ -105,7 +123,8 @@ struct Gen {
                 w->position += n;
                 return n;
             case TB_NOISE:  // :113-118
-                for (size_t i = 0; i < n; i++) out[i] = rng->next_f32() * 2.0f - 1.0f;
+                for (size_t i = 0; i < n; i++) out[i] = rng->sample(w->index, w->noise_drawn + i) * 2.0f - 1.0f;
+                w->noise_drawn += n;
                 return n;
             case TB_FIXED: {  // :119-131
                 if (w->st == St::Initial) {
@@ -533,6 +552,7 @@ static int build(tbo_program* p) {
     for (size_t i = 0; i < n; i++) {
         const tb_node& s = p->src[i];
         Node* w = p->nodes[i].get();
+        w->index = (uint32_t)i;
         w->kind = s.kind;
         w->op = s.op;
         w->value = s.value;
@@ -627,6 +647,7 @@ void tbo_initialize_state(tbo_program* p) {
         w->st = St::Initial;
         w->input.clear();
         w->output.clear();
+        w->noise_drawn = 0;  // a fresh tree replays its noise streams (the reference's global RNG would not)
     }
 }
 
@@ -648,7 +669,8 @@ int tbo_substitute_const(tbo_program* p, uint32_t mark_id, float value) {
 }
 
 uint64_t tbo_allocations(const tbo_program* p) { return p->allocations; }
-void tbo_seed_noise(tbo_program* p, uint64_t seed) { p->rng.s = seed ? seed : 1; }
+void tbo_seed_noise(tbo_program* p, uint64_t seed) { p->rng.seed = seed; }
+void tbo_set_voice(tbo_program* p, uint64_t voice) { p->rng.voice = voice; }
 
 uint64_t tbo_render_batch(const tbo_program* p, const float* params, uint32_t n_params,
                           uint32_t n_voices, uint64_t n_samples, uint32_t block, float* out,
@@ -671,6 +693,8 @@ uint64_t tbo_render_batch(const tbo_program* p, const float* params, uint32_t n_
             uint32_t v = next.fetch_add(1);
             if (v >= n_voices) break;
             tbo_initialize_state(q);
+            q->rng.seed = p->rng.seed;
+            q->rng.voice = p->rng.voice + v;  // voice v of the batch draws its own noise streams
             if (params) tbo_set_params(q, params + (size_t)v * n_params, n_params);
             uint64_t done = 0;
             while (done < n_samples) {

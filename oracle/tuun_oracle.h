@@ -11,7 +11,8 @@
  * (generator.rs:1353-1925, chunk sizes 1/2/4/8) by tests/test_oracle_golden.py.
  * `Noise` is "parity unpinned": the reference draws from fastrand 2.3.0's unseeded
  * thread-local generator (generator.rs:115, Cargo.lock:372), which no test pins; the oracle
- * substitutes a seeded xorshift stream with the same range [-1, 1).
+ * restates that crate's published generator (wyrand) and gives every Noise node of every voice
+ * its own seeded stream of it (tuun_oracle.cpp, struct Rng) — same distribution, reproducible.
  * The Rust reference itself cannot be compiled here (no cargo/rustc), so there is no
  * oracle/_ref build; libm is glibc's instead of Rust std's (same correctly-rounded-to-<1ulp
  * f64 sin; test_sine pins it to 1e-5 only).
@@ -53,6 +54,8 @@ int tbo_substitute_const(tbo_program* p, uint32_t mark_id, float value);
 /* Generator.allocations (generator.rs:53). */
 uint64_t tbo_allocations(const tbo_program* p);
 void tbo_seed_noise(tbo_program* p, uint64_t seed);
+/* Voice index of this program inside a batch (selects the Noise streams). */
+void tbo_set_voice(tbo_program* p, uint64_t voice);
 
 /*
  * The reference's offline shape (benches/tracker_benches.rs:19-34, tracker.rs:597-642): for

@@ -178,10 +178,10 @@ int main(int argc, char** argv) {
             EXPECT(e.status() == TB_ERR_INVALID, "empty feed_forward: status %d", e.status());
         }
         try {
-            lower_check(Noise());
-            EXPECT(false, "Noise accepted");
+            lower_check(Reset(sin_waveform(1.0f, 0.0f), Filter(Noise(), consts(2, 0.5f))));
+            EXPECT(false, "Filter inside a Reset accepted");
         } catch (const Error& e) {
-            EXPECT(e.status() == TB_ERR_UNSUPPORTED, "Noise: status %d", e.status());
+            EXPECT(e.status() == TB_ERR_UNSUPPORTED, "Filter inside a Reset: status %d", e.status());
         }
     } else {
         try {

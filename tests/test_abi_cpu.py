@@ -60,8 +60,9 @@ def test_invalid_op_list_rejected_before_cuda():
 
 
 def test_unsupported_is_reported_not_emulated():
-    rc, h, msg = _create(flatten(BinaryPointOp(Operator.Multiply, Noise(), Const(0.1))))
-    assert rc == _abi.TB_ERR_UNSUPPORTED and "Noise" in msg
+    inner = Filter(Noise(), [Const(0.5), Const(0.5)], [])
+    rc, h, msg = _create(flatten(Reset(Sine(Const(1.0), Const(0.0)), inner)))
+    assert rc == _abi.TB_ERR_UNSUPPORTED and "Filter inside a Reset" in msg
     w = Reset(Sine(Const(1.0), Const(0.0)), Filter(Time(), [Const(1.0)], []))
     rc, h, msg = _create(flatten(w))
     assert rc == _abi.TB_ERR_UNSUPPORTED and "Filter inside a Reset" in msg

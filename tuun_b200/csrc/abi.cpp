@@ -79,6 +79,7 @@ struct tb_program {
     size_t smem = 0;
     uint32_t warps = TB_WARPS_PER_CTA;  // voices per CTA; fewer when one voice needs a lot of shared memory
     uint64_t launches = 0;
+    uint64_t noise_seed = 0x7475756E2545F491ull, noise_first_voice = 0;  // tb_seed_noise
     uint32_t fast_mode = 2;  // FAST-class sines: 1 = f32 polynomial, 2 = MUFU (TUUN_B200_FAST_SINES)
 
     ~tb_program() {
@@ -185,6 +186,8 @@ void fill_launch(const tb_program* p, tb_launch* L) {
     L->n_filt = (uint32_t)p->low.filt.size();
     L->steady_ok = p->low.steady_ok;
     L->fast_mode = p->fast_mode;
+    L->noise_seed = p->noise_seed;
+    L->voice_base = p->noise_first_voice;
     L->state = p->d_state;
 }
 
@@ -320,6 +323,13 @@ int tb_set_stream(tb_program* p, void* cuda_stream) {
     return TB_OK;
 }
 
+int tb_seed_noise(tb_program* p, uint64_t seed, uint64_t first_voice) {
+    if (!p) return set_error(TB_ERR_INVALID, "NULL program");
+    p->noise_seed = seed;
+    p->noise_first_voice = first_voice;
+    return TB_OK;
+}
+
 int tb_reset(tb_program* p) {
     if (!p) return set_error(TB_ERR_INVALID, "NULL program");
     CU(cudaSetDevice(p->device));
@@ -420,6 +430,7 @@ int render_impl(tb_program* p, const float* params, uint32_t n_params, uint32_t 
                 const int b = k & 1;
                 if (k >= 2) CU(cudaStreamWaitEvent(p->stream, p->ev_copy[b], 0));
                 L.params = d_params ? d_params + (size_t)v0 * n_params : nullptr;
+                L.voice_base = p->noise_first_voice + v0;
                 L.state = p->d_state + (size_t)v0 * p->low.state_words;
                 L.out_len = p->d_len + v0;
                 L.done = cut_time ? p->d_done + v0 : nullptr;

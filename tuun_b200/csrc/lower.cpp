@@ -295,10 +295,7 @@ struct Lowerer {
             case TB_CONST: produced(emit(G_CONST, const_of(i))); break;
             case TB_TIME: produced(emit(G_TIME, state_of(i, 2))); break;
             case TB_FIXED: produced(emit(G_FIXED, state_of(i, 2), fixed_table(i))); break;
-            case TB_NOISE:
-                fail(TB_ERR_UNSUPPORTED,
-                     "Noise: the reference draws from an unseeded thread-local generator (generator.rs:115); "
-                     "supply the samples as a Fixed buffer");
+            case TB_NOISE: produced(emit(G_NOISE, state_of(i, 2), i)); break;
             case TB_MARKED:
             case TB_CAPTURED: emit_gen(n.a); break;
             case TB_BINARY: {
@@ -646,7 +643,7 @@ struct Lowerer {
                 emit(S_FIN, gi);
                 break;
             }
-            case TB_NOISE: fail(TB_ERR_UNSUPPORTED, "Noise (see generator.rs:115): supply a Fixed buffer");
+            case TB_NOISE: emit(S_NOISE, state_of(i, 2), i); break;
             case TB_FILTER: fail(TB_ERR_UNSUPPORTED, "Filter inside a Reset");
             case TB_APPEND: fail(TB_ERR_UNSUPPORTED, "Append inside a Reset");
             default: fail(TB_ERR_INVALID, "unknown node kind");
@@ -701,6 +698,7 @@ struct Lowerer {
         switch (n.kind) {
             case TB_CONST: s_produced(emit(ST_CONST, const_of(i))); return true;
             case TB_TIME: s_produced(emit(ST_TIME, state_of(i, 2))); return true;
+            case TB_NOISE: s_produced(emit(ST_NOISE, state_of(i, 2), i)); return true;
             case TB_MARKED:
             case TB_CAPTURED: return emit_steady(n.a);
             case TB_BINARY: {

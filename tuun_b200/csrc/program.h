@@ -37,7 +37,7 @@ enum tb_op : uint32_t {
     G_CONST,       // a = cval index
     G_TIME,        // a = state offset
     G_FIXED,       // a = state offset, b = fixed table index (off,len)
-    G_NOISE,       // a = node id
+    G_NOISE,       // a = state (samples drawn so far), b = node index
     G_BINC,        // a = operator, b = cval index, c = merge
     G_BIN_BEGIN,   // a = slot, b = merge, c = jump target (the matching G_BIN_END)
     G_BIN_END,     // a = slot, b = operator, c = merge
@@ -104,10 +104,12 @@ enum tb_op : uint32_t {
     S_RESET_BEGIN, // a = state, b = origin slot
     S_RESET_END,   // a = state
     S_FIN,         // a = goe table index   (static Time / const forms only)
+    S_NOISE,       // a = state, b = node index (noise is not restarted by a Reset)
     // ---- steady-state stream (steady.cuh): straight-line, every operand infinite ----
     ST_END,
     ST_CONST,      // a = cval index
     ST_TIME,       // a = state
+    ST_NOISE,      // a = state, b = node index
     ST_SAVE,       // a = slot                      acc -> slot
     ST_BIN,        // a = slot, b = operator        acc = slot (op) acc
     ST_SINE_CC,    // a = state, b = aux of the AUX_SINE_ROT block, c = aux of phase
@@ -202,6 +204,8 @@ struct tb_launch {
     uint32_t n_filt;
     uint32_t steady_ok;    // the generate program may run through the steady-state interpreter
     uint32_t fast_mode;    // FAST-class sine evaluation: 1 = f32 polynomial, 2 = MUFU
+    unsigned long long noise_seed;   // tb_seed_noise
+    unsigned long long voice_base;   // index of voice 0 of this launch inside the caller's batch
     // per call
     const float* params;
     uint32_t n_params, n_voices;

@@ -194,9 +194,30 @@ __device__ __forceinline__ void sin_turns_vec(float (&out)[C], const u64 (&ph)[C
 }
 
 // ------------------------------------------------------------------------------------------
+// Noise (generator.rs:113-118): `fastrand::f32() * 2 - 1`.  fastrand 2.3.0's generator is wyrand:
+// state += C0; t = state * (state ^ C1) as u128; out = lo(t) ^ hi(t); f32 = from_bits(0x3F800000 |
+// (u32 >> 9)) - 1.  The state advances by a constant, so sample k of a stream is a pure function of
+// (seed, k): every Noise node of every voice owns the stream
+//     state_k = seed + NODE_K (node + 1) + VOICE_K voice + C0 (k + 1)
+// (the reference draws from one UNSEEDED thread-local instance: no sequence of it is reproducible,
+// so parity for Noise is pinned against the oracle's restatement of the same streams only).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ u64 noise_stream(const tb_launch& P, uint32_t voice, int node) {
+    return P.noise_seed + 0x9e3779b97f4a7c15ull * (u64)(node + 1) + 0xd6e8feb86659fd93ull * (P.voice_base + (u64)voice);
+}
+__device__ __forceinline__ float noise_at(u64 stream, u64 k) {
+    const u64 s = stream + 0x2d358dccaa6c78a5ull * (k + 1ull);
+    const u64 m = s ^ 0x8bb84b93962eacc9ull;
+    const u64 r = (s * m) ^ __umul64hi(s, m);
+    const float f = __uint_as_float(0x3F800000u | ((uint32_t)r >> 9)) - 1.0f;
+    return __fsub_rn(__fmul_rn(f, 2.0f), 1.0f);
+}
+
+// ------------------------------------------------------------------------------------------
 // per-warp machine state
 // ------------------------------------------------------------------------------------------
 struct WarpMem {
+    uint32_t voice;
     float* cval;
     u64* aux;
     uint32_t* state;
@@ -738,6 +759,17 @@ __device__ void run_program(const tb_launch& P, const tb_insn* code, const WarpM
                 __syncwarp();
                 st_state64(M.state, in.a, pos + (u64)len);
                 cx.L = len;
+                break;
+            }
+            case G_NOISE:
+            case S_NOISE: {  // generator.rs:113-118; not restarted by an enclosing Reset (no tree state)
+                const u64 pos = ld_state64(M.state, in.a);
+                const u64 stream = noise_stream(P, M.voice, in.b);
+                UNROLL for (int j = 0; j < C; j++) acc[j] = noise_at(stream, pos + (u64)(i64)(l * C + j - cx.w0));
+                __syncwarp();
+                st_state64(M.state, in.a, pos + (u64)n);
+                if (op == G_NOISE) cx.L = n;
+                else cx.vm = 0xffu;
                 break;
             }
             case G_BINC: {  // generator.rs:538-549 (constant right-hand side)
@@ -1460,6 +1492,7 @@ tb_render_kernel(const tb_launch P) {
     const size_t per_warp = per_warp_slots + aux_b + cval_b + state_b + slen_b + svm_b;
     unsigned char* base = smem_raw + off + per_warp * warp;
     WarpMem M;
+    M.voice = voice;
     M.slots = reinterpret_cast<float*>(base); base += per_warp_slots;
     M.aux = reinterpret_cast<u64*>(base); base += aux_b;
     M.cval = reinterpret_cast<float*>(base); base += cval_b;

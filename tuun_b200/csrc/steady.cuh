@@ -354,6 +354,14 @@ __device__ __forceinline__ void run_steady(const tb_launch& P, uint32_t code_s, 
                 st_state64(M.state, in.a, pos0 + (u64)TILE_S);
                 break;
             }
+            case ST_NOISE: {  // generator.rs:113-118
+                const u64 pos = ld_state64(M.state, in.a);
+                const u64 stream = noise_stream(P, M.voice, in.b);
+                UNROLL for (int j = 0; j < CS; j++) acc[j] = noise_at(stream, pos + (u64)(l * CS + j));
+                __syncwarp();
+                st_state64(M.state, in.a, pos + (u64)TILE_S);
+                break;
+            }
             case ST_SAVE: sslot_store(M.slots, in.a, acc, l); break;
             case ST_BIN: {  // generator.rs:555-567 with both sides infinite
                 float av[CS];

@@ -69,6 +69,10 @@ class Program:
     def set_stream(self, cuda_stream: int):
         _abi.check(_abi.lib().tb_set_stream(self._h, ctypes.c_void_p(cuda_stream)))
 
+    def seed_noise(self, seed: int, first_voice: int = 0):
+        """tb_seed_noise: the seed of the per-node, per-voice Noise streams (generator.rs:113-118)."""
+        _abi.check(_abi.lib().tb_seed_noise(self._h, ctypes.c_uint64(seed), ctypes.c_uint64(first_voice)))
+
     def reset(self):
         """waveform::set_state(root, Initial) for every voice (waveform.rs:322)."""
         _abi.check(_abi.lib().tb_reset(self._h))
