@@ -93,3 +93,21 @@ def test_cfg4_filter_chains_60s(idx):
     assert len(got) == n
     assert bad == 0, f"{name}: {bad} samples beyond {TOL}, max {err}"
     assert float(np.max(np.abs(got[-SR:] - ref[-SR:]))) <= TOL
+
+
+@pytest.mark.parametrize("idx", range(5))
+def test_tracker_benches_shapes(idx):
+    """benches/tracker_benches.rs: the same trees driven the same way — N blocks of 1024 samples at
+    44.1 kHz from Initial state — against the oracle driven identically."""
+    name, w, n_blocks = W.tracker_benches()[idx]
+    n = n_blocks * 1024
+    # filter_1_1 / _linear integrate a ramp: outputs grow to ~1 (1_1) or stay O(1); filter_4_3 has
+    # poles near z = 1 (noise gain ~1e3 on an input that reaches 1.0): tolerance relative to the peak
+    ref = OracleProgram(w, SR).render(n, block=1024)
+    got = gpu_render(w, n, block=1024)
+    assert len(got) == len(ref)
+    if name == "marks_4_40":
+        assert len(ref) == 40 * 4 * 22050  # 3438 blocks overshoot the waveform slightly (bench comment)
+    peak = max(1.0, float(np.max(np.abs(ref)))) if len(ref) else 1.0
+    err = float(np.max(np.abs(got - ref))) if len(ref) else 0.0
+    assert err <= TOL * peak, f"{name}: max abs err {err} (peak {peak})"

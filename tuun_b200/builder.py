@@ -157,6 +157,12 @@ def unseq():
     return apply
 
 
+def mark(mark_id: int):
+    """`mark(n)`: tag a waveform so the tracker reports when it starts (builtins.rs, curried)."""
+    from .waveform import Marked
+    return _curry(lambda w: Marked(int(mark_id), w))
+
+
 def capture(stem: str):
     return _curry(lambda w: Captured(stem, w))
 

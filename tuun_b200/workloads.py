@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .waveform import (Alt, BinaryPointOp, Const, Filter, Fin, Fixed, Operator, Sine, Time, Waveform, add, mul)
+from .waveform import (Alt, Append, BinaryPointOp, Const, Filter, Fin, Fixed, Operator, Sine, Time, Waveform, add, mul)
 
 F = np.float32
 PI = F(3.14159265)  # lib/v0/std.tuun:7
@@ -157,3 +157,29 @@ def cfg4_filters(noise_seconds=60.0, sample_rate=44100):
         ("pulse-filter_4_3", pipe(s.pulse(0.5, 110), f43)),
     ]
     return [(name, _finish(v)) for name, v in progs]
+
+
+def tracker_benches(sample_rate=44100):
+    """The five shapes of the reference's own criterion benches (benches/tracker_benches.rs), each
+    driven there as N blocks of 1024 samples.  Returns [(name, waveform, n_blocks)]."""
+    from .builder import Std, fin, mark, minus, pipe, plus, seq, sequence, times, to_waveform
+    from .optimizer import optimize
+    from .waveform import Marked, Noise
+    t = Time()
+    filter_1_1 = Filter(Time(), [Const(0.5)], [Const(-0.5)])                       # :20-34
+    filter_1_1_linear = Filter(Time(), [add(mul(Time(), Const(-0.5)), Const(0.5))],  # :36-67
+                               [add(mul(Time(), Const(0.5)), Const(-0.5))])
+    filter_4_3 = Filter(Time(), [Const(0.00107949), Const(0.00323847), Const(0.00323847), Const(0.00107949)],
+                        [Const(-2.5610316), Const(2.2132402), Const(-0.6435727)])  # :69-89
+    # marks_4_40 (:92-117): 40 x Player::beats_waveform (player.rs:232-260) appended; tempo 120, 4 beats
+    spb = F(0.5)
+    beats = sequence([pipe(0, fin(minus(Time(), spb)), seq(minus(Time(), spb)), mark(i + 1)) for i in range(4)])
+    one = Marked(0, optimize(to_waveform(beats)))
+    marks = one
+    for _ in range(39):
+        marks = Append(marks, one)
+    # large_440 (:119-165): `triangle(55) + (noise * 0.2) | R(1.0, 1.0)`, evaluated but NOT optimized
+    s = Std(sample_rate=sample_rate)
+    large = times(plus(s.triangle(55), times(Noise(), 0.2)), s.Rw(1.0, 1.0))
+    return [("filter_1_1", filter_1_1, 43), ("filter_1_1_linear", filter_1_1_linear, 43),
+            ("filter_4_3", filter_4_3, 43), ("marks_4_40", marks, 3438), ("large_440", to_waveform(large), 43)]
