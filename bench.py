@@ -241,8 +241,23 @@ def main():
     peak, peak_src = 6650.0, "fallback"
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured"
-    alg_bytes = 4.0 * n_local * n_samples
-    avg_launch_s = (dev_ms / max(1, launches)) * 1e-3
+    # The dominant kernel: tb_render_lanes_kernel when the batch takes the lane-per-voice path (its
+    # own CUDA-event times on the launching stream, tb_lane_kernel_times; it renders all samples of
+    # a call but the first 256-sample tile and the last < 16), else the one tb_render_kernel launch.
+    info = prog.info
+    lane_ms = prog.lane_kernel_times(args.steps) if info.lane_launches else np.zeros(0)
+    if len(lane_ms):
+        kernel = "tb_render_lanes_kernel"
+        lane_samples = (n_samples - 256) // 16 * 16
+        alg_bytes = 4.0 * n_local * lane_samples
+        avg_launch_s = float(np.mean(lane_ms)) * 1e-3
+        dominant_share = float(np.sum(lane_ms)) / dev_ms if len(lane_ms) == args.steps else None
+    else:
+        kernel = "tb_render_kernel"
+        lane_samples = n_samples
+        alg_bytes = 4.0 * n_local * n_samples
+        avg_launch_s = (dev_ms / max(1, launches)) * 1e-3
+        dominant_share = 1.0
     achieved = alg_bytes / avg_launch_s / 1e9
     # DRAM traffic of the kernel from the committed ncu --set full capture (profiles/), which ran
     # the same kernel and per-voice work on a smaller launch: bytes per voice-sample x this launch.
@@ -250,10 +265,12 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
-        traffic = float(tj["dram_bytes_per_voice_sample"]) * n_local * n_samples
-        traffic_src = tj["source"]
+        if tj.get("kernel", "tb_render_kernel") == kernel:
+            traffic = float(tj["dram_bytes_per_voice_sample"]) * n_local * lane_samples
+            traffic_src = tj["source"]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_source": traffic_src, "kernel": "tb_render_kernel",
+                "traffic": traffic, "traffic_source": traffic_src, "kernel": kernel,
+                "share_of_step": dominant_share,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                 "avg_launch_ms": avg_launch_s * 1e3,
                 "note": "instruction-issue bound, not HBM bound: see profiles/README.md (issue-active %, "

@@ -172,8 +172,19 @@ typedef struct tb_program_info {
     uint32_t smem_bytes;      /* dynamic shared memory per CTA */
     uint32_t n_params;        /* highest param_slot + 1 */
     uint64_t kernel_launches; /* cumulative launches of this library's kernels */
+    uint64_t lane_launches;   /* of those, launches of the lane-per-voice kernel (large steady batches) */
+    uint32_t lane_smem_bytes; /* its dynamic shared memory per CTA; 0 when the program does not qualify */
+    uint32_t lane_min_voices; /* batches of at least this many voices take it */
 } tb_program_info;
 int tb_program_get_info(const tb_program* p, tb_program_info* info);
+
+/*
+ * Device durations (milliseconds, CUDA events on the program's stream) of the most recent launches
+ * of the lane-per-voice kernel, oldest first; at most `cap` (and at most 64) values, `*n` of them
+ * written.  Synchronizes the stream.  Measurement aid for bench.py's roofline line: the kernel's
+ * own launch time, apart from the two small bracketing launches of a call.
+ */
+int tb_lane_kernel_times(tb_program* p, float* ms, uint32_t cap, uint32_t* n);
 
 /*
  * Validate and lower an op list WITHOUT touching a device: the status a tb_program_create of the

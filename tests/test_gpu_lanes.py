@@ -1,0 +1,201 @@
+"""The lane-per-voice kernel (tuun_b200/csrc/lanes.cu): large batches of steady-state voices, one
+thread per voice.  Forced on small batches here (TUUN_B200_LANE_MIN_VOICES=1) and compared with the
+CPU oracle (generator.rs:86-515 restated), with the warp-per-voice kernel, and with itself across
+different call partitions.  Filters run the reference's own recurrence in its own operation order
+there, so filters over exactly representable inputs are bit-identical to the oracle."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle.binding import OracleProgram
+from tuun_b200.waveform import (Alt, BinaryPointOp, Const, Filter, Noise, Operator, Sine, Time, add, f32, mul, sub)
+
+pytestmark = pytest.mark.gpu
+SR = 44100
+TOL = 1e-4  # north_star
+TAU = f32(2 * math.pi)
+
+
+def program(w, monkeypatch, lanes=True):
+    from tuun_b200.generator import Program
+    if lanes:
+        monkeypatch.setenv("TUUN_B200_LANES", "1")
+        monkeypatch.setenv("TUUN_B200_LANE_MIN_VOICES", "1")
+    else:
+        monkeypatch.setenv("TUUN_B200_LANES", "0")
+    return Program(w, SR)
+
+
+def oracle_rows(w, params, V, N, seed=None):
+    o = OracleProgram(w, SR)
+    rows = np.zeros((V, N), dtype=np.float32)
+    for v in range(V):
+        o.initialize_state()
+        if seed is not None:
+            o.seed_noise(seed, v)
+        if params is not None:
+            o.set_params(params[v])
+        r = o.render(N)
+        assert len(r) == N
+        rows[v] = r
+    return rows
+
+
+def cfg5(V):
+    from tuun_b200.workloads import fm_filter_params, fm_filter_voice
+    ids = (np.arange(V) * 4099) % 65536
+    return fm_filter_voice(), fm_filter_params(ids)
+
+
+def test_cfg5_batch_against_oracle_and_warp_kernel(monkeypatch):
+    V, N = 1000, 256 + 16 * 220 + 7  # ragged: a partial CTA, a partial warp, a tail shorter than a tile
+    w, params = cfg5(V)
+    p = program(w, monkeypatch)
+    assert p.info.lane_smem_bytes > 0 and p.info.lane_min_voices == 1
+    out = np.full((V, N), np.inf, dtype=np.float32)
+    lens = p.render(out, params=params)
+    assert p.info.lane_launches == 1 and p.info.kernel_launches == 3  # head tile, lanes, tail
+    assert (lens == N).all()
+    o = OracleProgram(w, SR)
+    ref, olens, _, _ = o.render_batch(params, V, N)
+    assert (olens == N).all()
+    assert np.max(np.abs(out - ref)) <= TOL
+    q = program(w, monkeypatch, lanes=False)
+    assert q.info.lane_smem_bytes == 0
+    warp = np.zeros((V, N), dtype=np.float32)
+    q.render(warp, params=params)
+    assert q.info.lane_launches == 0
+    assert np.max(np.abs(out - warp)) <= TOL  # high-Q, low-cutoff voices: the round-off noise of the two feedback forms
+
+
+def test_cfg5_one_second_drift(monkeypatch):
+    """A whole second of the headline voices: the error against the oracle at the end of the render
+    is the error at its start (the 64-bit phase sums are exact, nothing accumulates)."""
+    V, N = 128, SR
+    w, params = cfg5(V)
+    out = np.zeros((V, N), dtype=np.float32)
+    program(w, monkeypatch).render(out, params=params)
+    ref, _, _, _ = OracleProgram(w, SR).render_batch(params, V, N)
+    d = np.abs(out - ref)
+    assert d.max() <= TOL
+    assert d[:, -4410:].max() <= max(2.0 * d[:, :4410].max(), 2e-5)
+
+
+def test_partition_invariance_and_device_rows(monkeypatch):
+    """One call, or the same samples over several calls of odd sizes (each call: general head tile,
+    lane tiles, general tail): the carried state makes them the same stream.  Device rows (torch)
+    take the same kernels as host rows."""
+    import torch
+    V, N = 200, 6000
+    w, params = cfg5(V)
+    one = np.zeros((V, N), dtype=np.float32)
+    program(w, monkeypatch).render(one, params=params)
+    p = program(w, monkeypatch)
+    parts = np.zeros((V, N), dtype=np.float32)
+    a = 0
+    for n in (1000, 273, 16, 2500, 2211):
+        blk = np.zeros((V, n), dtype=np.float32)
+        lens = p.render(blk, params=params)
+        assert (lens == n).all()
+        parts[:, a:a + n] = blk
+        a += n
+    assert a == N
+    # Every call renders its first 256 samples and its last < 16 with the general tiles, whose FAST
+    # sines round the same exact phase differently (32 top bits of 2^-44-turn sums there, 23 bits of
+    # 2^-32-turn sums in lane tiles): inputs of the filters differ by ~1e-6, which for most voices is
+    # what the outputs differ by; the high-Q 200 Hz low-passes (poles at radius 0.993) turn any
+    # input change into another realisation of their round-off noise (6e-5).
+    per_voice = np.max(np.abs(parts - one), axis=1)
+    assert per_voice.max() <= TOL
+    assert np.median(per_voice) <= 5e-6
+    dev = torch.zeros((V, N + 8), dtype=torch.float32, device="cuda")
+    q = program(w, monkeypatch)
+    q.render(dev[:, :N], params=torch.from_numpy(params).cuda())
+    torch.cuda.synchronize()
+    assert q.info.lane_launches == 1
+    np.testing.assert_array_equal(dev[:, :N].cpu().numpy(), one)
+    assert float(dev[:, N:].abs().max()) == 0.0
+
+
+def test_filters_bit_exact_on_exact_inputs(monkeypatch):
+    """Time, constants, Noise and Alt of them are exact on both sides, so every filter shape below
+    must reproduce the oracle's f32 recurrence bit for bit (generator.rs:496-507)."""
+    x = add(mul(Noise(), Const(0.25)), Alt(sub(mul(Time(), Const(3.0)), Const(0.05)), Const(0.5), Const(-0.5)))
+    shapes = [
+        ([0.2, 0.3, 0.2], [-1.2, 0.5]),                       # biquad
+        ([0.5], [-0.5]),                                      # tracker_benches.rs filter_1_1
+        ([0.4, 0.1], [0.3]),
+        ([0.1, 0.2, 0.3, 0.4], [-0.3, 0.2, -0.1]),            # tracker_benches.rs filter_4_3
+        ([0.25, 0.25, 0.25, 0.25], []),                       # pure FIR
+        ([0.1, 0.05, 0.02, 0.3, 0.1, 0.2, 0.05, 0.1, 0.08], [-0.2, 0.1, -0.05, 0.02]),  # K = 9, J = 4
+    ]
+    V, N = 70, 256 + 16 * 40 + 3
+    for ff, fb in shapes:
+        w = Filter(x, [Const(f32(c)) for c in ff], [Const(f32(c)) for c in fb])
+        p = program(w, monkeypatch)
+        p.seed_noise(7, 0)
+        out = np.zeros((V, N), dtype=np.float32)
+        p.render(out)
+        assert p.info.lane_launches == 1
+        ref = oracle_rows(w, None, V, N, seed=7)
+        np.testing.assert_array_equal(out, ref, err_msg=f"{ff} {fb}")
+    # a cascade, per-voice coefficients
+    w = Filter(Filter(x, [Const(1.0, param=0), Const(0.3)], [Const(0.0, param=1)]),
+               [Const(0.2), Const(0.0, param=2), Const(0.2)], [Const(-1.0), Const(0.0, param=3)])
+    rng = np.random.default_rng(3)
+    params = np.stack([rng.uniform(0.1, 0.9, V), rng.uniform(-0.8, 0.8, V), rng.uniform(0.1, 0.5, V),
+                       rng.uniform(0.1, 0.6, V)], axis=1).astype(np.float32)
+    p = program(w, monkeypatch)
+    p.seed_noise(7, 0)
+    out = np.zeros((V, N), dtype=np.float32)
+    p.render(out, params=params)
+    np.testing.assert_array_equal(out, oracle_rows(w, params, V, N, seed=7))
+
+
+def test_every_steady_operator(monkeypatch):
+    """A tree touching every word of the lane program: all four Sine forms in both precision
+    classes, Alt with waveform and constant branches, point operators with waveform and constant
+    right-hand sides (incl. Divide and Power), Time, Noise, slots."""
+    trig = Sine(Const(1.0, param=0), Const(0.3))                                   # CC, feeds a trigger: exact
+    fm = Sine(add(mul(Time(), Const(900.0)), Const(1.0, param=1)),                 # AA: frequency and phase waveforms
+              mul(Sine(Const(1.0, param=2), Const(0.5)), Const(2.0)))
+    pm = Sine(Const(1.0, param=1), mul(trig, Const(3.0)))                          # CA
+    ac = Sine(add(mul(fm, Const(500.0)), Const(2000.0)), Const(0.25))              # AC; makes fm exact-class
+    alt = Alt(trig, add(ac, pm), mul(pm, Const(-0.5)))
+    sq = Alt(Sine(Const(1.0, param=2), Const(0.0)), Const(1.0), Const(-1.0))
+    body = add(alt, mul(sq, mul(Noise(), Const(0.1))))
+    div = BinaryPointOp(Operator.Divide, body, add(Time(), Const(1.0)))
+    pw = BinaryPointOp(Operator.Power, add(mul(div, Const(0.25)), Const(1.5)), Const(2.0))
+    w = BinaryPointOp(Operator.Subtract, pw, BinaryPointOp(Operator.Divide, sq, Const(4.0)))
+    V, N = 96, 256 + 16 * 64 + 11
+    rng = np.random.default_rng(5)
+    params = np.stack([TAU * rng.uniform(20, 300, V), TAU * rng.uniform(100, 1500, V), TAU * rng.uniform(30, 700, V)],
+                      axis=1).astype(np.float32)
+    p = program(w, monkeypatch)
+    p.seed_noise(11, 0)
+    out = np.zeros((V, N), dtype=np.float32)
+    lens = p.render(out, params=params)
+    assert p.info.lane_launches == 1 and (lens == N).all()
+    ref = oracle_rows(w, params, V, N, seed=11)
+    d = np.abs(out - ref)
+    # Alt / square edges: a trigger within rounding of zero may flip one sample (hard part 1)
+    bad = int(np.count_nonzero(d > TOL))
+    assert bad <= 2, (bad, float(d.max()))
+    q = program(w, monkeypatch, lanes=False)
+    q.seed_noise(11, 0)
+    warp = np.zeros((V, N), dtype=np.float32)
+    q.render(warp, params=params)
+    assert int(np.count_nonzero(np.abs(out - warp) > 2e-5)) <= 2
+
+
+def test_default_threshold_keeps_small_batches_on_the_warp_kernel(monkeypatch):
+    from tuun_b200.generator import Program
+    monkeypatch.delenv("TUUN_B200_LANES", raising=False)
+    monkeypatch.delenv("TUUN_B200_LANE_MIN_VOICES", raising=False)
+    w, params = cfg5(64)
+    p = Program(w, SR)
+    assert p.info.lane_smem_bytes > 0 and p.info.lane_min_voices >= 148 * 64
+    out = np.zeros((64, 2000), dtype=np.float32)
+    p.render(out, params=params)
+    assert p.info.lane_launches == 0

@@ -27,7 +27,7 @@ TB_NO_VOICE_OUT = 4
 # every symbol include/tuun_b200.h declares
 EXPORTS = [
     "tb_program_create", "tb_program_destroy", "tb_render", "tb_render_mix", "tb_length", "tb_reset",
-    "tb_seed_noise", "tb_stream", "tb_set_stream", "tb_program_get_info", "tb_lower_check", "tb_last_error", "tb_abi_version",
+    "tb_seed_noise", "tb_stream", "tb_set_stream", "tb_program_get_info", "tb_lane_kernel_times", "tb_lower_check", "tb_last_error", "tb_abi_version",
 ]
 
 
@@ -42,6 +42,9 @@ class TbProgramInfo(ctypes.Structure):
         ("smem_bytes", ctypes.c_uint32),
         ("n_params", ctypes.c_uint32),
         ("kernel_launches", ctypes.c_uint64),
+        ("lane_launches", ctypes.c_uint64),
+        ("lane_smem_bytes", ctypes.c_uint32),
+        ("lane_min_voices", ctypes.c_uint32),
     ]
 
 
@@ -87,6 +90,8 @@ def lib():
     L.tb_set_stream.argtypes = [P, P]
     L.tb_program_get_info.restype = ctypes.c_int
     L.tb_program_get_info.argtypes = [P, ctypes.POINTER(TbProgramInfo)]
+    L.tb_lane_kernel_times.restype = ctypes.c_int
+    L.tb_lane_kernel_times.argtypes = [P, P, u32, ctypes.POINTER(u32)]
     L.tb_lower_check.restype = ctypes.c_int
     L.tb_lower_check.argtypes = [ctypes.POINTER(TbNode), u32, P, u32, u64, ctypes.POINTER(TbProgramInfo)]
     L.tb_last_error.restype = ctypes.c_char_p

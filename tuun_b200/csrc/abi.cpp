@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -18,6 +19,9 @@ extern "C" size_t tb_kernel_smem_bytes(uint32_t n_code, uint32_t n_slots, uint32
                                        uint32_t n_cval, uint32_t state_words, uint32_t steady_ok,
                                        uint32_t warps);
 extern "C" cudaError_t tb_kernel_launch(const tb_launch* P, size_t smem, uint32_t warps, cudaStream_t stream);
+extern "C" size_t tb_lanes_smem_bytes(uint32_t n_lane_code, uint32_t w_words, uint32_t q_units, uint32_t slots);
+extern "C" cudaError_t tb_lanes_launch(const tb_launch* P, size_t smem, cudaStream_t stream);
+extern "C" cudaError_t tb_lanes_occupancy(size_t smem, int* blocks_per_sm, int* n_sm);
 extern "C" cudaError_t tb_mix_launch(const float* rows, uint64_t stride, const unsigned long long* lens,
                                      uint32_t n_voices, uint64_t n_samples, uint64_t t0, float* mix,
                                      int accumulate, cudaStream_t stream);
@@ -62,6 +66,15 @@ struct tb_program {
     tb_filter_tab* d_filt = nullptr;
     tb_fixed_tab* d_fixed = nullptr;
     float* d_pool = nullptr;
+    tb_insn* d_lane_code = nullptr;
+    tb_lane_aux* d_lane_aux = nullptr;
+    size_t lane_smem = 0;           // 0: the lane-per-voice kernel does not apply to this program
+    uint32_t lane_min_voices = 0;   // batches at least this large take it
+    uint32_t* h_fault = nullptr;    // mapped pinned counter written by the lane kernel
+    uint32_t* d_fault = nullptr;
+    uint64_t lane_launches = 0;
+    static constexpr uint32_t kLaneEvents = 64;  // ring of (start, stop) events around the last lane launches
+    cudaEvent_t lane_ev[kLaneEvents][2] = {};
     uint32_t* d_state = nullptr;
     uint32_t n_voices = 0;
     bool fresh = true;  // no samples generated since create / tb_reset
@@ -87,6 +100,12 @@ struct tb_program {
         cudaFree(d_code); cudaFree(d_cexpr); cudaFree(d_aux); cudaFree(d_goe); cudaFree(d_goe_steps);
         cudaFree(d_filt); cudaFree(d_fixed); cudaFree(d_pool); cudaFree(d_state); cudaFree(d_params);
         cudaFree(d_len); cudaFree(d_done); cudaFree(d_mix); cudaFree(d_stage[0]); cudaFree(d_stage[1]);
+        cudaFree(d_lane_code); cudaFree(d_lane_aux);
+        if (h_fault) cudaFreeHost(h_fault);
+        for (auto& e : lane_ev) {
+            if (e[0]) cudaEventDestroy(e[0]);
+            if (e[1]) cudaEventDestroy(e[1]);
+        }
         for (int i = 0; i < 2; i++) {
             if (ev_render[i]) cudaEventDestroy(ev_render[i]);
             if (ev_copy[i]) cudaEventDestroy(ev_copy[i]);
@@ -189,12 +208,75 @@ void fill_launch(const tb_program* p, tb_launch* L) {
     L->noise_seed = p->noise_seed;
     L->voice_base = p->noise_first_voice;
     L->state = p->d_state;
+    L->lane_code = p->d_lane_code;
+    L->lane_aux = p->d_lane_aux;
+    L->n_lane_code = (uint32_t)p->low.lane_code.size();
+    L->n_lane_aux = (uint32_t)p->low.lane_aux.size();
+    L->lane_w_words = p->low.lane_w_words;
+    L->lane_q_units = p->low.lane_q_units;
+    L->lane_slots = p->low.lane_slots;
+    L->fault = p->d_fault;
 }
 
 int launch(tb_program* p, const tb_launch& L) {
     cudaError_t e = tb_kernel_launch(&L, p->smem, p->warps, p->stream);
     if (e != cudaSuccess) return cuda_fail(e, "tb_render_kernel launch");
     p->launches++;
+    return TB_OK;
+}
+
+// A generate launch.  Large batches of steady-state voices go through the lane-per-voice kernel
+// (lanes.cu): the first general tile of the call (filter pre-reads, generator.rs:234-252) and the
+// last < TB_LS samples stay on the warp-per-voice kernel; state blocks are shared, so the three
+// launches continue one stream.
+int launch_generate(tb_program* p, const tb_launch& L) {
+    const bool big = p->lane_smem != 0 && L.n_voices >= p->lane_min_voices && L.out != nullptr;
+    if (!big) return launch(p, L);
+    if (L.n_samples < (uint64_t)TB_TILE + TB_LS) {  // too short for a lane tile: same arithmetic, general tiles
+        tb_launch G = L;
+        G.exact_fb = 1;
+        return launch(p, G);
+    }
+    const uint64_t head = TB_TILE;
+    const uint64_t bulk = (L.n_samples - head) / TB_LS * TB_LS;
+    const uint64_t tail = L.n_samples - head - bulk;
+    tb_launch H = L;
+    H.n_samples = head;
+    H.exact_fb = 1;  // the bracketing tiles run the reference's recurrence too (see lanes.cu)
+    int rc = launch(p, H);
+    if (rc) return rc;
+    tb_launch B = L;
+    B.out = L.out + head;
+    B.n_samples = bulk;
+    B.accumulate = 1;
+    B.done = nullptr;  // every node of a steady program is infinite: no voice ever finishes
+    cudaEvent_t* ev = p->lane_ev[p->lane_launches % tb_program::kLaneEvents];
+    if (!ev[0]) {
+        CU(cudaEventCreate(&ev[0]));
+        CU(cudaEventCreate(&ev[1]));
+    }
+    CU(cudaEventRecord(ev[0], p->stream));
+    cudaError_t e = tb_lanes_launch(&B, p->lane_smem, p->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "tb_render_lanes_kernel launch");
+    CU(cudaEventRecord(ev[1], p->stream));
+    p->launches++;
+    p->lane_launches++;
+    if (tail) {
+        tb_launch T = L;
+        T.out = L.out + head + bulk;
+        T.n_samples = tail;
+        T.accumulate = 1;
+        T.exact_fb = 1;
+        if ((rc = launch(p, T))) return rc;
+    }
+    return TB_OK;
+}
+
+int check_fault(tb_program* p) {
+    if (p->h_fault && *p->h_fault != 0u) {
+        *p->h_fault = 0u;
+        return set_error(TB_ERR_STATE, "lane kernel met a voice without complete filter history");
+    }
     return TB_OK;
 }
 
@@ -222,6 +304,15 @@ int tb_program_create(const tb_node* nodes, uint32_t n_nodes, const int32_t* lis
         std::string msg = p->low.error;
         delete p;
         return set_error(rc, msg);
+    }
+    if (std::getenv("TUUN_B200_DEBUG")) {
+        std::fprintf(stderr, "[tuun_b200] lane_ok %u: W %u words, Q %u units, %u slots\n", p->low.lane_ok,
+                     p->low.lane_w_words, p->low.lane_q_units, p->low.lane_slots);
+        for (const tb_insn& i : p->low.lane_code)
+            std::fprintf(stderr, "  op %3u q/class %3u np %2u hi %3u   a %d b %d c %d\n", i.op & 0xffu, (i.op >> 8) & 0xffu,
+                         (i.op >> 16) & 0xffu, i.op >> 24, i.a, i.b, i.c);
+        for (const tb_lane_aux& x : p->low.lane_aux)
+            std::fprintf(stderr, "  aux kind %u a %d b %d c %d -> W %u Q %u\n", x.kind, x.a, x.b, x.c, x.w_off, x.q_off);
     }
     p->sample_rate = sample_rate;
     p->fast_mode = (fs && fs[0] == '1') ? 1u : 2u;  // "0" all exact, "1" f32 polynomial, default MUFU
@@ -266,6 +357,31 @@ int tb_program_create(const tb_node* nodes, uint32_t n_nodes, const int32_t* lis
         return bail(rc);
     if (!size_cta(p->low, &p->warps, &p->smem))
         return bail(set_error(TB_ERR_UNSUPPORTED, "program needs more shared memory than one CTA has"));
+    // The lane-per-voice kernel (lanes.cu): for batches large enough that one thread per voice fills
+    // the device.  TUUN_B200_LANES=0 disables it; TUUN_B200_LANE_MIN_VOICES moves the threshold.
+    const char* le = std::getenv("TUUN_B200_LANES");
+    if (p->low.lane_ok && !(le && le[0] == '0')) {
+        const size_t ls = tb_lanes_smem_bytes((uint32_t)p->low.lane_code.size(), p->low.lane_w_words,
+                                              p->low.lane_q_units, p->low.lane_slots);
+        int bps = 0, n_sm = 0;
+        if (ls <= 220 * 1024 && tb_lanes_occupancy(ls, &bps, &n_sm) == cudaSuccess && bps > 0) {
+            if ((rc = upload(p->low.lane_code, &p->d_lane_code)) || (rc = upload(p->low.lane_aux, &p->d_lane_aux)))
+                return bail(rc);
+            if (cudaHostAlloc(reinterpret_cast<void**>(&p->h_fault), 4, cudaHostAllocMapped) == cudaSuccess) {
+                *p->h_fault = 0u;
+                if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&p->d_fault), p->h_fault, 0) != cudaSuccess)
+                    p->d_fault = nullptr;
+            }
+            p->lane_smem = ls;
+            // Default threshold: a third of the voices the device holds in one wave of this kernel
+            // (below that the warp-per-voice kernel, which fills the device with far fewer voices, wins).
+            const char* mv = std::getenv("TUUN_B200_LANE_MIN_VOICES");
+            p->lane_min_voices = mv ? (uint32_t)std::strtoul(mv, nullptr, 10)
+                                    : (uint32_t)std::max(1, bps * n_sm * TB_LANE_THREADS / 3);
+        } else {
+            cudaGetLastError();
+        }
+    }
     *out_program = p;
     return TB_OK;
 }
@@ -293,6 +409,11 @@ int tb_lower_check(const tb_node* nodes, uint32_t n_nodes, const int32_t* lists,
         info->smem_bytes = (uint32_t)smem;
         info->n_params = low.n_params;
         info->kernel_launches = 0;
+        info->lane_launches = 0;
+        info->lane_smem_bytes = low.lane_ok ? (uint32_t)tb_lanes_smem_bytes((uint32_t)low.lane_code.size(), low.lane_w_words,
+                                                                          low.lane_q_units, low.lane_slots)
+                                            : 0u;
+        info->lane_min_voices = 0;
     }
     return TB_OK;
 }
@@ -308,6 +429,9 @@ int tb_program_get_info(const tb_program* p, tb_program_info* info) {
     info->smem_bytes = (uint32_t)p->smem;
     info->n_params = p->low.n_params;
     info->kernel_launches = p->launches;
+    info->lane_launches = p->lane_launches;
+    info->lane_smem_bytes = (uint32_t)p->lane_smem;
+    info->lane_min_voices = p->lane_min_voices;
     return TB_OK;
 }
 
@@ -395,7 +519,7 @@ int render_impl(tb_program* p, const float* params, uint32_t n_params, uint32_t 
         L.out = out;
         L.out_stride = out_stride;
         L.out_len = p->d_len;
-        if ((rc = launch(p, L))) return rc;
+        if ((rc = launch_generate(p, L))) return rc;
         if (want_mix) {
             cudaError_t e = tb_mix_launch(out, out_stride, p->d_len, n_voices, n_samples, 0, d_mix, 0, p->stream);
             if (e != cudaSuccess) return cuda_fail(e, "tb_mix_kernel launch");
@@ -439,7 +563,7 @@ int render_impl(tb_program* p, const float* params, uint32_t n_params, uint32_t 
                 L.n_samples = len;
                 L.out = p->d_stage[b];
                 L.out_stride = len;
-                if ((rc = launch(p, L))) return rc;
+                if ((rc = launch_generate(p, L))) return rc;
                 if (want_mix) {
                     cudaError_t e = tb_mix_launch(p->d_stage[b], len, p->d_len + v0, g, len, t0, d_mix + t0,
                                                   v0 > 0 ? 1 : 0, p->stream);
@@ -470,8 +594,10 @@ int render_impl(tb_program* p, const float* params, uint32_t n_params, uint32_t 
     if (out_len) {
         CU(cudaMemcpyAsync(out_len, p->d_len, (size_t)n_voices * 8, cudaMemcpyDeviceToHost, p->stream));
         CU(cudaStreamSynchronize(p->stream));
+        return check_fault(p);
     } else if (!dev_out) {
         CU(cudaStreamSynchronize(p->stream));
+        return check_fault(p);
     }
     return TB_OK;
 }
@@ -489,6 +615,23 @@ int tb_render(tb_program* p, const float* params, uint32_t n_params, uint32_t n_
 int tb_render_mix(tb_program* p, const float* params, uint32_t n_params, uint32_t n_voices, uint64_t n_samples,
                   float* out, uint64_t out_stride, uint64_t* out_len, float* mix, uint32_t flags) {
     return render_impl(p, params, n_params, n_voices, n_samples, out, out_stride, out_len, mix, true, flags);
+}
+
+int tb_lane_kernel_times(tb_program* p, float* ms, uint32_t cap, uint32_t* n) {
+    if (!p || !n) return set_error(TB_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(p->device));
+    CU(cudaStreamSynchronize(p->stream));
+    const uint64_t have = std::min<uint64_t>(p->lane_launches, tb_program::kLaneEvents);
+    const uint32_t take = (uint32_t)std::min<uint64_t>(have, cap);
+    for (uint32_t i = 0; i < take; i++) {  // oldest of the last `take` first
+        const uint64_t k = p->lane_launches - take + i;
+        cudaEvent_t* ev = p->lane_ev[k % tb_program::kLaneEvents];
+        float t = 0.f;
+        CU(cudaEventElapsedTime(&t, ev[0], ev[1]));
+        if (ms) ms[i] = t;
+    }
+    *n = take;
+    return TB_OK;
 }
 
 int tb_length(tb_program* p, const float* params, uint32_t n_params, uint32_t n_voices, uint64_t max,

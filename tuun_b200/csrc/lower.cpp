@@ -12,6 +12,7 @@
 #include "lower.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 
@@ -780,6 +781,140 @@ struct Lowerer {
         }
     }
 
+
+    // ---- lane-per-voice plan (lanes.cu) -------------------------------------------------------------
+    // The ST_* stream again, with every operand rewritten for a thread that keeps its own voice in
+    // its own column of shared memory (program.h): constants at W[0, n_cval), the state block at
+    // W[n_cval, n_cval + state_words), derived constants behind it.  Slots keep their indices.
+    int lane_slots_max = 0;
+    const tb_aux* aux_at(int off) const {
+        for (const tb_aux& e : out.aux)
+            if ((int)e.off == off) return &e;
+        return nullptr;
+    }
+    int lane_new_aux(uint32_t kind, int a, uint32_t w_words, uint32_t q_units, uint32_t* q_off, int b = 0, int c = 0) {
+        for (const tb_lane_aux& e : out.lane_aux)
+            if (e.kind == kind && e.a == a && e.b == b && e.c == c) {
+                if (q_off) *q_off = e.q_off;
+                return (int)e.w_off;
+            }
+        tb_lane_aux x{kind, a, b, c, out.lane_w_words, out.lane_q_units};
+        out.lane_aux.push_back(x);
+        out.lane_w_words += w_words;
+        out.lane_q_units += q_units;
+        if (q_off) *q_off = x.q_off;
+        return (int)x.w_off;
+    }
+    bool build_lane_plan() {
+        const int n_cval = (int)out.cexpr.size();
+        const int st0 = n_cval;
+        out.lane_w_words = (uint32_t)n_cval + out.state_words;
+        out.lane_q_units = 0;
+        out.lane_code.clear();
+        out.lane_aux.clear();
+        int max_slot = -1;
+        auto slot = [&](int s) { max_slot = std::max(max_slot, s); return s; };
+        for (size_t pc = out.pc_steady; pc < out.code.size(); pc++) {
+            tb_insn in = out.code[pc];
+            const uint32_t op = in.op & 0xffu;
+            switch (op) {
+                case ST_END: case ST_CONST: case ST_ALT_CC: case ST_AFFINE: case ST_OPC: break;
+                case ST_TIME: case ST_NOISE: in.a += st0; break;
+                case ST_SAVE: case ST_BIN: slot(in.a); break;
+                case ST_SINE_CC: {
+                    const tb_aux* rot = aux_at(in.b);
+                    const tb_aux* ph = aux_at(in.c);
+                    if (!rot || !ph) return false;
+                    uint32_t q = 0;
+                    in.a += st0;
+                    in.b = lane_new_aux(LA_ROT, rot->a, 6, TB_LS / 2 + 1, &q, in.a, ph->a);
+                    in.c = 0;
+                    if (q > 0xffu) return false;
+                    in.op = (in.op & ~0xff00u) | (q << 8);
+                    break;
+                }
+                case ST_SINE_AC: {
+                    const tb_aux* ph = aux_at(in.c);
+                    if (!ph) return false;
+                    in.a += st0;
+                    in.c = lane_new_aux(LA_PHASE, ph->a, 2, 0, nullptr);
+                    break;
+                }
+                case ST_SINE_CA: {
+                    const tb_aux* inc = aux_at(in.b);
+                    if (!inc) return false;
+                    in.a += st0;
+                    in.b = lane_new_aux(LA_INC, inc->a, 2, 0, nullptr);
+                    break;
+                }
+                case ST_SINE_AA: in.a += st0; slot(in.b); break;
+                case ST_ALT:
+                    slot(in.a);
+                    if (in.b >= 0) slot(in.b);
+                    break;
+                case ST_FILT: {
+                    const tb_aux* cf = aux_at(in.b);
+                    if (!cf) return false;
+                    const uint32_t K = (in.op >> 8) & 0xfu, J = (in.op >> 12) & 0x7u;
+                    in.a += st0;
+                    in.b = lane_new_aux(LA_COEF, cf->b, K + J, 0, nullptr);
+                    in.c = 0;
+                    break;
+                }
+                default: return false;
+            }
+            out.lane_code.push_back(in);
+            if (op == ST_END) break;
+        }
+        out.lane_slots = (uint32_t)(max_slot + 1);
+        const char* fe = std::getenv("TUUN_B200_LANE_FUSE");  // diagnostics: "0" keeps the plain ST_* words
+        if (!(fe && fe[0] == '0')) fuse_lane_fm();
+        return true;
+    }
+    // Peephole over the lane program: a constant-rate sine, scaled and offset, driving the frequency of
+    // a sine with constant phase (vibrato, FM: `$(c + m * $f)`), optionally straight into a biquad
+    // (every filter of lib/v0/std.tuun), becomes one LN_FM instruction (program.h).
+    void fuse_lane_fm() {
+        std::vector<tb_insn> in = out.lane_code, res;
+        for (size_t i = 0; i < in.size();) {
+            const tb_insn& cc = in[i];
+            const bool cand = (cc.op & 0xffu) == ST_SINE_CC && (cc.op >> 16) == 1 && i + 2 < in.size() &&
+                              (in[i + 1].op & 0xffu) == ST_AFFINE && (in[i + 2].op & 0xffu) == ST_SINE_AC;
+            if (!cand) {
+                // copy the instruction with its post-op words
+                const size_t n = 1 + (((cc.op & 0xffu) == ST_END) ? 0 : (cc.op >> 16));
+                for (size_t k = 0; k < n && i + k < in.size(); k++) res.push_back(in[i + k]);
+                i += n;
+                continue;
+            }
+            const tb_insn& aff = in[i + 1];
+            const tb_insn& ac = in[i + 2];
+            uint32_t np = ac.op >> 16;
+            size_t next = i + 3;  // first post-op word of the carrier, if any
+            tb_insn w0{}, w1{};
+            w0.op = LN_FM | (cc.op & 0xff00u) | (((ac.op >> 8) & 0xffu) << 24);
+            w0.a = cc.b + 2;
+            w0.b = ac.a;
+            w0.c = ac.c;
+            w1.op = 0;
+            w1.a = aff.b;
+            w1.b = aff.c;
+            w1.c = -1;
+            if (np == 0 && next < in.size() && (in[next].op & 0xffffu) == (ST_FILT | (3u << 8) | (2u << 12))) {
+                w1.c = in[next].a;
+                w1.op = (uint32_t)in[next].b;
+                np = in[next].op >> 16;
+                next++;
+            }
+            w0.op |= np << 16;
+            res.push_back(w0);
+            res.push_back(w1);
+            for (uint32_t k = 0; k < np; k++) res.push_back(in[next + k]);
+            i = next + np;
+        }
+        out.lane_code = res;
+    }
+
     void run() {
         validate();
         const_memo.assign(n_nodes, -2);
@@ -820,6 +955,7 @@ struct Lowerer {
         if (out.cexpr.empty()) literal_cexpr(0.f);
         if (out.aux_words == 0) out.aux_words = 1;
         if (out.n_slots == 0) out.n_slots = 1;
+        out.lane_ok = (out.steady_ok && build_lane_plan()) ? 1u : 0u;
         out.n_nodes = n_nodes;
     }
 };

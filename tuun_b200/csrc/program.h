@@ -22,6 +22,10 @@
 #endif
 #define TB_CS 16                 // samples per lane per tile of the steady-state interpreter (steady.cuh)
 #define TB_TILE_S (32 * TB_CS)
+#define TB_LS 16                 // samples per lane per tile of the lane-per-voice kernel (lanes.cu)
+#ifndef TB_LANE_THREADS
+#define TB_LANE_THREADS 64       // voices per CTA of the lane-per-voice kernel
+#endif
 #define TB_MAX_K 9   // feed-forward taps supported by the device path (K-1 <= C)
 #define TB_MAX_J 4   // feedback taps supported by the scan path
 #define TB_CTL_DEPTH 96
@@ -122,6 +126,11 @@ enum tb_op : uint32_t {
                    // K in op bits 8-11, J in bits 12-14
     ST_AFFINE,     // post-op word: acc = (acc * cval[b]) + cval[c], both operations rounded
     ST_OPC,        // post-op word: acc = acc (operator a) cval[b]
+    // ---- lane program only (lanes.cu; fused by lower.cpp build_lane_plan) ----
+    LN_FM,         // ST_SINE_CC + one ST_AFFINE + ST_SINE_AC [+ ST_FILT K=3 J=2], two words:
+                   //   word 0: a = W of the carried (sin, cos), b = W of the carrier's accumulator,
+                   //           c = W of its phase offset; op bits 8-15 rotation Q units, 24-31 carrier class
+                   //   word 1: a, b = cval of the affine map; c = W of the filter state or -1, op = W of its coefficients
     OP_COUNT
 };
 
@@ -157,6 +166,26 @@ struct tb_aux {
     uint32_t kind;
     int32_t a, b;
     uint32_t off;  // offset in 64-bit words inside the per-warp aux area
+};
+
+// Lane-per-voice rendering of the steady stream (lanes.cu): one THREAD owns one voice, so each
+// thread keeps its voice's constants, state and derived constants in its own column of shared
+// memory: 32-bit word w of thread t at W[w * TB_LANE_THREADS + t], 16-byte unit q at
+// Q[q * TB_LANE_THREADS + t] (conflict free).  W = [cval | state | derived].  The lane code is the
+// ST_* stream with every operand rewritten to a W word index (lower.cpp build_lane_plan).
+enum tb_lane_aux_kind : uint32_t {
+    LA_INC = 0,    // cval[a] rad/s -> phase increment, 2 W words
+    LA_PHASE = 1,  // cval[a] rad   -> phase offset, 2 W words
+    LA_ROT = 2,    // cval[a] rad/s -> increment (2 W words), then the carried (sin, cos) of the phase at the
+                   // centre of the coming tile as two doubles (4 W words; b = W index of the node's
+                   // accumulator, c = cval of its phase offset), + the rotations (cos, sin)(2 pi k inc / 2^64),
+                   // k = 1..TB_LS/2 and k = TB_LS, as double2 in TB_LS/2 + 1 Q units
+    LA_COEF = 3    // filter table a: K feed-forward then J feedback coefficient values, K + J W words
+};
+struct tb_lane_aux {
+    uint32_t kind;
+    int32_t a, b, c;
+    uint32_t w_off, q_off;
 };
 
 // greater_or_equals_at chain (generator.rs:787-862), flattened.
@@ -203,6 +232,12 @@ struct tb_launch {
     uint32_t sample_rate;
     uint32_t n_filt;
     uint32_t steady_ok;    // the generate program may run through the steady-state interpreter
+    // lane-per-voice plan (valid when lane_ok)
+    const tb_insn* lane_code;
+    const tb_lane_aux* lane_aux;
+    uint32_t n_lane_code, n_lane_aux;
+    uint32_t lane_w_words, lane_q_units, lane_slots;
+    uint32_t* fault;       // device counter: voices the lane kernel found without complete filter history
     uint32_t fast_mode;    // FAST-class sine evaluation: 1 = f32 polynomial, 2 = MUFU
     unsigned long long noise_seed;   // tb_seed_noise
     unsigned long long voice_base;   // index of voice 0 of this launch inside the caller's batch
@@ -217,5 +252,6 @@ struct tb_launch {
     uint32_t mode;         // 0 = generate, 1 = length only
     uint32_t pure_len;     // length program contains no G_* code
     uint32_t accumulate;   // out_len[v] += (chunked host-output renders) instead of =
+    uint32_t exact_fb;     // constant-coefficient feedback by the serial recurrence instead of the scan
     uint8_t* done;         // [n_voices] or NULL: voices that already returned short in this call
 };

@@ -20,198 +20,8 @@
 
 namespace {
 
-constexpr int C = TB_C;
-constexpr int TILE = TB_TILE;
-constexpr unsigned FULL = 0xffffffffu;
-typedef unsigned long long u64;
-typedef long long i64;
+#include "common.cuh"
 
-static_assert(C == 8, "slot layout and unrolled loops assume 8 samples per lane");
-
-#define TB_TAU 6.283185307179586476925286766559
-#define UNROLL _Pragma("unroll")
-
-// ------------------------------------------------------------------------------------------
-// small helpers
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
-
-// Rust `f as usize` (saturating, NaN -> 0), used on ceil(value * sr)  (generator.rs:813).
-__device__ __forceinline__ u64 f32_as_usize(float f) {
-    if (!(f > 0.f)) return 0ull;
-    if (f >= 18446744073709551616.0f) return ~0ull;
-    return (u64)f;
-}
-
-// Shared-memory slot: float4 #q (q = 0,1) of lane l sits at float4 index q*32 + l, so the two
-// 128-bit accesses of a warp are bank-conflict free.  Only the owning lane touches its samples,
-// except the serial feedback fallback which goes through slot_index().
-__device__ __forceinline__ void slot_store(float* slots, int s, const float (&v)[C]) {
-    float4* p = reinterpret_cast<float4*>(slots + (size_t)s * TILE);
-    const int l = lane_id();
-    p[l] = make_float4(v[0], v[1], v[2], v[3]);
-    p[32 + l] = make_float4(v[4], v[5], v[6], v[7]);
-}
-__device__ __forceinline__ void slot_load(const float* slots, int s, float (&v)[C]) {
-    const float4* p = reinterpret_cast<const float4*>(slots + (size_t)s * TILE);
-    const int l = lane_id();
-    float4 a = p[l], b = p[32 + l];
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-}
-__device__ __forceinline__ int slot_index(int i) {
-    const int l = i >> 3, j = i & 7;
-    return (((j >> 2) * 32 + l) << 2) + (j & 3);
-}
-
-// Inclusive warp prefix sum of 64-bit integers (exact and associative: the phase is
-// independent of tile size and launch size).
-__device__ __forceinline__ u64 warp_incl_sum(u64 x) {
-    const int l = lane_id();
-    UNROLL for (int d = 1; d < 32; d <<= 1) {
-        u64 t = __shfl_up_sync(FULL, x, d);
-        if (l >= d) x += t;
-    }
-    return x;
-}
-
-// ------------------------------------------------------------------------------------------
-// Sine: 64-bit fixed-point phase in units of 2^-64 turns (generator.rs:206-219).
-// ------------------------------------------------------------------------------------------
-struct SineK {
-    double kscale;    // 2^44 / (TAU * sample_rate): rad/s -> 2^-44 turns per sample
-    double pscale;    // 2^44 / TAU:                 rad   -> 2^-44 turns
-    double inv_turn;  // 1 / (TAU * sample_rate)
-    float flimit;     // |f| below which the magic-number conversion is exact
-    float plimit;
-};
-
-// rint(x) for |x| < 2^51 through the 1.5*2^52 trick; result shifted to 2^-64-turn units, so whole
-// turns wrap away exactly like rem_euclid(TAU) (generator.rs:218).
-__device__ __forceinline__ u64 magic_to_fx(double scaled_plus_magic) {
-    i64 q = __double_as_longlong(scaled_plus_magic) - 0x4338000000000000LL;
-    return (u64)q << 20;
-}
-// Full-precision conversion of a turn count of any magnitude (setup time and out-of-range inputs).
-__device__ __noinline__ u64 turns_to_fx_slow(double turns) {
-    if (!(fabs(turns) < 1e300)) return 0ull;  // inf / nan: the reference's phase is NaN too
-    double fr = turns - floor(turns);         // [0,1]
-    u64 v = __double2ull_rn(fr * 9223372036854775808.0);  // 2^63
-    return v << 1;
-}
-__device__ __forceinline__ u64 freq_to_inc(float f, const SineK& k) {
-    if (fabsf(f) < k.flimit) return magic_to_fx(fma((double)f, k.kscale, 6755399441055744.0));
-    return turns_to_fx_slow((double)f * k.inv_turn);
-}
-__device__ __forceinline__ u64 phase_to_fx(float p, const SineK& k) {
-    if (fabsf(p) < k.plimit) return magic_to_fx(fma((double)p, k.pscale, 6755399441055744.0));
-    return turns_to_fx_slow((double)p * (1.0 / TB_TAU));
-}
-// Vector forms: the magic-number conversion for all C samples, then ONE warp vote decides whether
-// any input was outside its exact range (|f| >= 100*TAU*sr: never for audio) and redoes those.
-__device__ __forceinline__ void freq_to_inc_vec(u64 (&inc)[C], const float (&f)[C], const SineK& k) {
-    float big = 0.0f;
-    UNROLL for (int j = 0; j < C; j++) {
-        inc[j] = magic_to_fx(fma((double)f[j], k.kscale, 6755399441055744.0));
-        big = fmaxf(big, fabsf(f[j]));
-    }
-    if (__any_sync(FULL, !(big < k.flimit))) {
-        UNROLL for (int j = 0; j < C; j++)
-            if (!(fabsf(f[j]) < k.flimit)) inc[j] = turns_to_fx_slow((double)f[j] * k.inv_turn);
-    }
-}
-__device__ __forceinline__ void phase_to_fx_vec(u64 (&ph)[C], const float (&p)[C], const SineK& k) {
-    float big = 0.0f;
-    UNROLL for (int j = 0; j < C; j++) {
-        ph[j] = magic_to_fx(fma((double)p[j], k.pscale, 6755399441055744.0));
-        big = fmaxf(big, fabsf(p[j]));
-    }
-    if (__any_sync(FULL, !(big < k.plimit))) {
-        UNROLL for (int j = 0; j < C; j++)
-            if (!(fabsf(p[j]) < k.plimit)) ph[j] = turns_to_fx_slow((double)p[j] * (1.0 / TB_TAU));
-    }
-}
-
-// sin(2*pi * ph / 2^64).  Fold to [-1/4, 1/4] turn with integer ops (exact, branch-free), then
-// sin(pi/2 x) = x P(x^2) on x in [-1, 1]; coefficients from tools/fit_sine.py.
-__device__ __forceinline__ u64 fold_quarter(u64 ph) {
-    const u64 m = (u64)((i64)(ph ^ (ph << 1)) >> 63);  // all ones in the 2nd and 3rd quarter turn
-    return ((ph ^ m) - m) ^ (m & 0x8000000000000000ull);  // there: 2^63 - ph
-}
-// EXACT: f64, 7 coefficients, |err| < 8e-14, rounded once to f32: the same f32 as the
-// reference's `(acc + ph).sin() as f32` except where the f64 values straddle an f32 rounding
-// boundary (measured: 0.02 % of the samples, by one ulp, sign-symmetric).  The coefficients carry
-// the 2^-62 scaling of the integer phase (c_k * 2^(-62 - 124 k)), so no extra multiply is needed.
-// The fold is done on the converted double: |x| > 2^62  ->  x = copysign(2^63, x) - x (exact).
-__constant__ double c_sin_exact[7] = {0x1.921fb54442bb4p-62,  -0x1.4abbce624ad99p-187, 0x1.466bc66ed3d1cp-314,
-                                      -0x1.32d2c9b2d1df5p-442, 0x1.50770f6a5a66bp-571,  -0x1.e29b82ab98ea9p-701,
-                                      0x1.d53abdeb199c1p-831};
-__device__ __forceinline__ float sin_turns_exact(u64 ph) {
-    double x = (double)(i64)ph;  // signed turns * 2^64, in [-2^63, 2^63]
-    const int hi = __double2hiint(x);
-    const double half = __hiloint2double((hi & 0x80000000) | 0x43e00000, 0);  // copysign(2^63, x)
-    const double folded = half - x;
-    x = ((hi & 0x7fffffff) > 0x43d00000) ? folded : x;  // |x| > 2^62 (the = case folds to itself)
-    const double z = x * x;
-    double p = c_sin_exact[6];
-    p = fma(p, z, c_sin_exact[5]);
-    p = fma(p, z, c_sin_exact[4]);
-    p = fma(p, z, c_sin_exact[3]);
-    p = fma(p, z, c_sin_exact[2]);
-    p = fma(p, z, c_sin_exact[1]);
-    p = fma(p, z, c_sin_exact[0]);
-    return (float)(x * p);
-}
-// FAST: f32, 5 coefficients, |err| < 2e-7 — for sines whose output reaches only the sample
-// stream (never a frequency, phase, trigger, length or filter coefficient).  Only the top 32
-// phase bits matter here, so the fold is 32-bit.
-__device__ __forceinline__ float sin_turns_fast(u64 ph) {
-    const int h = (int)(ph >> 32);
-    const int m = (h ^ (h << 1)) >> 31;
-    const int f = ((h ^ m) - m) ^ (m & (int)0x80000000);
-    const float x = (float)f * 9.31322574615478515625e-10f;  // 2^-30
-    const float z = x * x;
-    float p = 0.00015167170204222202f;
-    p = fmaf(p, z, -0.004674143623560667f);
-    p = fmaf(p, z, 0.07968991994857788f);
-    p = fmaf(p, z, -0.6459637880325317f);
-    p = fmaf(p, z, 1.5707963705062866f);
-    return x * p;
-}
-// FAST through the special-function unit (tb_launch::fast_mode == 2): the top 32 phase bits as
-// radians in [-pi, pi), sin.approx = range-reduction multiply + MUFU.SIN, |err| <= 2^-21.4.
-__device__ __forceinline__ float sin_turns_mufu(u64 ph) {
-    return __sinf((float)(int)(ph >> 32) * 1.4629180792671596e-09f);  // 2 pi / 2^32
-}
-// `fast`: 0 = EXACT, 1 = f32 polynomial, 2 = MUFU.
-__device__ __forceinline__ float sin_turns(u64 ph, int fast) {
-    return fast == 0 ? sin_turns_exact(ph) : (fast == 1 ? sin_turns_fast(ph) : sin_turns_mufu(ph));
-}
-__device__ __forceinline__ void sin_turns_vec(float (&out)[C], const u64 (&ph)[C], int fast) {
-    if (fast == 2) { UNROLL for (int j = 0; j < C; j++) out[j] = sin_turns_mufu(ph[j]); }
-    else if (fast == 1) { UNROLL for (int j = 0; j < C; j++) out[j] = sin_turns_fast(ph[j]); }
-    else      { UNROLL for (int j = 0; j < C; j++) out[j] = sin_turns_exact(ph[j]); }
-}
-
-// ------------------------------------------------------------------------------------------
-// Noise (generator.rs:113-118): `fastrand::f32() * 2 - 1`.  fastrand 2.3.0's generator is wyrand:
-// state += C0; t = state * (state ^ C1) as u128; out = lo(t) ^ hi(t); f32 = from_bits(0x3F800000 |
-// (u32 >> 9)) - 1.  The state advances by a constant, so sample k of a stream is a pure function of
-// (seed, k): every Noise node of every voice owns the stream
-//     state_k = seed + NODE_K (node + 1) + VOICE_K voice + C0 (k + 1)
-// (the reference draws from one UNSEEDED thread-local instance: no sequence of it is reproducible,
-// so parity for Noise is pinned against the oracle's restatement of the same streams only).
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ u64 noise_stream(const tb_launch& P, uint32_t voice, int node) {
-    return P.noise_seed + 0x9e3779b97f4a7c15ull * (u64)(node + 1) + 0xd6e8feb86659fd93ull * (P.voice_base + (u64)voice);
-}
-__device__ __forceinline__ float noise_at(u64 stream, u64 k) {
-    const u64 s = stream + 0x2d358dccaa6c78a5ull * (k + 1ull);
-    const u64 m = s ^ 0x8bb84b93962eacc9ull;
-    const u64 r = (s * m) ^ __umul64hi(s, m);
-    const float f = __uint_as_float(0x3F800000u | ((uint32_t)r >> 9)) - 1.0f;
-    return __fsub_rn(__fmul_rn(f, 2.0f), 1.0f);
-}
 
 // ------------------------------------------------------------------------------------------
 // per-warp machine state
@@ -257,17 +67,6 @@ __device__ __forceinline__ void st_state64(uint32_t* st, int off, u64 v) {
             break;                                                                   \
         default: UNROLL for (int j = 0; j < C; j++) DST[j] = powf(A, B); break;      \
     }
-
-__device__ __forceinline__ float apply1(uint32_t op, float a, float b) {
-    switch (op) {
-        case TB_ADD:
-        case TB_MERGE: return __fadd_rn(a, b);
-        case TB_SUBTRACT: return __fsub_rn(a, b);
-        case TB_MULTIPLY: return __fmul_rn(a, b);
-        case TB_DIVIDE: return b == 0.0f ? 0.0f : __fdiv_rn(a, b);
-        default: return powf(a, b);
-    }
-}
 
 // greater_or_equals_at(length, 0.0, max)  (generator.rs:787-862) over the flattened chain.
 // kind: 0 = Some(len), 1 = None, 2 = Maybe.
@@ -409,6 +208,34 @@ __device__ __forceinline__ void iir_scan_const(float (&acc)[C], const float (&u)
     }
 }
 
+// The same feedback with no scan: lane after lane, each running the reference's recurrence
+// (generator.rs:500-502) over its chunk from the state the previous lane left.  32 dependent steps
+// per tile — used for the few general tiles that bracket a lane-per-voice render (tb_launch::
+// exact_fb), so that the whole call carries the reference's own f32 recurrence.
+template <int J>
+__device__ __forceinline__ void iir_serial_exact(float (&acc)[C], const float (&u)[C], const float* a,
+                                                 const float* hy, int w0, int out_len) {
+    const int l = lane_id();
+    float s[J > 0 ? J : 1];
+    UNROLL for (int jj = 0; jj < J; jj++) s[jj] = hy[J - 1 - jj];
+    UNROLL for (int j = 0; j < C; j++) acc[j] = u[j];
+    _Pragma("unroll 1") for (int L = 0; L < 32; L++) {
+        if (l == L) {
+            UNROLL for (int j = 0; j < C; j++) {
+                const int i = l * C + j;
+                if (i >= w0 && i < w0 + out_len) {
+                    float y = u[j];
+                    UNROLL for (int jj = 0; jj < J; jj++) y = __fsub_rn(y, __fmul_rn(a[jj], s[jj]));
+                    UNROLL for (int jj = J - 1; jj > 0; jj--) s[jj] = s[jj - 1];
+                    s[0] = y;
+                    acc[j] = y;
+                }
+            }
+        }
+        UNROLL for (int jj = 0; jj < J; jj++) s[jj] = __shfl_sync(FULL, s[jj], L);
+    }
+}
+
 // Full-tile fast path of the constant-coefficient filter: window = whole tile, history complete,
 // nothing finishing.  Same arithmetic as filter_run below without any per-sample window test.
 template <int J>
@@ -499,7 +326,7 @@ __device__ void filter_run(const tb_launch& P, const WarpMem& M, Ctx& cx, float 
     int n, inner_len, out_len, h;
     int w0 = cx.w0;
     if (!had_begin && S[0] != 0u && cx.w0 == 0 && cx.w1 == TILE && cx.L == TILE && (int)S[1] == K - 1 &&
-        (J == 0 || ft->fb_const)) {
+        (J == 0 || (ft->fb_const && !P.exact_fb))) {
         switch (J) {
             case 0: filter_full_tile<0>(M, ft, acc, hx, hy); break;
             case 1: filter_full_tile<1>(M, ft, acc, hx, hy); break;
@@ -581,6 +408,14 @@ __device__ void filter_run(const tb_launch& P, const WarpMem& M, Ctx& cx, float 
         float a[TB_MAX_J];
         UNROLL for (int jj = 0; jj < TB_MAX_J; jj++) a[jj] = jj < J ? M.cval[~ft->coef[K + jj]] : 0.0f;
         const double* mp = reinterpret_cast<const double*>(M.aux + ft->pow_aux);
+        if (P.exact_fb) {
+            switch (J) {
+                case 1: iir_serial_exact<1>(acc, u, a, hy, w0, out_len); break;
+                case 2: iir_serial_exact<2>(acc, u, a, hy, w0, out_len); break;
+                case 3: iir_serial_exact<3>(acc, u, a, hy, w0, out_len); break;
+                default: iir_serial_exact<4>(acc, u, a, hy, w0, out_len); break;
+            }
+        } else
         switch (J) {
             case 1: iir_scan_const<1>(acc, u, a, mp, hy, w0, out_len); break;
             case 2: iir_scan_const<2>(acc, u, a, mp, hy, w0, out_len); break;

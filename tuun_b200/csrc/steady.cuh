@@ -53,52 +53,6 @@ __device__ __forceinline__ void sslot_load(const float* slots, int s, float (&v)
     }
 }
 
-// sin(2 pi ph / 2^64) as a double, 8 coefficients (|err| < 5e-16; tools/fit_sine.py SIN_D8 with
-// the 2^-62 scaling of the integer phase folded in).
-__constant__ double c_sin_exact8[8] = {0x1.921fb54442d17p-62,  -0x1.4abbce625bd83p-187, 0x1.466bc677522bdp-314,
-                                       -0x1.32d2cce1ea145p-442, 0x1.5078327046959p-571,  -0x1.e30631bdf732dp-701,
-                                       0x1.e89f6fe44fe7bp-831,  -0x1.62903d02bb153p-961};
-__device__ __forceinline__ double sin_turns_d8(u64 ph) {
-    double x = (double)(i64)ph;
-    const int hi = __double2hiint(x);
-    const double half = __hiloint2double((hi & 0x80000000) | 0x43e00000, 0);
-    const double folded = half - x;
-    x = ((hi & 0x7fffffff) > 0x43d00000) ? folded : x;
-    const double z = x * x;
-    double p = c_sin_exact8[7];
-    UNROLL for (int k = 6; k >= 0; k--) p = fma(p, z, c_sin_exact8[k]);
-    return x * p;
-}
-
-// FAST class from the top 32 phase bits h (2^-32 turns, two's complement = [-1/2, 1/2) turn).
-//   MODE 1: the f32 polynomial of the general path (|err| < 2e-7);
-//   MODE 2: the special-function unit — radians in [-pi, pi), sin.approx = range-reduction
-//           multiply + MUFU.SIN, |err| <= 2^-21.4 (CUDA math API, __sinf on [-pi, pi]).
-template <int MODE>
-__device__ __forceinline__ float sin_hi(int h) {
-    if (MODE == 2) return __sinf((float)h * 1.4629180792671596e-09f);  // 2 pi / 2^32
-    const int m = (h ^ (h << 1)) >> 31;
-    const int f = ((h ^ m) - m) ^ (m & (int)0x80000000);
-    const float x = (float)f * 9.31322574615478515625e-10f;  // 2^-30
-    const float z = x * x;
-    float p = 0.00015167170204222202f;
-    p = fmaf(p, z, -0.004674143623560667f);
-    p = fmaf(p, z, 0.07968991994857788f);
-    p = fmaf(p, z, -0.6459637880325317f);
-    p = fmaf(p, z, 1.5707963705062866f);
-    return x * p;
-}
-
-// Bits of (f * scale + 1.5 * 2^52): the low mantissa bits hold rint(f * scale) in 2^-44 turns.
-// Shifted left by 20 they are 2^-64 turns and the exponent / magic bits fall off the top, so
-// sums of raw words can be shifted once at the end:  (sum raw) << 20 == sum (q << 20) mod 2^64.
-__device__ __forceinline__ u64 magic_raw(float f, double scale) {
-    return (u64)__double_as_longlong(fma((double)f, scale, 6755399441055744.0));
-}
-__device__ __forceinline__ int raw_hi(u64 raw) {  // top 32 bits of raw << 20
-    return (int)__funnelshift_l((uint32_t)raw, (uint32_t)(raw >> 32), 20);
-}
-
 // Constant frequency and phase: angle addition against the per-voice rotation table
 // rot[j] = (cos, sin)(2 pi j inc / 2^64), j < CS  (setup_voice, AUX_SINE_INC).
 __device__ __forceinline__ void steady_sine_cc(float (&acc)[CS], u64 inc, u64 ph0, const double2* rot,

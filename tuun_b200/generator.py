@@ -62,6 +62,13 @@ class Program:
         _abi.check(_abi.lib().tb_program_get_info(self._h, ctypes.byref(info)))
         return info
 
+    def lane_kernel_times(self, last: int = 64) -> np.ndarray:
+        """tb_lane_kernel_times: device milliseconds of the most recent lane-per-voice launches."""
+        ms = np.zeros(min(int(last), 64), dtype=np.float32)
+        n = ctypes.c_uint32(0)
+        _abi.check(_abi.lib().tb_lane_kernel_times(self._h, _np_ptr(ms), len(ms), ctypes.byref(n)))
+        return ms[:n.value]
+
     @property
     def stream(self) -> int:
         return int(_abi.lib().tb_stream(self._h) or 0)
