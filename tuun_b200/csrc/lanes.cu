@@ -534,6 +534,183 @@ __device__ void finish_lane(const tb_launch& P, const LaneMem& M) {
     }
 }
 
+
+// ---- the row store of one tile ---------------------------------------------------------------------
+// Transposed read of the accumulator tile: lane l takes chunk (l & 3) of rows (l >> 2) + 8 i, so four
+// lanes cover the 64 bytes a row receives per tile.  Both __syncwarp()s belong to the tile protocol:
+// owners have written before the first, readers have read before the owners write again.
+struct RowStore {
+    float* rowp[4];
+    bool rowok[4];
+    const float4* tsrc;
+    bool fast, vec_ok;
+};
+__device__ __forceinline__ void store_tile(RowStore& R) {
+    __syncwarp();
+    float4 v[4];
+    UNROLL for (int i = 0; i < 4; i++) v[i] = R.tsrc[8 * i];
+    __syncwarp();
+    if (R.fast) {  // all 32 rows of the warp exist and are 16-byte aligned
+        UNROLL for (int i = 0; i < 4; i++) {
+            __stcs(reinterpret_cast<float4*>(R.rowp[i]), v[i]);
+            R.rowp[i] += LS;
+        }
+    } else {
+        UNROLL for (int i = 0; i < 4; i++) {
+            if (R.rowok[i]) {
+                if (R.vec_ok) __stcs(reinterpret_cast<float4*>(R.rowp[i]), v[i]);
+                else {
+                    float* d = R.rowp[i];
+                    d[0] = v[i].x; d[1] = v[i].y; d[2] = v[i].z; d[3] = v[i].w;
+                }
+            }
+            R.rowp[i] += LS;
+        }
+    }
+}
+
+// ---- a program that is ONE fused FM voice ----------------------------------------------------------
+// When the whole lane program is a single LN_FM (program.h) with a FAST carrier — the shape of the
+// 65,536-voice FM + low-pass batch — there is nothing to dispatch: the thread keeps the voice's
+// state in registers for the whole launch (carried sin/cos pair, 32-bit carrier phase, filter
+// history and its pending products) and runs tiles in a software-pipelined loop: the carrier tile
+// of step t is computed in the same basic block as the filter recurrence over the carrier tile of
+// step t-1, so the serial y[n] chain overlaps the f64 angle additions, conversions and MUFU sines.
+template <bool TAIL>
+__device__ __forceinline__ void fm_carrier_tile(float (&car)[LS], double& S, double& Cq, const double2* rot, u64 mm,
+                                                u64 cc, uint32_t& p, double ks) {
+    float f[LS];
+    f[LS / 2] = (float)S;
+    UNROLL for (int k = 1; k < LS / 2; k++) {
+        const double2 r = rot[(size_t)(k - 1) * LT];
+        const double b = Cq * r.y;
+        f[LS / 2 + k] = (float)fma(S, r.x, b);
+        f[LS / 2 - k] = (float)fma(S, r.x, -b);
+    }
+    {
+        const double2 r = rot[(size_t)(LS / 2 - 1) * LT];
+        f[0] = (float)fma(S, r.x, -(Cq * r.y));
+    }
+    const double2 r16 = rot[(size_t)(LS / 2) * LT];
+    const double S2 = fma(S, r16.x, Cq * r16.y);
+    Cq = fma(Cq, r16.x, -(S * r16.y));
+    S = S2;
+    UNROLL for (int j = 0; j < LS; j += 2) unpk2(add2(mul2(pk2(f[j], f[j + 1]), mm), cc), f[j], f[j + 1]);
+    UNROLL for (int j = 0; j < LS; j += 2) {
+        const uint32_t t0 = p;
+        p += magic_lo(f[j], ks);
+        const uint32_t t1 = p;
+        p += magic_lo(f[j + 1], ks);
+        sin_p32x2(t0, t1, car[j], car[j + 1]);
+    }
+}
+struct BiquadRegs {
+    float b0, b1, b2, a1, a2;
+    float x1, x2;      // x[-1], x[-2]
+    float p1, p2, q2;  // a1 y[-1], a2 y[-2], a2 y[-1]
+    float y1, y2;      // y[-1], y[-2] (for the state block)
+};
+// generator.rs:496-507 for K = 3, J = 2, operation order and roundings of lane_filter<3, 2>.
+__device__ __forceinline__ void biquad_tile(float (&y)[LS], const float (&x)[LS], BiquadRegs& F) {
+    const u64 bb0 = pk2(F.b0, F.b0), bb1 = pk2(F.b1, F.b1), bb2 = pk2(F.b2, F.b2), aa = pk2(F.a1, F.a2);
+    float pr1[LS + 1], pr2[LS + 2];  // pr1[1 + i] = b1 x[i], pr2[2 + i] = b2 x[i]
+    pr1[0] = __fmul_rn(F.b1, F.x1);
+    pr2[0] = __fmul_rn(F.b2, F.x2);
+    pr2[1] = __fmul_rn(F.b2, F.x1);
+    UNROLL for (int i = 0; i < LS; i += 2) {
+        const u64 xx = pk2(x[i], x[i + 1]);
+        unpk2(mul2(xx, bb1), pr1[1 + i], pr1[2 + i]);
+        if (i + 2 < LS) unpk2(mul2(xx, bb2), pr2[2 + i], pr2[3 + i]);
+    }
+    UNROLL for (int i = 0; i < LS; i += 2) {
+        float s0, s1;
+        unpk2(mul2(pk2(x[i], x[i + 1]), bb0), s0, s1);
+        s0 = __fadd_rn(s0, pr1[i]);
+        s1 = __fadd_rn(s1, pr1[i + 1]);
+        unpk2(add2(pk2(s0, s1), pk2(pr2[i], pr2[i + 1])), s0, s1);
+        const float y0 = __fsub_rn(__fsub_rn(s0, F.p1), F.p2);
+        float n1, n2;
+        unpk2(mul2(aa, pk2(y0, y0)), n1, n2);        // a1 y0, a2 y0
+        const float y1 = __fsub_rn(__fsub_rn(s1, n1), F.q2);
+        F.p2 = n2;
+        unpk2(mul2(aa, pk2(y1, y1)), F.p1, F.q2);    // a1 y1, a2 y1
+        y[i] = y0;
+        y[i + 1] = y1;
+    }
+    F.x1 = x[LS - 1];
+    F.x2 = x[LS - 2];
+    F.y1 = y[LS - 1];
+    F.y2 = y[LS - 2];
+}
+
+template <bool TAIL>
+__device__ __forceinline__ void run_fm_voice(const tb_launch& P, const tb_insn* code, const LaneMem& M, const SineK& sk,
+                                             RowStore& R, bool active) {
+    const tb_insn w0 = code[0], w1 = code[1];
+    double S = 0.0, Cq = 1.0;
+    const double2* rot = reinterpret_cast<const double2*>(M.Q + (size_t)((w0.op >> 8) & 0xffu) * LT);
+    u64 mm = 0, cc = 0;
+    uint32_t p = 0, p_start = 0;
+    BiquadRegs F = {};
+    const double ks = sk.kscale * (1.0 / 4096.0);
+    if (active) {
+        S = ldd(M, w0.a);
+        Cq = ldd(M, w0.a + 2);
+        const float m = ldf(M, w1.a), c = ldf(M, w1.b);
+        mm = pk2(m, m);
+        cc = pk2(c, c);
+        p_start = p = (uint32_t)((ld64(M, w0.b) + ld64(M, w0.c)) >> 32);
+        if (TAIL) {
+            const int wc = (int)w1.op, st = w1.c;
+            F.b0 = ldf(M, wc); F.b1 = ldf(M, wc + 1); F.b2 = ldf(M, wc + 2);
+            F.a1 = ldf(M, wc + 3); F.a2 = ldf(M, wc + 4);
+            F.x2 = ldf(M, st + 2); F.x1 = ldf(M, st + 3);
+            F.y2 = ldf(M, st + 4); F.y1 = ldf(M, st + 5);
+            F.p1 = __fmul_rn(F.a1, F.y1);
+            F.q2 = __fmul_rn(F.a2, F.y1);
+            F.p2 = __fmul_rn(F.a2, F.y2);
+        }
+    }
+    const u64 n_tiles = P.n_samples / (u64)LS;
+    float car[LS];
+    UNROLL for (int j = 0; j < LS; j++) car[j] = 0.0f;
+    if (!TAIL) {
+        for (u64 t = 0; t < n_tiles; t++) {
+            if (active) {
+                fm_carrier_tile<TAIL>(car, S, Cq, rot, mm, cc, p, ks);
+                lacc_store(M, car);
+            }
+            store_tile(R);
+        }
+    } else {
+        if (active) fm_carrier_tile<TAIL>(car, S, Cq, rot, mm, cc, p, ks);
+        for (u64 t = 1; t < n_tiles; t++) {
+            if (active) {
+                float y[LS], nxt[LS];
+                biquad_tile(y, car, F);                                   // tile t-1 leaves ...
+                fm_carrier_tile<TAIL>(nxt, S, Cq, rot, mm, cc, p, ks);    // ... while tile t is made
+                lacc_store(M, y);
+                UNROLL for (int j = 0; j < LS; j++) car[j] = nxt[j];
+            }
+            store_tile(R);
+        }
+        if (active) {
+            float y[LS];
+            biquad_tile(y, car, F);
+            lacc_store(M, y);
+        }
+        store_tile(R);
+    }
+    if (active) {  // registers -> state block; finish_lane advances the modulator's accumulator
+        stw(M, w0.b + 1, ldw(M, w0.b + 1) + (p - p_start));
+        if (TAIL) {
+            const int st = w1.c;
+            stf(M, st + 2, F.x2); stf(M, st + 3, F.x1);
+            stf(M, st + 4, F.y2); stf(M, st + 5, F.y1);
+        }
+    }
+}
+
 }  // namespace
 
 #ifndef TB_LANE_MIN_BLOCKS
@@ -586,50 +763,40 @@ tb_render_lanes_kernel(const tb_launch P) {
         UNROLL for (int q = 0; q < 4; q++) M.A[q * AS] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 
-    // Transposed store: lane l writes the 16 bytes of chunk (l & 3) of row (l >> 2) + 8 i, i < 4, so
-    // four lanes cover the 64 bytes a row receives per tile.
     const uint32_t v0 = blockIdx.x * LT + warp * 32;
-    float* rowp[4];
-    bool rowok[4];
+    RowStore R;
     UNROLL for (int i = 0; i < 4; i++) {
         const uint32_t r = v0 + (uint32_t)(l >> 2) + 8u * i;
-        rowok[i] = P.out != nullptr && r < P.n_voices;
-        rowp[i] = P.out + (size_t)r * P.out_stride + (size_t)(l & 3) * 4;
+        R.rowok[i] = P.out != nullptr && r < P.n_voices;
+        R.rowp[i] = P.out + (size_t)r * P.out_stride + (size_t)(l & 3) * 4;
     }
-    const float4* tsrc = atile + (l & 3) * AS + warp * 32 + (l >> 2);
-    const bool warp_live = __any_sync(FULL, active);
+    R.tsrc = atile + (l & 3) * AS + warp * 32 + (l >> 2);
     // Rows that are not 16-byte aligned (odd strides) take four scalar stores per lane instead.
-    const bool vec_ok = (reinterpret_cast<uintptr_t>(P.out) & 15) == 0 && (P.out_stride & 3) == 0;
+    R.vec_ok = (reinterpret_cast<uintptr_t>(P.out) & 15) == 0 && (P.out_stride & 3) == 0;
+    R.fast = R.vec_ok && P.out != nullptr && v0 + 32u <= P.n_voices;
+    const bool warp_live = __any_sync(FULL, active);
     const uint32_t code_s = (uint32_t)__cvta_generic_to_shared(code);
 
-    // The usual case — all 32 rows of the warp exist and are 16-byte aligned — stores without tests.
-    const bool fast_store = vec_ok && P.out != nullptr && v0 + 32u <= P.n_voices;
+    // Single fused FM voice (run_fm_voice): a FAST carrier on the special-function unit whose
+    // frequency is bounded by |m| + |c| for every voice of the warp.
+    bool fm_voice = false;
+    if (P.n_lane_code == 3 && (code[0].op & 0xffu) == LN_FM && ((code[0].op >> 16) & 0xffu) == 0 &&
+        (code[0].op >> 24) == TB_SINE_FAST && P.fast_mode == 2) {
+        bool ok = true;
+        if (active) ok = fabsf(ldf(M, code[1].a)) + fabsf(ldf(M, code[1].b)) < sk.flimit;
+        fm_voice = __all_sync(FULL, ok);
+    }
     if (warp_live) {
-        for (u64 tb = 0; tb < P.n_samples; tb += (u64)LS) {
-            if (active) {
-                if (P.fast_mode == 2) run_lane_tile<2>(P, code_s, M, voice, sk);
-                else run_lane_tile<1>(P, code_s, M, voice, sk);
-            }
-            __syncwarp();
-            float4 v[4];
-            UNROLL for (int i = 0; i < 4; i++) v[i] = tsrc[8 * i];
-            __syncwarp();
-            if (fast_store) {
-                UNROLL for (int i = 0; i < 4; i++) {
-                    __stcs(reinterpret_cast<float4*>(rowp[i]), v[i]);
-                    rowp[i] += LS;
+        if (fm_voice) {
+            if (code[1].c >= 0) run_fm_voice<true>(P, code, M, sk, R, active);
+            else run_fm_voice<false>(P, code, M, sk, R, active);
+        } else {
+            for (u64 tb = 0; tb < P.n_samples; tb += (u64)LS) {
+                if (active) {
+                    if (P.fast_mode == 2) run_lane_tile<2>(P, code_s, M, voice, sk);
+                    else run_lane_tile<1>(P, code_s, M, voice, sk);
                 }
-            } else {
-                UNROLL for (int i = 0; i < 4; i++) {
-                    if (rowok[i]) {
-                        if (vec_ok) __stcs(reinterpret_cast<float4*>(rowp[i]), v[i]);
-                        else {
-                            float* d = rowp[i];
-                            d[0] = v[i].x; d[1] = v[i].y; d[2] = v[i].z; d[3] = v[i].w;
-                        }
-                    }
-                    rowp[i] += LS;
-                }
+                store_tile(R);
             }
         }
     }
