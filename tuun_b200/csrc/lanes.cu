@@ -33,11 +33,12 @@ constexpr int LT = TB_LANE_THREADS;
 static_assert(LS == 16, "the symmetric rotation table and the row transpose assume 16 samples per tile");
 
 // ---- the thread's column of shared memory ----------------------------------------------------------
-constexpr int AS = LT + 2;  // chunk stride of the accumulator tile, in 16-byte units (see lacc_store)
+constexpr int AS = LT + 1;  // chunk stride of the accumulator tiles, in 16-byte units (see lacc_store)
 struct LaneMem {
     uint32_t* W;   // word w of this thread at W[w * LT]
     float4* Q;     // unit q of this thread at Q[q * LT]; slots follow the derived constants
-    float4* A;     // the accumulator tile: chunk c (samples 4c .. 4c+3) of this thread at A[c * AS]
+    float4* A;     // the accumulator tile of the current step: chunk c (samples 4c .. 4c+3) of this thread at
+                   // A[c * AS].  Two tiles alternate (chunks 0-3 and 4-7 of an 8-chunk buffer).
     uint32_t slot0;
 };
 __device__ __forceinline__ uint32_t ldw(const LaneMem& M, int w) { return M.W[w * LT]; }
@@ -66,9 +67,11 @@ __device__ __forceinline__ void lslot_load(const LaneMem& M, int s, float (&v)[L
 }
 // The running result of the program lives in shared memory between instructions (registers carry
 // it only inside one instruction: a 16-register value live across the dispatch costs a register
-// move per value and dispatch).  Its layout doubles as the staging of the row transpose: with a
-// chunk stride of LT + 2 units the owner's stores (8 consecutive threads, one chunk) and the
-// transposed loads (2 rows x 4 chunks) of a quarter warp both touch 8 distinct bank groups.
+// move per value and dispatch).  The buffer doubles as the staging of the row transpose: two
+// consecutive tiles sit side by side as chunks 0-3 and 4-7, and every second step a row leaves as
+// one whole 128-byte piece (eight lanes x 16 bytes).  With a chunk stride of LT + 1 units the
+// owner's stores (8 consecutive threads, one chunk) and the transposed loads (one row x 8 chunks)
+// of a quarter warp both touch 8 distinct bank groups.
 __device__ __forceinline__ void lacc_store(const LaneMem& M, const float (&v)[LS]) {
     UNROLL for (int q = 0; q < 4; q++) M.A[q * AS] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
 }
@@ -128,9 +131,19 @@ __device__ __forceinline__ void sin_p32x2(uint32_t p0, uint32_t p1, float& s0, f
     s0 = __sinf(x0);
     s1 = __sinf(x1);
 }
+// f as a double, by integer instructions: sign | (exponent + 896) << 20 | mantissa >> 3, mantissa << 29.
+// F2F.F64.F32 runs on the 16-lane conversion unit that also serves MUFU.SIN and the f64 -> f32
+// conversions of the exact sines — the busiest pipe of an FM voice; five ALU instructions are cheaper.
+// Zero and subnormal inputs come out as ~2^-127 (their increments still round to zero); infinities
+// and NaNs are excluded by the range test that guards the magic-number conversion.
+__device__ __forceinline__ double f32_to_f64_alu(float f) {
+    const uint32_t b = __float_as_uint(f);
+    const uint32_t hi = (((b >> 3) & 0x0fffffffu) + 0x38000000u) | (b & 0x80000000u);
+    return __hiloint2double((int)hi, (int)(b << 29));
+}
 // The low word of (f * scale + 1.5 * 2^52): rint(f * scale) mod 2^32.
 __device__ __forceinline__ uint32_t magic_lo(float f, double scale) {
-    return (uint32_t)__double2loint(fma((double)f, scale, 6755399441055744.0));
+    return (uint32_t)__double2loint(fma(f32_to_f64_alu(f), scale, 6755399441055744.0));
 }
 
 // ---- Sine, constant frequency and phase (generator.rs:206-219) -------------------------------------
@@ -535,38 +548,58 @@ __device__ void finish_lane(const tb_launch& P, const LaneMem& M) {
 }
 
 
-// ---- the row store of one tile ---------------------------------------------------------------------
-// Transposed read of the accumulator tile: lane l takes chunk (l & 3) of rows (l >> 2) + 8 i, so four
-// lanes cover the 64 bytes a row receives per tile.  Both __syncwarp()s belong to the tile protocol:
-// owners have written before the first, readers have read before the owners write again.
+// ---- the row stores --------------------------------------------------------------------------------
+// After every second tile the 32 samples x 32 voices of the warp leave: lane l takes chunk (l & 7) of
+// rows (l >> 3) + 4 i, i < 8, so eight lanes write the 128 contiguous bytes a row has gathered
+// (half the requests and address translations per byte of a store per tile: 65,536 rows are open
+// at once).  Both __syncwarp()s belong to the protocol: owners have written before the first,
+// readers have read before the owners write again.  An odd last tile leaves as 64 bytes per row.
 struct RowStore {
-    float* rowp[4];
-    bool rowok[4];
-    const float4* tsrc;
+    float* out;            // first sample of this launch, row 0
+    size_t stride;         // floats between rows
+    const float4* tbase;   // the warp's first row in the accumulator buffer
+    uint32_t v0, n_voices; // first voice of the warp
+    size_t off;            // samples already stored
     bool fast, vec_ok;
 };
-__device__ __forceinline__ void store_tile(RowStore& R) {
+__device__ __forceinline__ void put4(float* d, const float4& v, bool vec_ok) {
+    if (vec_ok) __stcs(reinterpret_cast<float4*>(d), v);
+    else { d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w; }
+}
+__device__ __forceinline__ void store_pair(RowStore& R, int l) {
+    __syncwarp();
+    float4 v[8];
+    const float4* src = R.tbase + (l & 7) * AS + (l >> 3);
+    UNROLL for (int i = 0; i < 8; i++) v[i] = src[4 * i];
+    __syncwarp();
+    float* d = R.out + (size_t)(R.v0 + (l >> 3)) * R.stride + R.off + (size_t)(l & 7) * 4;
+    const size_t step = 4 * R.stride;
+    if (R.fast) {  // all 32 rows of the warp exist and are 16-byte aligned
+        UNROLL for (int i = 0; i < 8; i++) __stcs(reinterpret_cast<float4*>(d + i * step), v[i]);
+    } else if (R.out) {
+        UNROLL for (int i = 0; i < 8; i++)
+            if (R.v0 + (uint32_t)(l >> 3) + 4u * i < R.n_voices) put4(d + i * step, v[i], R.vec_ok);
+    }
+    R.off += 2 * LS;
+}
+__device__ __forceinline__ void store_single(RowStore& R, int l, int half) {
     __syncwarp();
     float4 v[4];
-    UNROLL for (int i = 0; i < 4; i++) v[i] = R.tsrc[8 * i];
+    const float4* src = R.tbase + (4 * half + (l & 3)) * AS + (l >> 2);
+    UNROLL for (int i = 0; i < 4; i++) v[i] = src[8 * i];
     __syncwarp();
-    if (R.fast) {  // all 32 rows of the warp exist and are 16-byte aligned
-        UNROLL for (int i = 0; i < 4; i++) {
-            __stcs(reinterpret_cast<float4*>(R.rowp[i]), v[i]);
-            R.rowp[i] += LS;
-        }
-    } else {
-        UNROLL for (int i = 0; i < 4; i++) {
-            if (R.rowok[i]) {
-                if (R.vec_ok) __stcs(reinterpret_cast<float4*>(R.rowp[i]), v[i]);
-                else {
-                    float* d = R.rowp[i];
-                    d[0] = v[i].x; d[1] = v[i].y; d[2] = v[i].z; d[3] = v[i].w;
-                }
-            }
-            R.rowp[i] += LS;
-        }
+    float* d = R.out + (size_t)(R.v0 + (l >> 2)) * R.stride + R.off + (size_t)(l & 3) * 4;
+    const size_t step = 8 * R.stride;
+    if (R.out) {
+        UNROLL for (int i = 0; i < 4; i++)
+            if (R.v0 + (uint32_t)(l >> 2) + 8u * i < R.n_voices) put4(d + i * step, v[i], R.vec_ok);
     }
+    R.off += LS;
+}
+// Tile number t (from 0) of the launch has just been written to its half of the buffer.
+__device__ __forceinline__ void tile_done(RowStore& R, int l, u64 t, u64 n_tiles) {
+    if (t & 1) store_pair(R, l);
+    else if (t + 1 == n_tiles) store_single(R, l, 0);
 }
 
 // ---- a program that is ONE fused FM voice ----------------------------------------------------------
@@ -576,21 +609,33 @@ __device__ __forceinline__ void store_tile(RowStore& R) {
 // history and its pending products) and runs tiles in a software-pipelined loop: the carrier tile
 // of step t is computed in the same basic block as the filter recurrence over the carrier tile of
 // step t-1, so the serial y[n] chain overlaps the f64 angle additions, conversions and MUFU sines.
+#ifndef TB_ABL
+#define TB_ABL 0
+#endif
+#if TB_ABL == 3
+#define TB_D2F(x) __int_as_float(__double2hiint(x))
+#else
+#define TB_D2F(x) ((float)(x))
+#endif
 template <bool TAIL>
 __device__ __forceinline__ void fm_carrier_tile(float (&car)[LS], double& S, double& Cq, const double2* rot, u64 mm,
                                                 u64 cc, uint32_t& p, double ks) {
     float f[LS];
-    f[LS / 2] = (float)S;
+#if TB_ABL == 4
+    UNROLL for (int j = 0; j < LS; j++) f[j] = TB_D2F(S) + j;
+#else
+    f[LS / 2] = TB_D2F(S);
     UNROLL for (int k = 1; k < LS / 2; k++) {
         const double2 r = rot[(size_t)(k - 1) * LT];
         const double b = Cq * r.y;
-        f[LS / 2 + k] = (float)fma(S, r.x, b);
-        f[LS / 2 - k] = (float)fma(S, r.x, -b);
+        f[LS / 2 + k] = TB_D2F(fma(S, r.x, b));
+        f[LS / 2 - k] = TB_D2F(fma(S, r.x, -b));
     }
     {
         const double2 r = rot[(size_t)(LS / 2 - 1) * LT];
-        f[0] = (float)fma(S, r.x, -(Cq * r.y));
+        f[0] = TB_D2F(fma(S, r.x, -(Cq * r.y)));
     }
+#endif
     const double2 r16 = rot[(size_t)(LS / 2) * LT];
     const double S2 = fma(S, r16.x, Cq * r16.y);
     Cq = fma(Cq, r16.x, -(S * r16.y));
@@ -601,7 +646,11 @@ __device__ __forceinline__ void fm_carrier_tile(float (&car)[LS], double& S, dou
         p += magic_lo(f[j], ks);
         const uint32_t t1 = p;
         p += magic_lo(f[j + 1], ks);
+#if TB_ABL == 2
+        car[j] = __uint_as_float(mant23(t0)); car[j + 1] = __uint_as_float(mant23(t1));
+#else
         sin_p32x2(t0, t1, car[j], car[j + 1]);
+#endif
     }
 }
 struct BiquadRegs {
@@ -644,8 +693,9 @@ __device__ __forceinline__ void biquad_tile(float (&y)[LS], const float (&x)[LS]
 }
 
 template <bool TAIL>
-__device__ __forceinline__ void run_fm_voice(const tb_launch& P, const tb_insn* code, const LaneMem& M, const SineK& sk,
-                                             RowStore& R, bool active) {
+__device__ __forceinline__ void run_fm_voice(const tb_launch& P, const tb_insn* code, LaneMem& M, const SineK& sk,
+                                             RowStore& R, bool active, int l) {
+    float4* const abase = M.A;
     const tb_insn w0 = code[0], w1 = code[1];
     double S = 0.0, Cq = 1.0;
     const double2* rot = reinterpret_cast<const double2*>(M.Q + (size_t)((w0.op >> 8) & 0xffu) * LT);
@@ -678,28 +728,38 @@ __device__ __forceinline__ void run_fm_voice(const tb_launch& P, const tb_insn* 
         for (u64 t = 0; t < n_tiles; t++) {
             if (active) {
                 fm_carrier_tile<TAIL>(car, S, Cq, rot, mm, cc, p, ks);
+                M.A = abase + (t & 1) * 4 * AS;
                 lacc_store(M, car);
             }
-            store_tile(R);
+            tile_done(R, l, t, n_tiles);
         }
     } else {
         if (active) fm_carrier_tile<TAIL>(car, S, Cq, rot, mm, cc, p, ks);
         for (u64 t = 1; t < n_tiles; t++) {
             if (active) {
                 float y[LS], nxt[LS];
+#if TB_ABL == 1
+                UNROLL for (int j = 0; j < LS; j++) y[j] = car[j];
+#else
                 biquad_tile(y, car, F);                                   // tile t-1 leaves ...
+#endif
                 fm_carrier_tile<TAIL>(nxt, S, Cq, rot, mm, cc, p, ks);    // ... while tile t is made
+                M.A = abase + ((t - 1) & 1) * 4 * AS;
                 lacc_store(M, y);
                 UNROLL for (int j = 0; j < LS; j++) car[j] = nxt[j];
             }
-            store_tile(R);
+#if TB_ABL != 5
+            tile_done(R, l, t - 1, n_tiles);
+#endif
         }
         if (active) {
             float y[LS];
             biquad_tile(y, car, F);
+            M.A = abase + ((n_tiles - 1) & 1) * 4 * AS;
             lacc_store(M, y);
         }
-        store_tile(R);
+        tile_done(R, l, n_tiles - 1, n_tiles);
+        M.A = abase;
     }
     if (active) {  // registers -> state block; finish_lane advances the modulator's accumulator
         stw(M, w0.b + 1, ldw(M, w0.b + 1) + (p - p_start));
@@ -731,7 +791,7 @@ tb_render_lanes_kernel(const tb_launch P) {
     M.slot0 = P.lane_q_units;
     float4* atile = reinterpret_cast<float4*>(base + q_bytes);
     M.A = atile + t;
-    M.W = reinterpret_cast<uint32_t*>(base + q_bytes + (size_t)4 * AS * 16) + t;
+    M.W = reinterpret_cast<uint32_t*>(base + q_bytes + (size_t)8 * AS * 16) + t;
     __syncthreads();
 
     const uint32_t voice = blockIdx.x * LT + t;
@@ -760,17 +820,17 @@ tb_render_lanes_kernel(const tb_launch P) {
         }
     }
     if (!active) {
-        UNROLL for (int q = 0; q < 4; q++) M.A[q * AS] = make_float4(0.f, 0.f, 0.f, 0.f);
+        UNROLL for (int q = 0; q < 8; q++) M.A[q * AS] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 
     const uint32_t v0 = blockIdx.x * LT + warp * 32;
     RowStore R;
-    UNROLL for (int i = 0; i < 4; i++) {
-        const uint32_t r = v0 + (uint32_t)(l >> 2) + 8u * i;
-        R.rowok[i] = P.out != nullptr && r < P.n_voices;
-        R.rowp[i] = P.out + (size_t)r * P.out_stride + (size_t)(l & 3) * 4;
-    }
-    R.tsrc = atile + (l & 3) * AS + warp * 32 + (l >> 2);
+    R.out = P.out;
+    R.stride = P.out_stride;
+    R.tbase = atile + warp * 32;
+    R.v0 = v0;
+    R.n_voices = P.n_voices;
+    R.off = 0;
     // Rows that are not 16-byte aligned (odd strides) take four scalar stores per lane instead.
     R.vec_ok = (reinterpret_cast<uintptr_t>(P.out) & 15) == 0 && (P.out_stride & 3) == 0;
     R.fast = R.vec_ok && P.out != nullptr && v0 + 32u <= P.n_voices;
@@ -788,16 +848,20 @@ tb_render_lanes_kernel(const tb_launch P) {
     }
     if (warp_live) {
         if (fm_voice) {
-            if (code[1].c >= 0) run_fm_voice<true>(P, code, M, sk, R, active);
-            else run_fm_voice<false>(P, code, M, sk, R, active);
+            if (code[1].c >= 0) run_fm_voice<true>(P, code, M, sk, R, active, l);
+            else run_fm_voice<false>(P, code, M, sk, R, active, l);
         } else {
-            for (u64 tb = 0; tb < P.n_samples; tb += (u64)LS) {
+            const u64 n_tiles = P.n_samples / (u64)LS;
+            float4* const abase = M.A;
+            for (u64 t = 0; t < n_tiles; t++) {
                 if (active) {
+                    M.A = abase + (t & 1) * 4 * AS;
                     if (P.fast_mode == 2) run_lane_tile<2>(P, code_s, M, voice, sk);
                     else run_lane_tile<1>(P, code_s, M, voice, sk);
                 }
-                store_tile(R);
+                tile_done(R, l, t, n_tiles);
             }
+            M.A = abase;
         }
     }
     if (active) {
@@ -809,7 +873,7 @@ tb_render_lanes_kernel(const tb_launch P) {
 
 extern "C" size_t tb_lanes_smem_bytes(uint32_t n_lane_code, uint32_t w_words, uint32_t q_units, uint32_t slots) {
     return (size_t)n_lane_code * sizeof(tb_insn) + (size_t)(q_units + 4 * slots) * LT * 16 +
-           (size_t)4 * AS * 16 + (((size_t)w_words * LT * 4 + 15) & ~(size_t)15);
+           (size_t)8 * AS * 16 + (((size_t)w_words * LT * 4 + 15) & ~(size_t)15);
 }
 
 extern "C" cudaError_t tb_lanes_launch(const tb_launch* P, size_t smem, cudaStream_t stream) {
