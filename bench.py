@@ -273,8 +273,8 @@ def main():
                 "share_of_step": dominant_share,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                 "avg_launch_ms": avg_launch_s * 1e3,
-                "note": "instruction-issue bound, not HBM bound: see profiles/README.md (issue-active %, "
-                        "thread-instructions per voice-sample)"}
+                "note": "bound by instruction issue and the 16-lane conversion/special-function unit, not by HBM: "
+                        "see profiles/README.md (thread-instructions per voice-sample, pipe utilisation)"}
 
     # end to end through the C ABI with HOST buffers: H2D of the parameter table, D2H of every row.
     # All local voices are rendered; the pinned host window (e2e_group rows) is reused group after

@@ -132,18 +132,28 @@ __device__ __forceinline__ void sin_p32x2(uint32_t p0, uint32_t p1, float& s0, f
     s1 = __sinf(x1);
 }
 // f as a double, by integer instructions: sign | (exponent + 896) << 20 | mantissa >> 3, mantissa << 29.
-// F2F.F64.F32 runs on the 16-lane conversion unit that also serves MUFU.SIN and the f64 -> f32
-// conversions of the exact sines — the busiest pipe of an FM voice; five ALU instructions are cheaper.
-// Zero and subnormal inputs come out as ~2^-127 (their increments still round to zero); infinities
-// and NaNs are excluded by the range test that guards the magic-number conversion.
+// An alternative to F2F.F64.F32, which runs on the 16-lane conversion unit that also serves MUFU.SIN
+// and the f64 -> f32 conversions of the exact sines (tools/ubench/xu.cu: 14-16 results/clk/SM each).
+// Measured on the FM voice loop: 5 ALU instructions cost more issue slots than the conversion costs
+// unit time (32.3 ms against 31.1 ms per launch), so TB_F2F_ALU stays 0; kept for programs whose
+// conversion unit is the busier side.  Zero and subnormal inputs come out as ~2^-127 (their
+// increments still round to zero); infinities and NaNs are excluded by the range test that guards
+// the magic-number conversion.
 __device__ __forceinline__ double f32_to_f64_alu(float f) {
     const uint32_t b = __float_as_uint(f);
     const uint32_t hi = (((b >> 3) & 0x0fffffffu) + 0x38000000u) | (b & 0x80000000u);
     return __hiloint2double((int)hi, (int)(b << 29));
 }
 // The low word of (f * scale + 1.5 * 2^52): rint(f * scale) mod 2^32.
+#ifndef TB_F2F_ALU
+#define TB_F2F_ALU 0
+#endif
 __device__ __forceinline__ uint32_t magic_lo(float f, double scale) {
+#if TB_F2F_ALU
     return (uint32_t)__double2loint(fma(f32_to_f64_alu(f), scale, 6755399441055744.0));
+#else
+    return (uint32_t)__double2loint(fma((double)f, scale, 6755399441055744.0));
+#endif
 }
 
 // ---- Sine, constant frequency and phase (generator.rs:206-219) -------------------------------------
