@@ -195,7 +195,7 @@ def test_default_threshold_keeps_small_batches_on_the_warp_kernel(monkeypatch):
     monkeypatch.delenv("TUUN_B200_LANE_MIN_VOICES", raising=False)
     w, params = cfg5(64)
     p = Program(w, SR)
-    assert p.info.lane_smem_bytes > 0 and p.info.lane_min_voices >= 148 * 64
+    assert p.info.lane_smem_bytes > 0 and p.info.lane_min_voices >= 148 * 64  # one 64-voice CTA per SM
     out = np.zeros((64, 2000), dtype=np.float32)
     p.render(out, params=params)
     assert p.info.lane_launches == 0

@@ -237,7 +237,11 @@ int launch_generate(tb_program* p, const tb_launch& L) {
         G.exact_fb = 1;
         return launch(p, G);
     }
-    const uint64_t head = TB_TILE;
+    // The samples that do not fill a lane tile go in front when that keeps the rows of the lane launch
+    // 16-byte aligned (one general launch instead of two), else behind.
+    uint64_t head = TB_TILE;
+    const uint64_t rem = (L.n_samples - head) % TB_LS;
+    if ((rem & 3) == 0) head += rem;
     const uint64_t bulk = (L.n_samples - head) / TB_LS * TB_LS;
     const uint64_t tail = L.n_samples - head - bulk;
     tb_launch H = L;
@@ -373,11 +377,12 @@ int tb_program_create(const tb_node* nodes, uint32_t n_nodes, const int32_t* lis
                     p->d_fault = nullptr;
             }
             p->lane_smem = ls;
-            // Default threshold: a third of the voices the device holds in one wave of this kernel
-            // (below that the warp-per-voice kernel, which fills the device with far fewer voices, wins).
+            // Default threshold: a little over one CTA per SM.  Measured on config 5: the lane kernel takes
+            // the same time for 9,472 and 18,944 voices (one warp per scheduler, latency bound: 3.7e11 and
+            // 7.4e11 voice-samples/s) against 4.0e11 for the warp-per-voice kernel at any batch size.
             const char* mv = std::getenv("TUUN_B200_LANE_MIN_VOICES");
             p->lane_min_voices = mv ? (uint32_t)std::strtoul(mv, nullptr, 10)
-                                    : (uint32_t)std::max(1, bps * n_sm * TB_LANE_THREADS / 3);
+                                    : (uint32_t)std::max(1, n_sm * TB_LANE_THREADS * 9 / 8);
         } else {
             cudaGetLastError();
         }

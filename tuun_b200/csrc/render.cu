@@ -1252,6 +1252,7 @@ __device__ void setup_voice(const tb_launch& P, const WarpMem& M, const float* p
         if (a.kind == AUX_SINE_INC) {
             if (l == 0) M.aux[a.off] = turns_to_fx_slow((double)M.cval[a.a] / (TB_TAU * (double)P.sample_rate));
         } else if (a.kind == AUX_SINE_ROT) {  // steady stream: increment + the 16 rotations (cos, sin)(j * inc)
+            if (P.n_samples < (u64)TB_TILE_S) continue;  // no steady tile in this launch
             const u64 inc = turns_to_fx_slow((double)M.cval[a.a] / (TB_TAU * (double)P.sample_rate));
             if (l == 0) M.aux[a.off] = inc;
             if (l < TB_CS) {
@@ -1267,6 +1268,8 @@ __device__ void setup_voice(const tb_launch& P, const WarpMem& M, const float* p
             const tb_filter_tab* ft = &P.filt[a.b];
             float* cf = reinterpret_cast<float*>(M.aux + a.off);
             for (uint32_t e = l; e < ft->K + ft->J; e += 32) cf[e] = M.cval[~ft->coef[e]];
+        } else if (P.exact_fb) {  // AUX_FILT_POW is for the scans only
+            continue;
         } else if (l == 0) {  // AUX_FILT_POW: A^(8*2^k), k = 0..5, A the companion matrix of the feedback taps
             const tb_filter_tab* ft = &P.filt[a.b];
             const int J = ft->J, K = ft->K;
