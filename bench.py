@@ -341,7 +341,8 @@ def main():
             dist.all_reduce(mt, op=dist.ReduceOp.MAX)
         mixdown = {"value": n_total * n_samples * msteps / float(mt.item()), "unit": UNIT,
                    "ms_per_step": 1e3 * float(mt.item()) / msteps, "nccl_reduce_bytes": int(n_samples * 4) if world > 1 else 0,
-                   "mode": "tb_render_mix(TB_NO_VOICE_OUT | TB_OUT_DEVICE) per rank, then ncclReduce(sum,f32) to rank 0"}
+                   "mode": "tb_render_mix(TB_NO_VOICE_OUT | TB_OUT_DEVICE) per rank (voices summed on the chip inside the lane "
+                           "kernel, per-warp partial rows added in order), then ncclReduce(sum,f32) to rank 0"}
         del prog_m
 
     if rank == 0:

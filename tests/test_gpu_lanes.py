@@ -199,3 +199,47 @@ def test_default_threshold_keeps_small_batches_on_the_warp_kernel(monkeypatch):
     out = np.zeros((64, 2000), dtype=np.float32)
     p.render(out, params=params)
     assert p.info.lane_launches == 0
+
+
+def test_mixdown_on_chip(monkeypatch):
+    """tb_render_mix without rows on a large steady batch: the head tile is mixed in voice order, the
+    lane part is summed on the chip in blocks — 16 voices serially, two blocks per warp, warps in
+    order — and never written as rows.  Checked bit for bit against that order applied to the rows
+    the same kernels render, and against the oracle's serial mix within the per-voice tolerance."""
+    V, N = 1000, 256 + 16 * 50
+    w, params = cfg5(V)
+    rows = np.zeros((V, N), dtype=np.float32)
+    program(w, monkeypatch).render(rows, params=params)
+    p = program(w, monkeypatch)
+    mix = np.full(N, np.inf, dtype=np.float32)
+    lens = p.render_mix(mix, V, params=params)
+    assert p.info.lane_launches == 1 and (lens == N).all()
+    want = np.zeros(N, dtype=np.float32)
+    for v in range(V):
+        want[:256] += rows[v, :256]
+    padded = np.zeros((1024, N - 256), dtype=np.float32)
+    padded[:V] = rows[:, 256:]
+    for wi in range(0, 1024, 32):
+        lo = np.zeros(N - 256, dtype=np.float32)
+        hi = np.zeros(N - 256, dtype=np.float32)
+        lo += padded[wi]
+        hi += padded[wi + 16]
+        for v in range(1, 16):
+            lo += padded[wi + v]
+            hi += padded[wi + 16 + v]
+        part = lo + hi
+        if wi == 0:
+            want[256:] = part
+        else:
+            want[256:] += part
+    np.testing.assert_array_equal(mix, want)
+    # ragged length, device mix buffer, against the oracle
+    import torch
+    N2 = N + 5
+    q = program(w, monkeypatch)
+    dmix = torch.zeros(N2, dtype=torch.float32, device="cuda")
+    q.render_mix(dmix, V, params=torch.from_numpy(params).cuda())
+    torch.cuda.synchronize()
+    _, _, omix, _ = OracleProgram(w, SR).render_batch(params, V, N2, mix=True, threads=1)
+    assert np.max(np.abs(dmix.cpu().numpy() - omix)) <= TOL * V
+    assert np.max(np.abs(dmix.cpu().numpy()[:N] - mix)) <= 1e-3

@@ -276,6 +276,60 @@ int launch_generate(tb_program* p, const tb_launch& L) {
     return TB_OK;
 }
 
+// Mixdown of a large steady batch without rows (tb_render_mix, TB_NO_VOICE_OUT): the head of the call is
+// rendered by the general kernel into a small staging block and mixed in voice order; everything after
+// it is summed over the 32 voices of each warp inside the lane kernel (lanes.cu mix_tile) and the
+// per-warp partial rows are added in warp order.  No voice row of the lane part ever reaches memory.
+int render_mix_lanes(tb_program* p, const tb_launch& L, float* d_mix) {
+    uint64_t head = TB_TILE;
+    head += (L.n_samples - head) % TB_LS;
+    const uint64_t bulk = L.n_samples - head;
+    const uint64_t n_warps = (L.n_voices + 31) / 32;
+    const size_t need = std::max<size_t>((size_t)L.n_voices * head, (size_t)n_warps * bulk);
+    if (need > p->stage_cap) {
+        for (int i = 0; i < 2; i++) {
+            cudaFree(p->d_stage[i]);
+            p->d_stage[i] = nullptr;
+        }
+        p->stage_cap = 0;
+        for (int i = 0; i < 2; i++) CU(cudaMalloc(reinterpret_cast<void**>(&p->d_stage[i]), need * 4));
+        p->stage_cap = need;
+    }
+    tb_launch H = L;
+    H.out = p->d_stage[0];
+    H.out_stride = head;
+    H.n_samples = head;
+    H.exact_fb = 1;
+    int rc = launch(p, H);
+    if (rc) return rc;
+    cudaError_t e = tb_mix_launch(p->d_stage[0], head, L.out_len, L.n_voices, head, 0, d_mix, 0, p->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "tb_mix_kernel launch");
+    p->launches++;
+    tb_launch B = L;
+    B.out = nullptr;
+    B.out_stride = 0;
+    B.n_samples = bulk;
+    B.accumulate = 1;
+    B.done = nullptr;
+    B.mix_partial = p->d_stage[1];
+    B.mix_stride = bulk;
+    cudaEvent_t* ev = p->lane_ev[p->lane_launches % tb_program::kLaneEvents];
+    if (!ev[0]) {
+        CU(cudaEventCreate(&ev[0]));
+        CU(cudaEventCreate(&ev[1]));
+    }
+    CU(cudaEventRecord(ev[0], p->stream));
+    e = tb_lanes_launch(&B, p->lane_smem, p->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "tb_render_lanes_kernel launch");
+    CU(cudaEventRecord(ev[1], p->stream));
+    p->launches++;
+    p->lane_launches++;
+    e = tb_mix_launch(p->d_stage[1], bulk, nullptr, (uint32_t)n_warps, bulk, 0, d_mix + head, 0, p->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "tb_mix_kernel launch");
+    p->launches++;
+    return TB_OK;
+}
+
 int check_fault(tb_program* p) {
     if (p->h_fault && *p->h_fault != 0u) {
         *p->h_fault = 0u;
@@ -517,7 +571,13 @@ int render_impl(tb_program* p, const float* params, uint32_t n_params, uint32_t 
             d_mix = p->d_mix;
         }
     }
-    if (dev_out && !no_rows) {
+    if (no_rows && p->lane_smem != 0 && n_voices >= p->lane_min_voices && n_samples >= (uint64_t)TB_TILE + TB_LS) {
+        L.params = d_params;
+        L.n_voices = n_voices;
+        L.n_samples = n_samples;
+        L.out_len = p->d_len;
+        if ((rc = render_mix_lanes(p, L, d_mix))) return rc;
+    } else if (dev_out && !no_rows) {
         L.params = d_params;
         L.n_voices = n_voices;
         L.n_samples = n_samples;

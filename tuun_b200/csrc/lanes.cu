@@ -571,6 +571,7 @@ struct RowStore {
     uint32_t v0, n_voices; // first voice of the warp
     size_t off;            // samples already stored
     bool fast, vec_ok;
+    float* mix;            // mixdown without rows (tb_launch::mix_partial): this warp's row of partial sums
 };
 __device__ __forceinline__ void put4(float* d, const float4& v, bool vec_ok) {
     if (vec_ok) __stcs(reinterpret_cast<float4*>(d), v);
@@ -606,9 +607,27 @@ __device__ __forceinline__ void store_single(RowStore& R, int l, int half) {
     }
     R.off += LS;
 }
+// Mixdown without rows (tb_render_mix with TB_NO_VOICE_OUT): instead of leaving, the tile is summed over
+// the warp's 32 voices on the chip — lane l adds sample (l & 15) of voices 16 (l >> 4) .. +15 in voice
+// order, the two halves are added, and 64 bytes of partial sums go to the warp's row of
+// tb_launch::mix_partial.  tb_mix_kernel then adds the rows of all warps in warp order: the tracker's
+// serial `out[j] += tmp[j]` (tracker.rs:617-619) re-associated in blocks of 16 voices.
+__device__ __forceinline__ void mix_tile(RowStore& R, int l, int half) {
+    __syncwarp();
+    const int smp = l & 15;
+    const float* a = reinterpret_cast<const float*>(R.tbase + (4 * half + (smp >> 2)) * AS + 16 * (l >> 4)) + (smp & 3);
+    float s = a[0];
+    UNROLL for (int v = 1; v < 16; v++) s = __fadd_rn(s, a[4 * v]);
+    s = __fadd_rn(s, __shfl_down_sync(FULL, s, 16));
+    __syncwarp();
+    if (l < 16) R.mix[R.off + l] = s;
+    R.off += LS;
+}
 // Tile number t (from 0) of the launch has just been written to its half of the buffer.
+template <bool MIX>
 __device__ __forceinline__ void tile_done(RowStore& R, int l, u64 t, u64 n_tiles) {
-    if (t & 1) store_pair(R, l);
+    if (MIX) mix_tile(R, l, (int)(t & 1));
+    else if (t & 1) store_pair(R, l);
     else if (t + 1 == n_tiles) store_single(R, l, 0);
 }
 
@@ -702,7 +721,7 @@ __device__ __forceinline__ void biquad_tile(float (&y)[LS], const float (&x)[LS]
     F.y2 = y[LS - 2];
 }
 
-template <bool TAIL>
+template <bool TAIL, bool MIX>
 __device__ __forceinline__ void run_fm_voice(const tb_launch& P, const tb_insn* code, LaneMem& M, const SineK& sk,
                                              RowStore& R, bool active, int l) {
     float4* const abase = M.A;
@@ -741,7 +760,7 @@ __device__ __forceinline__ void run_fm_voice(const tb_launch& P, const tb_insn* 
                 M.A = abase + (t & 1) * 4 * AS;
                 lacc_store(M, car);
             }
-            tile_done(R, l, t, n_tiles);
+            tile_done<MIX>(R, l, t, n_tiles);
         }
     } else {
         if (active) fm_carrier_tile<TAIL>(car, S, Cq, rot, mm, cc, p, ks);
@@ -759,7 +778,7 @@ __device__ __forceinline__ void run_fm_voice(const tb_launch& P, const tb_insn* 
                 UNROLL for (int j = 0; j < LS; j++) car[j] = nxt[j];
             }
 #if TB_ABL != 5
-            tile_done(R, l, t - 1, n_tiles);
+            tile_done<MIX>(R, l, t - 1, n_tiles);
 #endif
         }
         if (active) {
@@ -768,7 +787,7 @@ __device__ __forceinline__ void run_fm_voice(const tb_launch& P, const tb_insn* 
             M.A = abase + ((n_tiles - 1) & 1) * 4 * AS;
             lacc_store(M, y);
         }
-        tile_done(R, l, n_tiles - 1, n_tiles);
+        tile_done<MIX>(R, l, n_tiles - 1, n_tiles);
         M.A = abase;
     }
     if (active) {  // registers -> state block; finish_lane advances the modulator's accumulator
@@ -788,8 +807,9 @@ __device__ __forceinline__ void run_fm_voice(const tb_launch& P, const tb_insn* 
 #endif
 // grid = ceil(n_voices / LT), block = LT.  P.n_samples is a multiple of TB_LS; P.out points at the
 // first sample of this launch.
-extern "C" __global__ void __launch_bounds__(TB_LANE_THREADS, TB_LANE_MIN_BLOCKS)
-tb_render_lanes_kernel(const tb_launch P) {
+namespace {
+template <bool MIX>
+__device__ __forceinline__ void lanes_body(const tb_launch& P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int t = threadIdx.x, l = t & 31, warp = t >> 5;
     tb_insn* code = reinterpret_cast<tb_insn*>(smem_raw);
@@ -844,6 +864,7 @@ tb_render_lanes_kernel(const tb_launch P) {
     // Rows that are not 16-byte aligned (odd strides) take four scalar stores per lane instead.
     R.vec_ok = (reinterpret_cast<uintptr_t>(P.out) & 15) == 0 && (P.out_stride & 3) == 0;
     R.fast = R.vec_ok && P.out != nullptr && v0 + 32u <= P.n_voices;
+    R.mix = MIX ? P.mix_partial + (size_t)(v0 >> 5) * P.mix_stride : nullptr;
     const bool warp_live = __any_sync(FULL, active);
     const uint32_t code_s = (uint32_t)__cvta_generic_to_shared(code);
 
@@ -856,10 +877,10 @@ tb_render_lanes_kernel(const tb_launch P) {
         if (active) ok = fabsf(ldf(M, code[1].a)) + fabsf(ldf(M, code[1].b)) < sk.flimit;
         fm_voice = __all_sync(FULL, ok);
     }
-    if (warp_live) {
+    if (warp_live || (MIX && v0 < P.n_voices)) {  // a warp without a live voice still owes its (zero) partial sums
         if (fm_voice) {
-            if (code[1].c >= 0) run_fm_voice<true>(P, code, M, sk, R, active, l);
-            else run_fm_voice<false>(P, code, M, sk, R, active, l);
+            if (code[1].c >= 0) run_fm_voice<true, MIX>(P, code, M, sk, R, active, l);
+            else run_fm_voice<false, MIX>(P, code, M, sk, R, active, l);
         } else {
             const u64 n_tiles = P.n_samples / (u64)LS;
             float4* const abase = M.A;
@@ -869,7 +890,7 @@ tb_render_lanes_kernel(const tb_launch P) {
                     if (P.fast_mode == 2) run_lane_tile<2>(P, code_s, M, voice, sk);
                     else run_lane_tile<1>(P, code_s, M, voice, sk);
                 }
-                tile_done(R, l, t, n_tiles);
+                tile_done<MIX>(R, l, t, n_tiles);
             }
             M.A = abase;
         }
@@ -880,6 +901,13 @@ tb_render_lanes_kernel(const tb_launch P) {
         if (P.out_len) P.out_len[voice] = (P.accumulate ? P.out_len[voice] : 0ull) + P.n_samples;
     }
 }
+}  // namespace
+
+extern "C" __global__ void __launch_bounds__(TB_LANE_THREADS, TB_LANE_MIN_BLOCKS)
+tb_render_lanes_kernel(const tb_launch P) { lanes_body<false>(P); }
+// The same program with the rows summed on the chip instead of stored (tb_launch::mix_partial).
+extern "C" __global__ void __launch_bounds__(TB_LANE_THREADS, TB_LANE_MIN_BLOCKS)
+tb_render_lanes_mix_kernel(const tb_launch P) { lanes_body<true>(P); }
 
 extern "C" size_t tb_lanes_smem_bytes(uint32_t n_lane_code, uint32_t w_words, uint32_t q_units, uint32_t slots) {
     return (size_t)n_lane_code * sizeof(tb_insn) + (size_t)(q_units + 4 * slots) * LT * 16 +
@@ -890,11 +918,14 @@ extern "C" cudaError_t tb_lanes_launch(const tb_launch* P, size_t smem, cudaStre
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(tb_render_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(tb_render_lanes_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
     const uint32_t grid = (P->n_voices + LT - 1) / LT;
-    tb_render_lanes_kernel<<<grid, LT, smem, stream>>>(*P);
+    if (P->mix_partial) tb_render_lanes_mix_kernel<<<grid, LT, smem, stream>>>(*P);
+    else tb_render_lanes_kernel<<<grid, LT, smem, stream>>>(*P);
     return cudaGetLastError();
 }
 

@@ -238,6 +238,8 @@ struct tb_launch {
     uint32_t n_lane_code, n_lane_aux;
     uint32_t lane_w_words, lane_q_units, lane_slots;
     uint32_t* fault;       // device counter: voices the lane kernel found without complete filter history
+    float* mix_partial;    // lane kernel, mixdown without rows: [ceil(n_voices / 32)][mix_stride] sums of 32 voices
+    uint64_t mix_stride;
     uint32_t fast_mode;    // FAST-class sine evaluation: 1 = f32 polynomial, 2 = MUFU
     unsigned long long noise_seed;   // tb_seed_noise
     unsigned long long voice_base;   // index of voice 0 of this launch inside the caller's batch

@@ -1466,7 +1466,8 @@ extern "C" cudaError_t tb_kernel_launch(const tb_launch* P, size_t smem, uint32_
 // ------------------------------------------------------------------------------------------
 // Mixdown: mix[i] (+)= sum over voices, in voice index order, of rows[v][i] for i < lens[v] —
 // the tracker's serial `out[filled + j] += tmp[j]` (tracker.rs:617-619).  One thread per sample,
-// rows read coalesced; `t0` is the time offset of this chunk inside the voices' streams.
+// rows read coalesced; `t0` is the time offset of this chunk inside the voices' streams.  lens == NULL:
+// every row is full (the per-warp partial sums of the lane kernel's on-chip mixdown).
 // ------------------------------------------------------------------------------------------
 extern "C" __global__ void __launch_bounds__(256)
 tb_mix_kernel(const float* __restrict__ rows, uint64_t stride, const unsigned long long* __restrict__ lens,
@@ -1486,7 +1487,7 @@ tb_mix_kernel(const float* __restrict__ rows, uint64_t stride, const unsigned lo
             float4 x[8];
             unsigned long long len[8];
             UNROLL for (int u = 0; u < 8; u++) {
-                len[u] = lens[v + u];
+                len[u] = lens ? lens[v + u] : ~0ull;
                 x[u] = __ldcs(reinterpret_cast<const float4*>(rows + (size_t)(v + u) * stride + i));
             }
             UNROLL for (int u = 0; u < 8; u++) {
@@ -1497,7 +1498,7 @@ tb_mix_kernel(const float* __restrict__ rows, uint64_t stride, const unsigned lo
             }
         }
         for (; v < n_voices; v++) {
-            const unsigned long long len = lens[v];
+            const unsigned long long len = lens ? lens[v] : ~0ull;
             const float4 x = __ldcs(reinterpret_cast<const float4*>(rows + (size_t)v * stride + i));
             if (t0 + i + 0 < len) s[0] = __fadd_rn(s[0], x.x);
             if (t0 + i + 1 < len) s[1] = __fadd_rn(s[1], x.y);
@@ -1506,7 +1507,7 @@ tb_mix_kernel(const float* __restrict__ rows, uint64_t stride, const unsigned lo
         }
     } else {
         for (uint32_t v = 0; v < n_voices; v++) {
-            const unsigned long long len = lens[v];  // total generated so far, including this chunk
+            const unsigned long long len = lens ? lens[v] : ~0ull;  // total generated so far, including this chunk
             UNROLL for (int k = 0; k < 4; k++)
                 if (i + k < n_samples && t0 + i + k < len) s[k] = __fadd_rn(s[k], rows[(size_t)v * stride + i + k]);
         }
