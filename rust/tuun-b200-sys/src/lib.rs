@@ -31,6 +31,24 @@ pub struct TbProgram {
     _private: [u8; 0],
 }
 
+/// `tb_program_info` (include/tuun_b200.h): launch geometry and launch counters of a program.
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct TbProgramInfo {
+    pub n_nodes: u32,
+    pub n_code_words: u32,
+    pub n_slots: u32,
+    pub state_words: u32,
+    pub tile: u32,
+    pub threads: u32,
+    pub smem_bytes: u32,
+    pub n_params: u32,
+    pub kernel_launches: u64,
+    pub lane_launches: u64,
+    pub lane_smem_bytes: u32,
+    pub lane_min_voices: u32,
+}
+
 pub const TB_OUT_DEVICE: u32 = 1;
 pub const TB_PARAMS_DEVICE: u32 = 2;
 pub const TB_NO_VOICE_OUT: u32 = 4;
@@ -56,6 +74,13 @@ extern "C" {
     pub fn tb_reset(p: *mut TbProgram) -> c_int;
     pub fn tb_stream(p: *mut TbProgram) -> *mut c_void;
     pub fn tb_set_stream(p: *mut TbProgram, cuda_stream: *mut c_void) -> c_int;
+    pub fn tb_seed_noise(p: *mut TbProgram, seed: u64, first_voice: u64) -> c_int;
+    pub fn tb_program_get_info(p: *const TbProgram, info: *mut TbProgramInfo) -> c_int;
+    pub fn tb_lane_kernel_times(p: *mut TbProgram, ms: *mut f32, cap: u32, n: *mut u32) -> c_int;
+    pub fn tb_lower_check(
+        nodes: *const TbNode, n_nodes: u32, lists: *const i32, n_lists: u32, fixed_len: u64,
+        info: *mut TbProgramInfo,
+    ) -> c_int;
     pub fn tb_last_error() -> *const c_char;
     pub fn tb_abi_version() -> u32;
 }
