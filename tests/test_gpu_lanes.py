@@ -243,3 +243,41 @@ def test_mixdown_on_chip(monkeypatch):
     _, _, omix, _ = OracleProgram(w, SR).render_batch(params, V, N2, mix=True, threads=1)
     assert np.max(np.abs(dmix.cpu().numpy() - omix)) <= TOL * V
     assert np.max(np.abs(dmix.cpu().numpy()[:N] - mix)) <= 1e-3
+
+
+def test_streaming_blocks_skip_the_general_head(monkeypatch):
+    """A caller that streams blocks (main.rs:42-43 uses 1024) pays the general head tile once per
+    stream: later calls go straight to the lane kernel — one launch per 1024-sample block — and the
+    stream is the one a single call renders (same tolerance as test_partition_invariance)."""
+    V, N = 160, 1024 * 5 + 777
+    w, params = cfg5(V)
+    one = np.zeros((V, N), dtype=np.float32)
+    program(w, monkeypatch).render(one, params=params)
+    p = program(w, monkeypatch)
+    parts = np.zeros((V, N), dtype=np.float32)
+    launches = []
+    for a in range(0, N, 1024):
+        b = min(N, a + 1024)
+        k0 = p.info.kernel_launches
+        blk = np.zeros((V, b - a), dtype=np.float32)
+        assert (p.render(blk, params=params) == b - a).all()
+        parts[:, a:b] = blk
+        launches.append(int(p.info.kernel_launches - k0))
+    assert launches == [2, 1, 1, 1, 1, 2]  # head + lanes; lanes only; ...; 777 = 9 general + 768 lanes
+    per_voice = np.max(np.abs(parts - one), axis=1)
+    assert per_voice.max() <= TOL and np.median(per_voice) <= 5e-6
+    ref, _, _, _ = OracleProgram(w, SR).render_batch(params, V, N)
+    assert np.max(np.abs(parts - ref)) <= TOL
+    # length() moves node positions by different amounts: the next render takes the general head again
+    p.lengths(V, 100, params=params)
+    k0 = p.info.kernel_launches
+    p.render(np.zeros((V, 1024), dtype=np.float32), params=params)
+    assert p.info.kernel_launches - k0 == 2
+    # a mixdown without rows continues a primed stream with the lane kernel alone
+    q = program(w, monkeypatch)
+    q.render_mix(np.zeros(1024, dtype=np.float32), V, params=params)
+    k0 = q.info.kernel_launches
+    mix = np.zeros(1024, dtype=np.float32)
+    q.render_mix(mix, V, params=params)
+    assert q.info.kernel_launches - k0 == 2  # lane kernel + the add of its partial rows
+    assert np.max(np.abs(mix - one[:, 1024:2048].sum(axis=0, dtype=np.float64))) <= TOL * V

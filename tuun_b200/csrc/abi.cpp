@@ -78,6 +78,8 @@ struct tb_program {
     uint32_t* d_state = nullptr;
     uint32_t n_voices = 0;
     bool fresh = true;  // no samples generated since create / tb_reset
+    uint64_t stream_pos = 0;   // samples every voice has generated since create / tb_reset
+    bool pos_known = true;     // false once tb_length has advanced the state (positions then differ per node)
     float* d_params = nullptr;
     size_t params_cap = 0;
     unsigned long long* d_len = nullptr;
@@ -226,33 +228,38 @@ int launch(tb_program* p, const tb_launch& L) {
 }
 
 // A generate launch.  Large batches of steady-state voices go through the lane-per-voice kernel
-// (lanes.cu): the first general tile of the call (filter pre-reads, generator.rs:234-252) and the
-// last < TB_LS samples stay on the warp-per-voice kernel; state blocks are shared, so the three
-// launches continue one stream.
-int launch_generate(tb_program* p, const tb_launch& L) {
+// (lanes.cu).  `pos` = samples the voices have generated before this launch: the first general tile of
+// a stream (filter pre-reads, generator.rs:234-252) stays on the warp-per-voice kernel, and so do the
+// < TB_LS samples of a call that do not fill a lane tile; a stream that is past its first tile goes
+// straight to the lane kernel (a caller streaming 1024-sample blocks pays one launch per block).
+// State blocks are shared, so all launches continue one stream.
+int launch_generate(tb_program* p, const tb_launch& L, uint64_t pos) {
     const bool big = p->lane_smem != 0 && L.n_voices >= p->lane_min_voices && L.out != nullptr;
     if (!big) return launch(p, L);
-    if (L.n_samples < (uint64_t)TB_TILE + TB_LS) {  // too short for a lane tile: same arithmetic, general tiles
+    const bool primed = p->pos_known && pos >= (uint64_t)TB_TILE;  // every filter holds its full history
+    uint64_t head = primed ? 0 : TB_TILE;
+    if (L.n_samples < head + TB_LS) {  // too short for a lane tile: same arithmetic, general tiles
         tb_launch G = L;
         G.exact_fb = 1;
         return launch(p, G);
     }
     // The samples that do not fill a lane tile go in front when that keeps the rows of the lane launch
     // 16-byte aligned (one general launch instead of two), else behind.
-    uint64_t head = TB_TILE;
     const uint64_t rem = (L.n_samples - head) % TB_LS;
     if ((rem & 3) == 0) head += rem;
     const uint64_t bulk = (L.n_samples - head) / TB_LS * TB_LS;
     const uint64_t tail = L.n_samples - head - bulk;
-    tb_launch H = L;
-    H.n_samples = head;
-    H.exact_fb = 1;  // the bracketing tiles run the reference's recurrence too (see lanes.cu)
-    int rc = launch(p, H);
-    if (rc) return rc;
+    int rc = TB_OK;
+    if (head) {
+        tb_launch H = L;
+        H.n_samples = head;
+        H.exact_fb = 1;  // the bracketing tiles run the reference's recurrence too (see lanes.cu)
+        if ((rc = launch(p, H))) return rc;
+    }
     tb_launch B = L;
     B.out = L.out + head;
     B.n_samples = bulk;
-    B.accumulate = 1;
+    B.accumulate = head ? 1 : L.accumulate;
     B.done = nullptr;  // every node of a steady program is infinite: no voice ever finishes
     cudaEvent_t* ev = p->lane_ev[p->lane_launches % tb_program::kLaneEvents];
     if (!ev[0]) {
@@ -280,8 +287,8 @@ int launch_generate(tb_program* p, const tb_launch& L) {
 // rendered by the general kernel into a small staging block and mixed in voice order; everything after
 // it is summed over the 32 voices of each warp inside the lane kernel (lanes.cu mix_tile) and the
 // per-warp partial rows are added in warp order.  No voice row of the lane part ever reaches memory.
-int render_mix_lanes(tb_program* p, const tb_launch& L, float* d_mix) {
-    uint64_t head = TB_TILE;
+int render_mix_lanes(tb_program* p, const tb_launch& L, float* d_mix, uint64_t pos) {
+    uint64_t head = (p->pos_known && pos >= (uint64_t)TB_TILE) ? 0 : TB_TILE;  // see launch_generate
     head += (L.n_samples - head) % TB_LS;
     const uint64_t bulk = L.n_samples - head;
     const uint64_t n_warps = (L.n_voices + 31) / 32;
@@ -295,21 +302,24 @@ int render_mix_lanes(tb_program* p, const tb_launch& L, float* d_mix) {
         for (int i = 0; i < 2; i++) CU(cudaMalloc(reinterpret_cast<void**>(&p->d_stage[i]), need * 4));
         p->stage_cap = need;
     }
-    tb_launch H = L;
-    H.out = p->d_stage[0];
-    H.out_stride = head;
-    H.n_samples = head;
-    H.exact_fb = 1;
-    int rc = launch(p, H);
-    if (rc) return rc;
-    cudaError_t e = tb_mix_launch(p->d_stage[0], head, L.out_len, L.n_voices, head, 0, d_mix, 0, p->stream);
-    if (e != cudaSuccess) return cuda_fail(e, "tb_mix_kernel launch");
-    p->launches++;
+    int rc = TB_OK;
+    cudaError_t e = cudaSuccess;
+    if (head) {
+        tb_launch H = L;
+        H.out = p->d_stage[0];
+        H.out_stride = head;
+        H.n_samples = head;
+        H.exact_fb = 1;
+        if ((rc = launch(p, H))) return rc;
+        e = tb_mix_launch(p->d_stage[0], head, L.out_len, L.n_voices, head, 0, d_mix, 0, p->stream);
+        if (e != cudaSuccess) return cuda_fail(e, "tb_mix_kernel launch");
+        p->launches++;
+    }
     tb_launch B = L;
     B.out = nullptr;
     B.out_stride = 0;
     B.n_samples = bulk;
-    B.accumulate = 1;
+    B.accumulate = head ? 1 : L.accumulate;
     B.done = nullptr;
     B.mix_partial = p->d_stage[1];
     B.mix_stride = bulk;
@@ -520,6 +530,8 @@ int tb_reset(tb_program* p) {
     if (p->d_state)
         CU(cudaMemsetAsync(p->d_state, 0, (size_t)p->n_voices * p->low.state_words * 4, p->stream));
     p->fresh = true;
+    p->stream_pos = 0;
+    p->pos_known = true;
     return TB_OK;
 }
 
@@ -571,12 +583,14 @@ int render_impl(tb_program* p, const float* params, uint32_t n_params, uint32_t 
             d_mix = p->d_mix;
         }
     }
-    if (no_rows && p->lane_smem != 0 && n_voices >= p->lane_min_voices && n_samples >= (uint64_t)TB_TILE + TB_LS) {
+    const bool primed = p->pos_known && p->stream_pos >= (uint64_t)TB_TILE;
+    if (no_rows && p->lane_smem != 0 && n_voices >= p->lane_min_voices &&
+        n_samples >= (primed ? 0 : (uint64_t)TB_TILE) + 2 * TB_LS) {
         L.params = d_params;
         L.n_voices = n_voices;
         L.n_samples = n_samples;
         L.out_len = p->d_len;
-        if ((rc = render_mix_lanes(p, L, d_mix))) return rc;
+        if ((rc = render_mix_lanes(p, L, d_mix, p->stream_pos))) return rc;
     } else if (dev_out && !no_rows) {
         L.params = d_params;
         L.n_voices = n_voices;
@@ -584,7 +598,7 @@ int render_impl(tb_program* p, const float* params, uint32_t n_params, uint32_t 
         L.out = out;
         L.out_stride = out_stride;
         L.out_len = p->d_len;
-        if ((rc = launch_generate(p, L))) return rc;
+        if ((rc = launch_generate(p, L, p->stream_pos))) return rc;
         if (want_mix) {
             cudaError_t e = tb_mix_launch(out, out_stride, p->d_len, n_voices, n_samples, 0, d_mix, 0, p->stream);
             if (e != cudaSuccess) return cuda_fail(e, "tb_mix_kernel launch");
@@ -628,7 +642,7 @@ int render_impl(tb_program* p, const float* params, uint32_t n_params, uint32_t 
                 L.n_samples = len;
                 L.out = p->d_stage[b];
                 L.out_stride = len;
-                if ((rc = launch_generate(p, L))) return rc;
+                if ((rc = launch_generate(p, L, p->stream_pos + t0))) return rc;
                 if (want_mix) {
                     cudaError_t e = tb_mix_launch(p->d_stage[b], len, p->d_len + v0, g, len, t0, d_mix + t0,
                                                   v0 > 0 ? 1 : 0, p->stream);
@@ -654,6 +668,7 @@ int render_impl(tb_program* p, const float* params, uint32_t n_params, uint32_t 
         }
         if (!no_rows) CU(cudaStreamSynchronize(p->copy_stream));
     }
+    p->stream_pos += n_samples;
     if (want_mix && !dev_out)
         CU(cudaMemcpyAsync(mix, d_mix, n_samples * 4, cudaMemcpyDeviceToHost, p->stream));
     if (out_len) {
@@ -717,6 +732,7 @@ int tb_length(tb_program* p, const float* params, uint32_t n_params, uint32_t n_
     L.n_samples = max;
     L.out_len = p->d_len;
     L.mode = 1;
+    p->pos_known = false;  // length() advances positions by per-node amounts (generator.rs:620-782)
     if ((rc = launch(p, L))) return rc;
     CU(cudaMemcpyAsync(len, p->d_len, (size_t)n_voices * 8, cudaMemcpyDeviceToHost, p->stream));
     CU(cudaStreamSynchronize(p->stream));
