@@ -247,7 +247,9 @@ def main():
     info = prog.info
     lane_ms = prog.lane_kernel_times(args.steps) if info.lane_launches else np.zeros(0)
     if len(lane_ms):
-        kernel = "tb_render_lanes_kernel"
+        groups = (n_local + 63) // 64
+        kernel = ("tb_render_lanes_fm_kernel" if info.lane_fm_capacity and groups <= info.lane_fm_capacity
+                  else "tb_render_lanes_queue_kernel" if groups > info.lane_capacity else "tb_render_lanes_kernel")
         lane_samples = (n_samples - 256) // 16 * 16
         alg_bytes = 4.0 * n_local * lane_samples
         avg_launch_s = float(np.mean(lane_ms)) * 1e-3

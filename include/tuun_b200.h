@@ -175,6 +175,8 @@ typedef struct tb_program_info {
     uint64_t lane_launches;   /* of those, launches of the lane-per-voice kernel (large steady batches) */
     uint32_t lane_smem_bytes; /* its dynamic shared memory per CTA; 0 when the program does not qualify */
     uint32_t lane_min_voices; /* batches of at least this many voices take it */
+    uint32_t lane_capacity;   /* 64-voice CTAs of the lane interpreter kernels the device holds at once (more: work queue) */
+    uint32_t lane_fm_capacity;/* same for the fused-FM-voice kernel; 0 when the program is not one fused FM voice */
 } tb_program_info;
 int tb_program_get_info(const tb_program* p, tb_program_info* info);
 

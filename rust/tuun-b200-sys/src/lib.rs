@@ -47,6 +47,8 @@ pub struct TbProgramInfo {
     pub lane_launches: u64,
     pub lane_smem_bytes: u32,
     pub lane_min_voices: u32,
+    pub lane_capacity: u32,
+    pub lane_fm_capacity: u32,
 }
 
 pub const TB_OUT_DEVICE: u32 = 1;

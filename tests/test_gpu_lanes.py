@@ -281,3 +281,34 @@ def test_streaming_blocks_skip_the_general_head(monkeypatch):
     q.render_mix(mix, V, params=params)
     assert q.info.kernel_launches - k0 == 2  # lane kernel + the add of its partial rows
     assert np.max(np.abs(mix - one[:, 1024:2048].sum(axis=0, dtype=np.float64))) <= TOL * V
+
+
+def test_work_queue_segments(monkeypatch):
+    """When a batch has more 64-voice groups than the device holds CTAs, the lane launch is cut into
+    time segments handed out through a work queue (forced here with TUUN_B200_LANE_QUEUE=1): same
+    stream as the plain launch (the constant-rate sines re-derive their carried sin/cos pair from the
+    exact accumulator at every segment start, hence 'within one f32 rounding' and not 'equal')."""
+    V, N = 1000, 256 + 16 * 300
+    w, params = cfg5(V)
+    monkeypatch.setenv("TUUN_B200_LANE_QUEUE", "0")
+    plain = np.zeros((V, N), dtype=np.float32)
+    program(w, monkeypatch).render(plain, params=params)
+    monkeypatch.setenv("TUUN_B200_LANE_QUEUE", "1")
+    p = program(w, monkeypatch)
+    q = np.full((V, N), np.inf, dtype=np.float32)
+    lens = p.render(q, params=params)
+    assert (lens == N).all() and p.info.lane_launches == 1
+    per_voice = np.max(np.abs(q - plain), axis=1)
+    assert per_voice.max() <= TOL and np.median(per_voice) <= 1e-6
+    ref, _, _, _ = OracleProgram(w, SR).render_batch(params, V, N)
+    assert np.max(np.abs(q - ref)) <= TOL
+    # a tree that runs through the interpreter (two more biquads behind the fused voice), and the mixdown
+    from tuun_b200.workloads import lpf
+    w3 = lpf(lpf(w, 2.0, 1600), 1.0, 3200)
+    a = np.zeros((V, N), dtype=np.float32)
+    program(w3, monkeypatch).render(a, params=params)
+    ref3, _, _, _ = OracleProgram(w3, SR).render_batch(params, V, N)
+    assert np.max(np.abs(a - ref3)) <= TOL
+    mix = np.zeros(N, dtype=np.float32)
+    program(w, monkeypatch).render_mix(mix, V, params=params)
+    assert np.max(np.abs(mix - q.sum(axis=0, dtype=np.float64))) <= 1e-3

@@ -1,0 +1,53 @@
+"""Throughput of the two kernels on several batch shapes (65,536 voices): the lane-per-voice kernel
+(interpreter and fused paths) against the warp-per-voice kernel.  usage: python tools/lane_shapes.py [seconds]"""
+import math, os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from tuun_b200.generator import Program
+from tuun_b200.waveform import Alt, Const, Filter, Noise, Sine, add, f32, mul
+from tuun_b200.workloads import fm_filter_params, fm_filter_voice, lpf
+
+SR, V = 44100, 65536
+N = int(float(sys.argv[1]) * SR) if len(sys.argv) > 1 else 2 * SR
+N -= N % 4
+TAU = f32(2 * math.pi)
+rng = np.random.default_rng(0)
+fr = (TAU * rng.uniform(50, 2000, (V, 3))).astype(np.float32)
+p5 = fm_filter_params(np.arange(V))
+fm = Sine(add(mul(Sine(Const(1.0, param=0), Const(f32(math.pi / 2))), Const(1.0, param=1)), Const(1.0, param=2)), Const(0.0))
+shapes = [
+    ("sine", Sine(Const(1.0, param=0), Const(0.0)), fr),
+    ("pm", Sine(Const(1.0, param=0), mul(Sine(Const(1.0, param=1), Const(0.0)), Const(6.0))), fr),
+    ("square|lpf", lpf(Alt(Sine(Const(1.0, param=0), Const(0.0)), Const(1.0), Const(-1.0)), 0.707, 2000), fr),
+    ("noise*0.1|lpf", lpf(mul(Noise(), Const(0.1)), 0.7, 2000), None),
+    ("fm", fm, p5),
+    ("fm|lpf (cfg5)", fm_filter_voice(), p5),
+    ("fm|lpf|lpf|lpf", lpf(lpf(fm_filter_voice(), 2.0, 1600), 1.0, 3200), p5),
+]
+out = torch.empty((V, N), dtype=torch.float32, device="cuda")
+
+
+def run(w, params, env):
+    for k in ("TUUN_B200_LANES", "TUUN_B200_LANE_FUSE"):
+        os.environ.pop(k, None)
+    os.environ.update(env)
+    p = Program(w, SR)
+    pd = None if params is None else torch.from_numpy(params).cuda()
+    ts = []
+    for i in range(4):
+        p.reset()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        p.render(out, params=pd)
+        torch.cuda.synchronize()
+        ts.append(time.perf_counter() - t0)
+    return V * N / min(ts[1:]), p.info.lane_launches > 0
+
+
+print(f"{V} voices x {N} samples; voice-samples/s")
+for name, w, params in shapes:
+    warp, _ = run(w, params, {"TUUN_B200_LANES": "0"})
+    lanes, used = run(w, params, {})
+    unf, _ = run(w, params, {"TUUN_B200_LANE_FUSE": "0"})
+    print(f"{name:16s} warp-per-voice {warp:9.3e}   lane-per-voice {lanes:9.3e} ({'lanes' if used else 'not used'})   unfused {unf:9.3e}   ratio {lanes / warp:4.2f}")

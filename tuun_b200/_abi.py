@@ -45,6 +45,8 @@ class TbProgramInfo(ctypes.Structure):
         ("lane_launches", ctypes.c_uint64),
         ("lane_smem_bytes", ctypes.c_uint32),
         ("lane_min_voices", ctypes.c_uint32),
+        ("lane_capacity", ctypes.c_uint32),
+        ("lane_fm_capacity", ctypes.c_uint32),
     ]
 
 

@@ -20,8 +20,8 @@ extern "C" size_t tb_kernel_smem_bytes(uint32_t n_code, uint32_t n_slots, uint32
                                        uint32_t warps);
 extern "C" cudaError_t tb_kernel_launch(const tb_launch* P, size_t smem, uint32_t warps, cudaStream_t stream);
 extern "C" size_t tb_lanes_smem_bytes(uint32_t n_lane_code, uint32_t w_words, uint32_t q_units, uint32_t slots);
-extern "C" cudaError_t tb_lanes_launch(const tb_launch* P, size_t smem, cudaStream_t stream);
-extern "C" cudaError_t tb_lanes_occupancy(size_t smem, int* blocks_per_sm, int* n_sm);
+extern "C" cudaError_t tb_lanes_launch(const tb_launch* P, size_t smem, int kind, cudaStream_t stream);
+extern "C" cudaError_t tb_lanes_occupancy(size_t smem, int kind, int* blocks_per_sm, int* n_sm);
 extern "C" cudaError_t tb_mix_launch(const float* rows, uint64_t stride, const unsigned long long* lens,
                                      uint32_t n_voices, uint64_t n_samples, uint64_t t0, float* mix,
                                      int accumulate, cudaStream_t stream);
@@ -70,6 +70,10 @@ struct tb_program {
     tb_lane_aux* d_lane_aux = nullptr;
     size_t lane_smem = 0;           // 0: the lane-per-voice kernel does not apply to this program
     uint32_t lane_min_voices = 0;   // batches at least this large take it
+    uint32_t lane_capacity = 0;     // CTAs of the lane interpreter kernels the device holds at once
+    uint32_t lane_fm_capacity = 0;  // same for the fused-FM-voice kernel; 0: the program is not one fused FM voice
+    uint32_t* d_lane_queue = nullptr;  // work queue of the persistent form (program.h tb_launch::lane_queue)
+    size_t lane_queue_cap = 0;
     uint32_t* h_fault = nullptr;    // mapped pinned counter written by the lane kernel
     uint32_t* d_fault = nullptr;
     uint64_t lane_launches = 0;
@@ -102,7 +106,7 @@ struct tb_program {
         cudaFree(d_code); cudaFree(d_cexpr); cudaFree(d_aux); cudaFree(d_goe); cudaFree(d_goe_steps);
         cudaFree(d_filt); cudaFree(d_fixed); cudaFree(d_pool); cudaFree(d_state); cudaFree(d_params);
         cudaFree(d_len); cudaFree(d_done); cudaFree(d_mix); cudaFree(d_stage[0]); cudaFree(d_stage[1]);
-        cudaFree(d_lane_code); cudaFree(d_lane_aux);
+        cudaFree(d_lane_code); cudaFree(d_lane_aux); cudaFree(d_lane_queue);
         if (h_fault) cudaFreeHost(h_fault);
         for (auto& e : lane_ev) {
             if (e[0]) cudaEventDestroy(e[0]);
@@ -227,6 +231,52 @@ int launch(tb_program* p, const tb_launch& L) {
     return TB_OK;
 }
 
+// One launch of the lane kernel over B.n_samples (a multiple of TB_LS).  When the batch has more
+// 64-voice groups than the device holds CTAs, the launch is cut into time segments handed out through a
+// work queue (lanes.cu lanes_kernel): a plain grid would run a second, mostly empty wave for the whole
+// duration of the render.
+int launch_lanes(tb_program* p, tb_launch& B) {
+    const uint32_t groups = (B.n_voices + TB_LANE_THREADS - 1) / TB_LANE_THREADS;
+    const char* qe = std::getenv("TUUN_B200_LANE_QUEUE");  // diagnostics: "0" never, "1" always
+    const bool want = qe ? qe[0] == '1' : groups > p->lane_capacity;
+    B.lane_queue = nullptr;
+    if (want && B.n_samples >= 4 * 2 * TB_LS) {
+        // 16 segments (or fewer, of at least 1024 samples): the last wave of units wastes < 1/16 of the time
+        uint64_t segs = std::min<uint64_t>(16, std::max<uint64_t>(1, B.n_samples / 1024));
+        uint64_t seg = (B.n_samples + segs - 1) / segs;
+        seg = (seg + 2 * TB_LS - 1) / (2 * TB_LS) * (2 * TB_LS);
+        segs = (B.n_samples + seg - 1) / seg;
+        const size_t words = (size_t)groups + 1;
+        if (words > p->lane_queue_cap) {
+            cudaFree(p->d_lane_queue);
+            p->d_lane_queue = nullptr;
+            p->lane_queue_cap = 0;
+            CU(cudaMalloc(reinterpret_cast<void**>(&p->d_lane_queue), words * 4));
+            p->lane_queue_cap = words;
+        }
+        CU(cudaMemsetAsync(p->d_lane_queue, 0, words * 4, p->stream));
+        B.lane_queue = p->d_lane_queue;
+        B.lane_groups = groups;
+        B.lane_segs = (uint32_t)segs;
+        B.lane_seg_samples = seg;
+        B.lane_grid = std::max<uint32_t>(1, p->lane_capacity);
+    }
+    // One fused FM voice and a batch the device holds at once: its own kernel (lanes_fm.cu).
+    const bool fm = p->lane_fm_capacity != 0 && groups <= p->lane_fm_capacity && !B.lane_queue;
+    cudaEvent_t* ev = p->lane_ev[p->lane_launches % tb_program::kLaneEvents];
+    if (!ev[0]) {
+        CU(cudaEventCreate(&ev[0]));
+        CU(cudaEventCreate(&ev[1]));
+    }
+    CU(cudaEventRecord(ev[0], p->stream));
+    cudaError_t e = tb_lanes_launch(&B, p->lane_smem, fm ? 2 : (B.lane_queue ? 1 : 0), p->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "lane kernel launch");
+    CU(cudaEventRecord(ev[1], p->stream));
+    p->launches++;
+    p->lane_launches++;
+    return TB_OK;
+}
+
 // A generate launch.  Large batches of steady-state voices go through the lane-per-voice kernel
 // (lanes.cu).  `pos` = samples the voices have generated before this launch: the first general tile of
 // a stream (filter pre-reads, generator.rs:234-252) stays on the warp-per-voice kernel, and so do the
@@ -261,17 +311,7 @@ int launch_generate(tb_program* p, const tb_launch& L, uint64_t pos) {
     B.n_samples = bulk;
     B.accumulate = head ? 1 : L.accumulate;
     B.done = nullptr;  // every node of a steady program is infinite: no voice ever finishes
-    cudaEvent_t* ev = p->lane_ev[p->lane_launches % tb_program::kLaneEvents];
-    if (!ev[0]) {
-        CU(cudaEventCreate(&ev[0]));
-        CU(cudaEventCreate(&ev[1]));
-    }
-    CU(cudaEventRecord(ev[0], p->stream));
-    cudaError_t e = tb_lanes_launch(&B, p->lane_smem, p->stream);
-    if (e != cudaSuccess) return cuda_fail(e, "tb_render_lanes_kernel launch");
-    CU(cudaEventRecord(ev[1], p->stream));
-    p->launches++;
-    p->lane_launches++;
+    if ((rc = launch_lanes(p, B))) return rc;
     if (tail) {
         tb_launch T = L;
         T.out = L.out + head + bulk;
@@ -323,17 +363,7 @@ int render_mix_lanes(tb_program* p, const tb_launch& L, float* d_mix, uint64_t p
     B.done = nullptr;
     B.mix_partial = p->d_stage[1];
     B.mix_stride = bulk;
-    cudaEvent_t* ev = p->lane_ev[p->lane_launches % tb_program::kLaneEvents];
-    if (!ev[0]) {
-        CU(cudaEventCreate(&ev[0]));
-        CU(cudaEventCreate(&ev[1]));
-    }
-    CU(cudaEventRecord(ev[0], p->stream));
-    e = tb_lanes_launch(&B, p->lane_smem, p->stream);
-    if (e != cudaSuccess) return cuda_fail(e, "tb_render_lanes_kernel launch");
-    CU(cudaEventRecord(ev[1], p->stream));
-    p->launches++;
-    p->lane_launches++;
+    if ((rc = launch_lanes(p, B))) return rc;
     e = tb_mix_launch(p->d_stage[1], bulk, nullptr, (uint32_t)n_warps, bulk, 0, d_mix + head, 0, p->stream);
     if (e != cudaSuccess) return cuda_fail(e, "tb_mix_kernel launch");
     p->launches++;
@@ -432,7 +462,7 @@ int tb_program_create(const tb_node* nodes, uint32_t n_nodes, const int32_t* lis
         const size_t ls = tb_lanes_smem_bytes((uint32_t)p->low.lane_code.size(), p->low.lane_w_words,
                                               p->low.lane_q_units, p->low.lane_slots);
         int bps = 0, n_sm = 0;
-        if (ls <= 220 * 1024 && tb_lanes_occupancy(ls, &bps, &n_sm) == cudaSuccess && bps > 0) {
+        if (ls <= 220 * 1024 && tb_lanes_occupancy(ls, 0, &bps, &n_sm) == cudaSuccess && bps > 0) {
             if ((rc = upload(p->low.lane_code, &p->d_lane_code)) || (rc = upload(p->low.lane_aux, &p->d_lane_aux)))
                 return bail(rc);
             if (cudaHostAlloc(reinterpret_cast<void**>(&p->h_fault), 4, cudaHostAllocMapped) == cudaSuccess) {
@@ -441,6 +471,15 @@ int tb_program_create(const tb_node* nodes, uint32_t n_nodes, const int32_t* lis
                     p->d_fault = nullptr;
             }
             p->lane_smem = ls;
+            p->lane_capacity = (uint32_t)(bps * n_sm);
+            // A program that is one fused FM voice with a FAST carrier has its own kernel (lanes_fm.cu).
+            const std::vector<tb_insn>& lc = p->low.lane_code;
+            const char* fe = std::getenv("TUUN_B200_LANE_FM_KERNEL");  // diagnostics: "0" keeps it on the interpreter kernels
+            if (lc.size() == 3 && (lc[0].op & 0xffu) == LN_FM && ((lc[0].op >> 16) & 0xffu) == 0 &&
+                (lc[0].op >> 24) == TB_SINE_FAST && p->fast_mode == 2 && !(fe && fe[0] == '0')) {
+                int fb = 0, fs = 0;
+                if (tb_lanes_occupancy(ls, 2, &fb, &fs) == cudaSuccess && fb > 0) p->lane_fm_capacity = (uint32_t)(fb * fs);
+            }
             // Default threshold: a little over one CTA per SM.  Measured on config 5: the lane kernel takes
             // the same time for 9,472 and 18,944 voices (one warp per scheduler, latency bound: 3.7e11 and
             // 7.4e11 voice-samples/s) against 4.0e11 for the warp-per-voice kernel at any batch size.
@@ -483,6 +522,8 @@ int tb_lower_check(const tb_node* nodes, uint32_t n_nodes, const int32_t* lists,
                                                                           low.lane_q_units, low.lane_slots)
                                             : 0u;
         info->lane_min_voices = 0;
+        info->lane_capacity = 0;
+        info->lane_fm_capacity = 0;
     }
     return TB_OK;
 }
@@ -501,6 +542,8 @@ int tb_program_get_info(const tb_program* p, tb_program_info* info) {
     info->lane_launches = p->lane_launches;
     info->lane_smem_bytes = (uint32_t)p->lane_smem;
     info->lane_min_voices = p->lane_min_voices;
+    info->lane_capacity = p->lane_capacity;
+    info->lane_fm_capacity = p->lane_fm_capacity;
     return TB_OK;
 }
 

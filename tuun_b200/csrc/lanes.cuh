@@ -1,0 +1,917 @@
+// lanes.cuh — the lane-per-voice kernels (lanes.cu, lanes_queue.cu, lanes_fm.cu): large batches of steady-state voices.
+//
+// render.cu gives every voice a warp and turns the reference's sequential state into warp scans.
+// With tens of thousands of voices in one call the batch itself is the parallel axis: here ONE
+// THREAD owns one voice and walks its time axis in tiles of TB_LS = 16 samples, so
+//   * the phase accumulator of a Sine (generator.rs:206-219) is a running 64-bit sum in registers,
+//   * the feedback of a Filter (generator.rs:500-507) is the reference's own recurrence, in the
+//     reference's operation order, from the carried history — bit-identical to it for identical
+//     inputs, with no scan, no shuffle and no second pass,
+//   * constants, state and derived constants of the voice sit in the thread's own column of shared
+//     memory (program.h: W words and Q units, conflict free), and so does the running result
+//     between two instructions of the program,
+//   * the 16 finished samples of the 32 voices of a warp leave through a transposed read of that
+//     tile, so that each output row receives whole 64-byte segments (two full 32-byte sectors per
+//     row and tile; four lanes cover one row with one 128-bit store each),
+//   * independent f32 operations of neighbouring samples are issued in pairs (FMUL2 / FADD2 / FFMA2).
+// The program is the ST_* stream of the steady-state interpreter (steady.cuh) with operands
+// rewritten by lower.cpp (build_lane_plan); state blocks are those of the other kernels, so the
+// host (abi.cpp) renders the first general tile and the last < 16 samples of a call with
+// tb_render_kernel and everything between with this kernel.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/tuun_b200.h"
+#include "program.h"
+
+#ifndef TB_LANE_MIN_BLOCKS
+#define TB_LANE_MIN_BLOCKS 7
+#endif
+
+namespace {
+
+#include "common.cuh"
+
+
+constexpr int LS = TB_LS;
+constexpr int LT = TB_LANE_THREADS;
+static_assert(LS == 16, "the symmetric rotation table and the row transpose assume 16 samples per tile");
+
+// ---- the thread's column of shared memory ----------------------------------------------------------
+constexpr int AS = LT + 1;  // chunk stride of the accumulator tiles, in 16-byte units (see lacc_store)
+struct LaneMem {
+    uint32_t* W;   // word w of this thread at W[w * LT]
+    float4* Q;     // unit q of this thread at Q[q * LT]; slots follow the derived constants
+    float4* A;     // the accumulator tile of the current step: chunk c (samples 4c .. 4c+3) of this thread at
+                   // A[c * AS].  Two tiles alternate (chunks 0-3 and 4-7 of an 8-chunk buffer).
+    uint32_t slot0;
+};
+__device__ __forceinline__ uint32_t ldw(const LaneMem& M, int w) { return M.W[w * LT]; }
+__device__ __forceinline__ float ldf(const LaneMem& M, int w) { return __uint_as_float(M.W[w * LT]); }
+__device__ __forceinline__ void stw(const LaneMem& M, int w, uint32_t v) { M.W[w * LT] = v; }
+__device__ __forceinline__ void stf(const LaneMem& M, int w, float v) { M.W[w * LT] = __float_as_uint(v); }
+__device__ __forceinline__ u64 ld64(const LaneMem& M, int w) {
+    return (u64)M.W[w * LT] | ((u64)M.W[(w + 1) * LT] << 32);
+}
+__device__ __forceinline__ void st64(const LaneMem& M, int w, u64 v) {
+    M.W[w * LT] = (uint32_t)v;
+    M.W[(w + 1) * LT] = (uint32_t)(v >> 32);
+}
+__device__ __forceinline__ double ldd(const LaneMem& M, int w) { return __longlong_as_double((i64)ld64(M, w)); }
+__device__ __forceinline__ void std_(const LaneMem& M, int w, double v) { st64(M, w, (u64)__double_as_longlong(v)); }
+__device__ __forceinline__ void lslot_store(const LaneMem& M, int s, const float (&v)[LS]) {
+    float4* p = M.Q + (size_t)(M.slot0 + 4 * s) * LT;
+    UNROLL for (int q = 0; q < 4; q++) p[q * LT] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
+__device__ __forceinline__ void lslot_load(const LaneMem& M, int s, float (&v)[LS]) {
+    const float4* p = M.Q + (size_t)(M.slot0 + 4 * s) * LT;
+    UNROLL for (int q = 0; q < 4; q++) {
+        const float4 t = p[q * LT];
+        v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+    }
+}
+// The running result of the program lives in shared memory between instructions (registers carry
+// it only inside one instruction: a 16-register value live across the dispatch costs a register
+// move per value and dispatch).  The buffer doubles as the staging of the row transpose: two
+// consecutive tiles sit side by side as chunks 0-3 and 4-7, and every second step a row leaves as
+// one whole 128-byte piece (eight lanes x 16 bytes).  With a chunk stride of LT + 1 units the
+// owner's stores (8 consecutive threads, one chunk) and the transposed loads (one row x 8 chunks)
+// of a quarter warp both touch 8 distinct bank groups.
+__device__ __forceinline__ void lacc_store(const LaneMem& M, const float (&v)[LS]) {
+    UNROLL for (int q = 0; q < 4; q++) M.A[q * AS] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
+__device__ __forceinline__ void lacc_load(const LaneMem& M, float (&v)[LS]) {
+    UNROLL for (int q = 0; q < 4; q++) {
+        const float4 t = M.A[q * AS];
+        v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+    }
+}
+
+// ---- packed f32x2 arithmetic (FMUL2 / FADD2 / FFMA2: one issue slot, two IEEE operations) ----------
+// Every operation rounds to nearest like its scalar form.  ptxas contracts a mul.rn.f32x2 whose only
+// use is an add.rn.f32x2 into one FFMA2 (one rounding instead of the reference's two); giving the
+// multiply .ftz makes the pair unfusable.  .ftz only changes products of or into subnormals
+// (|x| < 1.2e-38), far below anything audible or tested.
+__device__ __forceinline__ u64 pk2(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpk2(u64 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+    u64 r;
+    asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+    u64 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+    u64 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+// ---- FAST-class sine on the special-function unit from the top 23 phase bits -----------------------
+// p = phase in 2^-32 turns.  1.m with m = p >> 9 is the float 1 + frac (frac truncated to 2^-23), and
+//   sin(2 pi (frac + 2^-24)) = sin(pi - 2 pi (frac + 2^-24)) = sin(3 pi - 2 pi 2^-24 - 2 pi (1 + frac)):
+// one FFMA into (-pi, pi], then sin.approx (range multiply + MUFU.SIN).  The 2^-24 centres the
+// truncation.  No integer-to-float conversion: that unit is shared with MUFU and with the
+// f64 <-> f32 conversions of the exact sines.  Two samples share the FFMA (FFMA2).
+#define TB_SIN23_A (-6.2831853071795865f)
+#define TB_SIN23_B 9.4247776f  // 3 pi - 2 pi 2^-24
+__device__ __forceinline__ uint32_t mant23(uint32_t p) { return __umulhi(p, 0x00800000u) + 0x3f800000u; }
+__device__ __forceinline__ float sin_p32(uint32_t p) {
+    return __sinf(fmaf(__uint_as_float(mant23(p)), TB_SIN23_A, TB_SIN23_B));
+}
+__device__ __forceinline__ void sin_p32x2(uint32_t p0, uint32_t p1, float& s0, float& s1) {
+    float x0, x1;
+    unpk2(fma2(pk2(__uint_as_float(mant23(p0)), __uint_as_float(mant23(p1))), pk2(TB_SIN23_A, TB_SIN23_A),
+               pk2(TB_SIN23_B, TB_SIN23_B)),
+          x0, x1);
+    s0 = __sinf(x0);
+    s1 = __sinf(x1);
+}
+// f as a double, by integer instructions: sign | (exponent + 896) << 20 | mantissa >> 3, mantissa << 29.
+// An alternative to F2F.F64.F32, which runs on the 16-lane conversion unit that also serves MUFU.SIN
+// and the f64 -> f32 conversions of the exact sines (tools/ubench/xu.cu: 14-16 results/clk/SM each).
+// Measured on the FM voice loop: 5 ALU instructions cost more issue slots than the conversion costs
+// unit time (32.3 ms against 31.1 ms per launch), so TB_F2F_ALU stays 0; kept for programs whose
+// conversion unit is the busier side.  Zero and subnormal inputs come out as ~2^-127 (their
+// increments still round to zero); infinities and NaNs are excluded by the range test that guards
+// the magic-number conversion.
+__device__ __forceinline__ double f32_to_f64_alu(float f) {
+    const uint32_t b = __float_as_uint(f);
+    const uint32_t hi = (((b >> 3) & 0x0fffffffu) + 0x38000000u) | (b & 0x80000000u);
+    return __hiloint2double((int)hi, (int)(b << 29));
+}
+// The low word of (f * scale + 1.5 * 2^52): rint(f * scale) mod 2^32.
+#ifndef TB_F2F_ALU
+#define TB_F2F_ALU 0
+#endif
+__device__ __forceinline__ uint32_t magic_lo(float f, double scale) {
+#if TB_F2F_ALU
+    return (uint32_t)__double2loint(fma(f32_to_f64_alu(f), scale, 6755399441055744.0));
+#else
+    return (uint32_t)__double2loint(fma((double)f, scale, 6755399441055744.0));
+#endif
+}
+
+// ---- Sine, constant frequency and phase (generator.rs:206-219) -------------------------------------
+// The thread carries (sin, cos) of the phase at the centre of the coming tile as doubles (set from
+// the exact 64-bit accumulator when the kernel starts, setup_lane).  A tile is angle addition to
+// both sides of the centre against the voice's rotations (cos, sin)(k d), k = 1..8 — the products
+// are shared by samples 8 + k and 8 - k — and one more rotation by 16 d moves the pair to the next
+// centre.  Rounding errors of the carried pair grow by ~1e-16 per tile (a random walk; 1e-13 after
+// a minute of audio), against the 6e-8 of the f32 result.  The accumulator of the state block is
+// advanced once, when the kernel ends.
+__device__ __forceinline__ void lane_sine_cc(const LaneMem& M, float (&acc)[LS], int w_sc, int q) {
+    const double S = ldd(M, w_sc), Cq = ldd(M, w_sc + 2);
+    const double2* rot = reinterpret_cast<const double2*>(M.Q + (size_t)q * LT);
+    acc[LS / 2] = (float)S;
+    UNROLL for (int k = 1; k < LS / 2; k++) {
+        const double2 r = rot[(size_t)(k - 1) * LT];
+        const double b = Cq * r.y;
+        acc[LS / 2 + k] = (float)fma(S, r.x, b);
+        acc[LS / 2 - k] = (float)fma(S, r.x, -b);
+    }
+    {
+        const double2 r = rot[(size_t)(LS / 2 - 1) * LT];
+        acc[0] = (float)fma(S, r.x, -(Cq * r.y));
+    }
+    const double2 r16 = rot[(size_t)(LS / 2) * LT];
+    std_(M, w_sc, fma(S, r16.x, Cq * r16.y));
+    std_(M, w_sc + 2, fma(Cq, r16.x, -(S * r16.y)));
+}
+
+// ---- Sine with a frequency waveform (and optionally a phase waveform) ------------------------------
+// acc holds the phase offsets on entry when !UNIFORM_PH; f the frequencies.  The sample is taken
+// before the increment (generator.rs:212-218).
+//   MODE 2 (FAST class on the special-function unit): the tile's phases are 32-bit running sums of
+//   per-sample increments rounded to 2^-32 turns (1.5e-9 rad; the other kernels round to 2^-44), and
+//   the 64-bit accumulator of the state block advances by exactly their sum.
+//   CHECK = false: the caller has bounded |f| below the range limit of the magic-number conversion.
+template <bool UNIFORM_PH, int MODE, bool CHECK = true>
+__device__ __forceinline__ void lane_sine_var(const LaneMem& M, float (&acc)[LS], const float (&f)[LS], u64 ph0, int st,
+                                              const SineK& sk) {
+    const u64 a0 = ld64(M, st);
+    float big = 0.0f, bigp = 0.0f;
+    if (CHECK) {
+        UNROLL for (int j = 0; j < LS; j++) {
+            big = fmaxf(big, fabsf(f[j]));
+            if (!UNIFORM_PH) bigp = fmaxf(bigp, fabsf(acc[j]));
+        }
+    }
+    const bool slow = CHECK && (!(big < sk.flimit) || !(bigp < sk.plimit));
+    if (MODE == 2 && !slow) {
+        const uint32_t p0 = (uint32_t)((a0 + (UNIFORM_PH ? ph0 : 0ull)) >> 32);
+        uint32_t p = p0;
+        const double ks = sk.kscale * (1.0 / 4096.0), ps = sk.pscale * (1.0 / 4096.0);  // 2^32 / ... instead of 2^44 / ...
+        UNROLL for (int j = 0; j < LS; j += 2) {
+            const uint32_t t0 = UNIFORM_PH ? p : p + magic_lo(acc[j], ps);
+            p += magic_lo(f[j], ks);
+            const uint32_t t1 = UNIFORM_PH ? p : p + magic_lo(acc[j + 1], ps);
+            p += magic_lo(f[j + 1], ks);
+            sin_p32x2(t0, t1, acc[j], acc[j + 1]);
+        }
+        stw(M, st + 1, (uint32_t)(a0 >> 32) + (p - p0));
+        return;
+    }
+    u64 ph = a0;
+    UNROLL for (int j = 0; j < LS; j++) {
+        const u64 a = ph + (UNIFORM_PH ? ph0 : (slow ? phase_to_fx(acc[j], sk) : magic_raw(acc[j], sk.pscale) << 20));
+        ph += slow ? freq_to_inc(f[j], sk) : magic_raw(f[j], sk.kscale) << 20;
+        acc[j] = MODE == 0 ? sin_turns_exact(a) : (MODE == 1 ? sin_hi<1>((int)(a >> 32)) : sin_p32((uint32_t)(a >> 32)));
+    }
+    st64(M, st, ph);
+}
+
+// Constant frequency, phase offsets in acc (phase modulation).
+template <int MODE>
+__device__ __forceinline__ void lane_sine_ca(const LaneMem& M, float (&acc)[LS], u64 inc, int st, const SineK& sk) {
+    const u64 a0 = ld64(M, st);
+    float bigp = 0.0f;
+    UNROLL for (int j = 0; j < LS; j++) bigp = fmaxf(bigp, fabsf(acc[j]));
+    const bool slow = !(bigp < sk.plimit);
+    u64 b = a0;
+    if (MODE == 2 && !slow) {
+        const double ps = sk.pscale * (1.0 / 4096.0);
+        UNROLL for (int j = 0; j < LS; j += 2) {
+            const uint32_t t0 = (uint32_t)(b >> 32) + magic_lo(acc[j], ps);
+            b += inc;
+            const uint32_t t1 = (uint32_t)(b >> 32) + magic_lo(acc[j + 1], ps);
+            b += inc;
+            sin_p32x2(t0, t1, acc[j], acc[j + 1]);
+        }
+    } else {
+        UNROLL for (int j = 0; j < LS; j++) {
+            const u64 a = b + (slow ? phase_to_fx(acc[j], sk) : magic_raw(acc[j], sk.pscale) << 20);
+            b += inc;
+            acc[j] = MODE == 0 ? sin_turns_exact(a) : (MODE == 1 ? sin_hi<1>((int)(a >> 32)) : sin_p32((uint32_t)(a >> 32)));
+        }
+    }
+    st64(M, st, a0 + inc * (u64)LS);
+}
+
+// ---- Filter with constant coefficients and complete history (generator.rs:382-515) -----------------
+// The reference's per-sample evaluation, literally: y = x b0; y += b_i x[n-i] ...; y -= a_j y[n-j] ...,
+// every product and sum rounded (no FMA).  History layout of the state block is that of the other
+// kernels: S[2 ..] the last K-1 inputs oldest first, then the last J outputs oldest first.
+// Feed-forward products of two neighbouring samples share an FMUL2, and so do the sums whose
+// operands pair up (even tap distances); the feedback recurrence is scalar.
+template <int KT, int JT>
+__device__ __forceinline__ void lane_filter(const LaneMem& M, float (&acc)[LS], int st, int w_coef, int K, int J) {
+    constexpr int NK = KT >= 0 ? KT : TB_MAX_K;
+    constexpr int NJ = JT >= 0 ? JT : TB_MAX_J;
+    if (KT >= 0) K = KT;
+    if (JT >= 0) J = JT;
+    float b[NK > 0 ? NK : 1], a[NJ > 0 ? NJ : 1];
+    float hx[NK > 1 ? NK - 1 : 1], hy[NJ > 0 ? NJ : 1];  // hx[m] = x[-1-m], hy[m] = y[-1-m]
+    UNROLL for (int k = 0; k < NK; k++) b[k] = k < K ? ldf(M, w_coef + k) : 0.0f;
+    UNROLL for (int j = 0; j < NJ; j++) a[j] = j < J ? ldf(M, w_coef + K + j) : 0.0f;
+    const int wx = st + 2, wy = st + 2 + (K - 1);
+    UNROLL for (int m = 0; m < NK - 1; m++) hx[m] = m < K - 1 ? ldf(M, wx + (K - 2 - m)) : 0.0f;
+    UNROLL for (int m = 0; m < NJ; m++) hy[m] = m < J ? ldf(M, wy + (J - 1 - m)) : 0.0f;
+    float u[LS];
+    if (KT >= 1 && KT <= 4) {
+        // pr[k][i] = b_k x[i] for i in [-(K-1), LS): aligned sample pairs by FMUL2, history by FMUL.
+        float pr[NK][LS + NK];
+        UNROLL for (int k = 0; k < NK; k++) {
+            const u64 bb = pk2(b[k], b[k]);
+            UNROLL for (int i = 0; i < LS; i += 2) {
+                if (i + k < LS) unpk2(mul2(pk2(acc[i], acc[i + 1]), bb), pr[k][NK + i], pr[k][NK + i + 1]);
+            }
+            UNROLL for (int m = 1; m <= k; m++) pr[k][NK - m] = __fmul_rn(b[k], hx[m - 1]);
+        }
+        UNROLL for (int i = 0; i < LS; i += 2) {
+            u64 s = pk2(pr[0][NK + i], pr[0][NK + i + 1]);
+            UNROLL for (int k = 1; k < NK; k++) {
+                if (k % 2 == 0) {
+                    s = add2(s, pk2(pr[k][NK + i - k], pr[k][NK + i + 1 - k]));
+                } else {
+                    float s0, s1;
+                    unpk2(s, s0, s1);
+                    s0 = __fadd_rn(s0, pr[k][NK + i - k]);
+                    s1 = __fadd_rn(s1, pr[k][NK + i + 1 - k]);
+                    s = pk2(s0, s1);
+                }
+            }
+            unpk2(s, u[i], u[i + 1]);
+        }
+        UNROLL for (int m = 0; m < NK - 1; m++) hx[m] = acc[LS - 1 - m];
+    } else {
+        UNROLL for (int j = 0; j < LS; j++) {
+            const float x = acc[j];
+            float y = __fmul_rn(x, b[0]);
+            UNROLL for (int k = 1; k < NK; k++)
+                if (KT >= 0 || k < K) y = __fadd_rn(y, __fmul_rn(b[k], hx[k - 1]));
+            UNROLL for (int m = NK - 2; m > 0; m--) hx[m] = hx[m - 1];
+            if (NK > 1) hx[0] = x;
+            u[j] = y;
+        }
+    }
+    if (JT == 2) {
+        // y[n] = (u[n] - a1 y[n-1]) - a2 y[n-2]: both products of a new output, a1 y and a2 y, leave in
+        // one FMUL2; the second waits one sample for its turn.
+        const u64 aa = pk2(a[0], a[1]);
+        float p1, p2, q2;  // a1 y[n-1], a2 y[n-2]; a2 y[n-1] for the next sample
+        p1 = __fmul_rn(a[0], hy[0]);
+        q2 = __fmul_rn(a[1], hy[0]);
+        p2 = __fmul_rn(a[1], hy[1]);
+        UNROLL for (int j = 0; j < LS; j++) {
+            const float y = __fsub_rn(__fsub_rn(u[j], p1), p2);
+            p2 = q2;
+            unpk2(mul2(aa, pk2(y, y)), p1, q2);
+            acc[j] = y;
+        }
+        hy[0] = acc[LS - 1];
+        hy[1] = acc[LS - 2];
+    } else {
+        UNROLL for (int j = 0; j < LS; j++) {
+            float y = u[j];
+            UNROLL for (int m = 0; m < NJ; m++)
+                if (JT >= 0 || m < J) y = __fsub_rn(y, __fmul_rn(a[m], hy[m]));
+            UNROLL for (int m = NJ - 1; m > 0; m--) hy[m] = hy[m - 1];
+            if (NJ > 0) hy[0] = y;
+            acc[j] = y;
+        }
+    }
+    UNROLL for (int m = 0; m < NK - 1; m++)
+        if (m < K - 1) stf(M, wx + (K - 2 - m), hx[m]);
+    UNROLL for (int m = 0; m < NJ; m++)
+        if (m < J) stf(M, wy + (J - 1 - m), hy[m]);
+}
+
+#define APPLY_OP_L(OPV, DST, A, B)                                                    \
+    switch (OPV) {                                                                    \
+        case TB_ADD:                                                                  \
+        case TB_MERGE: UNROLL for (int j = 0; j < LS; j++) DST[j] = __fadd_rn(A, B); break; \
+        case TB_SUBTRACT: UNROLL for (int j = 0; j < LS; j++) DST[j] = __fsub_rn(A, B); break; \
+        case TB_MULTIPLY: UNROLL for (int j = 0; j < LS; j++) DST[j] = __fmul_rn(A, B); break; \
+        case TB_DIVIDE:                                                               \
+            UNROLL for (int j = 0; j < LS; j++) {                                     \
+                float bb_ = (B);                                                      \
+                DST[j] = bb_ == 0.0f ? 0.0f : __fdiv_rn(A, bb_);                      \
+            }                                                                         \
+            break;                                                                    \
+        default: UNROLL for (int j = 0; j < LS; j++) DST[j] = powf(A, B); break;      \
+    }
+
+__device__ __forceinline__ tb_insn lds_insn(uint32_t saddr) {
+    tb_insn r;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.op), "=r"(r.a), "=r"(r.b), "=r"(r.c)
+                 : "r"(saddr)
+                 : "memory");
+    return r;
+}
+
+// One tile of one voice; leaves the result in the accumulator tile M.A.  Control flow is uniform
+// over the CTA (every voice runs the same program).
+template <int FASTMODE>
+__device__ __forceinline__ void run_lane_tile(const tb_launch& P, uint32_t code_s, const LaneMem& M, uint32_t voice,
+                                              const SineK& sk) {
+    uint32_t ip = code_s;
+    tb_insn nxt = lds_insn(ip);
+    for (;;) {
+        const tb_insn in = nxt;
+        ip += sizeof(tb_insn);
+        nxt = lds_insn(ip);
+        const uint32_t op = in.op & 0xffu;
+        const bool fast = ((in.op >> 8) & 0xffu) == TB_SINE_FAST;
+        float acc[LS];
+        switch (op) {
+            case ST_END: return;
+            case ST_CONST: {
+                const float c = ldf(M, in.a);
+                UNROLL for (int j = 0; j < LS; j++) acc[j] = c;
+                break;
+            }
+            case ST_TIME: {  // generator.rs:101-111
+                const float srf = (float)P.sample_rate;
+                const u64 pos = ld64(M, in.a);
+                UNROLL for (int j = 0; j < LS; j++) acc[j] = __fdiv_rn(__ull2float_rn(pos + (u64)j), srf);
+                st64(M, in.a, pos + (u64)LS);
+                break;
+            }
+            case ST_NOISE: {  // generator.rs:113-118
+                const u64 pos = ld64(M, in.a);
+                const u64 stream = noise_stream(P, voice, in.b);
+                UNROLL for (int j = 0; j < LS; j++) acc[j] = noise_at(stream, pos + (u64)j);
+                st64(M, in.a, pos + (u64)LS);
+                break;
+            }
+            case ST_SAVE:
+                lacc_load(M, acc);
+                lslot_store(M, in.a, acc);
+                continue;  // the accumulator tile is unchanged; ST_SAVE never carries post-ops
+            case ST_BIN: {  // generator.rs:555-567 with both sides infinite
+                float av[LS];
+                lslot_load(M, in.a, av);
+                lacc_load(M, acc);
+                APPLY_OP_L((uint32_t)in.b, acc, av[j], acc[j])
+                break;
+            }
+            case ST_SINE_CC: lane_sine_cc(M, acc, in.b + 2, (int)((in.op >> 8) & 0xffu)); break;
+            case ST_SINE_AC: {
+                float f[LS];
+                lacc_load(M, f);
+                const u64 ph0 = ld64(M, in.c);
+                if (!fast) lane_sine_var<true, 0>(M, acc, f, ph0, in.a, sk);
+                else lane_sine_var<true, FASTMODE>(M, acc, f, ph0, in.a, sk);
+                break;
+            }
+            case ST_SINE_CA: {
+                const u64 inc = ld64(M, in.b);
+                lacc_load(M, acc);
+                if (!fast) lane_sine_ca<0>(M, acc, inc, in.a, sk);
+                else lane_sine_ca<FASTMODE>(M, acc, inc, in.a, sk);
+                break;
+            }
+            case ST_SINE_AA: {
+                float f[LS];
+                lslot_load(M, in.b, f);
+                lacc_load(M, acc);
+                if (!fast) lane_sine_var<false, 0>(M, acc, f, 0ull, in.a, sk);
+                else lane_sine_var<false, FASTMODE>(M, acc, f, 0ull, in.a, sk);
+                break;
+            }
+            case ST_ALT_CC: {  // generator.rs:335-341
+                const float cp = ldf(M, in.a), cn = ldf(M, in.b);
+                lacc_load(M, acc);
+                UNROLL for (int j = 0; j < LS; j++) acc[j] = acc[j] >= 0.0f ? cp : cn;
+                break;
+            }
+            case ST_ALT: {
+                float t[LS];
+                lslot_load(M, in.a, t);
+                if (in.c < 0) { const float c = ldf(M, ~in.c); UNROLL for (int j = 0; j < LS; j++) acc[j] = c; }
+                else lacc_load(M, acc);
+                if (in.b >= 0) {
+                    float pv[LS];
+                    lslot_load(M, in.b, pv);
+                    UNROLL for (int j = 0; j < LS; j++) acc[j] = t[j] >= 0.0f ? pv[j] : acc[j];
+                } else {
+                    const float c = ldf(M, ~in.b);
+                    UNROLL for (int j = 0; j < LS; j++) acc[j] = t[j] >= 0.0f ? c : acc[j];
+                }
+                break;
+            }
+            case LN_FM: {
+                // Fused by lower.cpp: Sine(const) * m + c  ->  frequency of a Sine with constant phase
+                // [ -> biquad ].  One dispatch, one basic block: the f64 angle additions, the phase
+                // sums, the MUFU sines and the filter recurrence overlap in the pipeline.
+                const tb_insn ex = nxt;
+                ip += sizeof(tb_insn);
+                nxt = lds_insn(ip);
+                const float m = ldf(M, ex.a), c = ldf(M, ex.b);
+                const u64 ph0 = ld64(M, in.c);
+                float f[LS];
+                lane_sine_cc(M, f, in.a, (int)((in.op >> 8) & 0xffu));
+                {
+                    const u64 mm = pk2(m, m), cc = pk2(c, c);
+                    UNROLL for (int j = 0; j < LS; j += 2) unpk2(add2(mul2(pk2(f[j], f[j + 1]), mm), cc), f[j], f[j + 1]);
+                }
+                const bool fastfm = ((in.op >> 24) & 0xffu) == TB_SINE_FAST;
+                if (fabsf(m) + fabsf(c) < sk.flimit) {  // |f| <= |m| + |c|: no per-sample range test
+                    if (!fastfm) lane_sine_var<true, 0, false>(M, acc, f, ph0, in.b, sk);
+                    else lane_sine_var<true, FASTMODE, false>(M, acc, f, ph0, in.b, sk);
+                } else {
+                    if (!fastfm) lane_sine_var<true, 0>(M, acc, f, ph0, in.b, sk);
+                    else lane_sine_var<true, FASTMODE>(M, acc, f, ph0, in.b, sk);
+                }
+                if (ex.c >= 0) lane_filter<3, 2>(M, acc, ex.c, (int)ex.op, 3, 2);
+                break;
+            }
+            case ST_FILT: {
+                const int K = (int)((in.op >> 8) & 0xfu), J = (int)((in.op >> 12) & 0x7u);
+                lacc_load(M, acc);
+                if (K == 3 && J == 2) lane_filter<3, 2>(M, acc, in.a, in.b, K, J);  // every filter of lib/v0/std.tuun
+                else if (K == 1 && J == 1) lane_filter<1, 1>(M, acc, in.a, in.b, K, J);
+                else if (K == 2 && J == 1) lane_filter<2, 1>(M, acc, in.a, in.b, K, J);
+                else lane_filter<-1, -1>(M, acc, in.a, in.b, K, J);
+                break;
+            }
+            default: return;  // unreachable: lower.cpp emits only the words above
+        }
+        for (uint32_t np = (in.op >> 16) & 0xffu; np > 0; np--) {  // constant point operators (generator.rs:541-548)
+            const tb_insn po = nxt;
+            ip += sizeof(tb_insn);
+            nxt = lds_insn(ip);
+            if ((po.op & 0xffu) == ST_AFFINE) {  // (acc * m) + a, both rounded
+                const float m = ldf(M, po.b), a = ldf(M, po.c);
+                const u64 mm = pk2(m, m), aa = pk2(a, a);
+                UNROLL for (int j = 0; j < LS; j += 2) unpk2(add2(mul2(pk2(acc[j], acc[j + 1]), mm), aa), acc[j], acc[j + 1]);
+            } else {
+                const float c = ldf(M, po.b);
+                APPLY_OP_L((uint32_t)po.a, acc, acc[j], c)
+            }
+        }
+        lacc_store(M, acc);
+    }
+}
+
+// Per-voice setup by the owning thread: constant table (is_const folding, generator.rs:574-612),
+// then the derived constants of the lane plan.  The state block is already in W.
+__device__ void setup_lane(const tb_launch& P, const LaneMem& M, const float* prow) {
+    for (uint32_t k = 0; k < P.n_cval; k++) {
+        const tb_cexpr e = P.cexpr[k];
+        float v;
+        if (e.kind == CE_LIT) v = e.value;
+        else if (e.kind == CE_PARAM) v = prow ? prow[e.a] : e.value;
+        else if (e.kind == CE_NEG) v = -ldf(M, e.a);
+        else v = apply1(e.op, ldf(M, e.a), ldf(M, e.b));
+        stf(M, (int)k, v);
+    }
+    for (uint32_t t = 0; t < P.n_lane_aux; t++) {
+        const tb_lane_aux a = P.lane_aux[t];
+        if (a.kind == LA_INC || a.kind == LA_ROT) {
+            const u64 inc = turns_to_fx_slow((double)ldf(M, a.a) / (TB_TAU * (double)P.sample_rate));
+            st64(M, (int)a.w_off, inc);
+            if (a.kind == LA_ROT) {
+                double2* rot = reinterpret_cast<double2*>(M.Q + (size_t)a.q_off * LT);
+                for (int k = 1; k <= LS / 2 + 1; k++) {  // k = 1..8, then the tile step 16
+                    const u64 ang = inc * (u64)(k <= LS / 2 ? k : LS);
+                    double2 r;
+                    r.x = sin_turns_d8(ang + 0x4000000000000000ull);
+                    r.y = sin_turns_d8(ang);
+                    rot[(size_t)(k - 1) * LT] = r;
+                }
+                // (sin, cos) at the centre of the first tile, from the exact accumulator and phase.
+                const u64 pc = ld64(M, a.b) + turns_to_fx_slow((double)ldf(M, a.c) / TB_TAU) + inc * (u64)(LS / 2);
+                std_(M, (int)a.w_off + 2, sin_turns_d8(pc));
+                std_(M, (int)a.w_off + 4, sin_turns_d8(pc + 0x4000000000000000ull));
+            }
+        } else if (a.kind == LA_PHASE) {
+            st64(M, (int)a.w_off, turns_to_fx_slow((double)ldf(M, a.a) / TB_TAU));
+        } else {  // LA_COEF
+            const tb_filter_tab* ft = &P.filt[a.a];
+            for (uint32_t e = 0; e < ft->K + ft->J; e++) stw(M, (int)(a.w_off + e), ldw(M, ~ft->coef[e]));
+        }
+    }
+}
+// When the kernel ends: the accumulators of the constant sines advance by the samples rendered.
+__device__ void finish_lane(const tb_launch& P, const LaneMem& M, u64 n_samples) {
+    for (uint32_t t = 0; t < P.n_lane_aux; t++) {
+        const tb_lane_aux a = P.lane_aux[t];
+        if (a.kind == LA_ROT) st64(M, a.b, ld64(M, a.b) + ld64(M, (int)a.w_off) * n_samples);
+    }
+}
+
+
+// ---- the row stores --------------------------------------------------------------------------------
+// After every second tile the 32 samples x 32 voices of the warp leave: lane l takes chunk (l & 7) of
+// rows (l >> 3) + 4 i, i < 8, so eight lanes write the 128 contiguous bytes a row has gathered
+// (half the requests and address translations per byte of a store per tile: 65,536 rows are open
+// at once).  Both __syncwarp()s belong to the protocol: owners have written before the first,
+// readers have read before the owners write again.  An odd last tile leaves as 64 bytes per row.
+struct RowStore {
+    float* out;            // first sample of this launch, row 0
+    size_t stride;         // floats between rows
+    const float4* tbase;   // the warp's first row in the accumulator buffer
+    uint32_t v0, n_voices; // first voice of the warp
+    size_t off;            // samples already stored
+    bool fast, vec_ok;
+    float* mix;            // mixdown without rows (tb_launch::mix_partial): this warp's row of partial sums
+};
+__device__ __forceinline__ void put4(float* d, const float4& v, bool vec_ok) {
+    if (vec_ok) __stcs(reinterpret_cast<float4*>(d), v);
+    else { d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w; }
+}
+__device__ __forceinline__ void store_pair(RowStore& R, int l) {
+    __syncwarp();
+    float4 v[8];
+    const float4* src = R.tbase + (l & 7) * AS + (l >> 3);
+    UNROLL for (int i = 0; i < 8; i++) v[i] = src[4 * i];
+    __syncwarp();
+    float* d = R.out + (size_t)(R.v0 + (l >> 3)) * R.stride + R.off + (size_t)(l & 7) * 4;
+    const size_t step = 4 * R.stride;
+    if (R.fast) {  // all 32 rows of the warp exist and are 16-byte aligned
+        UNROLL for (int i = 0; i < 8; i++) __stcs(reinterpret_cast<float4*>(d + i * step), v[i]);
+    } else if (R.out) {
+        UNROLL for (int i = 0; i < 8; i++)
+            if (R.v0 + (uint32_t)(l >> 3) + 4u * i < R.n_voices) put4(d + i * step, v[i], R.vec_ok);
+    }
+    R.off += 2 * LS;
+}
+__device__ __forceinline__ void store_single(RowStore& R, int l, int half) {
+    __syncwarp();
+    float4 v[4];
+    const float4* src = R.tbase + (4 * half + (l & 3)) * AS + (l >> 2);
+    UNROLL for (int i = 0; i < 4; i++) v[i] = src[8 * i];
+    __syncwarp();
+    float* d = R.out + (size_t)(R.v0 + (l >> 2)) * R.stride + R.off + (size_t)(l & 3) * 4;
+    const size_t step = 8 * R.stride;
+    if (R.out) {
+        UNROLL for (int i = 0; i < 4; i++)
+            if (R.v0 + (uint32_t)(l >> 2) + 8u * i < R.n_voices) put4(d + i * step, v[i], R.vec_ok);
+    }
+    R.off += LS;
+}
+// Mixdown without rows (tb_render_mix with TB_NO_VOICE_OUT): instead of leaving, the tile is summed over
+// the warp's 32 voices on the chip — lane l adds sample (l & 15) of voices 16 (l >> 4) .. +15 in voice
+// order, the two halves are added, and 64 bytes of partial sums go to the warp's row of
+// tb_launch::mix_partial.  tb_mix_kernel then adds the rows of all warps in warp order: the tracker's
+// serial `out[j] += tmp[j]` (tracker.rs:617-619) re-associated in blocks of 16 voices.
+__device__ __forceinline__ void mix_tile(RowStore& R, int l, int half) {
+    __syncwarp();
+    const int smp = l & 15;
+    const float* a = reinterpret_cast<const float*>(R.tbase + (4 * half + (smp >> 2)) * AS + 16 * (l >> 4)) + (smp & 3);
+    float s = a[0];
+    UNROLL for (int v = 1; v < 16; v++) s = __fadd_rn(s, a[4 * v]);
+    s = __fadd_rn(s, __shfl_down_sync(FULL, s, 16));
+    __syncwarp();
+    if (l < 16) R.mix[R.off + l] = s;
+    R.off += LS;
+}
+// Tile number t (from 0) of the launch has just been written to its half of the buffer.
+template <bool MIX>
+__device__ __forceinline__ void tile_done(RowStore& R, int l, u64 t, u64 n_tiles) {
+    if (MIX) mix_tile(R, l, (int)(t & 1));
+    else if (t & 1) store_pair(R, l);
+    else if (t + 1 == n_tiles) store_single(R, l, 0);
+}
+
+// ---- a program that is ONE fused FM voice ----------------------------------------------------------
+// When the whole lane program is a single LN_FM (program.h) with a FAST carrier — the shape of the
+// 65,536-voice FM + low-pass batch — there is nothing to dispatch: the thread keeps the voice's
+// state in registers for the whole launch (carried sin/cos pair, 32-bit carrier phase, filter
+// history and its pending products) and runs tiles in a software-pipelined loop: the carrier tile
+// of step t is computed in the same basic block as the filter recurrence over the carrier tile of
+// step t-1, so the serial y[n] chain overlaps the f64 angle additions, conversions and MUFU sines.
+#ifndef TB_ABL
+#define TB_ABL 0
+#endif
+#if TB_ABL == 3
+#define TB_D2F(x) __int_as_float(__double2hiint(x))
+#else
+#define TB_D2F(x) ((float)(x))
+#endif
+// SLOW: some voice of the warp has |m| + |c| beyond the exact range of the magic-number conversion
+// (100 x the sample rate): every increment goes through the full-precision conversion instead.
+template <bool SLOW>
+__device__ __forceinline__ void fm_carrier_tile(float (&car)[LS], double& S, double& Cq, const double2* rot, u64 mm,
+                                                u64 cc, uint32_t& p, double ks, const SineK& sk) {
+    float f[LS];
+#if TB_ABL == 4
+    UNROLL for (int j = 0; j < LS; j++) f[j] = TB_D2F(S) + j;
+#else
+    f[LS / 2] = TB_D2F(S);
+    UNROLL for (int k = 1; k < LS / 2; k++) {
+        const double2 r = rot[(size_t)(k - 1) * LT];
+        const double b = Cq * r.y;
+        f[LS / 2 + k] = TB_D2F(fma(S, r.x, b));
+        f[LS / 2 - k] = TB_D2F(fma(S, r.x, -b));
+    }
+    {
+        const double2 r = rot[(size_t)(LS / 2 - 1) * LT];
+        f[0] = TB_D2F(fma(S, r.x, -(Cq * r.y)));
+    }
+#endif
+    const double2 r16 = rot[(size_t)(LS / 2) * LT];
+    const double S2 = fma(S, r16.x, Cq * r16.y);
+    Cq = fma(Cq, r16.x, -(S * r16.y));
+    S = S2;
+    UNROLL for (int j = 0; j < LS; j += 2) unpk2(add2(mul2(pk2(f[j], f[j + 1]), mm), cc), f[j], f[j + 1]);
+    UNROLL for (int j = 0; j < LS; j += 2) {
+        const uint32_t t0 = p;
+        p += SLOW ? (uint32_t)(freq_to_inc(f[j], sk) >> 32) : magic_lo(f[j], ks);
+        const uint32_t t1 = p;
+        p += SLOW ? (uint32_t)(freq_to_inc(f[j + 1], sk) >> 32) : magic_lo(f[j + 1], ks);
+#if TB_ABL == 2
+        car[j] = __uint_as_float(mant23(t0)); car[j + 1] = __uint_as_float(mant23(t1));
+#else
+        sin_p32x2(t0, t1, car[j], car[j + 1]);
+#endif
+    }
+}
+struct BiquadRegs {
+    float b0, b1, b2, a1, a2;
+    float x1, x2;      // x[-1], x[-2]
+    float p1, p2, q2;  // a1 y[-1], a2 y[-2], a2 y[-1]
+    float y1, y2;      // y[-1], y[-2] (for the state block)
+};
+// generator.rs:496-507 for K = 3, J = 2, operation order and roundings of lane_filter<3, 2>.
+__device__ __forceinline__ void biquad_tile(float (&y)[LS], const float (&x)[LS], BiquadRegs& F) {
+    const u64 bb0 = pk2(F.b0, F.b0), bb1 = pk2(F.b1, F.b1), bb2 = pk2(F.b2, F.b2), aa = pk2(F.a1, F.a2);
+    float pr1[LS + 1], pr2[LS + 2];  // pr1[1 + i] = b1 x[i], pr2[2 + i] = b2 x[i]
+    pr1[0] = __fmul_rn(F.b1, F.x1);
+    pr2[0] = __fmul_rn(F.b2, F.x2);
+    pr2[1] = __fmul_rn(F.b2, F.x1);
+    UNROLL for (int i = 0; i < LS; i += 2) {
+        const u64 xx = pk2(x[i], x[i + 1]);
+        unpk2(mul2(xx, bb1), pr1[1 + i], pr1[2 + i]);
+        if (i + 2 < LS) unpk2(mul2(xx, bb2), pr2[2 + i], pr2[3 + i]);
+    }
+    UNROLL for (int i = 0; i < LS; i += 2) {
+        float s0, s1;
+        unpk2(mul2(pk2(x[i], x[i + 1]), bb0), s0, s1);
+        s0 = __fadd_rn(s0, pr1[i]);
+        s1 = __fadd_rn(s1, pr1[i + 1]);
+        unpk2(add2(pk2(s0, s1), pk2(pr2[i], pr2[i + 1])), s0, s1);
+        const float y0 = __fsub_rn(__fsub_rn(s0, F.p1), F.p2);
+        float n1, n2;
+        unpk2(mul2(aa, pk2(y0, y0)), n1, n2);        // a1 y0, a2 y0
+        const float y1 = __fsub_rn(__fsub_rn(s1, n1), F.q2);
+        F.p2 = n2;
+        unpk2(mul2(aa, pk2(y1, y1)), F.p1, F.q2);    // a1 y1, a2 y1
+        y[i] = y0;
+        y[i + 1] = y1;
+    }
+    F.x1 = x[LS - 1];
+    F.x2 = x[LS - 2];
+    F.y1 = y[LS - 1];
+    F.y2 = y[LS - 2];
+}
+
+template <bool TAIL, bool MIX, bool SLOW>
+__device__ __forceinline__ void run_fm_voice(const tb_insn* code, LaneMem& M, const SineK& sk, RowStore& R,
+                                             bool active, int l, u64 n_tiles) {
+    float4* const abase = M.A;
+    const tb_insn w0 = code[0], w1 = code[1];
+    double S = 0.0, Cq = 1.0;
+    const double2* rot = reinterpret_cast<const double2*>(M.Q + (size_t)((w0.op >> 8) & 0xffu) * LT);
+    u64 mm = 0, cc = 0;
+    uint32_t p = 0, p_start = 0;
+    BiquadRegs F = {};
+    const double ks = sk.kscale * (1.0 / 4096.0);
+    if (active) {
+        S = ldd(M, w0.a);
+        Cq = ldd(M, w0.a + 2);
+        const float m = ldf(M, w1.a), c = ldf(M, w1.b);
+        mm = pk2(m, m);
+        cc = pk2(c, c);
+        p_start = p = (uint32_t)((ld64(M, w0.b) + ld64(M, w0.c)) >> 32);
+        if (TAIL) {
+            const int wc = (int)w1.op, st = w1.c;
+            F.b0 = ldf(M, wc); F.b1 = ldf(M, wc + 1); F.b2 = ldf(M, wc + 2);
+            F.a1 = ldf(M, wc + 3); F.a2 = ldf(M, wc + 4);
+            F.x2 = ldf(M, st + 2); F.x1 = ldf(M, st + 3);
+            F.y2 = ldf(M, st + 4); F.y1 = ldf(M, st + 5);
+            F.p1 = __fmul_rn(F.a1, F.y1);
+            F.q2 = __fmul_rn(F.a2, F.y1);
+            F.p2 = __fmul_rn(F.a2, F.y2);
+        }
+    }
+    float car[LS];
+    UNROLL for (int j = 0; j < LS; j++) car[j] = 0.0f;
+    if (!TAIL) {
+        for (u64 t = 0; t < n_tiles; t++) {
+            if (active) {
+                fm_carrier_tile<SLOW>(car, S, Cq, rot, mm, cc, p, ks, sk);
+                M.A = abase + (t & 1) * 4 * AS;
+                lacc_store(M, car);
+            }
+            tile_done<MIX>(R, l, t, n_tiles);
+        }
+    } else {
+        if (active) fm_carrier_tile<SLOW>(car, S, Cq, rot, mm, cc, p, ks, sk);
+        for (u64 t = 1; t < n_tiles; t++) {
+            if (active) {
+                float y[LS], nxt[LS];
+#if TB_ABL == 1
+                UNROLL for (int j = 0; j < LS; j++) y[j] = car[j];
+#else
+                biquad_tile(y, car, F);                                   // tile t-1 leaves ...
+#endif
+                fm_carrier_tile<SLOW>(nxt, S, Cq, rot, mm, cc, p, ks, sk);    // ... while tile t is made
+                M.A = abase + ((t - 1) & 1) * 4 * AS;
+                lacc_store(M, y);
+                UNROLL for (int j = 0; j < LS; j++) car[j] = nxt[j];
+            }
+#if TB_ABL != 5
+            tile_done<MIX>(R, l, t - 1, n_tiles);
+#endif
+        }
+        if (active) {
+            float y[LS];
+            biquad_tile(y, car, F);
+            M.A = abase + ((n_tiles - 1) & 1) * 4 * AS;
+            lacc_store(M, y);
+        }
+        tile_done<MIX>(R, l, n_tiles - 1, n_tiles);
+        M.A = abase;
+    }
+    if (active) {  // registers -> state block; finish_lane advances the modulator's accumulator
+        stw(M, w0.b + 1, ldw(M, w0.b + 1) + (p - p_start));
+        if (TAIL) {
+            const int st = w1.c;
+            stf(M, st + 2, F.x2); stf(M, st + 3, F.x1);
+            stf(M, st + 4, F.y2); stf(M, st + 5, F.y1);
+        }
+    }
+}
+
+
+// One unit of work: the 64 voices of `group`, samples [s0, s0 + ns) of the launch (multiples of TB_LS).
+//   FM_ONLY: the kernels of lanes_fm.cu, launched by the host only for a program that is one fused FM
+//   voice (run_fm_voice; no interpreter in the kernel).
+template <bool MIX, bool FM_ONLY>
+__device__ __forceinline__ void lanes_body(const tb_launch& P, uint32_t group, u64 s0, u64 ns, bool accumulate) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int t = threadIdx.x, l = t & 31, warp = t >> 5;
+    tb_insn* code = reinterpret_cast<tb_insn*>(smem_raw);
+    for (uint32_t k = t; k < P.n_lane_code; k += LT) code[k] = P.lane_code[k];
+    const size_t q_bytes = (size_t)(P.lane_q_units + 4 * P.lane_slots) * LT * 16;
+    unsigned char* base = smem_raw + (size_t)P.n_lane_code * sizeof(tb_insn);
+    LaneMem M;
+    M.Q = reinterpret_cast<float4*>(base) + t;
+    M.slot0 = P.lane_q_units;
+    float4* atile = reinterpret_cast<float4*>(base + q_bytes);
+    M.A = atile + t;
+    M.W = reinterpret_cast<uint32_t*>(base + q_bytes + (size_t)8 * AS * 16) + t;
+    __syncthreads();
+
+    const uint32_t voice = group * LT + t;
+    const uint32_t v0 = group * LT + warp * 32;
+    bool active = voice < P.n_voices;
+    SineK sk;
+    sk.kscale = 17592186044416.0 / (TB_TAU * (double)P.sample_rate);
+    sk.pscale = 17592186044416.0 / TB_TAU;
+    sk.inv_turn = 1.0 / (TB_TAU * (double)P.sample_rate);
+    sk.flimit = (float)(100.0 * TB_TAU * (double)P.sample_rate);
+    sk.plimit = 600.0f;
+
+    uint32_t* gstate = P.state + (size_t)voice * P.state_words;
+    if (active) {
+        // ld.cg: with the work queue the block was last written by another CTA, possibly on another SM
+        for (uint32_t k = 0; k < P.state_words; k++) stw(M, (int)(P.n_cval + k), __ldcg(gstate + k));
+        setup_lane(P, M, P.params ? P.params + (size_t)voice * P.n_params : nullptr);
+        // Every filter must hold its full history (generator.rs:234-252): the host renders the
+        // first tile of a stream with the general interpreter before it comes here.
+        bool ready = true;
+        for (uint32_t fi = 0; fi < P.n_filt; fi++) {
+            const int so = (int)(P.n_cval + P.filt[fi].state_off);
+            ready = ready && ldw(M, so) != 0u && ldw(M, so + 1) == P.filt[fi].K - 1u;
+        }
+        if (!ready) {
+            if (P.fault) atomicAdd(P.fault, 1u);
+            active = false;
+        }
+    }
+    if (!active) {
+        UNROLL for (int q = 0; q < 8; q++) M.A[q * AS] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+
+    RowStore R;
+    R.out = P.out ? P.out + s0 : nullptr;
+    R.stride = P.out_stride;
+    R.tbase = atile + warp * 32;
+    R.v0 = v0;
+    R.n_voices = P.n_voices;
+    R.off = 0;
+    // Rows that are not 16-byte aligned (odd strides) take four scalar stores per lane instead.
+    R.vec_ok = (reinterpret_cast<uintptr_t>(P.out) & 15) == 0 && (P.out_stride & 3) == 0;
+    R.fast = R.vec_ok && P.out != nullptr && v0 + 32u <= P.n_voices;
+    R.mix = MIX ? P.mix_partial + (size_t)(v0 >> 5) * P.mix_stride + s0 : nullptr;
+    const bool warp_live = __any_sync(FULL, active);
+    const uint32_t code_s = (uint32_t)__cvta_generic_to_shared(code);
+    const u64 n_tiles = ns / (u64)LS;
+
+    // Single fused FM voice with a FAST carrier on the special-function unit (run_fm_voice).  The
+    // magic-number conversion of the carrier frequency is exact while |m| + |c| stays below its range
+    // limit; a warp holding a voice beyond it converts the slow way.
+    const bool fm_program = P.n_lane_code == 3 && (code[0].op & 0xffu) == LN_FM && ((code[0].op >> 16) & 0xffu) == 0 &&
+                            (code[0].op >> 24) == TB_SINE_FAST && P.fast_mode == 2;
+    bool fm_slow = false;
+    if (fm_program) {
+        bool ok = true;
+        if (active) ok = fabsf(ldf(M, code[1].a)) + fabsf(ldf(M, code[1].b)) < sk.flimit;
+        fm_slow = !__all_sync(FULL, ok);
+    }
+    if (warp_live || (MIX && v0 < P.n_voices)) {  // a warp without a live voice still owes its (zero) partial sums
+        if (fm_program) {
+            const bool tail = code[1].c >= 0;
+            if (!fm_slow) {
+                if (tail) run_fm_voice<true, MIX, false>(code, M, sk, R, active, l, n_tiles);
+                else run_fm_voice<false, MIX, false>(code, M, sk, R, active, l, n_tiles);
+            } else {
+                if (tail) run_fm_voice<true, MIX, true>(code, M, sk, R, active, l, n_tiles);
+                else run_fm_voice<false, MIX, true>(code, M, sk, R, active, l, n_tiles);
+            }
+        } else if constexpr (!FM_ONLY) {
+            float4* const abase = M.A;
+            for (u64 t = 0; t < n_tiles; t++) {
+                if (active) {
+                    M.A = abase + (t & 1) * 4 * AS;
+                    if (P.fast_mode == 2) run_lane_tile<2>(P, code_s, M, voice, sk);
+                    else run_lane_tile<1>(P, code_s, M, voice, sk);
+                }
+                tile_done<MIX>(R, l, t, n_tiles);
+            }
+            M.A = abase;
+        }
+    }
+    if (active) {
+        finish_lane(P, M, ns);
+        for (uint32_t k = 0; k < P.state_words; k++) gstate[k] = ldw(M, (int)(P.n_cval + k));
+        if (P.out_len) P.out_len[voice] = (accumulate ? __ldcg(P.out_len + voice) : 0ull) + ns;
+    }
+}
+
+}  // namespace

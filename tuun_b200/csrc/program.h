@@ -238,6 +238,9 @@ struct tb_launch {
     uint32_t n_lane_code, n_lane_aux;
     uint32_t lane_w_words, lane_q_units, lane_slots;
     uint32_t* fault;       // device counter: voices the lane kernel found without complete filter history
+    uint32_t* lane_queue;  // lane kernel work queue ([0] unit counter, [1 + g] segments finished by group g) or NULL
+    uint32_t lane_groups, lane_segs, lane_grid;  // voice groups, time segments, persistent CTAs
+    uint64_t lane_seg_samples;                   // samples per segment (a multiple of 2 * TB_LS)
     float* mix_partial;    // lane kernel, mixdown without rows: [ceil(n_voices / 32)][mix_stride] sums of 32 voices
     uint64_t mix_stride;
     uint32_t fast_mode;    // FAST-class sine evaluation: 1 = f32 polynomial, 2 = MUFU
