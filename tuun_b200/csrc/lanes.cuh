@@ -154,6 +154,9 @@ __device__ __forceinline__ double f32_to_f64_alu(float f) {
 #ifndef TB_F2F_ALU
 #define TB_F2F_ALU 0
 #endif
+#ifndef TB_F2F_ALU_EVERY
+#define TB_F2F_ALU_EVERY 1
+#endif
 __device__ __forceinline__ uint32_t magic_lo(float f, double scale) {
 #if TB_F2F_ALU
     return (uint32_t)__double2loint(fma(f32_to_f64_alu(f), scale, 6755399441055744.0));
@@ -579,6 +582,20 @@ struct RowStore {
     bool fast, vec_ok;
     float* mix;            // mixdown without rows (tb_launch::mix_partial): this warp's row of partial sums
 };
+#ifndef TB_ST
+#define TB_ST 2
+#endif
+__device__ __forceinline__ void st_row(float4* d, const float4& v) {
+#if TB_ST == 0
+    __stcs(d, v);
+#elif TB_ST == 1
+    *d = v;
+#elif TB_ST == 2
+    __stcg(d, v);
+#else
+    __stwt(d, v);
+#endif
+}
 __device__ __forceinline__ void put4(float* d, const float4& v, bool vec_ok) {
     if (vec_ok) __stcs(reinterpret_cast<float4*>(d), v);
     else { d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w; }
@@ -592,7 +609,7 @@ __device__ __forceinline__ void store_pair(RowStore& R, int l) {
     float* d = R.out + (size_t)(R.v0 + (l >> 3)) * R.stride + R.off + (size_t)(l & 7) * 4;
     const size_t step = 4 * R.stride;
     if (R.fast) {  // all 32 rows of the warp exist and are 16-byte aligned
-        UNROLL for (int i = 0; i < 8; i++) __stcs(reinterpret_cast<float4*>(d + i * step), v[i]);
+        UNROLL for (int i = 0; i < 8; i++) st_row(reinterpret_cast<float4*>(d + i * step), v[i]);
     } else if (R.out) {
         UNROLL for (int i = 0; i < 8; i++)
             if (R.v0 + (uint32_t)(l >> 3) + 4u * i < R.n_voices) put4(d + i * step, v[i], R.vec_ok);
@@ -678,17 +695,37 @@ __device__ __forceinline__ void fm_carrier_tile(float (&car)[LS], double& S, dou
     Cq = fma(Cq, r16.x, -(S * r16.y));
     S = S2;
     UNROLL for (int j = 0; j < LS; j += 2) unpk2(add2(mul2(pk2(f[j], f[j + 1]), mm), cc), f[j], f[j + 1]);
+    if (SLOW) {
+        UNROLL for (int j = 0; j < LS; j += 2) {
+            const uint32_t t0 = p;
+            p += (uint32_t)(freq_to_inc(f[j], sk) >> 32);
+            const uint32_t t1 = p;
+            p += (uint32_t)(freq_to_inc(f[j + 1], sk) >> 32);
+            sin_p32x2(t0, t1, car[j], car[j + 1]);
+        }
+        return;
+    }
+    // The running phase lives in the low word of a double kept at 1.5 * 2^52 + p (units of 2^-32
+    // turns): one DFMA per sample adds f * ks and rounds the sum to that grid, whole turns collect
+    // above bit 31 and are dropped when the double is rebuilt for the next tile.  (The sum is rounded,
+    // not the increments; the carried 64-bit accumulator still advances by exactly what was added.)
+    double Pd = __hiloint2double(0x43380000, (int)p);
     UNROLL for (int j = 0; j < LS; j += 2) {
-        const uint32_t t0 = p;
-        p += SLOW ? (uint32_t)(freq_to_inc(f[j], sk) >> 32) : magic_lo(f[j], ks);
-        const uint32_t t1 = p;
-        p += SLOW ? (uint32_t)(freq_to_inc(f[j + 1], sk) >> 32) : magic_lo(f[j + 1], ks);
+        const uint32_t t0 = (uint32_t)__double2loint(Pd);
+        Pd = fma((double)f[j], ks, Pd);
+        const uint32_t t1 = (uint32_t)__double2loint(Pd);
+#if TB_F2F_ALU == 2
+        Pd = fma(((j >> 1) % TB_F2F_ALU_EVERY == 0) ? f32_to_f64_alu(f[j + 1]) : (double)f[j + 1], ks, Pd);
+#else
+        Pd = fma((double)f[j + 1], ks, Pd);
+#endif
 #if TB_ABL == 2
         car[j] = __uint_as_float(mant23(t0)); car[j + 1] = __uint_as_float(mant23(t1));
 #else
         sin_p32x2(t0, t1, car[j], car[j + 1]);
 #endif
     }
+    p = (uint32_t)__double2loint(Pd);
 }
 struct BiquadRegs {
     float b0, b1, b2, a1, a2;
