@@ -154,9 +154,7 @@ __device__ __forceinline__ double f32_to_f64_alu(float f) {
 #ifndef TB_F2F_ALU
 #define TB_F2F_ALU 0
 #endif
-#ifndef TB_F2F_ALU_EVERY
-#define TB_F2F_ALU_EVERY 1
-#endif
+
 __device__ __forceinline__ uint32_t magic_lo(float f, double scale) {
 #if TB_F2F_ALU
     return (uint32_t)__double2loint(fma(f32_to_f64_alu(f), scale, 6755399441055744.0));
@@ -714,11 +712,7 @@ __device__ __forceinline__ void fm_carrier_tile(float (&car)[LS], double& S, dou
         const uint32_t t0 = (uint32_t)__double2loint(Pd);
         Pd = fma((double)f[j], ks, Pd);
         const uint32_t t1 = (uint32_t)__double2loint(Pd);
-#if TB_F2F_ALU == 2
-        Pd = fma(((j >> 1) % TB_F2F_ALU_EVERY == 0) ? f32_to_f64_alu(f[j + 1]) : (double)f[j + 1], ks, Pd);
-#else
         Pd = fma((double)f[j + 1], ks, Pd);
-#endif
 #if TB_ABL == 2
         car[j] = __uint_as_float(mant23(t0)); car[j + 1] = __uint_as_float(mant23(t1));
 #else
