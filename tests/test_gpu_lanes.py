@@ -312,3 +312,28 @@ def test_work_queue_segments(monkeypatch):
     mix = np.zeros(N, dtype=np.float32)
     program(w, monkeypatch).render_mix(mix, V, params=params)
     assert np.max(np.abs(mix - q.sum(axis=0, dtype=np.float64))) <= 1e-3
+
+
+@pytest.mark.parametrize("fast_sines", ["0", "1"])
+def test_sine_precision_modes(monkeypatch, fast_sines):
+    """TUUN_B200_FAST_SINES: "0" makes every sine EXACT class (f64 polynomial), "1" evaluates the FAST
+    class with the f32 polynomial instead of MUFU.SIN; the lane interpreter has its own code for both."""
+    monkeypatch.setenv("TUUN_B200_FAST_SINES", fast_sines)
+    V, N = 130, 256 + 16 * 90 + 4
+    w, params = cfg5(V)
+    p = program(w, monkeypatch)
+    out = np.zeros((V, N), dtype=np.float32)
+    p.render(out, params=params)
+    assert p.info.lane_launches == 1 and p.info.lane_fm_capacity == 0  # the FM kernel is for MUFU carriers only
+    ref, _, _, _ = OracleProgram(w, SR).render_batch(params, V, N)
+    assert np.max(np.abs(out - ref)) <= TOL
+    # phase-modulated and doubly modulated sines through the same modes
+    pm = Sine(Const(1.0, param=0), mul(Sine(add(mul(Sine(Const(1.0, param=1), Const(0.0)), Const(40.0)), Const(1.0, param=2)),
+                                            Const(0.2)), Const(4.0)))
+    rng = np.random.default_rng(9)
+    pr = np.stack([TAU * rng.uniform(100, 900, V), TAU * rng.uniform(1, 9, V), TAU * rng.uniform(50, 400, V)], axis=1).astype(np.float32)
+    q = program(pm, monkeypatch)
+    out = np.zeros((V, N), dtype=np.float32)
+    q.render(out, params=pr)
+    assert q.info.lane_launches == 1
+    assert np.max(np.abs(out - oracle_rows(pm, pr, V, N))) <= TOL
