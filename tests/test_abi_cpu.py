@@ -79,11 +79,16 @@ def test_no_device_fails_loudly():
 
 def test_lane_plan_of_the_headline_voice():
     """Host half only: the FM + low-pass voice of config 5 qualifies for the lane-per-voice kernel
-    (csrc/lanes.cu) and its lane program fuses into one LN_FM word; a finite tree does not qualify."""
+    (csrc/lanes.cuh) and its lane program fuses into one LN_FM word."""
     from tuun_b200.generator import lower_check
     from tuun_b200.workloads import cfg1_sine, fm_filter_voice
     info = lower_check(fm_filter_voice())
     assert info.tile == 512 and info.lane_smem_bytes > 0
     # code (LN_FM two words + END) + 9 rotation units + the 8-chunk accumulator buffer + W words, 64 voices per CTA
     assert info.lane_smem_bytes == 3 * 16 + 9 * 64 * 16 + 8 * 65 * 16 + 37 * 64 * 4
-    assert lower_check(cfg1_sine()).lane_smem_bytes == 0  # Fin: not a steady-state tree
+    # a note of fixed duration (root Fin with an analytic length over a steady tree) qualifies too, though
+    # not for the warp-per-voice steady interpreter (tile 256); a rendered length (Fin over a Sine) does not
+    fin = lower_check(cfg1_sine())
+    assert fin.lane_smem_bytes > 0 and fin.tile == 256
+    from tuun_b200.waveform import Const, Fin, Sine
+    assert lower_check(Fin(Sine(Const(1.0), Const(0.0)), Sine(Const(440.0), Const(0.0)))).lane_smem_bytes == 0

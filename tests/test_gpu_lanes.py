@@ -337,3 +337,50 @@ def test_sine_precision_modes(monkeypatch, fast_sines):
     q.render(out, params=pr)
     assert q.info.lane_launches == 1
     assert np.max(np.abs(out - oracle_rows(pm, pr, V, N))) <= TOL
+
+
+def test_notes_of_fixed_duration(monkeypatch):
+    """Root Fin with an analytic length over a steady tree — `$f * Qw` (config 1), any note with a fixed
+    duration: the lane kernel renders the inner tree and counts how much of it belongs to each voice.
+    Lengths are bit-exact (per-voice durations), samples within tolerance up to each voice's end (the
+    tail of a finished voice's row is undefined, generator.rs:76-95), later calls return 0."""
+    from tuun_b200.waveform import Fin
+    from tuun_b200.workloads import fm_filter_voice
+    V, N = 700, 256 + 16 * 1200 + 9
+    rng = np.random.default_rng(4)
+    dur = rng.uniform(0.003, 0.6, V).astype(np.float32)   # 132 .. 26,460 samples: some end inside the head tile,
+    dur[:5] = [0.0, 0.5, 1.0, 256 / SR, 19465 / SR]         # some never inside this call, some on tile edges
+    note = Fin(add(Time(), Const(0.0, param=0)), Sine(Const(1.0, param=1), Const(0.0)))   # cfg1 with swept Q and f
+    params = np.stack([-dur, TAU * rng.uniform(100, 2000, V).astype(np.float32)], axis=1).astype(np.float32)
+    p = program(note, monkeypatch)
+    out = np.full((V, N), np.inf, dtype=np.float32)
+    lens = p.render(out, params=params)
+    assert p.info.lane_launches == 1
+    o = OracleProgram(note, SR)
+    olens = np.zeros(V, dtype=np.int64)
+    for v in range(V):
+        o.initialize_state()
+        o.set_params(params[v])
+        ref = o.render(N)
+        olens[v] = len(ref)
+        assert lens[v] == len(ref), (v, dur[v])
+        assert np.max(np.abs(out[v, :len(ref)] - ref), initial=0.0) <= 1e-6, v
+    assert (olens == N).sum() > 50 and (olens < 256).sum() > 5
+    # the stream continues: unfinished voices go on where they were, finished ones return 0 for good
+    out2 = np.full((V, 4096), np.inf, dtype=np.float32)
+    lens2 = p.render(out2, params=params)
+    for v in range(V):
+        o.initialize_state()
+        o.set_params(params[v])
+        full = o.render(N + 4096)
+        assert lens2[v] == max(0, len(full) - N), v
+        assert np.max(np.abs(out2[v, :lens2[v]] - full[N:]), initial=0.0) <= 1e-6
+    # an FM + low-pass note: the fused voice kernel under a Fin
+    fmnote = Fin(sub(Time(), Const(0.25)), fm_filter_voice())
+    w, fp = cfg5(V)
+    q = program(fmnote, monkeypatch)
+    out = np.zeros((V, N), dtype=np.float32)
+    lens = q.render(out, params=fp)
+    assert (lens == 11025).all() and q.info.lane_launches == 1 and q.info.lane_fm_capacity > 0
+    ref, _, _, _ = OracleProgram(w, SR).render_batch(fp, V, 11025)
+    assert np.max(np.abs(out[:, :11025] - ref)) <= TOL

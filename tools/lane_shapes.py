@@ -5,7 +5,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from tuun_b200.generator import Program
-from tuun_b200.waveform import Alt, Const, Filter, Noise, Sine, add, f32, mul
+from tuun_b200.waveform import Alt, Const, Filter, Fin, Noise, Sine, Time, add, f32, mul, sub
 from tuun_b200.workloads import fm_filter_params, fm_filter_voice, lpf
 
 SR, V = 44100, 65536
@@ -24,6 +24,8 @@ shapes = [
     ("fm", fm, p5),
     ("fm|lpf (cfg5)", fm_filter_voice(), p5),
     ("fm|lpf|lpf|lpf", lpf(lpf(fm_filter_voice(), 2.0, 1600), 1.0, 3200), p5),
+    ("$f * note(N)", Fin(sub(Time(), Const(f32(N / SR))), Sine(Const(1.0, param=0), Const(0.0))), fr),   # cfg1 shape, swept f
+    ("(fm|lpf) * note(N)", Fin(sub(Time(), Const(f32(N / SR))), fm_filter_voice()), p5),
 ]
 out = torch.empty((V, N), dtype=torch.float32, device="cuda")
 

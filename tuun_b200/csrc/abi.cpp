@@ -222,6 +222,7 @@ void fill_launch(const tb_program* p, tb_launch* L) {
     L->lane_q_units = p->low.lane_q_units;
     L->lane_slots = p->low.lane_slots;
     L->fault = p->d_fault;
+    L->lane_fin_goe = p->low.lane_fin_goe;
 }
 
 int launch(tb_program* p, const tb_launch& L) {
@@ -286,7 +287,9 @@ int launch_lanes(tb_program* p, tb_launch& B) {
 int launch_generate(tb_program* p, const tb_launch& L, uint64_t pos) {
     const bool big = p->lane_smem != 0 && L.n_voices >= p->lane_min_voices && L.out != nullptr;
     if (!big) return launch(p, L);
-    const bool primed = p->pos_known && pos >= (uint64_t)TB_TILE;  // every filter holds its full history
+    // Primed: every filter holds its full history.  A root Fin decides "already over?" by the reference's
+    // per-call test (generator.rs:808-809), which the general tile at the head of every call applies.
+    const bool primed = p->pos_known && pos >= (uint64_t)TB_TILE && p->low.lane_fin_goe < 0;
     uint64_t head = primed ? 0 : TB_TILE;
     if (L.n_samples < head + TB_LS) {  // too short for a lane tile: same arithmetic, general tiles
         tb_launch G = L;
@@ -310,7 +313,8 @@ int launch_generate(tb_program* p, const tb_launch& L, uint64_t pos) {
     B.out = L.out + head;
     B.n_samples = bulk;
     B.accumulate = head ? 1 : L.accumulate;
-    B.done = nullptr;  // every node of a steady program is infinite: no voice ever finishes
+    B.call_pos = L.call_pos + head;
+    B.done = nullptr;  // the lane kernel renders finished voices too (their tails are undefined) and counts
     if ((rc = launch_lanes(p, B))) return rc;
     if (tail) {
         tb_launch T = L;
@@ -318,6 +322,7 @@ int launch_generate(tb_program* p, const tb_launch& L, uint64_t pos) {
         T.n_samples = tail;
         T.accumulate = 1;
         T.exact_fb = 1;
+        T.mid_call = 1;
         if ((rc = launch(p, T))) return rc;
     }
     return TB_OK;
@@ -627,7 +632,7 @@ int render_impl(tb_program* p, const float* params, uint32_t n_params, uint32_t 
         }
     }
     const bool primed = p->pos_known && p->stream_pos >= (uint64_t)TB_TILE;
-    if (no_rows && p->lane_smem != 0 && n_voices >= p->lane_min_voices &&
+    if (no_rows && p->lane_smem != 0 && p->low.lane_fin_goe < 0 && n_voices >= p->lane_min_voices &&
         n_samples >= (primed ? 0 : (uint64_t)TB_TILE) + 2 * TB_LS) {
         L.params = d_params;
         L.n_voices = n_voices;
@@ -681,6 +686,8 @@ int render_impl(tb_program* p, const float* params, uint32_t n_params, uint32_t 
                 L.out_len = p->d_len + v0;
                 L.done = cut_time ? p->d_done + v0 : nullptr;
                 L.accumulate = t0 > 0;
+                L.mid_call = t0 > 0;
+                L.call_pos = t0;
                 L.n_voices = g;
                 L.n_samples = len;
                 L.out = p->d_stage[b];

@@ -940,8 +940,34 @@ __device__ __forceinline__ void lanes_body(const tb_launch& P, uint32_t group, u
     }
     if (active) {
         finish_lane(P, M, ns);
+        u64 mine = ns;  // samples of this unit that belong to the voice
+        const u64 before = (accumulate && P.out_len) ? __ldcg(P.out_len + voice) : 0ull;
+        if (P.lane_fin_goe >= 0) {
+            // Root Fin (generator.rs:133-168): the inner tree was rendered for the whole unit (the tail of a
+            // finished voice's row is undefined by contract, generator.rs:76-95); what counts is how far the
+            // analytic length reaches (greater_or_equals_at, :787-862, the arithmetic of goe_eval in render.cu).
+            const tb_goe g = P.goe[P.lane_fin_goe];
+            float value = 0.0f;
+            for (uint32_t k = 0; k < g.n_steps; k++) {
+                const int sign = P.goe_steps[g.step_off + 2 * k];
+                const float c = ldf(M, P.goe_steps[g.step_off + 2 * k + 1]);
+                value = sign > 0 ? __fadd_rn(value, c) : __fsub_rn(value, c);
+            }
+            u64 rem = ~0ull;
+            if (g.term == GOE_TIME) {
+                const int wt = (int)P.n_cval + g.term_arg;
+                const u64 pos = ld64(M, wt);
+                const u64 target = f32_as_usize(ceilf(__fmul_rn(value, (float)P.sample_rate)));
+                rem = target > pos ? target - pos : 0ull;
+                st64(M, wt, pos + ns);  // Fin advances both children to the end of the block (:141-167)
+            } else if (ldf(M, g.term_arg) >= value) {
+                rem = 0ull;
+            }
+            if (before < P.call_pos + s0) rem = 0ull;  // returned short earlier in this call
+            mine = rem < ns ? rem : ns;
+        }
         for (uint32_t k = 0; k < P.state_words; k++) gstate[k] = ldw(M, (int)(P.n_cval + k));
-        if (P.out_len) P.out_len[voice] = (accumulate ? __ldcg(P.out_len + voice) : 0ull) + ns;
+        if (P.out_len) P.out_len[voice] = before + mine;
     }
 }
 

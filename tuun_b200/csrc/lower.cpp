@@ -935,7 +935,29 @@ struct Lowerer {
             const size_t code0 = out.code.size(), cexpr0 = out.cexpr.size(), aux0 = out.aux.size();
             const uint32_t aux_words0 = out.aux_words, slots0 = out.n_slots;
             out.pc_steady = (uint32_t)here();
-            if (emit_steady(root)) {
+            // A root Fin whose length is found analytically (generator.rs:787-862: Time, constants, +- constants)
+            // over a steady tree — `$440 * Qw`, any note with a fixed duration — is rendered by the lane kernel
+            // as its inner tree; the lane kernel only has to count how much of it belongs to the voice
+            // (tb_launch::lane_fin_goe).  The warp-per-voice steady interpreter does not take such trees.
+            int sroot = root;
+            while (nodes[sroot].kind == TB_MARKED || nodes[sroot].kind == TB_CAPTURED) sroot = nodes[sroot].a;
+            bool fin_ok = false;
+            if (nodes[sroot].kind == TB_FIN) {
+                const size_t goe0 = out.goe.size(), steps0 = out.goe_steps.size();
+                const int gi = build_goe(nodes[sroot].a);
+                const tb_goe g = out.goe[gi];
+                if ((g.term == GOE_TIME || g.term == GOE_CONST) && !g.through_append && emit_steady(nodes[sroot].b)) {
+                    emit(ST_END);
+                    out.lane_fin_goe = gi;
+                    fin_ok = true;
+                } else {
+                    out.goe.resize(goe0);
+                    out.goe_steps.resize(steps0);
+                }
+            }
+            if (fin_ok) {
+                out.steady_ok = 0;
+            } else if (nodes[sroot].kind != TB_FIN && emit_steady(root)) {
                 emit(ST_END);
                 out.steady_ok = 1;
             } else {
@@ -955,7 +977,8 @@ struct Lowerer {
         if (out.cexpr.empty()) literal_cexpr(0.f);
         if (out.aux_words == 0) out.aux_words = 1;
         if (out.n_slots == 0) out.n_slots = 1;
-        out.lane_ok = (out.steady_ok && build_lane_plan()) ? 1u : 0u;
+        out.lane_ok = ((out.steady_ok || out.lane_fin_goe >= 0) && build_lane_plan()) ? 1u : 0u;
+        if (!out.lane_ok) out.lane_fin_goe = -1;
         out.n_nodes = n_nodes;
     }
 };

@@ -238,6 +238,10 @@ struct tb_launch {
     uint32_t n_lane_code, n_lane_aux;
     uint32_t lane_w_words, lane_q_units, lane_slots;
     uint32_t* fault;       // device counter: voices the lane kernel found without complete filter history
+    int32_t lane_fin_goe;  // lane kernel: the program is Fin{analytic length, steady tree}; goe entry of the length, else -1
+    uint32_t mid_call;     // this launch continues a generate call (Fin keeps the cut the call's first tile made)
+    uint64_t call_pos;     // samples of the current call rendered before this launch (lane kernel: voices whose
+                           // out_len is below it returned short earlier in the call)
     uint32_t* lane_queue;  // lane kernel work queue ([0] unit counter, [1 + g] segments finished by group g) or NULL
     uint32_t lane_groups, lane_segs, lane_grid;  // voice groups, time segments, persistent CTAs
     uint64_t lane_seg_samples;                   // samples per segment (a multiple of 2 * TB_LS)

@@ -1400,7 +1400,7 @@ tb_render_kernel(const tb_launch P) {
             cx.w0 = 0;
             cx.w1 = left < (u64)TILE ? (int)left : TILE;
             cx.L = 0;
-            cx.first_tile = tbase == 0;
+            cx.first_tile = tbase == 0 && !P.mid_call;
             run_program(P, code, M, cx, acc, (int)P.pc_gen, sk, ctl);
             const int L = cx.L;
             if (row) {
@@ -1427,7 +1427,7 @@ tb_render_kernel(const tb_launch P) {
             cx.w0 = 0;
             cx.w1 = left < step ? (int)left : (int)step;
             cx.L = 0;
-            cx.first_tile = tbase == 0;
+            cx.first_tile = tbase == 0 && !P.mid_call;
             run_program(P, code, M, cx, acc, (int)P.pc_len, sk, ctl);
             total += (u64)cx.L;
             if (cx.L < cx.w1) break;
