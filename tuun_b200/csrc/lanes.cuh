@@ -471,15 +471,19 @@ __device__ __forceinline__ void run_lane_tile(const tb_launch& P, uint32_t code_
                 ip += sizeof(tb_insn);
                 nxt = lds_insn(ip);
                 const float m = ldf(M, ex.a), c = ldf(M, ex.b);
-                const u64 ph0 = ld64(M, in.c);
+                const u64 ph0 = ld64(M, in.c);  // phase offset of the carrier (TB_LN_FM_PHASE: its increment)
                 float f[LS];
                 lane_sine_cc(M, f, in.a, (int)((in.op >> 8) & 0xffu));
                 {
                     const u64 mm = pk2(m, m), cc = pk2(c, c);
                     UNROLL for (int j = 0; j < LS; j += 2) unpk2(add2(mul2(pk2(f[j], f[j + 1]), mm), cc), f[j], f[j + 1]);
                 }
-                const bool fastfm = ((in.op >> 24) & 0xffu) == TB_SINE_FAST;
-                if (fabsf(m) + fabsf(c) < sk.flimit) {  // |f| <= |m| + |c|: no per-sample range test
+                const bool fastfm = ((in.op >> 24) & 0x3fu) == TB_SINE_FAST;
+                if ((in.op >> 24) & TB_LN_FM_PHASE) {  // phase modulation: constant increment, f holds the phases
+                    UNROLL for (int j = 0; j < LS; j++) acc[j] = f[j];
+                    if (!fastfm) lane_sine_ca<0>(M, acc, ph0, in.b, sk);
+                    else lane_sine_ca<FASTMODE>(M, acc, ph0, in.b, sk);
+                } else if (fabsf(m) + fabsf(c) < sk.flimit) {  // |f| <= |m| + |c|: no per-sample range test
                     if (!fastfm) lane_sine_var<true, 0, false>(M, acc, f, ph0, in.b, sk);
                     else lane_sine_var<true, FASTMODE, false>(M, acc, f, ph0, in.b, sk);
                 } else {

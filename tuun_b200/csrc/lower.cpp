@@ -872,14 +872,16 @@ struct Lowerer {
         return true;
     }
     // Peephole over the lane program: a constant-rate sine, scaled and offset, driving the frequency of
-    // a sine with constant phase (vibrato, FM: `$(c + m * $f)`), optionally straight into a biquad
-    // (every filter of lib/v0/std.tuun), becomes one LN_FM instruction (program.h).
+    // a sine with constant phase (vibrato, FM: `$(c + m * $f)`) or the phase of a sine with constant
+    // frequency (PM: `sine(f, m * $g)`), optionally straight into a biquad (every filter of
+    // lib/v0/std.tuun), becomes one LN_FM instruction (program.h).
     void fuse_lane_fm() {
         std::vector<tb_insn> in = out.lane_code, res;
         for (size_t i = 0; i < in.size();) {
             const tb_insn& cc = in[i];
             const bool cand = (cc.op & 0xffu) == ST_SINE_CC && (cc.op >> 16) == 1 && i + 2 < in.size() &&
-                              (in[i + 1].op & 0xffu) == ST_AFFINE && (in[i + 2].op & 0xffu) == ST_SINE_AC;
+                              (in[i + 1].op & 0xffu) == ST_AFFINE &&
+                              ((in[i + 2].op & 0xffu) == ST_SINE_AC || (in[i + 2].op & 0xffu) == ST_SINE_CA);
             if (!cand) {
                 // copy the instruction with its post-op words
                 const size_t n = 1 + (((cc.op & 0xffu) == ST_END) ? 0 : (cc.op >> 16));
@@ -892,10 +894,11 @@ struct Lowerer {
             uint32_t np = ac.op >> 16;
             size_t next = i + 3;  // first post-op word of the carrier, if any
             tb_insn w0{}, w1{};
-            w0.op = LN_FM | (cc.op & 0xff00u) | (((ac.op >> 8) & 0xffu) << 24);
+            const bool pm = (ac.op & 0xffu) == ST_SINE_CA;  // the scaled sine drives the phase, not the frequency
+            w0.op = LN_FM | (cc.op & 0xff00u) | (((ac.op >> 8) & 0xffu) << 24) | (pm ? TB_LN_FM_PHASE << 24 : 0u);
             w0.a = cc.b + 2;
             w0.b = ac.a;
-            w0.c = ac.c;
+            w0.c = pm ? ac.b : ac.c;
             w1.op = 0;
             w1.a = aff.b;
             w1.b = aff.c;

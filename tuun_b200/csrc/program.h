@@ -127,9 +127,10 @@ enum tb_op : uint32_t {
     ST_AFFINE,     // post-op word: acc = (acc * cval[b]) + cval[c], both operations rounded
     ST_OPC,        // post-op word: acc = acc (operator a) cval[b]
     // ---- lane program only (lanes.cu; fused by lower.cpp build_lane_plan) ----
-    LN_FM,         // ST_SINE_CC + one ST_AFFINE + ST_SINE_AC [+ ST_FILT K=3 J=2], two words:
+    LN_FM,         // ST_SINE_CC + one ST_AFFINE + ST_SINE_AC (or ST_SINE_CA) [+ ST_FILT K=3 J=2], two words:
                    //   word 0: a = W of the carried (sin, cos), b = W of the carrier's accumulator,
-                   //           c = W of its phase offset; op bits 8-15 rotation Q units, 24-31 carrier class
+                   //           c = W of its phase offset (TB_LN_FM_PHASE: of its increment); op bits 8-15
+                   //           rotation Q units, 24-31 carrier class | TB_LN_FM_PHASE
                    //   word 1: a, b = cval of the affine map; c = W of the filter state or -1, op = W of its coefficients
     OP_COUNT
 };
@@ -137,6 +138,8 @@ enum tb_op : uint32_t {
 // Operand encoding for instructions that take "a waveform that may be constant":
 //   >= 0  shared-memory slot index;   < 0  ~cval index.
 #define TB_OPERAND_CONST(k) (~(int32_t)(k))
+
+#define TB_LN_FM_PHASE 0x40u  // LN_FM: the scaled sine is the carrier's phase (ST_SINE_CA), not its frequency
 
 // Sine precision classes (op >> 8 of the G_SINE_* / S_SINE_* instructions).
 #define TB_SINE_EXACT 0u  // f64 polynomial, rounds like the reference's (f64 sin) as f32
