@@ -128,7 +128,7 @@ namespace {
 bool size_cta(const tb::Lowered& low, uint32_t* warps, size_t* smem) {
     for (uint32_t w = TB_WARPS_PER_CTA; w >= 1; w >>= 1) {
         const size_t s = tb_kernel_smem_bytes((uint32_t)low.code.size(), low.n_slots, low.aux_words,
-                                              (uint32_t)low.cexpr.size(), low.state_words, low.steady_ok, w);
+                                              (uint32_t)low.cexpr.size(), low.state_words, low.steady_ok || low.lane_fin_goe >= 0, w);
         if (s <= 220 * 1024) {
             *warps = w;
             *smem = s;
@@ -420,7 +420,11 @@ int tb_program_create(const tb_node* nodes, uint32_t n_nodes, const int32_t* lis
     p->sample_rate = sample_rate;
     p->fast_mode = (fs && fs[0] == '1') ? 1u : 2u;  // "0" all exact, "1" f32 polynomial, default MUFU
     if (const char* se = std::getenv("TUUN_B200_STEADY"))
-        if (se[0] == '0') p->low.steady_ok = 0;  // diagnostics: force the general interpreter
+        if (se[0] == '0') {  // diagnostics: force the general interpreter (and with it the warp-per-voice kernel)
+            p->low.steady_ok = 0;
+            p->low.lane_ok = 0;
+            p->low.lane_fin_goe = -1;
+        }
     // Everything below needs a device: no CPU path exists.
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);

@@ -1321,7 +1321,11 @@ tb_render_kernel(const tb_launch P) {
     }
 
     size_t off = ((size_t)P.n_code * sizeof(tb_insn) + 15) & ~(size_t)15;
-    const size_t per_warp_slots = (size_t)P.n_slots * (P.steady_ok ? TILE_S : TILE) * sizeof(float);
+    // A root Fin with an analytic length over a steady tree (tb_launch::lane_fin_goe, lower.cpp) carries the
+    // ST_* stream of its inner tree: whole tiles well inside the note run through the steady interpreter too.
+    const bool fin = P.lane_fin_goe >= 0;
+    const bool st_cap = P.steady_ok || fin;
+    const size_t per_warp_slots = (size_t)P.n_slots * (st_cap ? TILE_S : TILE) * sizeof(float);
     const size_t aux_b = ((size_t)P.aux_words * 8 + 15) & ~(size_t)15;
     const size_t cval_b = ((size_t)P.n_cval * 4 + 15) & ~(size_t)15;
     const size_t state_b = ((size_t)P.state_words * 4 + 15) & ~(size_t)15;
@@ -1370,7 +1374,26 @@ tb_render_kernel(const tb_launch P) {
             }
             return ready;
         };
-        bool steady = P.steady_ok && filters_ready();
+        bool steady = st_cap && filters_ready();
+        // Root Fin: where the note ends (greater_or_equals_at over the flattened chain, goe_eval) and the
+        // position state of the Time node its length is measured on.
+        u64 fin_target = ~0ull;
+        int fin_time = -1;
+        if (fin) {
+            const tb_goe g = P.goe[P.lane_fin_goe];
+            float value = 0.0f;
+            for (uint32_t k = 0; k < g.n_steps; k++) {
+                const int sign = P.goe_steps[g.step_off + 2 * k];
+                const float c = M.cval[P.goe_steps[g.step_off + 2 * k + 1]];
+                value = sign > 0 ? __fadd_rn(value, c) : __fsub_rn(value, c);
+            }
+            if (g.term == GOE_TIME) {
+                fin_time = g.term_arg;
+                fin_target = f32_as_usize(ceilf(__fmul_rn(value, (float)P.sample_rate)));
+            } else if (M.cval[g.term_arg] >= value) {
+                fin_target = 0ull;  // over before it starts: the general tile says so
+            }
+        }
         // The lane index held in a register for the steady loop (S2R would otherwise be re-issued,
         // with its latency, wherever the compiler rematerialises threadIdx).
         int lane_pinned;
@@ -1378,7 +1401,13 @@ tb_render_kernel(const tb_launch P) {
         u64 tbase = 0;
         while (tbase < P.n_samples) {
             const u64 left = P.n_samples - tbase;
-            if (steady && left >= (u64)TILE_S) {
+            bool inside = true;  // a root Fin: the whole tile lies inside the note, and it is not the tile that
+                                 // applies the reference's per-call "already over?" test (generator.rs:808-809)
+            if (fin) {
+                const u64 pos = fin_time >= 0 ? ld_state64(M.state, fin_time) : 0ull;
+                inside = (tbase > 0 || P.mid_call) && fin_target >= pos + (u64)TILE_S;
+            }
+            if (steady && inside && left >= (u64)TILE_S) {
                 // Whole tile, every node infinite, histories complete: the steady-state interpreter.
                 float sacc[CS];
                 if (P.fast_mode == 2) run_steady<2>(P, code_s, M, sacc, sk, lane_pinned);
@@ -1392,6 +1421,13 @@ tb_render_kernel(const tb_launch P) {
                     } else {
                         UNROLL for (int j = 0; j < CS; j++) dst[j] = sacc[j];
                     }
+                }
+                if (fin_time >= 0) {  // Fin advances both children to the end of the block (generator.rs:141-167)
+                    __syncwarp();
+                    const u64 pos = ld_state64(M.state, fin_time);
+                    __syncwarp();
+                    if (l == 0) st_state64(M.state, fin_time, pos + (u64)TILE_S);
+                    __syncwarp();
                 }
                 total += (u64)TILE_S;
                 tbase += (u64)TILE_S;
@@ -1415,7 +1451,7 @@ tb_render_kernel(const tb_launch P) {
             total += (u64)L;
             if (L < cx.w1) break;
             tbase += (u64)TILE;
-            if (P.steady_ok && !steady) {
+            if (st_cap && !steady) {
                 __syncwarp();
                 steady = filters_ready();
             }
