@@ -384,3 +384,38 @@ def test_notes_of_fixed_duration(monkeypatch):
     assert (lens == 11025).all() and q.info.lane_launches == 1 and q.info.lane_fm_capacity > 0
     ref, _, _, _ = OracleProgram(w, SR).render_batch(fp, V, 11025)
     assert np.max(np.abs(out[:, :11025] - ref)) <= TOL
+
+
+def test_full_batch_of_65536_voices():
+    """BASELINE.json config 5 at its full voice count (default kernel selection, device rows, 4096
+    samples per voice): 512 voices spread over the sweep against the oracle, every length, the
+    mixdown against the rows, and the stream continued by a second call against one longer call."""
+    import torch
+    from tuun_b200.generator import Program
+    from tuun_b200.workloads import fm_filter_params, fm_filter_voice
+    V, N = 65536, 4096
+    w = fm_filter_voice()
+    params = fm_filter_params(np.arange(V))
+    pd = torch.from_numpy(params).cuda()
+    p = Program(w, SR)
+    assert p.info.lane_min_voices <= V and p.info.lane_fm_capacity * 64 >= V
+    out = torch.zeros((V, 2 * N), dtype=torch.float32, device="cuda")
+    lens = np.zeros(V, dtype=np.uint64)
+    p.render(out[:, :N], params=pd, out_len=lens)
+    assert (lens == N).all() and p.info.lane_launches == 1
+    p.render(out[:, N:], params=pd, out_len=lens)       # primed stream: the lane kernel alone
+    assert (lens == N).all() and p.info.lane_launches == 2 and p.info.kernel_launches == 3
+    pick = (np.arange(512) * 127 + 5) % V
+    got = out[torch.from_numpy(pick).cuda()].cpu().numpy()
+    ref, _, _, _ = OracleProgram(w, SR).render_batch(params[pick], len(pick), 2 * N, threads=4)
+    assert np.max(np.abs(got - ref)) <= TOL
+    one = torch.zeros((V, 2 * N), dtype=torch.float32, device="cuda")
+    Program(w, SR).render(one, params=pd)
+    d = (one - out).abs().amax(dim=1)
+    assert float(d.max()) <= TOL and float(d.median()) <= 5e-6
+    assert bool(torch.isfinite(out).all())
+    mix = torch.zeros(2 * N, dtype=torch.float32, device="cuda")
+    Program(w, SR).render_mix(mix, V, params=pd)
+    want = one.sum(dim=0, dtype=torch.float64)
+    # 65,536 f32 terms summed in blocks against an f64 sum (the voices start in phase: |mix| reaches thousands)
+    assert float((mix.double() - want).abs().max()) <= 0.05 + 2e-4 * float(want.abs().max())
