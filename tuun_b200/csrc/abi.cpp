@@ -236,10 +236,18 @@ int launch(tb_program* p, const tb_launch& L) {
 // 64-voice groups than the device holds CTAs, the launch is cut into time segments handed out through a
 // work queue (lanes.cu lanes_kernel): a plain grid would run a second, mostly empty wave for the whole
 // duration of the render.
+// One fused FM voice and a batch the device holds at once: the kernel of its own (lanes_fm.cu).
+bool fm_kernel_applies(const tb_program* p, uint32_t n_voices) {
+    const uint32_t groups = (n_voices + TB_LANE_THREADS - 1) / TB_LANE_THREADS;
+    const char* qe = std::getenv("TUUN_B200_LANE_QUEUE");
+    return p->lane_fm_capacity != 0 && groups <= p->lane_fm_capacity && !(qe && qe[0] == '1');
+}
+
 int launch_lanes(tb_program* p, tb_launch& B) {
     const uint32_t groups = (B.n_voices + TB_LANE_THREADS - 1) / TB_LANE_THREADS;
+    const bool fm = fm_kernel_applies(p, B.n_voices);
     const char* qe = std::getenv("TUUN_B200_LANE_QUEUE");  // diagnostics: "0" never, "1" always
-    const bool want = qe ? qe[0] == '1' : groups > p->lane_capacity;
+    const bool want = !fm && (qe ? qe[0] == '1' : groups > p->lane_capacity);
     B.lane_queue = nullptr;
     if (want && B.n_samples >= 4 * 2 * TB_LS) {
         // 16 segments (or fewer, of at least 1024 samples): the last wave of units wastes < 1/16 of the time
@@ -262,8 +270,6 @@ int launch_lanes(tb_program* p, tb_launch& B) {
         B.lane_seg_samples = seg;
         B.lane_grid = std::max<uint32_t>(1, p->lane_capacity);
     }
-    // One fused FM voice and a batch the device holds at once: its own kernel (lanes_fm.cu).
-    const bool fm = p->lane_fm_capacity != 0 && groups <= p->lane_fm_capacity && !B.lane_queue;
     cudaEvent_t* ev = p->lane_ev[p->lane_launches % tb_program::kLaneEvents];
     if (!ev[0]) {
         CU(cudaEventCreate(&ev[0]));
@@ -287,6 +293,14 @@ int launch_lanes(tb_program* p, tb_launch& B) {
 int launch_generate(tb_program* p, const tb_launch& L, uint64_t pos) {
     const bool big = p->lane_smem != 0 && L.n_voices >= p->lane_min_voices && L.out != nullptr;
     if (!big) return launch(p, L);
+    // The fused-FM-voice kernel starts a stream itself (the filter's read-ahead, run_fm_voice) and takes
+    // the samples that do not fill a tile: one launch for the whole call.  (A root Fin keeps its general
+    // head tile: the reference's per-call "already over?" test lives there.)
+    if (fm_kernel_applies(p, L.n_voices) && p->low.lane_fin_goe < 0 && p->pos_known && L.n_samples >= TB_LS) {
+        tb_launch B = L;
+        B.done = nullptr;
+        return launch_lanes(p, B);
+    }
     // Primed: every filter holds its full history.  A root Fin decides "already over?" by the reference's
     // per-call test (generator.rs:808-809), which the general tile at the head of every call applies.
     const bool primed = p->pos_known && pos >= (uint64_t)TB_TILE && p->low.lane_fin_goe < 0;

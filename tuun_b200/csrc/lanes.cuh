@@ -673,9 +673,11 @@ __device__ __forceinline__ void tile_done(RowStore& R, int l, u64 t, u64 n_tiles
 #endif
 // SLOW: some voice of the warp has |m| + |c| beyond the exact range of the magic-number conversion
 // (100 x the sample rate): every increment goes through the full-precision conversion instead.
-template <bool SLOW>
+//   CAP: also report in p_cap the phase before sample `cap` (the phase after `cap` samples of the tile).
+template <bool SLOW, bool CAP = false>
 __device__ __forceinline__ void fm_carrier_tile(float (&car)[LS], double& S, double& Cq, const double2* rot, u64 mm,
-                                                u64 cc, uint32_t& p, double ks, const SineK& sk) {
+                                                u64 cc, uint32_t& p, double ks, const SineK& sk, int cap = 0,
+                                                uint32_t* p_cap = nullptr) {
     float f[LS];
 #if TB_ABL == 4
     UNROLL for (int j = 0; j < LS; j++) f[j] = TB_D2F(S) + j;
@@ -703,6 +705,8 @@ __device__ __forceinline__ void fm_carrier_tile(float (&car)[LS], double& S, dou
             p += (uint32_t)(freq_to_inc(f[j], sk) >> 32);
             const uint32_t t1 = p;
             p += (uint32_t)(freq_to_inc(f[j + 1], sk) >> 32);
+            if (CAP && j == cap) *p_cap = t0;
+            if (CAP && j + 1 == cap) *p_cap = t1;
             sin_p32x2(t0, t1, car[j], car[j + 1]);
         }
         return;
@@ -717,6 +721,8 @@ __device__ __forceinline__ void fm_carrier_tile(float (&car)[LS], double& S, dou
         Pd = fma((double)f[j], ks, Pd);
         const uint32_t t1 = (uint32_t)__double2loint(Pd);
         Pd = fma((double)f[j + 1], ks, Pd);
+        if (CAP && j == cap) *p_cap = t0;
+        if (CAP && j + 1 == cap) *p_cap = t1;
 #if TB_ABL == 2
         car[j] = __uint_as_float(mant23(t0)); car[j + 1] = __uint_as_float(mant23(t1));
 #else
@@ -764,9 +770,44 @@ __device__ __forceinline__ void biquad_tile(float (&y)[LS], const float (&x)[LS]
     F.y2 = y[LS - 2];
 }
 
+// What run_fm_voice needs to know about the modulator beyond the LN_FM words (from its LA_ROT entry).
+struct FmPrime {
+    int acc_w;     // W index of the modulator's 64-bit accumulator
+    int ph_cval;   // cval of its phase offset
+    bool fresh;    // this voice's stream starts here: the filter has never run (state block all zero)
+};
+// The last `rem` < 16 samples of a launch: the tile is in the accumulator half `half`; rows get only
+// their first `rem` samples (the next row starts right behind).
+__device__ __forceinline__ void store_partial(RowStore& R, int l, int half, int rem) {
+    __syncwarp();
+    float4 v[4];
+    const float4* src = R.tbase + (4 * half + (l & 3)) * AS + (l >> 2);
+    UNROLL for (int i = 0; i < 4; i++) v[i] = src[8 * i];
+    __syncwarp();
+    if (R.out) {
+        float* d = R.out + (size_t)(R.v0 + (l >> 2)) * R.stride + R.off + (size_t)(l & 3) * 4;
+        const size_t step = 8 * R.stride;
+        const int e0 = (l & 3) * 4;
+        UNROLL for (int i = 0; i < 4; i++) {
+            if (R.v0 + (uint32_t)(l >> 2) + 8u * i < R.n_voices) {
+                float* q = d + i * step;
+                if (e0 + 0 < rem) q[0] = v[i].x;
+                if (e0 + 1 < rem) q[1] = v[i].y;
+                if (e0 + 2 < rem) q[2] = v[i].z;
+                if (e0 + 3 < rem) q[3] = v[i].w;
+            }
+        }
+    }
+    R.off += rem;
+}
+
+// n_tiles whole tiles, then `rem` < 16 more samples (a last tile of which only the first `rem` samples
+// count: its state is taken where they end).  A voice whose stream starts here (FmPrime::fresh) first does
+// what the filter's first call does in the reference — reads K - 1 = 2 carrier samples ahead and starts
+// from zero outputs (generator.rs:234-252) — so a call needs no launch of the general kernel at all.
 template <bool TAIL, bool MIX, bool SLOW>
 __device__ __forceinline__ void run_fm_voice(const tb_insn* code, LaneMem& M, const SineK& sk, RowStore& R,
-                                             bool active, int l, u64 n_tiles) {
+                                             bool active, int l, u64 n_tiles, int rem, const FmPrime& prime) {
     float4* const abase = M.A;
     const tb_insn w0 = code[0], w1 = code[1];
     double S = 0.0, Cq = 1.0;
@@ -786,8 +827,30 @@ __device__ __forceinline__ void run_fm_voice(const tb_insn* code, LaneMem& M, co
             const int wc = (int)w1.op, st = w1.c;
             F.b0 = ldf(M, wc); F.b1 = ldf(M, wc + 1); F.b2 = ldf(M, wc + 2);
             F.a1 = ldf(M, wc + 3); F.a2 = ldf(M, wc + 4);
-            F.x2 = ldf(M, st + 2); F.x1 = ldf(M, st + 3);
-            F.y2 = ldf(M, st + 4); F.y1 = ldf(M, st + 5);
+            if (prime.fresh) {
+                // The two carrier samples the filter reads ahead: the modulator by the exact polynomial,
+                // the affine map and the phase steps as in a tile.
+                const u64 inc = ld64(M, w0.a - 2);
+                const u64 am = ld64(M, prime.acc_w);
+                const u64 phm = turns_to_fx_slow((double)ldf(M, prime.ph_cval) / TB_TAU);
+                const float f0 = __fadd_rn(__fmul_rn((float)sin_turns_d8(am + phm), m), c);
+                const float f1 = __fadd_rn(__fmul_rn((float)sin_turns_d8(am + phm + inc), m), c);
+                F.x2 = sin_p32(p);
+                p += SLOW ? (uint32_t)(freq_to_inc(f0, sk) >> 32) : magic_lo(f0, ks);
+                F.x1 = sin_p32(p);
+                p += SLOW ? (uint32_t)(freq_to_inc(f1, sk) >> 32) : magic_lo(f1, ks);
+                F.y1 = F.y2 = 0.0f;
+                const u64 am2 = am + 2ull * inc;
+                st64(M, prime.acc_w, am2);
+                const u64 pc = am2 + phm + inc * (u64)(LS / 2);
+                S = sin_turns_d8(pc);
+                Cq = sin_turns_d8(pc + 0x4000000000000000ull);
+                stw(M, st, 1u);      // initialised,
+                stw(M, st + 1, 2u);  // K - 1 inputs held
+            } else {
+                F.x2 = ldf(M, st + 2); F.x1 = ldf(M, st + 3);
+                F.y2 = ldf(M, st + 4); F.y1 = ldf(M, st + 5);
+            }
             F.p1 = __fmul_rn(F.a1, F.y1);
             F.q2 = __fmul_rn(F.a2, F.y1);
             F.p2 = __fmul_rn(F.a2, F.y2);
@@ -804,7 +867,7 @@ __device__ __forceinline__ void run_fm_voice(const tb_insn* code, LaneMem& M, co
             }
             tile_done<MIX>(R, l, t, n_tiles);
         }
-    } else {
+    } else if (n_tiles > 0) {
         if (active) fm_carrier_tile<SLOW>(car, S, Cq, rot, mm, cc, p, ks, sk);
         for (u64 t = 1; t < n_tiles; t++) {
             if (active) {
@@ -830,8 +893,32 @@ __device__ __forceinline__ void run_fm_voice(const tb_insn* code, LaneMem& M, co
             lacc_store(M, y);
         }
         tile_done<MIX>(R, l, n_tiles - 1, n_tiles);
-        M.A = abase;
     }
+    if (!MIX && rem > 0) {  // the samples that do not fill a tile (rows only: the on-chip mixdown gets whole tiles)
+        const int half = (int)(n_tiles & 1);
+        if (active) {
+            uint32_t p_rem = p;
+            fm_carrier_tile<SLOW, true>(car, S, Cq, rot, mm, cc, p, ks, sk, rem, &p_rem);
+            p = p_rem;
+            float y[LS];
+            if (TAIL) {
+                float ex[LS + 2], ey[LS + 2];  // history ++ tile, to take the state where the `rem` samples end
+                ex[0] = F.x2; ex[1] = F.x1;
+                ey[0] = F.y2; ey[1] = F.y1;
+                biquad_tile(y, car, F);
+                UNROLL for (int j = 0; j < LS; j++) { ex[2 + j] = car[j]; ey[2 + j] = y[j]; }
+                UNROLL for (int j = 0; j < LS; j++) {
+                    if (j == rem) { F.x2 = ex[j]; F.x1 = ex[j + 1]; F.y2 = ey[j]; F.y1 = ey[j + 1]; }
+                }
+            } else {
+                UNROLL for (int j = 0; j < LS; j++) y[j] = car[j];
+            }
+            M.A = abase + half * 4 * AS;
+            lacc_store(M, y);
+        }
+        store_partial(R, l, half, rem);
+    }
+    M.A = abase;
     if (active) {  // registers -> state block; finish_lane advances the modulator's accumulator
         stw(M, w0.b + 1, ldw(M, w0.b + 1) + (p - p_start));
         if (TAIL) {
@@ -841,7 +928,6 @@ __device__ __forceinline__ void run_fm_voice(const tb_insn* code, LaneMem& M, co
         }
     }
 }
-
 
 // One unit of work: the 64 voices of `group`, samples [s0, s0 + ns) of the launch (multiples of TB_LS).
 //   FM_ONLY: the kernels of lanes_fm.cu, launched by the host only for a program that is one fused FM
@@ -865,6 +951,19 @@ __device__ __forceinline__ void lanes_body(const tb_launch& P, uint32_t group, u
     const uint32_t voice = group * LT + t;
     const uint32_t v0 = group * LT + warp * 32;
     bool active = voice < P.n_voices;
+    // Single fused FM voice with a FAST carrier on the special-function unit (run_fm_voice).
+    const bool fm_program = P.n_lane_code == 3 && (code[0].op & 0xffu) == LN_FM && ((code[0].op >> 16) & 0xffu) == 0 &&
+                            (code[0].op >> 24) == TB_SINE_FAST && P.fast_mode == 2;
+    FmPrime prime = {0, 0, false};
+    if (fm_program) {
+        for (uint32_t k = 0; k < P.n_lane_aux; k++) {
+            const tb_lane_aux a = P.lane_aux[k];
+            if (a.kind == LA_ROT && (int)a.w_off + 2 == code[0].a) {
+                prime.acc_w = a.b;
+                prime.ph_cval = a.c;
+            }
+        }
+    }
     SineK sk;
     sk.kscale = 17592186044416.0 / (TB_TAU * (double)P.sample_rate);
     sk.pscale = 17592186044416.0 / TB_TAU;
@@ -885,8 +984,12 @@ __device__ __forceinline__ void lanes_body(const tb_launch& P, uint32_t group, u
             ready = ready && ldw(M, so) != 0u && ldw(M, so + 1) == P.filt[fi].K - 1u;
         }
         if (!ready) {
-            if (P.fault) atomicAdd(P.fault, 1u);
-            active = false;
+            // The fused FM voice starts its own stream (run_fm_voice): its one filter has never run.
+            if (fm_program && P.n_filt == 1 && code[1].c >= 0 && ldw(M, code[1].c) == 0u) prime.fresh = true;
+            else {
+                if (P.fault) atomicAdd(P.fault, 1u);
+                active = false;
+            }
         }
     }
     if (!active) {
@@ -908,26 +1011,24 @@ __device__ __forceinline__ void lanes_body(const tb_launch& P, uint32_t group, u
     const uint32_t code_s = (uint32_t)__cvta_generic_to_shared(code);
     const u64 n_tiles = ns / (u64)LS;
 
-    // Single fused FM voice with a FAST carrier on the special-function unit (run_fm_voice).  The
-    // magic-number conversion of the carrier frequency is exact while |m| + |c| stays below its range
+    // The magic-number conversion of the carrier frequency is exact while |m| + |c| stays below its range
     // limit; a warp holding a voice beyond it converts the slow way.
-    const bool fm_program = P.n_lane_code == 3 && (code[0].op & 0xffu) == LN_FM && ((code[0].op >> 16) & 0xffu) == 0 &&
-                            (code[0].op >> 24) == TB_SINE_FAST && P.fast_mode == 2;
     bool fm_slow = false;
     if (fm_program) {
         bool ok = true;
         if (active) ok = fabsf(ldf(M, code[1].a)) + fabsf(ldf(M, code[1].b)) < sk.flimit;
         fm_slow = !__all_sync(FULL, ok);
     }
+    const int rem = (int)(ns % (u64)LS);  // only the fused FM voice is launched with samples beyond whole tiles
     if (warp_live || (MIX && v0 < P.n_voices)) {  // a warp without a live voice still owes its (zero) partial sums
         if (fm_program) {
             const bool tail = code[1].c >= 0;
             if (!fm_slow) {
-                if (tail) run_fm_voice<true, MIX, false>(code, M, sk, R, active, l, n_tiles);
-                else run_fm_voice<false, MIX, false>(code, M, sk, R, active, l, n_tiles);
+                if (tail) run_fm_voice<true, MIX, false>(code, M, sk, R, active, l, n_tiles, rem, prime);
+                else run_fm_voice<false, MIX, false>(code, M, sk, R, active, l, n_tiles, rem, prime);
             } else {
-                if (tail) run_fm_voice<true, MIX, true>(code, M, sk, R, active, l, n_tiles);
-                else run_fm_voice<false, MIX, true>(code, M, sk, R, active, l, n_tiles);
+                if (tail) run_fm_voice<true, MIX, true>(code, M, sk, R, active, l, n_tiles, rem, prime);
+                else run_fm_voice<false, MIX, true>(code, M, sk, R, active, l, n_tiles, rem, prime);
             }
         } else if constexpr (!FM_ONLY) {
             float4* const abase = M.A;

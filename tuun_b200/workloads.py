@@ -67,6 +67,34 @@ def fm_filter_params(voice_ids, sample_rate=44100) -> np.ndarray:
     return np.ascontiguousarray(p, dtype=F)
 
 
+def biquad_noise_gain(a1, a2, n=16384) -> np.ndarray:
+    """Round-off noise gain of the reference's direct-form recurrence y -= a1*y[n-1]; y -= a2*y[n-2]
+    (generator.rs:500-502): the l2 norm of the impulse response of 1 / (1 + a1 z^-1 + a2 z^-2).  Every f32
+    rounding inside the recurrence (about 6e-8 * |y| each) reaches the output multiplied by it."""
+    a1 = np.atleast_1d(np.asarray(a1, dtype=np.float64))
+    a2 = np.atleast_1d(np.asarray(a2, dtype=np.float64))
+    y1 = np.zeros_like(a1)
+    y2 = np.zeros_like(a1)
+    acc = np.zeros_like(a1)
+    for i in range(n):
+        y = (1.0 if i == 0 else 0.0) - a1 * y1 - a2 * y2
+        acc += y * y
+        y2, y1 = y1, y
+    return np.sqrt(acc)
+
+
+def fm_filter_tolerance(params, base=1e-4) -> np.ndarray:
+    """Per-voice max-abs tolerance of config 5 against the reference's f32 render: `base` (BASELINE.json),
+    widened for the low, resonant filters whose own round-off noise is larger than that.  Two f32 evaluations
+    of the reference's recurrence whose inputs differ in the last bit (libm sin vs any other correctly working
+    sine) decorrelate to twice that noise floor; measured peaks over 10 s are ~1e-6 x the noise gain, which
+    exceeds 1e-4 only for the 200 Hz cutoffs with Q >= 0.75 (gain 107..209; every other voice has < 55)."""
+    params = np.asarray(params)
+    uniq, inv = np.unique(params[:, 6:8], axis=0, return_inverse=True)
+    g = biquad_noise_gain(uniq[:, 0], uniq[:, 1])
+    return (base * np.maximum(1.0, g / 100.0))[inv.reshape(-1)]
+
+
 def square(freq_rad: Waveform) -> Waveform:
     """lib/v0/std.tuun:21."""
     return Alt(Sine(freq_rad, Const(0.0)), Const(1.0), Const(-1.0))
