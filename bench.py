@@ -250,7 +250,9 @@ def main():
         groups = (n_local + 63) // 64
         kernel = ("tb_render_lanes_fm_kernel" if info.lane_fm_capacity and groups <= info.lane_fm_capacity
                   else "tb_render_lanes_queue_kernel" if groups > info.lane_capacity else "tb_render_lanes_kernel")
-        lane_samples = (n_samples - 256) // 16 * 16
+        # the fused-FM-voice kernel renders the whole call in one launch; the interpreter kernels leave the first
+        # 256-sample tile and the < 16 samples past the last lane tile to the general kernel
+        lane_samples = n_samples if launches == args.steps else (n_samples - 256) // 16 * 16
         alg_bytes = 4.0 * n_local * lane_samples
         avg_launch_s = float(np.mean(lane_ms)) * 1e-3
         dominant_share = float(np.sum(lane_ms)) / dev_ms if len(lane_ms) == args.steps else None
