@@ -234,7 +234,7 @@ int launch(tb_program* p, const tb_launch& L) {
 
 // One launch of the lane kernel over B.n_samples (a multiple of TB_LS).  When the batch has more
 // 64-voice groups than the device holds CTAs, the launch is cut into time segments handed out through a
-// work queue (lanes.cu lanes_kernel): a plain grid would run a second, mostly empty wave for the whole
+// work queue (lanes_queue.cu): a plain grid would run a second, mostly empty wave for the whole
 // duration of the render.
 // One fused FM voice and a batch the device holds at once: the kernel of its own (lanes_fm.cu).
 bool fm_kernel_applies(const tb_program* p, uint32_t n_voices) {
@@ -285,7 +285,7 @@ int launch_lanes(tb_program* p, tb_launch& B) {
 }
 
 // A generate launch.  Large batches of steady-state voices go through the lane-per-voice kernel
-// (lanes.cu).  `pos` = samples the voices have generated before this launch: the first general tile of
+// (lanes.cuh).  `pos` = samples the voices have generated before this launch: the first general tile of
 // a stream (filter pre-reads, generator.rs:234-252) stays on the warp-per-voice kernel, and so do the
 // < TB_LS samples of a call that do not fill a lane tile; a stream that is past its first tile goes
 // straight to the lane kernel (a caller streaming 1024-sample blocks pays one launch per block).
@@ -320,7 +320,7 @@ int launch_generate(tb_program* p, const tb_launch& L, uint64_t pos) {
     if (head) {
         tb_launch H = L;
         H.n_samples = head;
-        H.exact_fb = 1;  // the bracketing tiles run the reference's recurrence too (see lanes.cu)
+        H.exact_fb = 1;  // the bracketing tiles run the reference's recurrence too (see lanes.cuh)
         if ((rc = launch(p, H))) return rc;
     }
     tb_launch B = L;
@@ -344,7 +344,7 @@ int launch_generate(tb_program* p, const tb_launch& L, uint64_t pos) {
 
 // Mixdown of a large steady batch without rows (tb_render_mix, TB_NO_VOICE_OUT): the head of the call is
 // rendered by the general kernel into a small staging block and mixed in voice order; everything after
-// it is summed over the 32 voices of each warp inside the lane kernel (lanes.cu mix_tile) and the
+// it is summed over the 32 voices of each warp inside the lane kernel (lanes.cuh mix_tile) and the
 // per-warp partial rows are added in warp order.  No voice row of the lane part ever reaches memory.
 int render_mix_lanes(tb_program* p, const tb_launch& L, float* d_mix, uint64_t pos) {
     uint64_t head = (p->pos_known && pos >= (uint64_t)TB_TILE) ? 0 : TB_TILE;  // see launch_generate
@@ -478,7 +478,7 @@ int tb_program_create(const tb_node* nodes, uint32_t n_nodes, const int32_t* lis
         return bail(rc);
     if (!size_cta(p->low, &p->warps, &p->smem))
         return bail(set_error(TB_ERR_UNSUPPORTED, "program needs more shared memory than one CTA has"));
-    // The lane-per-voice kernel (lanes.cu): for batches large enough that one thread per voice fills
+    // The lane-per-voice kernels (lanes.cuh): for batches large enough that one thread per voice fills
     // the device.  TUUN_B200_LANES=0 disables it; TUUN_B200_LANE_MIN_VOICES moves the threshold.
     const char* le = std::getenv("TUUN_B200_LANES");
     if (p->low.lane_ok && !(le && le[0] == '0')) {

@@ -1,5 +1,5 @@
 // common.cuh — device helpers shared by the kernels of render.cu (one warp per voice) and
-// lanes.cu (one lane per voice): fixed-point sine phase, sine cores, noise streams, state words.
+// lanes.cuh (one lane per voice): fixed-point sine phase, sine cores, noise streams, state words.
 // Included inside each translation unit's anonymous namespace.
 #pragma once
 

@@ -10,14 +10,16 @@
 //   * constants, state and derived constants of the voice sit in the thread's own column of shared
 //     memory (program.h: W words and Q units, conflict free), and so does the running result
 //     between two instructions of the program,
-//   * the 16 finished samples of the 32 voices of a warp leave through a transposed read of that
-//     tile, so that each output row receives whole 64-byte segments (two full 32-byte sectors per
-//     row and tile; four lanes cover one row with one 128-bit store each),
+//   * every second tile the 32 finished samples of the 32 voices of a warp leave through a transposed
+//     read of that buffer, so that each output row receives a whole 128-byte piece (eight lanes cover
+//     one row with one 128-bit store each),
 //   * independent f32 operations of neighbouring samples are issued in pairs (FMUL2 / FADD2 / FFMA2).
 // The program is the ST_* stream of the steady-state interpreter (steady.cuh) with operands
-// rewritten by lower.cpp (build_lane_plan); state blocks are those of the other kernels, so the
-// host (abi.cpp) renders the first general tile and the last < 16 samples of a call with
-// tb_render_kernel and everything between with this kernel.
+// rewritten and common chains fused by lower.cpp (build_lane_plan, fuse_lane_fm); state blocks are
+// those of the other kernels, so launches of either kind continue one stream.  The host (abi.cpp
+// launch_generate) renders the first general tile of a stream and the < 16 samples of a call that
+// do not fill a tile with tb_render_kernel — except for a program that is one fused FM voice, whose
+// loop (run_fm_voice) starts the stream and takes those samples itself.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -782,7 +782,7 @@ struct Lowerer {
     }
 
 
-    // ---- lane-per-voice plan (lanes.cu) -------------------------------------------------------------
+    // ---- lane-per-voice plan (lanes.cuh) -------------------------------------------------------------
     // The ST_* stream again, with every operand rewritten for a thread that keeps its own voice in
     // its own column of shared memory (program.h): constants at W[0, n_cval), the state block at
     // W[n_cval, n_cval + state_words), derived constants behind it.  Slots keep their indices.

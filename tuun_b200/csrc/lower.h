@@ -23,7 +23,7 @@ struct Lowered {
     uint32_t n_slots = 0, state_words = 0, n_params = 0, n_nodes = 0;
     uint32_t pure_len = 1;
     uint32_t steady_ok = 0;  // the generate program runs through the steady-state interpreter too
-    // lane-per-voice plan of the steady stream (lanes.cu); lane_ok = 0 when it does not apply
+    // lane-per-voice plan of the steady stream (lanes.cuh); lane_ok = 0 when it does not apply
     uint32_t lane_ok = 0;
     std::vector<tb_insn> lane_code;
     std::vector<tb_lane_aux> lane_aux;

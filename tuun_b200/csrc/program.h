@@ -22,7 +22,7 @@
 #endif
 #define TB_CS 16                 // samples per lane per tile of the steady-state interpreter (steady.cuh)
 #define TB_TILE_S (32 * TB_CS)
-#define TB_LS 16                 // samples per lane per tile of the lane-per-voice kernel (lanes.cu)
+#define TB_LS 16                 // samples per lane per tile of the lane-per-voice kernels (lanes.cuh)
 #ifndef TB_LANE_THREADS
 #define TB_LANE_THREADS 64       // voices per CTA of the lane-per-voice kernel
 #endif
@@ -126,7 +126,7 @@ enum tb_op : uint32_t {
                    // K in op bits 8-11, J in bits 12-14
     ST_AFFINE,     // post-op word: acc = (acc * cval[b]) + cval[c], both operations rounded
     ST_OPC,        // post-op word: acc = acc (operator a) cval[b]
-    // ---- lane program only (lanes.cu; fused by lower.cpp build_lane_plan) ----
+    // ---- lane program only (lanes.cuh; fused by lower.cpp build_lane_plan) ----
     LN_FM,         // ST_SINE_CC + one ST_AFFINE + ST_SINE_AC (or ST_SINE_CA) [+ ST_FILT K=3 J=2], two words:
                    //   word 0: a = W of the carried (sin, cos), b = W of the carrier's accumulator,
                    //           c = W of its phase offset (TB_LN_FM_PHASE: of its increment); op bits 8-15
@@ -171,7 +171,7 @@ struct tb_aux {
     uint32_t off;  // offset in 64-bit words inside the per-warp aux area
 };
 
-// Lane-per-voice rendering of the steady stream (lanes.cu): one THREAD owns one voice, so each
+// Lane-per-voice rendering of the steady stream (lanes.cuh): one THREAD owns one voice, so each
 // thread keeps its voice's constants, state and derived constants in its own column of shared
 // memory: 32-bit word w of thread t at W[w * TB_LANE_THREADS + t], 16-byte unit q at
 // Q[q * TB_LANE_THREADS + t] (conflict free).  W = [cval | state | derived].  The lane code is the
