@@ -448,3 +448,48 @@ def test_full_batch_of_65536_voices():
     want = one.sum(dim=0, dtype=torch.float64)
     # 65,536 f32 terms summed in blocks against an f64 sum (the voices start in phase: |mix| reaches thousands)
     assert float((mix.double() - want).abs().max()) <= 0.05 + 2e-4 * float(want.abs().max())
+
+
+def test_fm_voice_kernel_edges(monkeypatch):
+    """The fused-FM-voice kernel at the edges of its loop: calls shorter than two tiles, lengths around
+    tile multiples, fresh and continued streams, few voices, the voice without a filter, and a voice whose
+    carrier frequency bound is beyond the exact range of the magic-number conversion (slow conversion)."""
+    from tuun_b200.workloads import fm_filter_params, fm_filter_voice
+    w = fm_filter_voice()
+    for V in (1, 31, 33, 65):
+        params = fm_filter_params((np.arange(V) * 4099 + 17) % 65536)
+        o = OracleProgram(w, SR)
+        for sizes in ((16,), (17, 15, 1, 31), (33, 16, 47), (5, 300), (255, 257, 16)):
+            p = program(w, monkeypatch)
+            total = sum(sizes)
+            got = np.zeros((V, total), dtype=np.float32)
+            a = 0
+            for n in sizes:
+                blk = np.full((V, n), np.inf, dtype=np.float32)
+                lens = p.render(blk, params=params)
+                assert (lens == n).all()
+                got[:, a:a + n] = blk
+                a += n
+            assert p.info.lane_launches == sum(1 for n in sizes if n >= 16), sizes
+            ref, _, _, _ = o.render_batch(params, V, total)
+            within(got, ref, params)
+    # no filter behind the pair
+    fm = Sine(add(mul(Sine(Const(1.0, param=0), Const(f32(math.pi / 2))), Const(1.0, param=1)), Const(1.0, param=2)), Const(0.0))
+    V = 40
+    params = fm_filter_params(np.arange(V) * 997 % 65536)
+    for n in (16, 23, 1000 + 9):
+        p = program(fm, monkeypatch)
+        out = np.zeros((V, n), dtype=np.float32)
+        p.render(out, params=params)
+        assert p.info.lane_launches == 1 and p.info.kernel_launches == 1
+        assert np.max(np.abs(out - oracle_rows(fm, params, V, n))) <= 5e-6
+    # one voice with an absurd modulation gain: its warp converts frequencies the slow, exact way
+    big = params.copy()
+    big[3, 1] = 6.0e7   # rad/s peak deviation, above 100 x 2 pi x 44100
+    p = program(w, monkeypatch)
+    out = np.zeros((V, 2000), dtype=np.float32)
+    p.render(out, params=big)
+    ref = oracle_rows(w, big, V, 2000)
+    assert np.max(np.abs(np.delete(out - ref, 3, axis=0))) <= TOL
+    # the wild voice itself (its frequency aliases hundreds of times per sample): same stream
+    assert np.max(np.abs(out[3] - ref[3])) <= 1e-3
