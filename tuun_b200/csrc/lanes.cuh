@@ -510,10 +510,16 @@ __device__ __forceinline__ void run_lane_tile(const tb_launch& P, uint32_t code_
             const tb_insn po = nxt;
             ip += sizeof(tb_insn);
             nxt = lds_insn(ip);
-            if ((po.op & 0xffu) == ST_AFFINE) {  // (acc * m) + a, both rounded
+            const uint32_t pk = po.op & 0xffu;
+            if (pk == ST_AFFINE) {  // (acc * m) + a, both rounded
                 const float m = ldf(M, po.b), a = ldf(M, po.c);
                 const u64 mm = pk2(m, m), aa = pk2(a, a);
                 UNROLL for (int j = 0; j < LS; j += 2) unpk2(add2(mul2(pk2(acc[j], acc[j + 1]), mm), aa), acc[j], acc[j + 1]);
+            } else if (pk == ST_ALT_CC) {  // folded by lower.cpp fold_lane_postops (generator.rs:335-341)
+                const float cp = ldf(M, po.a), cn = ldf(M, po.b);
+                UNROLL for (int j = 0; j < LS; j++) acc[j] = acc[j] >= 0.0f ? cp : cn;
+            } else if (pk == ST_FILT) {    // folded biquad
+                lane_filter<3, 2>(M, acc, po.a, po.b, 3, 2);
             } else {
                 const float c = ldf(M, po.b);
                 APPLY_OP_L((uint32_t)po.a, acc, acc[j], c)

@@ -868,9 +868,39 @@ struct Lowerer {
         }
         out.lane_slots = (uint32_t)(max_slot + 1);
         const char* fe = std::getenv("TUUN_B200_LANE_FUSE");  // diagnostics: "0" keeps the plain ST_* words
-        if (!(fe && fe[0] == '0')) fuse_lane_fm();
+        if (!(fe && fe[0] == '0')) {
+            fuse_lane_fm();
+            fold_lane_postops();
+        }
         return true;
     }
+    // In the lane program an instruction that only transforms the running result in place — Alt with two
+    // constant branches (square waves), a biquad with constant coefficients — rides as one more post-op
+    // word of the instruction that produced the result: one dispatch and one trip through shared memory
+    // less per tile each (`square(f) | lpf(..)` becomes a single instruction with two post-op words).
+    void fold_lane_postops() {
+        std::vector<tb_insn> in = out.lane_code, res;
+        long last = -1;  // index in res of the last instruction that may take post-ops
+        for (size_t i = 0; i < in.size();) {
+            const uint32_t op = in[i].op & 0xffu;
+            const size_t words = (op == LN_FM ? 2 : 1);
+            const uint32_t np = op == ST_END ? 0 : ((in[i].op >> 16) & 0xffu);
+            const bool foldable = op == ST_ALT_CC || (in[i].op & 0xffffu) == (ST_FILT | (3u << 8) | (2u << 12));
+            if (foldable && last >= 0 && ((res[last].op >> 16) & 0xffu) + 1 + np <= 0xffu) {
+                res[last].op += (1u + np) << 16;
+                tb_insn w = in[i];
+                w.op &= 0xffffu;  // a post-op word carries no count of its own
+                res.push_back(w);
+                for (uint32_t k = 0; k < np; k++) res.push_back(in[i + 1 + k]);
+            } else {
+                last = (op == ST_SAVE || op == ST_END) ? -1 : (long)res.size();
+                for (size_t k = 0; k < words + np && i + k < in.size(); k++) res.push_back(in[i + k]);
+            }
+            i += words + np;
+        }
+        out.lane_code = res;
+    }
+
     // Peephole over the lane program: a constant-rate sine, scaled and offset, driving the frequency of
     // a sine with constant phase (vibrato, FM: `$(c + m * $f)`) or the phase of a sine with constant
     // frequency (PM: `sine(f, m * $g)`), optionally straight into a biquad (every filter of
