@@ -1,7 +1,7 @@
 """Diagnostics for the lane-per-voice kernel: where do partitioned renders / the oracle differ?"""
 import os, sys
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 os.environ["TUUN_B200_LANE_MIN_VOICES"] = "1"
 from oracle.binding import OracleProgram
 from tuun_b200.generator import Program
