@@ -1,7 +1,7 @@
 """GPU diagnostics: error of individual building blocks against the CPU oracle."""
 import math, os, sys
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle.binding import OracleProgram
 from tuun_b200.generator import Program
 from tuun_b200.waveform import *
