@@ -285,7 +285,9 @@ def main():
     # group, the way a consumer draining the rows would.
     e2e = None
     if not args.no_e2e:
-        grp = min(n_local, args.e2e_voices or 8192)
+        # pinned host window per rank: 8192 rows (14.4 GB) on one GPU, shrunk with the rank count so that the
+        # box's pinned memory stays the same when 8 ranks run side by side
+        grp = min(n_local, args.e2e_voices or max(1024, 8192 // world))
         host = torch.empty((grp, n_samples), dtype=torch.float32, pin_memory=True)
         host_np = host.numpy()
         ph = params_h
