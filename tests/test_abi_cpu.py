@@ -68,6 +68,13 @@ def test_unsupported_is_reported_not_emulated():
     assert rc == _abi.TB_ERR_UNSUPPORTED and "Filter inside a Reset" in msg
     rc, h, msg = _create(flatten(Filter(Time(), [Const(1.0)] * 12, [])))
     assert rc == _abi.TB_ERR_UNSUPPORTED
+    # Append inside a Reset needs a first part whose end is known without rendering it
+    from tuun_b200.waveform import Append, Fin, Fixed
+    trig = Sine(Const(1.0), Const(0.0))
+    rc, h, msg = _create(flatten(Reset(trig, Append(Fixed([1.0, 2.0]), Const(0.0)))))
+    assert rc == _abi.TB_ERR_UNSUPPORTED and "first part is not a Fin" in msg
+    rc, h, msg = _create(flatten(Reset(trig, Append(Fin(Sine(Const(3.0), Const(0.0)), Const(1.0)), Const(0.0)))))
+    assert rc == _abi.TB_ERR_UNSUPPORTED and "analytic length" in msg
 
 
 @pytest.mark.skipif(_has_gpu(), reason="checks the no-device behaviour")

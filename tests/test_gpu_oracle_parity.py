@@ -255,3 +255,29 @@ def test_finite_voices_and_lengths_in_batch():
         ref = o.render(N)
         assert lens[v] == len(ref), v
         assert np.max(np.abs(out[v, :len(ref)] - ref), initial=0.0) <= 1e-6
+
+
+def test_retriggered_envelope_append_inside_reset():
+    """Append under a Reset (a retriggered envelope): every restart begins the envelope again, inside
+    a run each piece starts where the previous Fin ends (generator.rs:169-188, 273-318).  Evaluated for
+    all runs of a tile at once; pieces longer and shorter than a tile, runs longer and shorter than
+    the envelope, a nested Reset and a modulated sine inside the later pieces, streaming in blocks."""
+    def seg(c, m, d):
+        return Fin(add(Time(), Const(-d)), add(mul(Time(), Const(m)), Const(c)))
+    a, d, r = 0.004, 0.011, 0.05   # 177, 486, 2205 samples: shorter than, about, and longer than a 256-sample tile
+    env = Append(seg(0.0, 1 / a, a), Append(seg(1.0, -0.5 / d, d), seg(0.5, -0.5 / r, r)))
+    for trig_hz, n in ((13.0, SR), (40.0, SR // 2), (3.0, SR)):   # 3392-, 1102- and 14700-sample runs
+        w = mul(Sine(hz(330), Const(0.0)), Reset(Sine(hz(trig_hz), Const(0.0)), env))
+        check(w, n, tol=1e-5)
+        check(w, n, tol=1e-5, block=1024)
+        check(w, n, tol=1e-5, block=333)
+    # later pieces with state of their own: a vibrato sine, a nested hard-sync saw, a sustained tail
+    saw = mul(add(Reset(Sine(hz(700), Const(0.0)), mul(Time(), Const(-700.0))), Const(0.5)), Const(2.0))
+    vib = Sine(add(mul(Sine(hz(6), Const(0.0)), Const(f32(TAU * 20))), hz(500)), Const(0.0))
+    body = Append(Fin(add(Time(), Const(-0.01)), vib), Append(Fin(sub(Time(), Const(0.03)), saw), mul(vib, Const(0.25))))
+    w = Reset(Sine(hz(9), Const(0.0)), body)
+    check(w, SR, tol=2e-5)
+    check(w, SR, tol=2e-5, block=777)
+    # an empty first piece and a trigger that restarts faster than the first piece lasts
+    w = Reset(Sine(hz(300), Const(0.0)), Append(Fin(Time(), Const(3.0)), Append(seg(0.0, 100.0, 0.01), Const(7.0))))
+    check(w, 20000, tol=1e-5)

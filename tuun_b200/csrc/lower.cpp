@@ -551,6 +551,19 @@ struct Lowerer {
         }
     }
 
+    // A waveform that never returns short: constants, clocks, noise and what is made of them.
+    bool never_ends(int i) const {
+        const tb_node& n = nodes[i];
+        switch (n.kind) {
+            case TB_CONST: case TB_TIME: case TB_NOISE: return true;
+            case TB_MARKED: case TB_CAPTURED: return never_ends(n.a);
+            case TB_SINE: return never_ends(n.a) && never_ends(n.b);
+            case TB_BINARY: return n.op == TB_MERGE ? (never_ends(n.a) || never_ends(n.b)) : (never_ends(n.a) && never_ends(n.b));
+            case TB_RESET: case TB_ALT: return never_ends(n.a);  // as long as the trigger (generator.rs:273-343)
+            default: return false;
+        }
+    }
+
     // ---- segmented (inside a Reset) ----------------------------------------------------------------
     void emit_seg(int i) {
         const tb_node& n = nodes[i];
@@ -646,7 +659,34 @@ struct Lowerer {
             }
             case TB_NOISE: emit(S_NOISE, state_of(i, 2), i); break;
             case TB_FILTER: fail(TB_ERR_UNSUPPORTED, "Filter inside a Reset");
-            case TB_APPEND: fail(TB_ERR_UNSUPPORTED, "Append inside a Reset");
+            case TB_APPEND: {
+                // Append under a Reset (a retriggered envelope: `Fin(..) ++ Fin(..) ++ ..`).  Every run restarts
+                // the Append; inside a run the second part starts, from its Initial state, where the first
+                // one ends (generator.rs:169-188).  Evaluated for all runs of a tile at once when that point is
+                // known without rendering: the first part is a Fin whose length is analytic in the run's own
+                // Time (greater_or_equals_at, :787-862) over a waveform that cannot end earlier.
+                int a = n.a;
+                while (nodes[a].kind == TB_MARKED || nodes[a].kind == TB_CAPTURED) a = nodes[a].a;
+                if (nodes[a].kind != TB_FIN)
+                    fail(TB_ERR_UNSUPPORTED, "Append inside a Reset whose first part is not a Fin");
+                const int gi = build_goe(nodes[a].a);
+                const tb_goe g = out.goe[gi];
+                if (g.term != GOE_TIME || g.through_append || !never_ends(nodes[a].b))
+                    fail(TB_ERR_UNSUPPORTED,
+                         "Append inside a Reset: the first part needs an analytic length over an infinite waveform");
+                const int sa = alloc_slot(), so = alloc_slot();
+                emit(S_APP_BEGIN, gi);
+                emit_seg(n.a);
+                emit(S_APP_MID, sa, so, gi);
+                const uint32_t st_begin = out.state_words;
+                emit_seg(n.b);
+                const uint32_t st_count = out.state_words - st_begin;
+                if (st_begin >= 0x10000u || st_count >= 0x8000u) fail(TB_ERR_UNSUPPORTED, "Append inside a Reset: too much state");
+                emit(S_APP_END, sa, so, (int)(st_begin | (st_count << 16)));
+                free_slot();
+                free_slot();
+                break;
+            }
             default: fail(TB_ERR_INVALID, "unknown node kind");
         }
     }

@@ -109,6 +109,9 @@ enum tb_op : uint32_t {
     S_RESET_END,   // a = state
     S_FIN,         // a = goe table index   (static Time / const forms only)
     S_NOISE,       // a = state, b = node index (noise is not restarted by a Reset)
+    S_APP_BEGIN,   // a = goe table index of the first part's Fin: remembers its local time at the window start
+    S_APP_MID,     // a = slot (first part), b = origin slot of the second part, c = goe table index
+    S_APP_END,     // a = slot (first part), b = origin slot, c = first state word | (state words << 16) of the second part
     // ---- steady-state stream (steady.cuh): straight-line, every operand infinite ----
     ST_END,
     ST_CONST,      // a = cval index

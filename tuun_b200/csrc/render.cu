@@ -1187,6 +1187,82 @@ __device__ void run_program(const tb_launch& P, const tb_insn* code, const WarpM
                 cx.seg_slot = POP();
                 break;
             }
+            case S_APP_BEGIN: {  // Append under a Reset (lower.cpp emit_seg): local time of the live run at w0
+                const u64 pos = ld_state64(M.state, P.goe[in.a].term_arg);
+                PUSH((int)(pos < 0x3fffffffull ? pos : 0x3fffffffull));
+                break;
+            }
+            case S_APP_MID: {
+                // The first part is in acc with its validity.  Where does the second part start in each run?
+                // Run origin o >= 0: at o + La; a run that began before this tile (o = -1) and stood at local
+                // time P0 at w0: it is already running when P0 >= La (origin -1: its own carried state),
+                // else it starts at w0 + La - P0.  Samples before that point get an origin beyond
+                // themselves; the stateful nodes of the second part compute garbage there, masked in
+                // S_APP_END.
+                const int P0 = POP();
+                const tb_goe g = P.goe[in.c];
+                float value = 0.0f;
+                for (uint32_t s = 0; s < g.n_steps; s++) {
+                    const int sign = P.goe_steps[g.step_off + 2 * s];
+                    const float c = M.cval[P.goe_steps[g.step_off + 2 * s + 1]];
+                    value = sign > 0 ? __fadd_rn(value, c) : __fsub_rn(value, c);
+                }
+                const u64 target = f32_as_usize(ceilf(__fmul_rn(value, srf)));
+                const int La = (int)(target < 0x3fffffffull ? target : 0x3fffffffull);
+                slot_store(M.slots, in.a, acc);
+                M.slot_vm[in.a * 32 + l] = (uint8_t)cx.vm;
+                float ov[C];
+                slot_load(M.slots, cx.seg_slot, ov);
+                const int far = 0x3fffffff;
+                int mine = far;
+                const int last_pos = cx.w1 - 1;
+                UNROLL for (int j = 0; j < C; j++) {
+                    const int i = l * C + j;
+                    const int o = __float_as_int(ov[j]);
+                    int ob;
+                    if (o >= 0) ob = La < far - o ? o + La : far;
+                    else ob = P0 >= La ? -1 : (La - P0 < far - cx.w0 ? cx.w0 + (La - P0) : far);
+                    ov[j] = __int_as_float(ob);
+                    if (i == last_pos) mine = ob;
+                }
+                slot_store(M.slots, in.b, ov);
+                int ob_last = __shfl_sync(FULL, mine, (last_pos >> 3) & 31);
+                if (n <= 0) ob_last = -1;
+                // The run live at the end of the window: second part running since before the tile (-1),
+                // started inside it (its origin), or not started (w1: "zero samples in", state stays Initial).
+                PUSH(cx.seg_slot);
+                PUSH(cx.o_last);
+                cx.seg_slot = in.b;
+                cx.o_last = ob_last < 0 ? -1 : (ob_last > last_pos ? cx.w1 : ob_last);
+                cx.vm = 0xffu;
+                break;
+            }
+            case S_APP_END: {
+                float ov[C], av[C];
+                slot_load(M.slots, in.b, ov);
+                slot_load(M.slots, in.a, av);
+                const uint32_t va = M.slot_vm[in.a * 32 + l];
+                uint32_t vm = 0;
+                UNROLL for (int j = 0; j < C; j++) {
+                    const int i = l * C + j;
+                    const int ob = __float_as_int(ov[j]);
+                    const bool in_a = (va >> j) & 1u;
+                    const bool in_b = !in_a && (ob < 0 || i >= ob) && ((cx.vm >> j) & 1u);
+                    acc[j] = in_a ? av[j] : (in_b ? acc[j] : 0.0f);
+                    vm |= ((in_a || in_b) ? 1u : 0u) << j;
+                }
+                const bool idle = cx.o_last >= cx.w1;  // the second part has not started in the live run
+                cx.o_last = POP();
+                cx.seg_slot = POP();
+                cx.vm = vm;
+                if (idle) {  // ... so it is still in its Initial state, whatever the masked samples left behind
+                    __syncwarp();
+                    const int s0 = in.c & 0xffff, sn = (in.c >> 16) & 0x7fff;
+                    for (int k = l; k < sn; k += 32) M.state[s0 + k] = 0u;
+                    __syncwarp();
+                }
+                break;
+            }
             case S_FIN: {  // Fin with an analytic length inside a Reset run
                 const tb_goe g = P.goe[in.a];
                 float value = 0.0f;
