@@ -5,7 +5,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from tuun_b200.generator import Program
-from tuun_b200.waveform import Alt, Const, Filter, Fin, Noise, Sine, Time, add, f32, mul, sub
+from tuun_b200.waveform import Alt, Const, Filter, Fin, Noise, Reset, Sine, Time, add, f32, mul, sub
 from tuun_b200.workloads import fm_filter_params, fm_filter_voice, lpf
 
 SR, V = 44100, 65536
@@ -16,6 +16,12 @@ rng = np.random.default_rng(0)
 fr = (TAU * rng.uniform(50, 2000, (V, 3))).astype(np.float32)
 p5 = fm_filter_params(np.arange(V))
 fm = Sine(add(mul(Sine(Const(1.0, param=0), Const(f32(math.pi / 2))), Const(1.0, param=1)), Const(1.0, param=2)), Const(0.0))
+fo = rng.uniform(30.0, 1800.0, V).astype(np.float32)
+osc = np.stack([TAU * fo, -fo, f32(4) * fo, f32(-4) * fo], axis=1).astype(np.float32)
+_trig = lambda: Sine(Const(1.0, param=0), Const(0.0))
+saw = mul(add(Reset(_trig(), mul(Time(), Const(1.0, param=1))), Const(0.5)), Const(2.0))      # std.tuun:19
+tri = Alt(_trig(), Reset(_trig(), add(mul(Time(), Const(1.0, param=2)), Const(-1.0))),
+          Reset(_trig(), add(mul(Time(), Const(1.0, param=3)), Const(3.0))))                  # std.tuun:23-28
 shapes = [
     ("sine", Sine(Const(1.0, param=0), Const(0.0)), fr),
     ("pm", Sine(Const(1.0, param=0), mul(Sine(Const(1.0, param=1), Const(0.0)), Const(6.0))), fr),
@@ -26,6 +32,9 @@ shapes = [
     ("fm|lpf|lpf|lpf", lpf(lpf(fm_filter_voice(), 2.0, 1600), 1.0, 3200), p5),
     ("$f * note(N)", Fin(sub(Time(), Const(f32(N / SR))), Sine(Const(1.0, param=0), Const(0.0))), fr),   # cfg1 shape, swept f
     ("(fm|lpf) * note(N)", Fin(sub(Time(), Const(f32(N / SR))), fm_filter_voice()), p5),
+    ("sawtooth(f)", saw, osc),
+    ("pulse(0.3,f)|lpf", lpf(Alt(sub(saw, Const(0.3)), Const(1.0), Const(-1.0)), 0.707, 2000), osc),
+    ("triangle(f)", tri, osc),
 ]
 out = torch.empty((V, N), dtype=torch.float32, device="cuda")
 

@@ -128,7 +128,7 @@ namespace {
 bool size_cta(const tb::Lowered& low, uint32_t* warps, size_t* smem) {
     for (uint32_t w = TB_WARPS_PER_CTA; w >= 1; w >>= 1) {
         const size_t s = tb_kernel_smem_bytes((uint32_t)low.code.size(), low.n_slots, low.aux_words,
-                                              (uint32_t)low.cexpr.size(), low.state_words, low.steady_ok || low.lane_fin_goe >= 0, w);
+                                              (uint32_t)low.cexpr.size(), low.state_words, low.steady_ok || (low.lane_fin_goe >= 0 && !low.lane_clk), w);
         if (s <= 220 * 1024) {
             *warps = w;
             *smem = s;
@@ -223,6 +223,7 @@ void fill_launch(const tb_program* p, tb_launch* L) {
     L->lane_slots = p->low.lane_slots;
     L->fault = p->d_fault;
     L->lane_fin_goe = p->low.lane_fin_goe;
+    L->lane_clk = p->low.lane_clk;
 }
 
 int launch(tb_program* p, const tb_launch& L) {
@@ -438,6 +439,7 @@ int tb_program_create(const tb_node* nodes, uint32_t n_nodes, const int32_t* lis
             p->low.steady_ok = 0;
             p->low.lane_ok = 0;
             p->low.lane_fin_goe = -1;
+            p->low.lane_clk = 0;
         }
     // Everything below needs a device: no CPU path exists.
     int count = 0;

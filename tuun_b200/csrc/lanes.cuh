@@ -413,6 +413,57 @@ __device__ __forceinline__ void run_lane_tile(const tb_launch& P, uint32_t code_
                 lacc_load(M, acc);
                 lslot_store(M, in.a, acc);
                 continue;  // the accumulator tile is unchanged; ST_SAVE never carries post-ops
+            case ST_RESET_CLK: {
+                // Reset (generator.rs:273-318): the running result is the trigger.  A restart happens at the
+                // first non-negative sample after a negative one (the state word remembers the class of the
+                // last sample; -0.0 counts as non-negative but re-arms).  What the inner tree needs is each
+                // sample's local time: j - o behind a restart at o, else "j samples into a run that began
+                // before this tile", encoded -1 - j, which every clocked node adds to its own carried position.
+                lacc_load(M, acc);
+                bool neg = ldw(M, in.a) == 0u;
+                int o = -1;
+                float clk[LS];
+                UNROLL for (int j = 0; j < LS; j++) {
+                    const float x = acc[j];
+                    if (neg && x >= 0.0f) {
+                        o = j;
+                        neg = signbit(x);
+                    } else if (!neg && x < 0.0f) {
+                        neg = true;
+                    }
+                    clk[j] = __int_as_float(o >= 0 ? j - o : -1 - j);
+                }
+                lslot_store(M, in.b, clk);
+                stw(M, in.a, neg ? 0u : 1u);
+                continue;
+            }
+            case ST_TIME_CLK: {  // Time under a Reset: (local time) as f32 / sample_rate (generator.rs:101-111)
+                const float srf = (float)P.sample_rate;
+                float clk[LS];
+                lslot_load(M, in.b, clk);
+                const u64 pos = ld64(M, in.a);
+                UNROLL for (int j = 0; j < LS; j++) {
+                    const int c = __float_as_int(clk[j]);
+                    const u64 nloc = c >= 0 ? (u64)c : pos + (u64)(-1 - c);
+                    acc[j] = __fdiv_rn(__ull2float_rn(nloc), srf);
+                }
+                const int cl = __float_as_int(clk[LS - 1]);
+                st64(M, in.a, cl >= 0 ? (u64)cl + 1ull : pos + (u64)LS);
+                break;
+            }
+            case ST_SINE_CLK: {  // constant rate and phase under a Reset: the accumulator restarts with the clock
+                float clk[LS];
+                lslot_load(M, (int)(in.op >> 24), clk);
+                const u64 a0 = ld64(M, in.a), inc = ld64(M, in.b), ph0 = ld64(M, in.c);
+                UNROLL for (int j = 0; j < LS; j++) {
+                    const int c = __float_as_int(clk[j]);
+                    const u64 ph = (c >= 0 ? inc * (u64)c : a0 + inc * (u64)(-1 - c)) + ph0;
+                    acc[j] = !fast ? sin_turns_exact(ph) : (FASTMODE == 2 ? sin_p32((uint32_t)(ph >> 32)) : sin_hi<1>((int)(ph >> 32)));
+                }
+                const int cl = __float_as_int(clk[LS - 1]);
+                st64(M, in.a, cl >= 0 ? inc * ((u64)cl + 1ull) : a0 + inc * (u64)LS);
+                break;
+            }
             case ST_BIN: {  // generator.rs:555-567 with both sides infinite
                 float av[LS];
                 lslot_load(M, in.a, av);

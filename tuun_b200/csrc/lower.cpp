@@ -734,11 +734,35 @@ struct Lowerer {
             emit(ST_OPC, (int)op, cidx, 0);
         }
     }
+    // A Reset in the steady stream (lane kernels only): the trigger is rendered, ST_RESET_CLK turns it into a
+    // per-sample local clock (samples since the last restart), and the inner tree is emitted with clk_slot set —
+    // which admits only nodes that are closed-form in that clock: constants, Time, sines with constant rate
+    // and phase, point operators, Alt, noise (not restarted by a Reset).  That covers sawtooth, pulse and
+    // triangle of lib/v0/std.tuun (Appendix B of SURVEY.md); anything else keeps the general interpreter.
+    int clk_slot = -1;
+    bool lane_steady_root = false;  // the steady stream renders the whole (infinite) tree
     bool emit_steady(int i) {
         const tb_node& n = nodes[i];
         switch (n.kind) {
             case TB_CONST: s_produced(emit(ST_CONST, const_of(i))); return true;
-            case TB_TIME: s_produced(emit(ST_TIME, state_of(i, 2))); return true;
+            case TB_TIME:
+                if (clk_slot >= 0) s_produced(emit(ST_TIME_CLK, state_of(i, 2), clk_slot));
+                else s_produced(emit(ST_TIME, state_of(i, 2)));
+                return true;
+            case TB_RESET: {
+                if (clk_slot >= 0) return false;  // nested
+                if (!emit_steady(n.a)) return false;
+                const int s = s_alloc();
+                if (s > 0xff) return false;
+                emit(ST_RESET_CLK, state_of(i, 1), s);
+                s_last = -1;
+                clk_slot = s;
+                const bool ok = emit_steady(n.b);
+                clk_slot = -1;
+                s_slots--;
+                out.lane_clk = 1;
+                return ok;
+            }
             case TB_NOISE: s_produced(emit(ST_NOISE, state_of(i, 2), i)); return true;
             case TB_MARKED:
             case TB_CAPTURED: return emit_steady(n.a);
@@ -763,6 +787,11 @@ struct Lowerer {
                 const uint32_t fl = sine_flags(i);
                 const int aux_inc = cf >= 0 ? new_aux(AUX_SINE_INC, cf, 0, 1) : 0;
                 const int aux_ph = cp >= 0 ? new_aux(AUX_SINE_PHASE, cp, 0, 1) : 0;
+                if (clk_slot >= 0) {
+                    if (cf < 0 || cp < 0) return false;  // a phase sum would have to restart with the clock
+                    s_produced(emit(ST_SINE_CLK | fl | ((uint32_t)clk_slot << 24), st, aux_inc, aux_ph));
+                    return true;
+                }
                 if (cf >= 0 && cp >= 0) {
                     s_produced(emit(ST_SINE_CC, st, new_aux(AUX_SINE_ROT, cf, 0, 2 + 2 * TB_CS), aux_ph));
                 } else if (cp >= 0) {
@@ -807,6 +836,7 @@ struct Lowerer {
                 return true;
             }
             case TB_FILTER: {
+                if (clk_slot >= 0) return false;  // a filter's history restarts with its Reset
                 const int fi = filter_table(i);
                 const int st = filter_state(i);
                 const uint32_t K = n.ff_count, J = n.fb_count;
@@ -860,6 +890,17 @@ struct Lowerer {
             switch (op) {
                 case ST_END: case ST_CONST: case ST_ALT_CC: case ST_AFFINE: case ST_OPC: break;
                 case ST_TIME: case ST_NOISE: in.a += st0; break;
+                case ST_RESET_CLK: case ST_TIME_CLK: in.a += st0; slot(in.b); break;
+                case ST_SINE_CLK: {
+                    const tb_aux* inc = aux_at(in.b);
+                    const tb_aux* ph = aux_at(in.c);
+                    if (!inc || !ph) return false;
+                    in.a += st0;
+                    in.b = lane_new_aux(LA_INC, inc->a, 2, 0, nullptr);
+                    in.c = lane_new_aux(LA_PHASE, ph->a, 2, 0, nullptr);
+                    slot((int)(in.op >> 24));
+                    break;
+                }
                 case ST_SAVE: case ST_BIN: slot(in.a); break;
                 case ST_SINE_CC: {
                     const tb_aux* rot = aux_at(in.b);
@@ -933,7 +974,7 @@ struct Lowerer {
                 res.push_back(w);
                 for (uint32_t k = 0; k < np; k++) res.push_back(in[i + 1 + k]);
             } else {
-                last = (op == ST_SAVE || op == ST_END) ? -1 : (long)res.size();
+                last = (op == ST_SAVE || op == ST_RESET_CLK || op == ST_END) ? -1 : (long)res.size();
                 for (size_t k = 0; k < words + np && i + k < in.size(); k++) res.push_back(in[i + k]);
             }
             i += words + np;
@@ -1032,8 +1073,10 @@ struct Lowerer {
                 out.steady_ok = 0;
             } else if (nodes[sroot].kind != TB_FIN && emit_steady(root)) {
                 emit(ST_END);
-                out.steady_ok = 1;
+                out.steady_ok = out.lane_clk ? 0 : 1;  // clocked words: lane kernels only
+                lane_steady_root = true;
             } else {
+                out.lane_clk = 0;
                 out.code.resize(code0);
                 out.cexpr.resize(cexpr0);
                 for (int& m : const_memo)
@@ -1050,8 +1093,11 @@ struct Lowerer {
         if (out.cexpr.empty()) literal_cexpr(0.f);
         if (out.aux_words == 0) out.aux_words = 1;
         if (out.n_slots == 0) out.n_slots = 1;
-        out.lane_ok = ((out.steady_ok || out.lane_fin_goe >= 0) && build_lane_plan()) ? 1u : 0u;
-        if (!out.lane_ok) out.lane_fin_goe = -1;
+        out.lane_ok = ((out.steady_ok || out.lane_fin_goe >= 0 || lane_steady_root) && build_lane_plan()) ? 1u : 0u;
+        if (!out.lane_ok) {
+            out.lane_fin_goe = -1;
+            out.lane_clk = 0;
+        }
         out.n_nodes = n_nodes;
     }
 };

@@ -28,6 +28,7 @@ struct Lowered {
     std::vector<tb_insn> lane_code;
     std::vector<tb_lane_aux> lane_aux;
     uint32_t lane_w_words = 0, lane_q_units = 0, lane_slots = 0;
+    uint32_t lane_clk = 0;      // the steady stream uses the clocked words (Reset): lane kernels only
     int32_t lane_fin_goe = -1;  // root Fin with an analytic length over a steady tree: its goe entry, else -1
     int status = 0;
     std::string error;

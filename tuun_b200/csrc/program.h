@@ -129,6 +129,11 @@ enum tb_op : uint32_t {
                    // K in op bits 8-11, J in bits 12-14
     ST_AFFINE,     // post-op word: acc = (acc * cval[b]) + cval[c], both operations rounded
     ST_OPC,        // post-op word: acc = acc (operator a) cval[b]
+    // ---- steady words only the lane kernels run (a Reset over a tree whose nodes are closed-form in the run's
+    //      own time: the sawtooth / pulse / triangle oscillators of lib/v0/std.tuun) ----
+    ST_RESET_CLK,  // a = state (sign word), b = slot: acc = trigger -> slot = per-sample local clock, see lanes.cuh
+    ST_TIME_CLK,   // a = state, b = clock slot
+    ST_SINE_CLK,   // a = state, b = aux of increment, c = aux of phase; clock slot in op bits 24-31; class in op >> 8
     // ---- lane program only (lanes.cuh; fused by lower.cpp build_lane_plan) ----
     LN_FM,         // ST_SINE_CC + one ST_AFFINE + ST_SINE_AC (or ST_SINE_CA) [+ ST_FILT K=3 J=2], two words:
                    //   word 0: a = W of the carried (sin, cos), b = W of the carrier's accumulator,
@@ -244,6 +249,7 @@ struct tb_launch {
     uint32_t n_lane_code, n_lane_aux;
     uint32_t lane_w_words, lane_q_units, lane_slots;
     uint32_t* fault;       // device counter: voices the lane kernel found without complete filter history
+    uint32_t lane_clk;     // the steady stream holds ST_*_CLK words: the warp-per-voice steady interpreter must not run it
     int32_t lane_fin_goe;  // lane kernel: the program is Fin{analytic length, steady tree}; goe entry of the length, else -1
     uint32_t mid_call;     // this launch continues a generate call (Fin keeps the cut the call's first tile made)
     uint64_t call_pos;     // samples of the current call rendered before this launch (lane kernel: voices whose

@@ -1400,7 +1400,7 @@ tb_render_kernel(const tb_launch P) {
     // A root Fin with an analytic length over a steady tree (tb_launch::lane_fin_goe, lower.cpp) carries the
     // ST_* stream of its inner tree: whole tiles well inside the note run through the steady interpreter too.
     const bool fin = P.lane_fin_goe >= 0;
-    const bool st_cap = P.steady_ok || fin;
+    const bool st_cap = P.steady_ok || (fin && !P.lane_clk);  // clocked words (ST_*_CLK) are for the lane kernels
     const size_t per_warp_slots = (size_t)P.n_slots * (st_cap ? TILE_S : TILE) * sizeof(float);
     const size_t aux_b = ((size_t)P.aux_words * 8 + 15) & ~(size_t)15;
     const size_t cval_b = ((size_t)P.n_cval * 4 + 15) & ~(size_t)15;
