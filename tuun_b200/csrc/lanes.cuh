@@ -350,6 +350,32 @@ __device__ __forceinline__ void lane_filter(const LaneMem& M, float (&acc)[LS], 
         if (m < J) stf(M, wy + (J - 1 - m), hy[m]);
 }
 
+// (n as f32) / (sample_rate as f32), correctly rounded (generator.rs:105-110).  For n < 2^24 — every clock
+// within 6 minutes of its origin at 44.1 kHz — the quotient comes from the correctly rounded reciprocal and
+// one exact residual (Markstein's sequence: q0 = RN(n r), e = n - q0 b exactly by FMA, q = RN(q0 + e r);
+// correctly rounded for every b whose mantissa is not all ones; checked exhaustively over n < 2^24 for the
+// common sample rates): 4 instructions instead of the ~12 of an IEEE division.
+struct TimeDiv {
+    float b, r;
+    bool ok;
+};
+__device__ __forceinline__ TimeDiv time_div_setup(uint32_t sample_rate) {
+    TimeDiv t;
+    t.b = (float)sample_rate;
+    t.r = __frcp_rn(t.b);
+    t.ok = (__float_as_uint(t.b) & 0x007fffffu) != 0x007fffffu;
+    return t;
+}
+__device__ __forceinline__ float time_div(u64 n, const TimeDiv& t) {
+    if (t.ok && n < 16777216ull) {
+        const float a = (float)(uint32_t)n;
+        const float q0 = __fmul_rn(a, t.r);
+        const float e = fmaf(-q0, t.b, a);
+        return fmaf(e, t.r, q0);
+    }
+    return __fdiv_rn(__ull2float_rn(n), t.b);
+}
+
 #define APPLY_OP_L(OPV, DST, A, B)                                                    \
     switch (OPV) {                                                                    \
         case TB_ADD:                                                                  \
@@ -396,9 +422,9 @@ __device__ __forceinline__ void run_lane_tile(const tb_launch& P, uint32_t code_
                 break;
             }
             case ST_TIME: {  // generator.rs:101-111
-                const float srf = (float)P.sample_rate;
+                const TimeDiv td = time_div_setup(P.sample_rate);
                 const u64 pos = ld64(M, in.a);
-                UNROLL for (int j = 0; j < LS; j++) acc[j] = __fdiv_rn(__ull2float_rn(pos + (u64)j), srf);
+                UNROLL for (int j = 0; j < LS; j++) acc[j] = time_div(pos + (u64)j, td);
                 st64(M, in.a, pos + (u64)LS);
                 break;
             }
@@ -438,14 +464,14 @@ __device__ __forceinline__ void run_lane_tile(const tb_launch& P, uint32_t code_
                 continue;
             }
             case ST_TIME_CLK: {  // Time under a Reset: (local time) as f32 / sample_rate (generator.rs:101-111)
-                const float srf = (float)P.sample_rate;
+                const TimeDiv td = time_div_setup(P.sample_rate);
                 float clk[LS];
                 lslot_load(M, in.b, clk);
                 const u64 pos = ld64(M, in.a);
                 UNROLL for (int j = 0; j < LS; j++) {
                     const int c = __float_as_int(clk[j]);
                     const u64 nloc = c >= 0 ? (u64)c : pos + (u64)(-1 - c);
-                    acc[j] = __fdiv_rn(__ull2float_rn(nloc), srf);
+                    acc[j] = time_div(nloc, td);
                 }
                 const int cl = __float_as_int(clk[LS - 1]);
                 st64(M, in.a, cl >= 0 ? (u64)cl + 1ull : pos + (u64)LS);
