@@ -48,6 +48,8 @@ def lib():
         L.tbo_allocations.restype = ctypes.c_uint64
         L.tbo_allocations.argtypes = [P]
         L.tbo_seed_noise.argtypes = [P, ctypes.c_uint64]
+        L.tbo_set_clean_tails.restype = None
+        L.tbo_set_clean_tails.argtypes = [P, ctypes.c_int]
         L.tbo_set_voice.argtypes = [P, ctypes.c_uint64]
         L.tbo_render_batch.restype = ctypes.c_uint64
         L.tbo_render_batch.argtypes = [P, P, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64,
@@ -99,6 +101,10 @@ class OracleProgram:
         """Seed and voice index of the Noise streams (same convention as tb_seed_noise)."""
         lib().tbo_seed_noise(self._h, ctypes.c_uint64(seed))
         lib().tbo_set_voice(self._h, ctypes.c_uint64(voice))
+
+    def set_clean_tails(self, on: bool = True):
+        """Zero scratch tails instead of reading the producers' leftovers (tuun_oracle.cpp Gen::clean_tails)."""
+        lib().tbo_set_clean_tails(self._h, 1 if on else 0)
 
     def substitute_const(self, mark_id: int, value: float) -> int:
         return lib().tbo_substitute_const(self._h, mark_id, value)

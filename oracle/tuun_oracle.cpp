@@ -94,6 +94,12 @@ struct Gen {
     uint32_t sample_rate;
     size_t allocations = 0;
     Rng* rng;
+    // The reference reads scratch buffers past the length their producer returned (generator.rs:555-567,
+    // 206-220, 320-343); what sits there is whatever the producer's in-place rendering left behind ("tail
+    // undefined", :76-95) on top of the vec![0.0] initialisation.  clean_tails zeroes those tails instead —
+    // the documented semantics ("missing samples are zeros", overview.md:147-160) — so that tests can tell a
+    // tree that depends on such leftovers from a real difference.
+    bool clean_tails = false;
 
     static float apply(uint32_t op, float a, float b) {  // generator.rs:262-270
         switch (op) {
@@ -174,6 +180,7 @@ struct Gen {
                 std::vector<float> ph_out(f_len, 0.0f);
                 allocations += f_len;
                 size_t ph_len = generate(w->b, ph_out.data(), f_len);
+                if (clean_tails) for (size_t i = ph_len; i < f_len; i++) ph_out[i] = 0.0f;
                 for (size_t i = 0; i < f_len; i++) {
                     float sample = (float)std::sin(w->accumulator + (double)ph_out[i]);
                     double f = (double)out[i];
@@ -232,8 +239,12 @@ struct Gen {
                 size_t t_len = generate(w->a, out, n);
                 std::vector<float> pos(t_len, 0.0f), neg(t_len, 0.0f);
                 allocations += 2 * t_len;
-                (void)generate(w->b, pos.data(), t_len);
-                (void)generate(w->c, neg.data(), t_len);
+                const size_t p_len = generate(w->b, pos.data(), t_len);
+                const size_t n_len = generate(w->c, neg.data(), t_len);
+                if (clean_tails) {
+                    for (size_t i = p_len; i < t_len; i++) pos[i] = 0.0f;
+                    for (size_t i = n_len; i < t_len; i++) neg[i] = 0.0f;
+                }
                 for (size_t i = 0; i < t_len; i++) out[i] = out[i] >= 0.0f ? pos[i] : neg[i];
                 return t_len;
             }
@@ -274,13 +285,15 @@ struct Gen {
             for (Node* c : w->ff) {
                 std::vector<float> o(out_len, 0.0f);
                 allocations += out_len;
-                (void)generate(c, o.data(), out_len);
+                const size_t c_len = generate(c, o.data(), out_len);
+                if (clean_tails) for (size_t i = c_len; i < out_len; i++) o[i] = 0.0f;
                 ff_outs.push_back(std::move(o));
             }
             for (Node* c : w->fb) {
                 std::vector<float> o(out_len, 0.0f);
                 allocations += out_len;
-                (void)generate(c, o.data(), out_len);
+                const size_t c_len = generate(c, o.data(), out_len);
+                if (clean_tails) for (size_t i = c_len; i < out_len; i++) o[i] = 0.0f;
                 fb_outs.push_back(std::move(o));
             }
         }
@@ -326,6 +339,7 @@ struct Gen {
         std::vector<float> b_out(len, 0.0f);
         allocations += len;
         size_t b_len = generate(b, b_out.data(), len);
+        if (clean_tails) for (size_t i = b_len; i < b_out.size(); i++) b_out[i] = 0.0f;
         len = extend ? std::max(a_len, b_len) : std::min(a_len, b_len);
         for (size_t i = a_len; i < len; i++) out[i] = 0.0f;
         for (size_t i = 0; i < len; i++) out[i] = apply(op, out[i], b_out[i]);
@@ -535,6 +549,7 @@ struct tbo_program {
     uint32_t sample_rate = 0;
     Rng rng;
     size_t allocations = 0;
+    bool clean_tails = false;
     // source for cloning
     std::vector<tb_node> src;
     std::vector<int32_t> lists;
@@ -627,14 +642,14 @@ int tbo_set_params(tbo_program* p, const float* params, uint32_t n_params) {
 }
 
 uint64_t tbo_generate(tbo_program* p, float* out, uint64_t n) {
-    Gen g{p->sample_rate, 0, &p->rng};
+    Gen g{p->sample_rate, 0, &p->rng, p->clean_tails};
     size_t len = g.generate(p->root, out, n);
     p->allocations += g.allocations;
     return len;
 }
 
 uint64_t tbo_length(tbo_program* p, uint64_t max) {
-    Gen g{p->sample_rate, 0, &p->rng};
+    Gen g{p->sample_rate, 0, &p->rng, p->clean_tails};
     size_t len = g.length(p->root, max);
     p->allocations += g.allocations;
     return len;
@@ -670,6 +685,7 @@ int tbo_substitute_const(tbo_program* p, uint32_t mark_id, float value) {
 
 uint64_t tbo_allocations(const tbo_program* p) { return p->allocations; }
 void tbo_seed_noise(tbo_program* p, uint64_t seed) { p->rng.seed = seed; }
+void tbo_set_clean_tails(tbo_program* p, int on) { p->clean_tails = on != 0; }
 void tbo_set_voice(tbo_program* p, uint64_t voice) { p->rng.voice = voice; }
 
 uint64_t tbo_render_batch(const tbo_program* p, const float* params, uint32_t n_params,

@@ -54,6 +54,8 @@ int tbo_substitute_const(tbo_program* p, uint32_t mark_id, float value);
 /* Generator.allocations (generator.rs:53). */
 uint64_t tbo_allocations(const tbo_program* p);
 void tbo_seed_noise(tbo_program* p, uint64_t seed);
+/* Zero the scratch-buffer tails the reference reads past a producer's returned length (see Gen::clean_tails). */
+void tbo_set_clean_tails(tbo_program* p, int on);
 /* Voice index of this program inside a batch (selects the Noise streams). */
 void tbo_set_voice(tbo_program* p, uint64_t voice);
 

@@ -75,6 +75,16 @@ def test_unsupported_is_reported_not_emulated():
     assert rc == _abi.TB_ERR_UNSUPPORTED and "first part is not a Fin" in msg
     rc, h, msg = _create(flatten(Reset(trig, Append(Fin(Sine(Const(3.0), Const(0.0)), Const(1.0)), Const(0.0)))))
     assert rc == _abi.TB_ERR_UNSUPPORTED and "analytic length" in msg
+    # Noise that a run draws a data-dependent number of samples from (generator.rs:113-118, :164)
+    from tuun_b200.waveform import add, mul
+    burst = Fin(add(Time(), Const(-0.003)), mul(Noise(), Const(0.3)))
+    rc, h, msg = _create(flatten(Reset(trig, burst)))
+    assert rc == _abi.TB_ERR_UNSUPPORTED and "Noise under a Fin" in msg
+    rc, h, msg = _create(flatten(Reset(trig, mul(Fin(add(Time(), Const(-0.003)), Const(1.0)), Noise()))))
+    assert rc == _abi.TB_ERR_UNSUPPORTED and "Noise under a Fin" in msg
+    # ... but not a Noise every run draws whole (`noise * envelope`: the left operand is asked for the whole run)
+    rc, h, msg = _create(flatten(Reset(trig, mul(Noise(), Fin(add(Time(), Const(-0.003)), Const(1.0))))))
+    assert rc != _abi.TB_ERR_UNSUPPORTED, msg
 
 
 @pytest.mark.skipif(_has_gpu(), reason="checks the no-device behaviour")

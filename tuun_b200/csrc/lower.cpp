@@ -565,6 +565,17 @@ struct Lowerer {
     }
 
     // ---- segmented (inside a Reset) ----------------------------------------------------------------
+    // seg_gated > 0 while lowering an operand the reference asks for fewer samples than the run has left
+    // (the inner of a Fin, the parts of an Append, the right-hand side of a point operator / the phase of a
+    // Sine / the branches of an Alt / the inner of a nested Reset whose first operand can end).  A Noise there
+    // draws a data-dependent number of samples per run (generator.rs:113-118 draws exactly what it is asked
+    // for), and S_NOISE counts whole tiles: not taken.
+    int seg_gated = 0;
+    void emit_seg_gated(int i, bool gated) {
+        seg_gated += gated;
+        emit_seg(i);
+        seg_gated -= gated;
+    }
     void emit_seg(int i) {
         const tb_node& n = nodes[i];
         switch (n.kind) {
@@ -582,7 +593,7 @@ struct Lowerer {
                 } else {
                     const int s = alloc_slot();
                     emit(S_BIN_BEGIN, s);
-                    emit_seg(n.b);
+                    emit_seg_gated(n.b, !merge && !never_ends(n.a));  // generator.rs:538-549: b renders a_len samples
                     emit(S_BIN_END, s, (int)n.op, merge);
                     free_slot();
                 }
@@ -606,7 +617,7 @@ struct Lowerer {
                     emit_seg(n.a);
                     const int s = alloc_slot();
                     emit(S_SINE_BEGIN, s);
-                    emit_seg(n.b);
+                    emit_seg_gated(n.b, !never_ends(n.a));  // generator.rs:206: the phase renders f_len samples
                     emit(S_SINE_END | fl, st, s, 0);
                     free_slot();
                 }
@@ -622,14 +633,15 @@ struct Lowerer {
                     emit(S_ALT_BEGIN, st);
                     int opp = TB_OPERAND_CONST(cp), opn = TB_OPERAND_CONST(cn);
                     int extra = 0;
+                    const bool gated = !never_ends(n.a);  // generator.rs:320-343: both branches render t_len samples
                     if (cp < 0) {
-                        emit_seg(n.b);
+                        emit_seg_gated(n.b, gated);
                         opp = alloc_slot();
                         extra = 1;
                         emit(S_ALT_POS, opp);
                     }
                     if (cn < 0) {
-                        emit_seg(n.c);
+                        emit_seg_gated(n.c, gated);
                         opn = 0;
                     }
                     emit(S_ALT_END, st, opp, opn);
@@ -643,7 +655,7 @@ struct Lowerer {
                 emit_seg(n.a);
                 const int s = alloc_slot();
                 emit(S_RESET_BEGIN, st, s);
-                emit_seg(n.b);
+                emit_seg_gated(n.b, !never_ends(n.a));
                 emit(S_RESET_END, st);
                 free_slot();
                 break;
@@ -653,11 +665,15 @@ struct Lowerer {
                 const tb_goe g = out.goe[gi];
                 if (g.term == GOE_MAYBE || g.through_append)
                     fail(TB_ERR_UNSUPPORTED, "Fin with a rendered (non-analytic) length inside a Reset");
-                emit_seg(n.b);
+                emit_seg_gated(n.b, true);  // generator.rs:164: the inner renders `len` samples
                 emit(S_FIN, gi);
                 break;
             }
-            case TB_NOISE: emit(S_NOISE, state_of(i, 2), i); break;
+            case TB_NOISE:
+                if (seg_gated > 0)
+                    fail(TB_ERR_UNSUPPORTED, "Noise under a Fin, an Append or a finite operand inside a Reset");
+                emit(S_NOISE, state_of(i, 2), i);
+                break;
             case TB_FILTER: fail(TB_ERR_UNSUPPORTED, "Filter inside a Reset");
             case TB_APPEND: {
                 // Append under a Reset (a retriggered envelope: `Fin(..) ++ Fin(..) ++ ..`).  Every run restarts
@@ -679,7 +695,7 @@ struct Lowerer {
                 emit_seg(n.a);
                 emit(S_APP_MID, sa, so, gi);
                 const uint32_t st_begin = out.state_words;
-                emit_seg(n.b);
+                emit_seg_gated(n.b, true);  // generator.rs:186: the second part renders what the first left
                 const uint32_t st_count = out.state_words - st_begin;
                 if (st_begin >= 0x10000u || st_count >= 0x8000u) fail(TB_ERR_UNSUPPORTED, "Append inside a Reset: too much state");
                 emit(S_APP_END, sa, so, (int)(st_begin | (st_count << 16)));
