@@ -29,6 +29,9 @@ class Gen:
     def dur(self):
         return f32(self.r.choice([0.0, self.r.uniform(0.0002, 0.004), self.r.uniform(0.004, 0.05)]))
 
+    def neg_dur(self):
+        return Const(-self.dur())
+
     def tree(self, depth, in_reset=False):
         r = self.r
         k = int(r.integers(0, 14 if depth > 0 else 4))
@@ -43,12 +46,12 @@ class Gen:
                 return mul(Noise(), Const(0.3))
             return Fixed([f32(x) for x in r.uniform(-1, 1, int(r.integers(1, 700)))])
         if k == 4:
-            return Fin(add(Time(), Const(-self.dur())), self.tree(depth - 1, in_reset))
+            return Fin(add(Time(), self.neg_dur()), self.tree(depth - 1, in_reset))
         if k == 5 and not in_reset:  # rendered length: first sample where the length waveform is >= 0
             return Fin(sub(mul(Time(), Const(f32(r.uniform(20, 400)))), Const(f32(r.uniform(0.1, 3)))) if r.random() < 0.5
                        else Sine(self.hz(5, 60), Const(f32(r.uniform(3.3, 6.0)))), self.tree(depth - 1))
         if k == 6:
-            return Append(Fin(add(Time(), Const(-self.dur())), self.tree(depth - 1, in_reset)), self.tree(depth - 1, in_reset))
+            return Append(Fin(add(Time(), self.neg_dur()), self.tree(depth - 1, in_reset)), self.tree(depth - 1, in_reset))
         if k == 7:
             op = Operator(int(r.choice([0, 1, 2])))
             return BinaryPointOp(op, self.tree(depth - 1, in_reset), self.tree(depth - 1, in_reset))
@@ -126,3 +129,73 @@ def test_random_tree(seed):
             scale = max(1.0, float(np.max(np.abs(ref))))
             bad = int(np.count_nonzero(d / scale > 1e-4))
             assert bad <= 6, (seed, block, bad, float(d.max()), int(np.argmax(d)), str(w)[:700])
+
+
+N_PARAMS = 4
+
+
+class GenP(Gen):
+    """The same trees with some rates, note lengths and constants read from the voice's parameter row."""
+
+    def hz(self, lo, hi):
+        if self.r.random() < 0.35:
+            return Const(1.0, param=int(self.r.integers(0, 2)))  # params 0, 1: rates (rad/s)
+        return super().hz(lo, hi)
+
+    def neg_dur(self):
+        if self.r.random() < 0.5:
+            return Const(-0.01, param=2)  # param 2: minus a note length (s)
+        return super().neg_dur()
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("TUUN_FUZZ_SEEDS", "40"))))
+def test_random_tree_batch(seed):
+    """A batch of voices whose parts end at different samples (per-voice note lengths and rates), two calls."""
+    from tuun_b200._abi import TuunB200Error, TB_ERR_UNSUPPORTED
+    from tuun_b200.generator import Program
+    g = GenP(17000 + seed)
+    w = g.tree(int(os.environ.get("TUUN_FUZZ_DEPTH", "3")))
+    V = 11
+    n1, n2 = int(g.r.integers(300, 3000)), int(g.r.integers(1, 2500))
+    n = n1 + n2
+    params = np.stack([TAU * g.r.uniform(30, 2500, V), TAU * g.r.uniform(2, 60, V),
+                       -g.r.choice([0.0, 0.0007, 0.003, 0.011, 0.03, 0.09], V) * g.r.uniform(0.5, 1.0, V),
+                       g.r.uniform(-1, 1, V)], axis=1).astype(np.float32)
+    try:
+        p = Program(w, SR)
+    except TuunB200Error as e:
+        if e.status == TB_ERR_UNSUPPORTED:
+            pytest.skip(e.message)
+        raise
+    p.seed_noise(0x7475756E2545F491, 0)
+
+    def oracle(v, block, clean):
+        o = OracleProgram(w, SR)
+        o.seed_noise(0x7475756E2545F491, v)
+        o.set_params(params[v])
+        o.set_clean_tails(clean)
+        return o.render(n, block=block)
+
+    ref = np.zeros((V, n), dtype=np.float32)
+    rlen = np.zeros(V, dtype=np.int64)
+    for v in range(V):
+        r = oracle(v, 1024, False)
+        for block, clean in ((1024, True), (256, False), (197, False), (64, False)):
+            q = oracle(v, block, clean)
+            if len(q) != len(r) or np.max(np.abs(q - r), initial=0.0) > 1e-5 * max(1.0, float(np.max(np.abs(r), initial=0.0))):
+                pytest.skip("the reference's result depends on scratch-buffer leftovers or on the block size")
+        ref[v, :len(r)] = r
+        rlen[v] = len(r)
+    a = np.full((V, n1), np.inf, dtype=np.float32)
+    b = np.full((V, n2), np.inf, dtype=np.float32)
+    l1 = np.asarray(p.render(a, params=params)).astype(np.int64)
+    l2 = np.asarray(p.render(b, params=params)).astype(np.int64)
+    # a voice that returned short is finished (generator.rs:76-95); the reference would not be called again
+    total = np.where(l1 < n1, l1, l1 + l2)
+    assert (total == rlen).all(), (seed, total.tolist(), rlen.tolist(), str(w)[:700])
+    for v in range(V):
+        got = np.concatenate([a[v, :l1[v]], b[v, :l2[v]] if l1[v] == n1 else np.zeros(0, np.float32)])
+        d = np.abs(got - ref[v, :rlen[v]])
+        scale = max(1.0, float(np.max(np.abs(ref[v, :rlen[v]]), initial=0.0)))
+        bad = int(np.count_nonzero(d / scale > 1e-4))
+        assert bad <= 6, (seed, v, bad, float(d.max()), int(np.argmax(d)), str(w)[:700])
