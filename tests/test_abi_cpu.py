@@ -60,31 +60,30 @@ def test_invalid_op_list_rejected_before_cuda():
 
 
 def test_unsupported_is_reported_not_emulated():
-    inner = Filter(Noise(), [Const(0.5), Const(0.5)], [])
-    rc, h, msg = _create(flatten(Reset(Sine(Const(1.0), Const(0.0)), inner)))
-    assert rc == _abi.TB_ERR_UNSUPPORTED and "Filter inside a Reset" in msg
-    w = Reset(Sine(Const(1.0), Const(0.0)), Filter(Time(), [Const(1.0)], []))
-    rc, h, msg = _create(flatten(w))
-    assert rc == _abi.TB_ERR_UNSUPPORTED and "Filter inside a Reset" in msg
     rc, h, msg = _create(flatten(Filter(Time(), [Const(1.0)] * 12, [])))
     assert rc == _abi.TB_ERR_UNSUPPORTED
-    # Append inside a Reset needs a first part whose end is known without rendering it
-    from tuun_b200.waveform import Append, Fin, Fixed
+
+
+def test_reset_over_any_tree_lowers():
+    """What the all-runs-at-once form of a Reset does not take (a Filter, an Append whose first part has no
+    analytic length, a Fin with a rendered length, a Noise a run draws only part of) lowers to the run-by-run
+    form (generator.rs:288-316) instead of being refused."""
+    from tuun_b200.generator import lower_check
+    from tuun_b200.waveform import Append, Fin, Fixed, add, mul
     trig = Sine(Const(1.0), Const(0.0))
-    rc, h, msg = _create(flatten(Reset(trig, Append(Fixed([1.0, 2.0]), Const(0.0)))))
-    assert rc == _abi.TB_ERR_UNSUPPORTED and "first part is not a Fin" in msg
-    rc, h, msg = _create(flatten(Reset(trig, Append(Fin(Sine(Const(3.0), Const(0.0)), Const(1.0)), Const(0.0)))))
-    assert rc == _abi.TB_ERR_UNSUPPORTED and "analytic length" in msg
-    # Noise that a run draws a data-dependent number of samples from (generator.rs:113-118, :164)
-    from tuun_b200.waveform import add, mul
     burst = Fin(add(Time(), Const(-0.003)), mul(Noise(), Const(0.3)))
-    rc, h, msg = _create(flatten(Reset(trig, burst)))
-    assert rc == _abi.TB_ERR_UNSUPPORTED and "Noise under a Fin" in msg
-    rc, h, msg = _create(flatten(Reset(trig, mul(Fin(add(Time(), Const(-0.003)), Const(1.0)), Noise()))))
-    assert rc == _abi.TB_ERR_UNSUPPORTED and "Noise under a Fin" in msg
-    # ... but not a Noise every run draws whole (`noise * envelope`: the left operand is asked for the whole run)
-    rc, h, msg = _create(flatten(Reset(trig, mul(Noise(), Fin(add(Time(), Const(-0.003)), Const(1.0))))))
-    assert rc != _abi.TB_ERR_UNSUPPORTED, msg
+    seg = lower_check(Reset(trig, mul(Noise(), Fin(add(Time(), Const(-0.003)), Const(1.0))))).n_code_words
+    for inner in (Filter(Noise(), [Const(0.5), Const(0.5)], []),
+                  Filter(Time(), [Const(1.0)], []),
+                  Append(Fixed([1.0, 2.0]), Const(0.0)),
+                  Append(Fin(Sine(Const(3.0), Const(0.0)), Const(1.0)), Const(0.0)),
+                  Fin(Sine(Const(3.0), Const(0.0)), Time()),
+                  burst,
+                  mul(Fin(add(Time(), Const(-0.003)), Const(1.0)), Noise()),
+                  Reset(Sine(Const(9.0), Const(0.0)), burst)):
+        info = lower_check(Reset(trig, inner))
+        assert info.n_code_words > 0 and info.state_words >= 1
+    assert seg > 0
 
 
 @pytest.mark.skipif(_has_gpu(), reason="checks the no-device behaviour")

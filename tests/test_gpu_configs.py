@@ -110,3 +110,31 @@ def test_tracker_benches_shapes(idx):
     peak = max(1.0, float(np.max(np.abs(ref)))) if len(ref) else 1.0
     err = float(np.max(np.abs(got - ref))) if len(ref) else 0.0
     assert err <= TOL * peak, f"{name}: max abs err {err} (peak {peak})"
+
+
+def _docs_flute(rate_hz=1 / 3):
+    """docs/instruments.md:186-199: `reset($(1/3), sawtooth(freq) | lpf(0.5, lpf_cutoff) | ADSR(..))` — a note replayed
+    every three seconds, with its filter, its oscillator's own Reset and its envelope inside the Reset."""
+    from tuun_b200.builder import pipe, reset
+    s = W._std()
+    dur, attack, release = 1.75, 0.27, 0.17
+    flute = pipe(s.sawtooth(546), s.lpf(0.5, 2000), s.ADSR(attack, 0.0, 1.0, dur - attack - release, release))
+    return W._finish(reset(s.hz(rate_hz), flute))
+
+
+def test_docs_flute_replayed_by_a_reset():
+    w = _docs_flute()
+    n = int(3.4 * SR)  # one restart, at 3 s
+    worst, bad, got, ref = compare(w, n, tol=2e-4)
+    assert bad == 0, (worst, bad)
+    assert np.abs(ref[:SR]).max() > 0.3 and np.abs(ref[int(1.8 * SR):int(2.9 * SR)]).max() == 0.0  # the note, then silence
+    assert np.abs(ref[int(3.1 * SR):]).max() > 0.3                                               # ... and the note again
+    worst, bad, _, _ = compare(w, n, tol=2e-4, block=1024)
+    assert bad == 0, (worst, bad)
+
+
+def test_note_replayed_at_audio_rate():
+    """Many runs per tile: the same instrument restarted 300 times a second."""
+    w = _docs_flute(300.0)
+    worst, bad, _, _ = compare(w, SR // 2, tol=2e-4)
+    assert bad <= 4, (worst, bad)

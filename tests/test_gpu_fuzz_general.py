@@ -79,10 +79,34 @@ class Gen:
 
 @pytest.mark.parametrize("seed", range(int(os.environ.get("TUUN_FUZZ_SEEDS", "40"))))
 def test_random_tree(seed):
-    from tuun_b200._abi import TuunB200Error, TB_ERR_UNSUPPORTED
-    from tuun_b200.generator import Generator
     g = Gen(9000 + seed)
     w = g.tree(int(os.environ.get("TUUN_FUZZ_DEPTH", "3")))
+    _check_tree(g, w, seed)
+
+
+class GenR(Gen):
+    """Anything inside a Reset: filters, rendered lengths, Appends of any kind, gated noise, more Resets."""
+
+    def tree(self, depth, in_reset=False):
+        return super().tree(depth, False)
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("TUUN_FUZZ_SEEDS", "40"))))
+def test_random_tree_under_reset(seed):
+    """Reset over an arbitrary tree (the run-by-run form, generator.rs:288-316), e.g. `reset($(1/3), flute(..))` of
+    docs/instruments.md:199 with its filter and envelope inside."""
+    g = GenR(31000 + seed)
+    r = g.r
+    trig = Sine(g.hz(8, 400), Const(f32(r.uniform(0, 6))))
+    w = Reset(trig, g.tree(int(os.environ.get("TUUN_FUZZ_DEPTH", "3"))))
+    if r.random() < 0.3:
+        w = mul(w, Const(f32(0.5)))
+    _check_tree(g, w, seed)
+
+
+def _check_tree(g, w, seed):
+    from tuun_b200._abi import TuunB200Error, TB_ERR_UNSUPPORTED
+    from tuun_b200.generator import Generator
     n = int(g.r.integers(600, 6000))
     gen = Generator(SR)
     try:

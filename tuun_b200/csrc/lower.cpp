@@ -31,6 +31,7 @@ struct Lowerer {
 
     std::vector<int> const_memo;   // node -> cval index, -2 = not computed, -1 = not const
     std::vector<int> state_off;    // node -> offset of its state block (or -1)
+    std::vector<int> state_len;    // node -> words of that block
     std::vector<int> fixed_idx;    // node -> fixed table index
     std::vector<int> filt_idx;     // node -> filter table index
     std::vector<uint8_t> sensitive;  // node output reaches a phase / trigger / length / coefficient
@@ -162,9 +163,29 @@ struct Lowerer {
     int state_of(int i, int words) {
         if (state_off[i] < 0) {
             state_off[i] = (int)out.state_words;
+            state_len[i] = words;
             out.state_words += words;
         }
         return state_off[i];
+    }
+    // State blocks `waveform::set_state(w, Initial)` clears (waveform.rs:322-392): every node of the subtree
+    // except the coefficient waveforms of a Filter (appendix A10: those iterators are dropped unconsumed).
+    void collect_state(int i, std::vector<std::pair<int, int>>& r) const {
+        const tb_node& n = nodes[i];
+        if (state_off[i] >= 0 && n.kind != TB_NOISE) r.emplace_back(state_off[i], state_len[i]);  // a Noise has no tree state
+        switch (n.kind) {
+            case TB_FIN: case TB_APPEND: case TB_SINE: case TB_RESET: case TB_BINARY:
+                collect_state(n.a, r);
+                collect_state(n.b, r);
+                break;
+            case TB_ALT:
+                collect_state(n.a, r);
+                collect_state(n.b, r);
+                collect_state(n.c, r);
+                break;
+            case TB_MARKED: case TB_CAPTURED: case TB_FILTER: collect_state(n.a, r); break;
+            default: break;
+        }
     }
 
     // ---- which sines may use the f32 polynomial ------------------------------------------
@@ -454,12 +475,49 @@ struct Lowerer {
             case TB_RESET: {
                 const int st = state_of(i, 1);
                 emit_gen(n.a);
-                const int s = alloc_slot();
-                const int b0 = emit(G_RESET_BEGIN, st, s, 0);
-                emit_seg(n.b);
-                out.code[b0].c = emit(G_RESET_END, st);
-                produced(out.code[b0].c);
-                free_slot();
+                // All runs of a tile at once (the segmented form) when the inner tree allows it; else run by run,
+                // the way the reference does it (generator.rs:288-316): the inner tree's generate code over the
+                // window of each run, its state cleared where a run starts.
+                const Lowered out0 = out;
+                const std::vector<int> memo0 = const_memo, off0 = state_off, len0 = state_len, fixed0 = fixed_idx,
+                                       filt0 = filt_idx;
+                const int slots0 = slots_in_use, label0 = label_at, prod0 = last_producer, gated0 = seg_gated;
+                bool segmented = true;
+                try {
+                    const int s = alloc_slot();
+                    const int b0 = emit(G_RESET_BEGIN, st, s, 0);
+                    emit_seg(n.b);
+                    out.code[b0].c = emit(G_RESET_END, st);
+                    produced(out.code[b0].c);
+                    free_slot();
+                } catch (int status) {
+                    if (status != TB_ERR_UNSUPPORTED) throw;
+                    segmented = false;
+                    out = out0;
+                    const_memo = memo0, state_off = off0, state_len = len0, fixed_idx = fixed0, filt_idx = filt0;
+                    slots_in_use = slots0, label_at = label0, last_producer = prod0, seg_gated = gated0;
+                }
+                if (!segmented) {
+                    const int so = alloc_slot(), sr = alloc_slot();
+                    const int b0 = emit(G_RUNS_BEGIN, st, so, 0);
+                    const int body = label();
+                    emit_gen(n.b);
+                    std::vector<std::pair<int, int>> ranges, merged;
+                    collect_state(n.b, ranges);
+                    std::sort(ranges.begin(), ranges.end());
+                    for (const auto& r : ranges) {
+                        if (!merged.empty() && merged.back().first + merged.back().second == r.first) merged.back().second += r.second;
+                        else merged.push_back(r);
+                    }
+                    if (merged.empty()) merged.emplace_back(0, 0);
+                    out.code[b0].c = emit(G_RUNS_END, so, sr, body);
+                    for (size_t k = 0; k < merged.size(); k++)  // data words, never executed
+                        emit(G_RUNS_END, merged[k].first, merged[k].second, k + 1 == merged.size());
+                    produced(-1);
+                    (void)label();
+                    free_slot();
+                    free_slot();
+                }
                 break;
             }
             default: fail(TB_ERR_INVALID, "unknown node kind");
@@ -1049,6 +1107,7 @@ struct Lowerer {
         validate();
         const_memo.assign(n_nodes, -2);
         state_off.assign(n_nodes, -1);
+        state_len.assign(n_nodes, 0);
         fixed_idx.assign(n_nodes, -1);
         filt_idx.assign(n_nodes, -1);
         sensitive.assign(n_nodes, 0);

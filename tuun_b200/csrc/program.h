@@ -70,6 +70,9 @@ enum tb_op : uint32_t {
     G_APP_END,     // b = slot
     G_RESET_BEGIN, // a = state, b = origin slot, c = jump target (G_RESET_END)
     G_RESET_END,   // a = state
+    G_RUNS_BEGIN,  // Reset run by run: a = state, b = origin slot, c = its G_RUNS_END
+    G_RUNS_END,    // a = origin slot, b = result slot, c = first instruction of the inner tree; followed by
+                   // data words {a = first state word, b = words, c = 1 on the last}: what a restart clears
     G_SAVE,        // a = slot        acc -> slot (with its length)
     G_RESTORE,     // a = slot
     // ---- length ----

@@ -897,6 +897,81 @@ __device__ void run_program(const tb_launch& P, const tb_insn* code, const WarpM
                 cx.L = t_len;
                 break;
             }
+            case G_RUNS_BEGIN: {  // generator.rs:281-318, one run at a time: acc = trigger over [w0, w0 + t_len)
+                const int t_len = cx.L;
+                if (t_len == 0) {  // skip the inner tree, G_RUNS_END and its data words
+                    pc = in.c + 1;
+                    while (!code[pc++].c) {}
+                    break;
+                }
+                PUSH(cx.w0);
+                PUSH(cx.w1);
+                PUSH(t_len);
+                const int end = cx.w0 + t_len;
+                (void)reset_origins(M, acc, 0xffu, cx.w0, t_len, in.a, in.b, -1);
+                __syncwarp();
+                float ov[C];
+                slot_load(M.slots, in.b, ov);
+                bool at0 = false;
+                int nxt = end;
+                UNROLL for (int j = 0; j < C; j++) {
+                    const int i = l * C + j;
+                    if (i >= cx.w0 && i < end && __float_as_int(ov[j]) == i) {
+                        if (i == cx.w0) at0 = true;
+                        else nxt = min(nxt, i);
+                    }
+                }
+                nxt = __reduce_min_sync(FULL, nxt);
+                if (__any_sync(FULL, at0)) {  // a restart on the first sample: the (empty) run before it renders nothing
+                    for (int q = in.c + 1;; q++) {
+                        const tb_insn z = code[q];
+                        for (int k = l; k < z.b; k += 32) M.state[z.a + k] = 0u;
+                        if (z.c) break;
+                    }
+                }
+                cx.w1 = nxt;
+                break;
+            }
+            case G_RUNS_END: {  // a run [w0, w1) of the inner tree is in acc, cx.L samples of it (zeros after, :309)
+                const int t_len = ctl[sp - 1], w1s = ctl[sp - 2], w0s = ctl[sp - 3];
+                const int end = w0s + t_len;
+                const int rs = cx.w0, re = cx.w1, got = cx.L;
+                float rv[C];
+                if (rs > w0s) slot_load(M.slots, in.b, rv);
+                UNROLL for (int j = 0; j < C; j++) {
+                    const int i = l * C + j;
+                    if (i >= rs && i < re) rv[j] = i < rs + got ? acc[j] : 0.0f;
+                    else if (rs <= w0s) rv[j] = 0.0f;
+                }
+                if (re < end) {  // a restart at `re`: set_state(inner, Initial) (:311-313), then the next run
+                    __syncwarp();
+                    slot_store(M.slots, in.b, rv);
+                    for (int q = pc;; q++) {
+                        const tb_insn z = code[q];
+                        for (int k = l; k < z.b; k += 32) M.state[z.a + k] = 0u;
+                        if (z.c) break;
+                    }
+                    float ov[C];
+                    slot_load(M.slots, in.a, ov);
+                    int nxt = end;
+                    UNROLL for (int j = 0; j < C; j++) {
+                        const int i = l * C + j;
+                        if (i > re && i < end && __float_as_int(ov[j]) == i) nxt = min(nxt, i);
+                    }
+                    nxt = __reduce_min_sync(FULL, nxt);
+                    cx.w0 = re;
+                    cx.w1 = nxt;
+                    pc = in.c;
+                } else {
+                    UNROLL for (int j = 0; j < C; j++) acc[j] = rv[j];
+                    sp -= 3;
+                    cx.w0 = w0s;
+                    cx.w1 = w1s;
+                    cx.L = t_len;
+                    while (!code[pc++].c) {}
+                }
+                break;
+            }
             case G_SAVE: {
                 slot_store(M.slots, in.a, acc);
                 M.slot_len[in.a] = cx.L;
