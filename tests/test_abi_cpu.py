@@ -108,3 +108,18 @@ def test_lane_plan_of_the_headline_voice():
     assert fin.lane_smem_bytes > 0 and fin.tile == 256
     from tuun_b200.waveform import Const, Fin, Sine
     assert lower_check(Fin(Sine(Const(1.0), Const(0.0)), Sine(Const(440.0), Const(0.0)))).lane_smem_bytes == 0
+
+
+def test_nesting_is_checked_against_the_kernel_control_stack():
+    """A sequence is a right-nested Append chain (optimizer.rs:212-229): two control-stack words per note."""
+    from tuun_b200.generator import lower_check
+    from tuun_b200.waveform import Append, Fin, add
+    def chain(notes):
+        w = Const(0.0)
+        for k in range(notes):
+            w = Append(Fin(add(Time(), Const(-0.01)), Sine(Const(2000.0 + k), Const(0.0))), w)
+        return w
+    assert lower_check(chain(100)).n_code_words > 0
+    with pytest.raises(_abi.TuunB200Error) as e:
+        lower_check(chain(400))
+    assert e.value.status == _abi.TB_ERR_UNSUPPORTED and "nested too deeply" in e.value.message

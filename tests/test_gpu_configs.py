@@ -138,3 +138,16 @@ def test_note_replayed_at_audio_rate():
     w = _docs_flute(300.0)
     worst, bad, _, _ = compare(w, SR // 2, tol=2e-4)
     assert bad <= 4, (worst, bad)
+
+
+def test_sequence_of_one_hundred_notes():
+    """A right-nested Append chain 100 deep (what `<[..100 notes..]>` optimizes to, optimizer.rs:212-229)."""
+    from tuun_b200.waveform import Append, Const, Fin, Sine, Time, add, f32
+    w = Const(0.0)
+    for k in reversed(range(100)):
+        w = Append(Fin(add(Time(), Const(f32(-0.004 - 0.0001 * (k % 7)))), Sine(Const(f32(2000.0 + 31 * k)), Const(0.0))), w)
+    w = Fin(add(Time(), Const(-0.5)), w)
+    worst, bad, got, ref = compare(w, SR, tol=TOL)
+    assert len(ref) == SR // 2 and bad == 0, (worst, bad)
+    worst, bad, _, _ = compare(w, SR, tol=TOL, block=1024)
+    assert bad == 0, (worst, bad)

@@ -609,6 +609,26 @@ struct Lowerer {
         }
     }
 
+    // Control-stack words the interpreter (render.cu: PUSH / POP) may hold while it is inside node i — the
+    // largest over the generate, length and segmented forms of each kind, so a bound, not a count.
+    int ctl_need(int i) const {
+        const tb_node& n = nodes[i];
+        switch (n.kind) {
+            case TB_MARKED: case TB_CAPTURED: return ctl_need(n.a);
+            case TB_BINARY: case TB_SINE: return std::max(ctl_need(n.a), 1 + ctl_need(n.b));
+            case TB_ALT: return std::max(ctl_need(n.a), 1 + std::max(ctl_need(n.b), ctl_need(n.c)));
+            case TB_FIN: return 3 + std::max(ctl_need(n.a), ctl_need(n.b));
+            case TB_APPEND: return std::max(1 + ctl_need(n.a), 2 + ctl_need(n.b));
+            case TB_RESET: return std::max(ctl_need(n.a), 4 + ctl_need(n.b));
+            case TB_FILTER: {
+                int m = ctl_need(n.a);
+                for (uint32_t j = 0; j < n.ff_count + n.fb_count; j++) m = std::max(m, ctl_need(lists[n.list_off + j]));
+                return 3 + m;
+            }
+            default: return 0;
+        }
+    }
+
     // A waveform that never returns short: constants, clocks, noise and what is made of them.
     bool never_ends(int i) const {
         const tb_node& n = nodes[i];
@@ -1112,6 +1132,9 @@ struct Lowerer {
         filt_idx.assign(n_nodes, -1);
         sensitive.assign(n_nodes, 0);
         const int root = (int)n_nodes - 1;
+        if (ctl_need(root) > TB_CTL_DEPTH)
+            fail(TB_ERR_UNSUPPORTED, "tree nested too deeply: needs " + std::to_string(ctl_need(root)) +
+                                         " control-stack words, the kernel has " + std::to_string(TB_CTL_DEPTH));
         mark_sensitive(root, false);
         out.pure_len = 1;
         out.pc_gen = (uint32_t)here();

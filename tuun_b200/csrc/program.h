@@ -28,7 +28,7 @@
 #endif
 #define TB_MAX_K 9   // feed-forward taps supported by the device path (K-1 <= C)
 #define TB_MAX_J 4   // feedback taps supported by the scan path
-#define TB_CTL_DEPTH 96
+#define TB_CTL_DEPTH 256  // control-stack words per warp (lower.cpp ctl_need checks a tree against it)
 
 struct tb_insn {
     uint32_t op;
