@@ -60,8 +60,15 @@ def test_invalid_op_list_rejected_before_cuda():
 
 
 def test_unsupported_is_reported_not_emulated():
-    rc, h, msg = _create(flatten(Filter(Time(), [Const(1.0)] * 12, [])))
-    assert rc == _abi.TB_ERR_UNSUPPORTED
+    from tuun_b200.generator import lower_check
+    rc, h, msg = _create(flatten(Filter(Time(), [Const(1.0)] * 34, [])))
+    assert rc == _abi.TB_ERR_UNSUPPORTED and "feed-forward taps" in msg
+    rc, h, msg = _create(flatten(Filter(Time(), [Const(1.0)], [Const(0.1)] * 5)))
+    assert rc == _abi.TB_ERR_UNSUPPORTED and "feedback taps" in msg
+    rc, h, msg = _create(flatten(Filter(Time(), [Const(1.0)] * 11 + [Time()], [])))
+    assert rc == _abi.TB_ERR_UNSUPPORTED and "waveforms" in msg
+    long_fir = lower_check(Filter(Time(), [Const(1.0)] * 33, [Const(0.5)]))  # moving_average(32) and a pole
+    assert long_fir.n_code_words > 0 and long_fir.lane_smem_bytes == 0       # general interpreter only
 
 
 def test_reset_over_any_tree_lowers():

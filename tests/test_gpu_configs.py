@@ -151,3 +151,22 @@ def test_sequence_of_one_hundred_notes():
     assert len(ref) == SR // 2 and bad == 0, (worst, bad)
     worst, bad, _, _ = compare(w, SR, tol=TOL, block=1024)
     assert bad == 0, (worst, bad)
+
+
+@pytest.mark.parametrize("n_avg", [9, 16, 32])
+def test_moving_average_longer_than_a_lane(n_avg):
+    """`moving_average(n)` (std.tuun:114-115) with n + 1 > 9 taps: the general interpreter's long FIR; over a
+    finite input (tail of K-1 zero-extended outputs), streamed, and with a pole behind it."""
+    from tuun_b200.builder import pipe
+    from tuun_b200.waveform import Const, Filter, Fin, Noise, Sine, Time, add, f32, mul
+    s = W._std()
+    w = W._finish(pipe(s.sawtooth(330), s.moving_average(n_avg)))
+    for block in (None, 1024, 100):
+        worst, bad, _, _ = compare(w, 20000, tol=TOL, block=block)
+        assert bad == 0, (n_avg, block, worst, bad)
+    note = Fin(add(Time(), Const(f32(-0.05))), Sine(Const(f32(3000.0)), Const(0.0)))
+    taps = [Const(f32(1.0 / (n_avg + 1)))] * (n_avg + 1)
+    w = Filter(note, taps, [Const(f32(-0.6))])
+    for block in (None, 777):
+        worst, bad, got, ref = compare(w, 4000, tol=TOL, block=block)
+        assert bad == 0 and len(ref) == 2205, (n_avg, block, worst, bad, len(ref))

@@ -272,7 +272,11 @@ struct Lowerer {
         if (filt_idx[i] >= 0) return filt_idx[i];
         const tb_node& n = nodes[i];
         const uint32_t K = n.ff_count, J = n.fb_count;
-        if (K > TB_MAX_K) fail(TB_ERR_UNSUPPORTED, "Filter with more than " + std::to_string(TB_MAX_K) + " feed-forward taps");
+        if (K > TB_MAX_K_GEN) fail(TB_ERR_UNSUPPORTED, "Filter with more than " + std::to_string(TB_MAX_K_GEN) + " feed-forward taps");
+        if (K > TB_MAX_K)  // the long form reads its taps as constants (moving_average(n), std.tuun:114-115)
+            for (uint32_t j = 0; j < K; j++)
+                if (const_of(lists[n.list_off + j]) < 0)
+                    fail(TB_ERR_UNSUPPORTED, "Filter with more than " + std::to_string(TB_MAX_K) + " feed-forward taps that are waveforms");
         if (J > TB_MAX_J) fail(TB_ERR_UNSUPPORTED, "Filter with more than " + std::to_string(TB_MAX_J) + " feedback taps");
         tb_filter_tab t{};
         t.K = K;
@@ -407,9 +411,11 @@ struct Lowerer {
                 emit_gen(n.a);
                 bool any_code = false;
                 for (int j = 0; j < K + J; j++) any_code |= const_of(lists[n.list_off + j]) < 0;
-                const bool need_u = J > 0 && !out.filt[fi].fb_const;
+                const bool need_u = (J > 0 && !out.filt[fi].fb_const) || K > TB_MAX_K;
                 if (!any_code) {
+                    if (need_u) out.filt[fi].u_slot = alloc_slot();  // long FIR: the input tile, staged for taps 9..
                     produced(emit(G_FILT_RUN, st, fi, 0));
+                    if (need_u) free_slot();
                 } else {
                     int used = 0;
                     const int xs = alloc_slot();
@@ -931,6 +937,7 @@ struct Lowerer {
             }
             case TB_FILTER: {
                 if (clk_slot >= 0) return false;  // a filter's history restarts with its Reset
+                if (n.ff_count > TB_MAX_K) return false;  // long FIR: general interpreter only
                 const int fi = filter_table(i);
                 const int st = filter_state(i);
                 const uint32_t K = n.ff_count, J = n.fb_count;

@@ -325,7 +325,7 @@ __device__ void filter_run(const tb_launch& P, const WarpMem& M, Ctx& cx, float 
     float* hy = hx + (K - 1);
     int n, inner_len, out_len, h;
     int w0 = cx.w0;
-    if (!had_begin && S[0] != 0u && cx.w0 == 0 && cx.w1 == TILE && cx.L == TILE && (int)S[1] == K - 1 &&
+    if (!had_begin && K <= TB_MAX_K && S[0] != 0u && cx.w0 == 0 && cx.w1 == TILE && cx.L == TILE && (int)S[1] == K - 1 &&
         (J == 0 || (ft->fb_const && !P.exact_fb))) {
         switch (J) {
             case 0: filter_full_tile<0>(M, ft, acc, hx, hy); break;
@@ -400,6 +400,21 @@ __device__ void filter_run(const tb_launch& P, const WarpMem& M, Ctx& cx, float 
                 u[j] = __fadd_rn(u[j], __fmul_rn(bk[j], xv));
             }
         }
+    }
+    if (K > TB_MAX_K) {  // long FIR (constant taps): taps 9.. read the staged input tile, in the reference's order
+        const float* xs = M.slots + (size_t)ft->u_slot * TILE;
+        __syncwarp();
+        slot_store(M.slots, ft->u_slot, xe);
+        __syncwarp();
+        for (int k = TB_MAX_K; k < K; k++) {
+            const float bk = M.cval[~ft->coef[k]];
+            UNROLL for (int j = 0; j < C; j++) {
+                const int idx = l * C + j - k;
+                const float xv = idx >= 0 ? xs[slot_index(idx)] : hist_at(K - 1 + (idx - w0));
+                u[j] = __fadd_rn(u[j], __fmul_rn(bk, xv));
+            }
+        }
+        __syncwarp();
     }
     // Feedback.
     if (J == 0) {
@@ -747,8 +762,8 @@ __device__ void run_program(const tb_launch& P, const tb_insn* code, const WarpM
                 uint32_t* S = M.state + in.a;
                 float* hx = reinterpret_cast<float*>(S + 2);
                 float* hy = hx + (in.b - 1);
+                UNROLL for (int j = 0; j < C; j++) if (l * C + j < cx.L) hx[l * C + j] = acc[j];
                 if (l == 0) {
-                    UNROLL for (int j = 0; j < C; j++) if (j < cx.L) hx[j] = acc[j];
                     S[0] = 1u;
                     S[1] = (uint32_t)cx.L;
                 }
