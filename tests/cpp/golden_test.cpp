@@ -177,11 +177,16 @@ int main(int argc, char** argv) {
         } catch (const Error& e) {
             EXPECT(e.status() == TB_ERR_INVALID, "empty feed_forward: status %d", e.status());
         }
-        try {
+        try {  // a Filter inside a Reset lowers to the run-by-run form (generator.rs:288-316)
             lower_check(Reset(sin_waveform(1.0f, 0.0f), Filter(Noise(), consts(2, 0.5f))));
-            EXPECT(false, "Filter inside a Reset accepted");
         } catch (const Error& e) {
-            EXPECT(e.status() == TB_ERR_UNSUPPORTED, "Filter inside a Reset: status %d", e.status());
+            EXPECT(false, "Filter inside a Reset: status %d: %s", e.status(), e.what());
+        }
+        try {
+            lower_check(Filter(Time(), consts(40, 0.025f)));
+            EXPECT(false, "40-tap Filter accepted");
+        } catch (const Error& e) {
+            EXPECT(e.status() == TB_ERR_UNSUPPORTED, "40-tap Filter: status %d", e.status());
         }
     } else {
         try {
