@@ -63,8 +63,9 @@ def test_unsupported_is_reported_not_emulated():
     from tuun_b200.generator import lower_check
     rc, h, msg = _create(flatten(Filter(Time(), [Const(1.0)] * 34, [])))
     assert rc == _abi.TB_ERR_UNSUPPORTED and "feed-forward taps" in msg
-    rc, h, msg = _create(flatten(Filter(Time(), [Const(1.0)], [Const(0.1)] * 5)))
+    rc, h, msg = _create(flatten(Filter(Time(), [Const(1.0)], [Const(0.1)] * 9)))
     assert rc == _abi.TB_ERR_UNSUPPORTED and "feedback taps" in msg
+    assert lower_check(Filter(Time(), [Const(1.0)], [Const(0.1)] * 8)).lane_smem_bytes == 0
     rc, h, msg = _create(flatten(Filter(Time(), [Const(1.0)] * 11 + [Time()], [])))
     assert rc == _abi.TB_ERR_UNSUPPORTED and "waveforms" in msg
     long_fir = lower_check(Filter(Time(), [Const(1.0)] * 33, [Const(0.5)]))  # moving_average(32) and a pole

@@ -170,3 +170,15 @@ def test_moving_average_longer_than_a_lane(n_avg):
     for block in (None, 777):
         worst, bad, got, ref = compare(w, 4000, tol=TOL, block=block)
         assert bad == 0 and len(ref) == 2205, (n_avg, block, worst, bad, len(ref))
+
+
+def test_filter_with_eight_feedback_taps():
+    """More feedback taps than the scan's 4x4 matrices: the serial recurrence, constant and waveform coefficients."""
+    from tuun_b200.waveform import Const, Filter, Sine, Time, add, f32, mul
+    x = W.square(Const(f32(2 * np.pi * 220.0)))
+    fb = [Const(f32(c)) for c in (-0.3, 0.12, -0.08, 0.05, 0.04, -0.03, 0.02, 0.01)]
+    for taps in (fb[:5], fb, fb[:6] + [mul(Sine(Const(f32(12.0)), Const(0.0)), Const(f32(0.05))), fb[7]]):
+        w = Filter(x, [Const(f32(0.3)), Const(f32(0.2))], taps)
+        for block in (None, 333):
+            worst, bad, _, _ = compare(w, 12000, tol=TOL, block=block)
+            assert bad == 0, (len(taps), block, worst, bad)

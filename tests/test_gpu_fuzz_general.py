@@ -70,6 +70,8 @@ class Gen:
                 return Filter(x, [add(mul(Time(), Const(-0.5)), Const(0.5))], [mul(Sine(self.hz(1, 20), Const(0.0)), Const(0.4))])
             taps = int(r.integers(1, 6)) if r.random() < 0.6 else int(r.integers(10, 34))  # long: general interpreter only
             fb = [Const(f32(r.uniform(-0.8, 0.8)))] if r.random() < 0.3 else []
+            if r.random() < 0.15:  # more feedback taps than the scan takes: the serial recurrence
+                fb = [Const(f32(c)) for c in r.uniform(-0.12, 0.12, int(r.integers(5, 9)))]
             return Filter(x, [Const(f32(c)) for c in r.uniform(-0.4, 0.4, taps)], fb)
         if k == 11:
             return Reset(Sine(self.hz(5, 900), Const(f32(r.uniform(0, 3)))), self.tree(depth - 1, True))

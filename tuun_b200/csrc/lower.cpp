@@ -277,7 +277,7 @@ struct Lowerer {
             for (uint32_t j = 0; j < K; j++)
                 if (const_of(lists[n.list_off + j]) < 0)
                     fail(TB_ERR_UNSUPPORTED, "Filter with more than " + std::to_string(TB_MAX_K) + " feed-forward taps that are waveforms");
-        if (J > TB_MAX_J) fail(TB_ERR_UNSUPPORTED, "Filter with more than " + std::to_string(TB_MAX_J) + " feedback taps");
+        if (J > TB_MAX_J_GEN) fail(TB_ERR_UNSUPPORTED, "Filter with more than " + std::to_string(TB_MAX_J_GEN) + " feedback taps");
         tb_filter_tab t{};
         t.K = K;
         t.J = J;
@@ -291,6 +291,7 @@ struct Lowerer {
             t.coef[j] = k >= 0 ? TB_OPERAND_CONST(k) : 0;  // slots are filled in by emit_gen
             if (j >= K && k < 0) t.fb_const = 0;
         }
+        if (J > TB_MAX_J) t.fb_const = 0;  // past the scan's matrix size: the serial recurrence
         out.filt.push_back(t);
         filt_idx[i] = (int)out.filt.size() - 1;
         if (t.fb_const && J > 0) {
@@ -937,7 +938,7 @@ struct Lowerer {
             }
             case TB_FILTER: {
                 if (clk_slot >= 0) return false;  // a filter's history restarts with its Reset
-                if (n.ff_count > TB_MAX_K) return false;  // long FIR: general interpreter only
+                if (n.ff_count > TB_MAX_K || n.fb_count > TB_MAX_J) return false;  // long filters: general interpreter only
                 const int fi = filter_table(i);
                 const int st = filter_state(i);
                 const uint32_t K = n.ff_count, J = n.fb_count;

@@ -29,6 +29,7 @@
 #define TB_MAX_K 9   // feed-forward taps of the register / shuffle filter paths (K-1 <= C), steady and lane kernels
 #define TB_MAX_K_GEN 33  // feed-forward taps the general interpreter takes (K-1 <= 32: one history word per lane)
 #define TB_MAX_J 4   // feedback taps supported by the scan path
+#define TB_MAX_J_GEN 8  // feedback taps the general interpreter takes (serial recurrence past TB_MAX_J)
 #define TB_CTL_DEPTH 256  // control-stack words per warp (lower.cpp ctl_need checks a tree against it)
 
 struct tb_insn {
@@ -221,7 +222,7 @@ struct tb_filter_tab {
     uint32_t state_off;    // the node's state block
     int32_t x_slot;        // slot holding the zero-extended input when not all-const
     int32_t u_slot;        // scratch slot for the serial feedback fallback
-    int32_t coef[TB_MAX_K_GEN + TB_MAX_J + 3];  // K feed-forward then J feedback operands
+    int32_t coef[TB_MAX_K_GEN + TB_MAX_J_GEN + 3];  // K feed-forward then J feedback operands
 };
 
 struct tb_fixed_tab {

@@ -443,7 +443,7 @@ __device__ void filter_run(const tb_launch& P, const WarpMem& M, Ctx& cx, float 
         slot_store(M.slots, ft->u_slot, u);
         __syncwarp();
         if (l == 0) {
-            float yh[TB_MAX_J];
+            float yh[TB_MAX_J_GEN];
             for (int jj = 0; jj < J; jj++) yh[jj] = hy[J - 1 - jj];
             for (int m = 0; m < out_len; m++) {
                 const int si = slot_index(w0 + m);
