@@ -227,7 +227,23 @@ void fill_launch(const tb_program* p, tb_launch* L) {
 }
 
 int launch(tb_program* p, const tb_launch& L) {
-    cudaError_t e = tb_kernel_launch(&L, p->smem, p->warps, p->stream);
+    // Up to TB_WARPS_PER_CTA voices share a CTA (and its copy of the byte-code); a batch too small to give every
+    // SM a CTA that way is spread out instead.
+    static int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0)
+            n_sm = 148;
+    }
+    uint32_t warps = p->warps;
+    size_t smem = p->smem;
+    while (warps > 1 && (L.n_voices + warps - 1) / warps < 2u * (uint32_t)n_sm) warps >>= 1;
+    if (warps != p->warps)
+        smem = tb_kernel_smem_bytes((uint32_t)p->low.code.size(), p->low.n_slots, p->low.aux_words,
+                                    (uint32_t)p->low.cexpr.size(), p->low.state_words,
+                                    p->low.steady_ok || (p->low.lane_fin_goe >= 0 && !p->low.lane_clk), warps);
+    cudaError_t e = tb_kernel_launch(&L, smem, warps, p->stream);
     if (e != cudaSuccess) return cuda_fail(e, "tb_render_kernel launch");
     p->launches++;
     return TB_OK;

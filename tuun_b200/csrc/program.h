@@ -18,7 +18,7 @@
 #define TB_C 8               // samples per lane per tile
 #define TB_TILE (32 * TB_C)  // samples per tile
 #ifndef TB_WARPS_PER_CTA
-#define TB_WARPS_PER_CTA 4
+#define TB_WARPS_PER_CTA 8
 #endif
 #define TB_CS 16                 // samples per lane per tile of the steady-state interpreter (steady.cuh)
 #define TB_TILE_S (32 * TB_CS)

@@ -1469,7 +1469,7 @@ __device__ void setup_voice(const tb_launch& P, const WarpMem& M, const float* p
 // program's per-warp shared-memory footprint forces fewer (abi.cpp).
 // ------------------------------------------------------------------------------------------
 #ifndef TB_MIN_BLOCKS
-#define TB_MIN_BLOCKS 4
+#define TB_MIN_BLOCKS 2
 #endif
 extern "C" __global__ void __launch_bounds__(32 * TB_WARPS_PER_CTA, TB_MIN_BLOCKS)
 tb_render_kernel(const tb_launch P) {
