@@ -532,8 +532,25 @@ struct Lowerer {
     }
 
     // ---- length ----------------------------------------------------------------------------------
+    // Subtrees whose `length` (generator.rs:620-782) touches no state and returns `max`: constants, noise and
+    // what is made of them (a Sine's length does not move its accumulator).  One L_INF stands for the whole
+    // subtree, and a point operator / Sine / Alt with such an operand needs no PUSH .. MIN around the other.
+    bool len_trivial(int i) const {
+        const tb_node& n = nodes[i];
+        switch (n.kind) {
+            case TB_CONST: case TB_NOISE: return true;
+            case TB_MARKED: case TB_CAPTURED: case TB_RESET: return len_trivial(n.a);
+            case TB_BINARY: case TB_SINE: return len_trivial(n.a) && len_trivial(n.b);
+            case TB_ALT: return len_trivial(n.a) && len_trivial(n.b) && len_trivial(n.c);
+            default: return false;
+        }
+    }
     void emit_len(int i) {
         const tb_node& n = nodes[i];
+        if (len_trivial(i)) {
+            emit(L_INF);
+            return;
+        }
         switch (n.kind) {
             case TB_CONST:
             case TB_NOISE: emit(L_INF); break;
@@ -543,12 +560,19 @@ struct Lowerer {
             case TB_CAPTURED: emit_len(n.a); break;
             case TB_SINE:
                 (void)state_of(i, 2);
+                if (len_trivial(n.b)) { emit_len(n.a); break; }
+                if (len_trivial(n.a)) { emit_len(n.b); break; }
                 emit_len(n.a);
                 emit(L_PUSH);
                 emit_len(n.b);
                 emit(L_MIN);
                 break;
             case TB_BINARY:
+                if (len_trivial(n.a) || len_trivial(n.b)) {  // min(x, max) = x; Merge: max(x, max) = max
+                    emit_len(len_trivial(n.a) ? n.b : n.a);
+                    if (n.op == TB_MERGE) emit(L_INF);
+                    break;
+                }
                 emit_len(n.a);
                 emit(L_PUSH);
                 emit_len(n.b);
@@ -560,6 +584,7 @@ struct Lowerer {
                 break;
             case TB_ALT:
                 emit_len(n.a);
+                if (len_trivial(n.b) && len_trivial(n.c)) break;  // nothing to advance in the branches
                 emit(L_PUSH);
                 emit_len(n.b);
                 emit_len(n.c);
