@@ -461,9 +461,11 @@ struct Lowerer {
                 if (scan >= 0) out.code[scan].c = label();
                 const int in0 = emit(G_FIN_INNER, 0, 0, 0);
                 emit_gen(n.b);
-                out.code[in0].c = emit(G_FIN_ADV);
+                const int adv = emit(G_FIN_ADV, has_unreached_filter(n.b, false) ? 0 : 1, 0, 0);
+                out.code[in0].c = adv;
                 emit_len(n.b);
                 emit(G_FIN_END);
+                out.code[adv].c = label();
                 break;
             }
             case TB_APPEND: {
@@ -532,6 +534,29 @@ struct Lowerer {
     }
 
     // ---- length ----------------------------------------------------------------------------------
+    // Does the subtree hold a Filter that a non-empty `generate` of the subtree may not have reached — one in the
+    // second part of an Append, inside a nested Fin or Reset, in a length or coefficient waveform?  `length(w, 0)`
+    // turns such a Filter from Initial into zero history without its look-ahead (generator.rs:690-704), so the
+    // empty advance at the end of a Fin (:166) must still run for it.  Any other node is left as it is by
+    // `length(w, 0)`.
+    bool has_unreached_filter(int i, bool under) const {
+        const tb_node& n = nodes[i];
+        switch (n.kind) {
+            case TB_FILTER:
+                if (under) return true;
+                for (uint32_t j = 0; j < n.ff_count + n.fb_count; j++)
+                    if (has_unreached_filter(lists[n.list_off + j], true)) return true;
+                return has_unreached_filter(n.a, under);
+            case TB_APPEND: return has_unreached_filter(n.a, under) || has_unreached_filter(n.b, true);
+            case TB_FIN: return has_unreached_filter(n.a, true) || has_unreached_filter(n.b, true);
+            case TB_RESET: return has_unreached_filter(n.a, under) || has_unreached_filter(n.b, true);
+            case TB_BINARY: case TB_SINE: return has_unreached_filter(n.a, under) || has_unreached_filter(n.b, under);
+            case TB_ALT:
+                return has_unreached_filter(n.a, under) || has_unreached_filter(n.b, under) || has_unreached_filter(n.c, under);
+            case TB_MARKED: case TB_CAPTURED: return has_unreached_filter(n.a, under);
+            default: return false;
+        }
+    }
     // Subtrees whose `length` (generator.rs:620-782) touches no state and returns `max`: constants, noise and
     // what is made of them (a Sine's length does not move its accumulator).  One L_INF stands for the whole
     // subtree, and a point operator / Sine / Alt with such an operand needs no PUSH .. MIN around the other.

@@ -65,7 +65,7 @@ enum tb_op : uint32_t {
     G_FIN_SCAN,    // c = jump target (join)
     G_FIN_STATIC,  //
     G_FIN_INNER,   // c = jump target (G_FIN_ADV)
-    G_FIN_ADV,     //
+    G_FIN_ADV,     // a = 1: an empty advance may be skipped, c = jump target (past G_FIN_END)
     G_FIN_END,     //
     G_APP_BEGIN,   // a = state, c = jump target (G_APP_MID)
     G_APP_MID,     // a = state, b = slot, c = jump target (just past G_APP_END)

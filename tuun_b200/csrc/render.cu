@@ -846,6 +846,11 @@ __device__ void run_program(const tb_launch& P, const tb_insn* code, const WarpM
                 const int inner_len = cx.L;
                 cx.w1 = POP();
                 const int len = POP();
+                if (in.a && len > 0 && cx.w0 + len == cx.w1) {  // the Fin does not cut this block: `length(inner, 0)`
+                    cx.L = inner_len;                          // would change nothing (lower.cpp has_unreached_filter)
+                    pc = in.c;
+                    break;
+                }
                 PUSH(inner_len);
                 PUSH(cx.w0);
                 cx.w0 = cx.w0 + len;
