@@ -39,3 +39,10 @@ for v in range(V):
         # runs of bad samples
         runs = np.split(bad, np.nonzero(np.diff(bad) > 1)[0] + 1)
         print("  runs", [(int(x[0]), len(x)) for x in runs][:12])
+if len(sys.argv) > 4:  # show the values of voice V around sample T
+    v, t = int(sys.argv[4]), int(sys.argv[5])
+    o = OracleProgram(w, SR); o.seed_noise(0x7475756E2545F491, v); o.set_params(params[v])
+    r = o.render(n, block=1024)
+    got = np.concatenate([a[v], b[v]])
+    np.set_printoptions(precision=4, linewidth=200)
+    print("got", got[t - 6:t + 8]); print("ref", r[t - 6:t + 8])
