@@ -87,6 +87,8 @@ def test_every_named_config_lowers_on_the_host():
     for name, w in trees:
         info = lower_check(w)
         assert info.smem_bytes <= 220 * 1024 and info.threads in (32, 64, 128, 256), name
+        if name == "cfg2":  # length programs fold their constant subtrees (lower.cpp len_trivial): 1,681 words before
+            assert info.n_code_words // 4 < 1000, info.n_code_words
     # infinite, window-free trees take the 512-sample steady tiles; finite ones the general 256
     assert lower_check(W.fm_filter_voice()).tile == 512
     assert lower_check(W.cfg1_from_source()).tile == 256
