@@ -121,19 +121,19 @@ def cpu_baseline(args, n_samples, target_seconds, threads):
     from oracle.binding import OracleProgram
     from tuun_b200.workloads import fm_filter_params, fm_filter_voice
     o = OracleProgram(fm_filter_voice(), SAMPLE_RATE)
-    probe_ids = (np.arange(threads) * 4099) % args.voices
+    probe_ids = (np.arange(threads) * 40503 + 49230) % args.voices
     t = time.perf_counter()
     o.render_batch(fm_filter_params(probe_ids), len(probe_ids), min(n_samples, 44100), keep=False, threads=threads)
     dt = time.perf_counter() - t
     rate = len(probe_ids) * min(n_samples, 44100) / max(dt, 1e-6)
     n_v = int(max(threads, min(args.voices, rate * target_seconds / n_samples)))
     n_v = max(threads, (n_v // threads) * threads)
-    ids = (np.arange(n_v) * 4099) % args.voices
+    ids = (np.arange(n_v) * 40503 + 49230) % args.voices
     t = time.perf_counter()
     _, _, _, total = o.render_batch(fm_filter_params(ids), n_v, n_samples, keep=False, threads=threads)
     dt = time.perf_counter() - t
     return {"value": total / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{n_v} voices (ids v*4099 mod {args.voices}) x {n_samples} samples, 1024-sample blocks, "
+            "sample": f"{n_v} voices (ids (v*40503+49230) mod {args.voices}) x {n_samples} samples, 1024-sample blocks, "
                       f"{dt:.1f} s wall"}, dt
 
 

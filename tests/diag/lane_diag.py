@@ -8,7 +8,7 @@ from tuun_b200.generator import Program
 from tuun_b200.workloads import fm_filter_params, fm_filter_voice
 
 V, N = 200, 6000
-ids = (np.arange(V) * 4099) % 65536
+ids = (np.arange(V) * 40503 + 49230) % 65536
 w, params = fm_filter_voice(), fm_filter_params(ids)
 one = np.zeros((V, N), np.float32)
 Program(w, 44100).render(one, params=params)

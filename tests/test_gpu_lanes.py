@@ -43,8 +43,8 @@ def oracle_rows(w, params, V, N, seed=None):
 
 
 def cfg5(V):
-    from tuun_b200.workloads import fm_filter_params, fm_filter_voice
-    ids = (np.arange(V) * 4099) % 65536
+    from tuun_b200.workloads import fm_filter_params, fm_filter_sample_ids, fm_filter_voice
+    ids = fm_filter_sample_ids(V)  # every bit field of the sweep changes from one pick to the next
     return fm_filter_voice(), fm_filter_params(ids)
 
 
@@ -457,7 +457,7 @@ def test_fm_voice_kernel_edges(monkeypatch):
     from tuun_b200.workloads import fm_filter_params, fm_filter_voice
     w = fm_filter_voice()
     for V in (1, 31, 33, 65):
-        params = fm_filter_params((np.arange(V) * 4099 + 17) % 65536)
+        params = fm_filter_params((np.arange(V) * 40503 + 17) % 65536)
         o = OracleProgram(w, SR)
         for sizes in ((16,), (17, 15, 1, 31), (33, 16, 47), (5, 300), (255, 257, 16)):
             p = program(w, monkeypatch)

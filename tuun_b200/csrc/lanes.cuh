@@ -139,6 +139,36 @@ __device__ __forceinline__ void sin_p32x2(uint32_t p0, uint32_t p1, float& s0, f
     s0 = __sinf(x0);
     s1 = __sinf(x1);
 }
+// ---- the running phase of a frequency-modulated FAST sine ----------------------------------------
+// Pd = 1.5 * 2^52 + P with P the phase in units of 2^-44 turns: the low 44 mantissa bits are the
+// fraction of a turn, whole turns collect in the 7 bits above (and fall away when pd_make rebuilds
+// the double, once per tile).  One DFMA per sample adds f * kscale exactly and rounds the SUM to the
+// grid, so an increment is off by at most 2^-45 turns — for a constant rate a systematic 2^-45
+// turns per sample, 7.9e-8 rad after 441,000 samples and 4.7e-7 rad after a minute (the 2^-32-turn
+// grid this loop used before drifted 3.2e-4 rad in 10 s on constant-rate carriers).  The warp
+// kernel's scan rounds increments to the same 2^-44 turns.  The reference's own f64 accumulator
+// (generator.rs:212-218) is some 1e-11 rad off the exact phase after 10 s.
+// Range: a tile may add up to +-2^51 units = +-128 turns; callers bound |f| to TB_FM_TURNS turns a
+// sample (16 samples x 4 turns = 64) and convert the slow way beyond.
+#define TB_FM_TURNS 4.0
+#define TB_P44_MASK 0x00000fffffffffffull
+__device__ __forceinline__ double pd_make(u64 p44) {
+    return __longlong_as_double((i64)(0x4338000000000000ull | (p44 & TB_P44_MASK)));
+}
+__device__ __forceinline__ u64 pd_bits(double Pd) { return (u64)__double_as_longlong(Pd); }
+// The float 1.m whose mantissa is the top 23 phase bits (what mant23 makes of a 32-bit phase).
+__device__ __forceinline__ uint32_t pd_m23(double Pd) {
+    return (__funnelshift_l((uint32_t)__double2loint(Pd), (uint32_t)__double2hiint(Pd), 11) & 0x007fffffu) | 0x3f800000u;
+}
+__device__ __forceinline__ uint32_t p44_m23(u64 p44) { return ((uint32_t)(p44 >> 21) & 0x007fffffu) | 0x3f800000u; }
+__device__ __forceinline__ float sin_m23(uint32_t m) { return __sinf(fmaf(__uint_as_float(m), TB_SIN23_A, TB_SIN23_B)); }
+__device__ __forceinline__ void sin_m23x2(uint32_t m0, uint32_t m1, float& s0, float& s1) {
+    float x0, x1;
+    unpk2(fma2(pk2(__uint_as_float(m0), __uint_as_float(m1)), pk2(TB_SIN23_A, TB_SIN23_A), pk2(TB_SIN23_B, TB_SIN23_B)),
+          x0, x1);
+    s0 = __sinf(x0);
+    s1 = __sinf(x1);
+}
 // f as a double, by integer instructions: sign | (exponent + 896) << 20 | mantissa >> 3, mantissa << 29.
 // An alternative to F2F.F64.F32, which runs on the 16-lane conversion unit that also serves MUFU.SIN
 // and the f64 -> f32 conversions of the exact sines (tools/ubench/xu.cu: 14-16 results/clk/SM each).
@@ -195,9 +225,8 @@ __device__ __forceinline__ void lane_sine_cc(const LaneMem& M, float (&acc)[LS],
 // ---- Sine with a frequency waveform (and optionally a phase waveform) ------------------------------
 // acc holds the phase offsets on entry when !UNIFORM_PH; f the frequencies.  The sample is taken
 // before the increment (generator.rs:212-218).
-//   MODE 2 (FAST class on the special-function unit): the tile's phases are 32-bit running sums of
-//   per-sample increments rounded to 2^-32 turns (1.5e-9 rad; the other kernels round to 2^-44), and
-//   the 64-bit accumulator of the state block advances by exactly their sum.
+//   MODE 2 (FAST class on the special-function unit): the tile's phases are running sums on the 2^-44-turn
+//   grid of the other kernels, and the 64-bit accumulator of the state block advances by exactly their sum.
 //   CHECK = false: the caller has bounded |f| below the range limit of the magic-number conversion.
 template <bool UNIFORM_PH, int MODE, bool CHECK = true>
 __device__ __forceinline__ void lane_sine_var(const LaneMem& M, float (&acc)[LS], const float (&f)[LS], u64 ph0, int st,
@@ -212,17 +241,24 @@ __device__ __forceinline__ void lane_sine_var(const LaneMem& M, float (&acc)[LS]
     }
     const bool slow = CHECK && (!(big < sk.flimit) || !(bigp < sk.plimit));
     if (MODE == 2 && !slow) {
-        const uint32_t p0 = (uint32_t)((a0 + (UNIFORM_PH ? ph0 : 0ull)) >> 32);
-        uint32_t p = p0;
-        const double ks = sk.kscale * (1.0 / 4096.0), ps = sk.pscale * (1.0 / 4096.0);  // 2^32 / ... instead of 2^44 / ...
-        UNROLL for (int j = 0; j < LS; j += 2) {
-            const uint32_t t0 = UNIFORM_PH ? p : p + magic_lo(acc[j], ps);
-            p += magic_lo(f[j], ks);
-            const uint32_t t1 = UNIFORM_PH ? p : p + magic_lo(acc[j + 1], ps);
-            p += magic_lo(f[j + 1], ks);
-            sin_p32x2(t0, t1, acc[j], acc[j + 1]);
+        // Running phase on the 2^-44-turn grid in the mantissa of a double (pd_make): one DFMA per sample
+        // adds the increment, a second one the phase offset of a phase waveform (not accumulated).  Whole
+        // turns are dropped every 4 samples: 4 x TB_FM_TURNS + plimit (96 turns) stays inside the +-128 turns
+        // the field holds.
+        const u64 p0 = (a0 + (UNIFORM_PH ? ph0 : 0ull)) >> 20;
+        u64 p = p0;
+        UNROLL for (int j = 0; j < LS; j += 4) {
+            double Pd = pd_make(p);
+            UNROLL for (int i = j; i < j + 4; i += 2) {
+                const double T0 = UNIFORM_PH ? Pd : fma((double)acc[i], sk.pscale, Pd);
+                Pd = fma((double)f[i], sk.kscale, Pd);
+                const double T1 = UNIFORM_PH ? Pd : fma((double)acc[i + 1], sk.pscale, Pd);
+                Pd = fma((double)f[i + 1], sk.kscale, Pd);
+                sin_m23x2(pd_m23(T0), pd_m23(T1), acc[i], acc[i + 1]);
+            }
+            p = pd_bits(Pd);
         }
-        stw(M, st + 1, (uint32_t)(a0 >> 32) + (p - p0));
+        st64(M, st, a0 + ((p - p0) << 20));
         return;
     }
     u64 ph = a0;
@@ -756,13 +792,13 @@ __device__ __forceinline__ void tile_done(RowStore& R, int l, u64 t, u64 n_tiles
 #else
 #define TB_D2F(x) ((float)(x))
 #endif
-// SLOW: some voice of the warp has |m| + |c| beyond the exact range of the magic-number conversion
-// (100 x the sample rate): every increment goes through the full-precision conversion instead.
+// SLOW: some voice of the warp has |m| + |c| beyond TB_FM_TURNS turns a sample (nothing audible: the
+// Nyquist rate is half a turn): every increment goes through the integer conversion instead.
+//   p: the carrier phase in 2^-44 turns (bits above 43 are ignored and may hold anything).
 //   CAP: also report in p_cap the phase before sample `cap` (the phase after `cap` samples of the tile).
 template <bool SLOW, bool CAP = false>
 __device__ __forceinline__ void fm_carrier_tile(float (&car)[LS], double& S, double& Cq, const double2* rot, u64 mm,
-                                                u64 cc, uint32_t& p, double ks, const SineK& sk, int cap = 0,
-                                                uint32_t* p_cap = nullptr) {
+                                                u64 cc, u64& p, const SineK& sk, int cap = 0, u64* p_cap = nullptr) {
     float f[LS];
 #if TB_ABL == 4
     UNROLL for (int j = 0; j < LS; j++) f[j] = TB_D2F(S) + j;
@@ -786,35 +822,32 @@ __device__ __forceinline__ void fm_carrier_tile(float (&car)[LS], double& S, dou
     UNROLL for (int j = 0; j < LS; j += 2) unpk2(add2(mul2(pk2(f[j], f[j + 1]), mm), cc), f[j], f[j + 1]);
     if (SLOW) {
         UNROLL for (int j = 0; j < LS; j += 2) {
-            const uint32_t t0 = p;
-            p += (uint32_t)(freq_to_inc(f[j], sk) >> 32);
-            const uint32_t t1 = p;
-            p += (uint32_t)(freq_to_inc(f[j + 1], sk) >> 32);
+            const u64 t0 = p;
+            p += freq_to_inc(f[j], sk) >> 20;
+            const u64 t1 = p;
+            p += freq_to_inc(f[j + 1], sk) >> 20;
             if (CAP && j == cap) *p_cap = t0;
             if (CAP && j + 1 == cap) *p_cap = t1;
-            sin_p32x2(t0, t1, car[j], car[j + 1]);
+            sin_m23x2(p44_m23(t0), p44_m23(t1), car[j], car[j + 1]);
         }
         return;
     }
-    // The running phase lives in the low word of a double kept at 1.5 * 2^52 + p (units of 2^-32
-    // turns): one DFMA per sample adds f * ks and rounds the sum to that grid, whole turns collect
-    // above bit 31 and are dropped when the double is rebuilt for the next tile.  (The sum is rounded,
-    // not the increments; the carried 64-bit accumulator still advances by exactly what was added.)
-    double Pd = __hiloint2double(0x43380000, (int)p);
+    // One DFMA per sample adds f * kscale to the running phase and rounds the sum to 2^-44 turns (pd_make).
+    double Pd = pd_make(p);
     UNROLL for (int j = 0; j < LS; j += 2) {
-        const uint32_t t0 = (uint32_t)__double2loint(Pd);
-        Pd = fma((double)f[j], ks, Pd);
-        const uint32_t t1 = (uint32_t)__double2loint(Pd);
-        Pd = fma((double)f[j + 1], ks, Pd);
-        if (CAP && j == cap) *p_cap = t0;
-        if (CAP && j + 1 == cap) *p_cap = t1;
+        const double T0 = Pd;
+        Pd = fma((double)f[j], sk.kscale, Pd);
+        const double T1 = Pd;
+        Pd = fma((double)f[j + 1], sk.kscale, Pd);
+        if (CAP && j == cap) *p_cap = pd_bits(T0);
+        if (CAP && j + 1 == cap) *p_cap = pd_bits(T1);
 #if TB_ABL == 2
-        car[j] = __uint_as_float(mant23(t0)); car[j + 1] = __uint_as_float(mant23(t1));
+        car[j] = __uint_as_float(pd_m23(T0)); car[j + 1] = __uint_as_float(pd_m23(T1));
 #else
-        sin_p32x2(t0, t1, car[j], car[j + 1]);
+        sin_m23x2(pd_m23(T0), pd_m23(T1), car[j], car[j + 1]);
 #endif
     }
-    p = (uint32_t)__double2loint(Pd);
+    p = pd_bits(Pd);
 }
 struct BiquadRegs {
     float b0, b1, b2, a1, a2;
@@ -898,16 +931,16 @@ __device__ __forceinline__ void run_fm_voice(const tb_insn* code, LaneMem& M, co
     double S = 0.0, Cq = 1.0;
     const double2* rot = reinterpret_cast<const double2*>(M.Q + (size_t)((w0.op >> 8) & 0xffu) * LT);
     u64 mm = 0, cc = 0;
-    uint32_t p = 0, p_start = 0;
+    u64 p = 0, p_start = 0;  // carrier phase, 2^-44 turns
     BiquadRegs F = {};
-    const double ks = sk.kscale * (1.0 / 4096.0);
+    const double ks = sk.kscale;
     if (active) {
         S = ldd(M, w0.a);
         Cq = ldd(M, w0.a + 2);
         const float m = ldf(M, w1.a), c = ldf(M, w1.b);
         mm = pk2(m, m);
         cc = pk2(c, c);
-        p_start = p = (uint32_t)((ld64(M, w0.b) + ld64(M, w0.c)) >> 32);
+        p_start = p = (ld64(M, w0.b) + ld64(M, w0.c)) >> 20;
         if (TAIL) {
             const int wc = (int)w1.op, st = w1.c;
             F.b0 = ldf(M, wc); F.b1 = ldf(M, wc + 1); F.b2 = ldf(M, wc + 2);
@@ -920,10 +953,10 @@ __device__ __forceinline__ void run_fm_voice(const tb_insn* code, LaneMem& M, co
                 const u64 phm = turns_to_fx_slow((double)ldf(M, prime.ph_cval) / TB_TAU);
                 const float f0 = __fadd_rn(__fmul_rn((float)sin_turns_d8(am + phm), m), c);
                 const float f1 = __fadd_rn(__fmul_rn((float)sin_turns_d8(am + phm + inc), m), c);
-                F.x2 = sin_p32(p);
-                p += SLOW ? (uint32_t)(freq_to_inc(f0, sk) >> 32) : magic_lo(f0, ks);
-                F.x1 = sin_p32(p);
-                p += SLOW ? (uint32_t)(freq_to_inc(f1, sk) >> 32) : magic_lo(f1, ks);
+                F.x2 = sin_m23(p44_m23(p));
+                p += SLOW ? freq_to_inc(f0, sk) >> 20 : magic_raw(f0, ks);
+                F.x1 = sin_m23(p44_m23(p));
+                p += SLOW ? freq_to_inc(f1, sk) >> 20 : magic_raw(f1, ks);
                 F.y1 = F.y2 = 0.0f;
                 const u64 am2 = am + 2ull * inc;
                 st64(M, prime.acc_w, am2);
@@ -946,14 +979,14 @@ __device__ __forceinline__ void run_fm_voice(const tb_insn* code, LaneMem& M, co
     if (!TAIL) {
         for (u64 t = 0; t < n_tiles; t++) {
             if (active) {
-                fm_carrier_tile<SLOW>(car, S, Cq, rot, mm, cc, p, ks, sk);
+                fm_carrier_tile<SLOW>(car, S, Cq, rot, mm, cc, p, sk);
                 M.A = abase + (t & 1) * 4 * AS;
                 lacc_store(M, car);
             }
             tile_done<MIX>(R, l, t, n_tiles);
         }
     } else if (n_tiles > 0) {
-        if (active) fm_carrier_tile<SLOW>(car, S, Cq, rot, mm, cc, p, ks, sk);
+        if (active) fm_carrier_tile<SLOW>(car, S, Cq, rot, mm, cc, p, sk);
         for (u64 t = 1; t < n_tiles; t++) {
             if (active) {
                 float y[LS], nxt[LS];
@@ -962,7 +995,7 @@ __device__ __forceinline__ void run_fm_voice(const tb_insn* code, LaneMem& M, co
 #else
                 biquad_tile(y, car, F);                                   // tile t-1 leaves ...
 #endif
-                fm_carrier_tile<SLOW>(nxt, S, Cq, rot, mm, cc, p, ks, sk);    // ... while tile t is made
+                fm_carrier_tile<SLOW>(nxt, S, Cq, rot, mm, cc, p, sk);    // ... while tile t is made
                 M.A = abase + ((t - 1) & 1) * 4 * AS;
                 lacc_store(M, y);
                 UNROLL for (int j = 0; j < LS; j++) car[j] = nxt[j];
@@ -982,8 +1015,8 @@ __device__ __forceinline__ void run_fm_voice(const tb_insn* code, LaneMem& M, co
     if (!MIX && rem > 0) {  // the samples that do not fill a tile (rows only: the on-chip mixdown gets whole tiles)
         const int half = (int)(n_tiles & 1);
         if (active) {
-            uint32_t p_rem = p;
-            fm_carrier_tile<SLOW, true>(car, S, Cq, rot, mm, cc, p, ks, sk, rem, &p_rem);
+            u64 p_rem = p;
+            fm_carrier_tile<SLOW, true>(car, S, Cq, rot, mm, cc, p, sk, rem, &p_rem);
             p = p_rem;
             float y[LS];
             if (TAIL) {
@@ -1005,7 +1038,8 @@ __device__ __forceinline__ void run_fm_voice(const tb_insn* code, LaneMem& M, co
     }
     M.A = abase;
     if (active) {  // registers -> state block; finish_lane advances the modulator's accumulator
-        stw(M, w0.b + 1, ldw(M, w0.b + 1) + (p - p_start));
+        // the magic bits above the phase cancel in the difference or leave at the top of the shift
+        st64(M, w0.b, ld64(M, w0.b) + ((p - p_start) << 20));
         if (TAIL) {
             const int st = w1.c;
             stf(M, st + 2, F.x2); stf(M, st + 3, F.x1);
@@ -1053,7 +1087,7 @@ __device__ __forceinline__ void lanes_body(const tb_launch& P, uint32_t group, u
     sk.kscale = 17592186044416.0 / (TB_TAU * (double)P.sample_rate);
     sk.pscale = 17592186044416.0 / TB_TAU;
     sk.inv_turn = 1.0 / (TB_TAU * (double)P.sample_rate);
-    sk.flimit = (float)(100.0 * TB_TAU * (double)P.sample_rate);
+    sk.flimit = (float)(TB_FM_TURNS * TB_TAU * (double)P.sample_rate);  // tighter than render.cu's 100: see pd_make
     sk.plimit = 600.0f;
 
     uint32_t* gstate = P.state + (size_t)voice * P.state_words;

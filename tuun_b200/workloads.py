@@ -211,3 +211,22 @@ def tracker_benches(sample_rate=44100):
     large = times(plus(s.triangle(55), times(Noise(), 0.2)), s.Rw(1.0, 1.0))
     return [("filter_1_1", filter_1_1, 43), ("filter_1_1_linear", filter_1_1_linear, 43),
             ("filter_4_3", filter_4_3, 43), ("marks_4_40", marks, 3438), ("large_440", to_waveform(large), 43)]
+
+
+def fm_filter_sample_ids(n, first=0) -> np.ndarray:
+    """`n` voices of the config 5 sweep picked by an odd multiplier (a permutation of 0..65535 whose
+    neighbours differ in every bit field: carrier, modulation index, ratio, cutoff and Q all change from
+    one pick to the next).  Pick 0 is voice 49230, a constant-rate carrier (index 0) under the 200 Hz, Q = 2
+    low-pass.  Use this — not a small stride — wherever a subset of the sweep stands for the sweep."""
+    k = np.arange(first, first + n, dtype=np.int64)
+    return (k * 40503 + 49230) % 65536
+
+
+def fm_filter_cover_ids(per_class=2) -> np.ndarray:
+    """Voices covering every (modulation index, ratio, cutoff) class of the sweep — the 256 values of
+    bits 8..15 — `per_class` times with different carriers; Q = 0.5 + 0.25 (v mod 7) takes all 7 values for
+    every cutoff along the way (28 filter shapes)."""
+    hi = np.repeat(np.arange(256, dtype=np.int64), per_class)
+    k = np.tile(np.arange(per_class, dtype=np.int64), 256)
+    lo = (hi * 89 + k * 131 + 17) % 256
+    return (hi << 8) | lo
