@@ -1,4 +1,4 @@
-"""Why six of config 5's 28 filter shapes carry a tolerance above 1e-4 (workloads.fm_filter_tolerance): a CPU
+"""Why two of config 5's 28 filter shapes carry a tolerance above 1e-4 (workloads.fm_filter_tolerance): a CPU
 experiment on the REFERENCE's arithmetic alone (the oracle, generator.rs:382-515 restated) — no GPU code.
 
 The carrier of a voice is rendered by the oracle and fed to the oracle's own Filter twice: as is, and with
@@ -6,9 +6,10 @@ every sample moved by at most 4e-7 (the size of the error of a FAST-class sine; 
 bit-for-bit libm's moves samples by at least an ulp, 6e-8).  In exact arithmetic the filter output moves by
 ~1e-7.  The reference's f32 recurrence turns the change into another realisation of its round-off noise:
 for the 200 Hz low-passes with Q >= 0.75 (b0 ~ 2e-4, poles at radius > 0.99, noise gain 107..209) the two
-reference renders differ by several 1e-5 and up to ~1e-4 over 10 s.  So 1e-4 x gain / 100 is the
-reference's own reproducibility there, not a property of this implementation; every other shape stays far
-below 1e-4 and keeps the flat tolerance."""
+reference renders differ by several 1e-5 and up to ~1e-4 over 10 s on single voices (8e-5 on the handful
+below; over thousands of voices the largest peaks pass 1e-4 for gains >= 190, see fm_filter_tolerance).  That is
+the reference's own reproducibility there, not a property of this implementation; every other shape stays
+far below 1e-4."""
 import numpy as np
 from scipy.signal import lfilter
 
@@ -51,10 +52,11 @@ def test_reference_recurrence_is_its_own_noise_floor():
         rows.append((v, g, tol, d_ref, d_exact))
         assert d_exact < 5e-7                       # the change itself is tiny
         assert d_ref <= tol, (v, g, d_ref, tol)     # and the stated tolerance covers what the reference does to it
+        assert (tol > 1e-4) == (g >= 190)
         if g < 100:
-            assert tol == 1e-4 and d_ref < 5e-5, (v, g, d_ref)
+            assert d_ref < 5e-5, (v, g, d_ref)
         else:
-            assert tol > 1e-4 and d_ref > 10 * d_exact, (v, g, d_ref, d_exact)  # scales with |y| too (voice 200: 0.2)
+            assert d_ref > 10 * d_exact, (v, g, d_ref, d_exact)  # scales with |y| too (voice 200: 0.2)
     wide = [r for r in rows if r[1] >= 100]
     assert max(r[3] for r in wide) > 5e-5           # the reference vs itself: most of 1e-4 is gone already
     for r in rows:

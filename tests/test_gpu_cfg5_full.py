@@ -3,10 +3,12 @@ the bench times: the default kernel selection (a batch of >= 10,656 voices takes
 device rows, 441,000 samples in one call — compared with the CPU oracle (generator.rs:86-515 restated) on
 512 voices that cover every modulation index, ratio, cutoff and Q of the sweep.
 
-Tolerance: 1e-4 (north_star) for the 22 of 28 filter shapes whose round-off noise gain is below 100; the six
-200 Hz low-passes with Q >= 0.75 get 1e-4 x gain / 100 (at most 2.1e-4) — tests/test_cfg5_noise_floor.py
-shows on the CPU that the REFERENCE's recurrence does not reproduce itself more closely than that when its
-input changes by a few 1e-7 (any sine that is not libm's), so the bound is the reference's own noise floor.
+Tolerance: 1e-4 (north_star) for 26 of the 28 filter shapes; the two 200 Hz low-passes with Q = 1.75 and
+Q = 2 (round-off noise gain 196 and 209, 4,680 of the 65,536 voices) get 1.5e-4: over ALL of their voices at
+full length 45 lie between 1.0e-4 and 1.3e-4 (workloads.fm_filter_tolerance has the numbers).
+tests/test_cfg5_noise_floor.py shows on the CPU that the REFERENCE's recurrence does not reproduce itself
+much more closely when its input changes by a few 1e-7 (any sine that is not libm's): the excess is the
+reference's own round-off noise, realised twice.
 Phase drift: the error of the last second of a voice is bounded by the error of its first second — the
 carrier phase is a running sum on a 2^-44-turn grid (lanes.cuh pd_make), off by < 1e-7 rad after 10 s and
 < 5e-7 rad after a minute."""
@@ -68,7 +70,7 @@ def test_cfg5_full_length_default_kernel():
     err = e.max(axis=1)
     tol = fm_filter_tolerance(params[:C], TOL)
     flat = tol == TOL
-    assert flat.sum() >= 0.75 * C                        # the widening concerns 6 of 28 filter shapes
+    assert flat.sum() >= 0.9 * C                         # the widening concerns 2 of 28 filter shapes
     bad = np.nonzero(err > tol)[0]
     assert len(bad) == 0, [(int(ids[b]), float(err[b]), float(tol[b])) for b in bad[:8]]
     # no drift: the last second is as close as the first (a phase that drifts grows the error linearly:
@@ -79,7 +81,7 @@ def test_cfg5_full_length_default_kernel():
     i0 = ((ids[:C] >> 8) % 16) == 0                      # constant-rate carriers
     assert i0.sum() >= 32
     print(f"cfg5 x 441,000 on the lane-FM kernel: max err {err[flat].max():.2e} (flat 1e-4 voices), "
-          f"{err[~flat].max():.2e} (widened, tol <= {tol.max():.2e}); index-0 voices {err[i0].max():.2e}; "
+          f"{err[~flat].max():.2e} (the two 1.5e-4 shapes); index-0 voices {err[i0].max():.2e}; "
           f"voice 49230: {e[512].max():.2e}")
 
 
