@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TB_ABI_VERSION 1u
+#define TB_ABI_VERSION 2u
 
 /* enum Waveform variants, src/lib/waveform.rs:23-100 (same order). */
 typedef enum tb_kind {
@@ -120,6 +120,14 @@ void tb_program_destroy(tb_program* p);
  * where the previous one stopped ("pick up where this one left off", generator.rs:76-78).
  * `params` may be NULL (use the constants in the tree); n_voices must stay the same for the
  * life of the stream (until tb_reset).
+ *
+ * Few voices, many samples: a steady program (sines, clocks, noise, point operators, Alt,
+ * constant-coefficient filters) is cut along TIME as well — every voice becomes S segments rendered
+ * side by side, each from the state the reference's serial walk would have reached there (phase sums:
+ * exclusive u64 prefix sums of per-segment increments, exact; filter histories: a scan of affine maps
+ * X' = M^L X + z over the segments).  Sample values of sines do not depend on S; filtered samples differ
+ * from the serial f32 recurrence by its round-off noise.  Automatic when it pays; TUUN_B200_SPLIT=0
+ * disables it, TUUN_B200_SPLIT=S forces S segments.  tb_program_info reports what happened.
  */
 int tb_render(tb_program* p, const float* params, uint32_t n_params, uint32_t n_voices,
               uint64_t n_samples, float* out, uint64_t out_stride, uint64_t* out_len,
@@ -177,6 +185,11 @@ typedef struct tb_program_info {
     uint32_t lane_min_voices; /* batches of at least this many voices take it */
     uint32_t lane_capacity;   /* 64-voice CTAs of the lane interpreter kernels the device holds at once (more: work queue) */
     uint32_t lane_fm_capacity;/* same for the fused-FM-voice kernel; 0 when the program is not one fused FM voice */
+    /* time-axis split (few voices, long calls: a voice rendered as S segments side by side, see tb_render) */
+    uint32_t split_passes;    /* render passes a split call makes (summary passes + the one that writes samples); 0: never split */
+    uint32_t split_segments;  /* S of the first (largest) round of the most recent split call; 0: no call was split yet */
+    uint64_t split_seg_samples; /* samples per segment of that round */
+    uint64_t split_rounds;    /* split rounds so far */
 } tb_program_info;
 int tb_program_get_info(const tb_program* p, tb_program_info* info);
 

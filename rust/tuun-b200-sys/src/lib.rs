@@ -49,6 +49,10 @@ pub struct TbProgramInfo {
     pub lane_min_voices: u32,
     pub lane_capacity: u32,
     pub lane_fm_capacity: u32,
+    pub split_passes: u32,
+    pub split_segments: u32,
+    pub split_seg_samples: u64,
+    pub split_rounds: u64,
 }
 
 pub const TB_OUT_DEVICE: u32 = 1;

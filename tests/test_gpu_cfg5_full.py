@@ -18,7 +18,6 @@ import numpy as np
 import pytest
 
 from oracle.binding import OracleProgram
-from tuun_b200.waveform import Const, Sine, add, mul
 
 pytestmark = pytest.mark.gpu
 SR = 44100
@@ -32,13 +31,6 @@ def per_second_error(out, ref):
     secs = N // SR
     d = np.abs(out[:, :secs * SR] - ref[:, :secs * SR]).reshape(V, secs, SR)
     return d.max(axis=2)
-
-
-def fm_pair():
-    """The carrier of config 5 without its filter: its error against the oracle is the phase error itself."""
-    from tuun_b200.workloads import F, PI
-    mod = Sine(Const(1.0, param=0), Const(PI / F(2.0)))
-    return Sine(add(mul(mod, Const(1.0, param=1)), Const(1.0, param=2)), Const(0.0))
 
 
 def test_cfg5_full_length_default_kernel():
@@ -94,13 +86,13 @@ def test_carrier_phase_after_a_minute(monkeypatch):
     up to 1e-7 rad for good — a random walk (measured: 1.0e-5 after 60 s on the deepest modulation, index
     9.4 at ratio 3), not a drift of the accumulator: constant-rate carriers stay at 1e-6."""
     from tuun_b200.generator import Program
-    from tuun_b200.workloads import fm_filter_cover_ids, fm_filter_params
+    from tuun_b200.workloads import fm_filter_cover_ids, fm_filter_params, fm_pair_voice
     monkeypatch.setenv("TUUN_B200_LANE_MIN_VOICES", "1")
     N = 60 * SR
     ids = np.concatenate([[49230], fm_filter_cover_ids(1)[::2]])   # 129 voices, every I and D
     V = len(ids)
     params = fm_filter_params(ids)
-    w = fm_pair()
+    w = fm_pair_voice()
     p = Program(w, SR)
     out = np.zeros((V, N), dtype=np.float32)
     lens = p.render(out, params=params)

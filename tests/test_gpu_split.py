@@ -1,0 +1,156 @@
+"""Time-axis split (tuun_b200/csrc/split.cu, abi.cpp render_split): one voice rendered as S segments side by
+side must be the stream the serial walk produces (generator.rs:76-85: "pick up where this one left off").
+
+Partition invariance, S = 1 against many: sines — whose state is a sum of phase increments, kept as an exact
+u64 — come out bit-identical; filters, whose histories come out of an f64 scan of affine maps instead of
+the serial f32 recurrence, agree to the recurrence's own round-off noise (<= 1e-6 for the plain low-passes
+here, a few 1e-6 for resonant ones: 1e-7 x the noise gain of workloads.biquad_noise_gain).  Every case is also
+held against the CPU oracle at north_star's 1e-4."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle.binding import OracleProgram
+from tuun_b200.waveform import Alt, Const, Filter, Noise, Sine, Time, add, f32, mul
+
+pytestmark = pytest.mark.gpu
+SR = 44100
+TAU = f32(2 * math.pi)
+
+
+def render(w, n, monkeypatch, split, params=None, voices=1, calls=None, seed=None):
+    """Rows [voices, n] through tb_render with TUUN_B200_SPLIT=split ("0": serial); `calls` cuts the render
+    into several calls."""
+    from tuun_b200.generator import Program
+    monkeypatch.setenv("TUUN_B200_SPLIT", str(split))
+    p = Program(w, SR)
+    if seed is not None:
+        p.seed_noise(seed)
+    out = np.zeros((voices, n), dtype=np.float32)
+    a = 0
+    for c in (calls or [n]):
+        blk = np.zeros((voices, c), dtype=np.float32)
+        lens = p.render(blk, params=params)
+        assert (lens == c).all()
+        out[:, a:a + c] = blk
+        a += c
+    assert a == n
+    return out, p.info
+
+
+def oracle(w, n, params=None, voices=1, seed=None):
+    o = OracleProgram(w, SR)
+    rows = np.zeros((voices, n), dtype=np.float32)
+    for v in range(voices):
+        o.initialize_state()
+        if seed is not None:
+            o.seed_noise(seed, v)
+        if params is not None:
+            o.set_params(params[v])
+        rows[v] = o.render(n)
+    return rows
+
+
+def lpf(x, q, fc):
+    from tuun_b200.workloads import lpf as _lpf
+    return _lpf(x, q, fc)
+
+
+def test_sine_is_bit_identical_for_any_partition(monkeypatch):
+    w = Sine(Const(TAU * f32(440.0)), Const(0.25))
+    n = 256 + 37 * 512 + 99
+    serial, i0 = render(w, n, monkeypatch, 0)
+    assert i0.split_passes == 1 and i0.split_rounds == 0
+    for s in (2, 8, 32):
+        got, info = render(w, n, monkeypatch, s)
+        assert info.split_rounds >= 1 and info.split_segments >= 2
+        assert np.array_equal(got, serial), (s, np.abs(got - serial).max())
+    assert np.abs(serial - oracle(w, n)).max() <= 1e-6
+
+
+def test_fm_phase_sum_is_exact_across_segments(monkeypatch):
+    """A frequency-modulated carrier: the accumulator at a segment's start is the u64 sum of all earlier
+    increments, from per-segment sums of a first pass (two passes)."""
+    from tuun_b200.workloads import fm_filter_params, fm_filter_sample_ids, fm_pair_voice
+    w = fm_pair_voice()
+    params = fm_filter_params(fm_filter_sample_ids(6))
+    n = 256 + 64 * 512
+    serial, i0 = render(w, n, monkeypatch, 0, params=params, voices=6)
+    assert i0.split_passes == 2
+    for s in (4, 64):
+        got, info = render(w, n, monkeypatch, s, params=params, voices=6)
+        assert info.split_rounds >= 1
+        assert np.array_equal(got, serial), (s, np.abs(got - serial).max())
+    assert np.abs(serial - oracle(w, n, params=params, voices=6)).max() <= 1e-5
+
+
+def test_filters_agree_to_their_round_off_noise(monkeypatch):
+    """square | lpf (config 4), a three-biquad cascade (one more pass per filter), noise | lpf, the
+    tracker_benches shapes filter_1_1 / filter_4_3 over a clock."""
+    sq = Alt(Sine(Const(TAU * f32(220.0)), Const(0.0)), Const(1.0), Const(-1.0))
+    cases = [
+        ("square-lpf", lpf(sq, 0.707, 2000.0), 2, 1e-6, None),
+        ("cascade", lpf(lpf(lpf(sq, 4.0, 800.0), 2.0, 1600.0), 1.0, 3200.0), 4, 1e-5, None),  # Q = 4: noise gain 19
+        ("noise-lpf", lpf(mul(Noise(), Const(0.1)), 0.7, 2000.0), 2, 1e-6, 77),
+        ("filter_4_3", Filter(sq, [Const(0.00107949), Const(0.00323847), Const(0.00323847), Const(0.00107949)],
+                              [Const(-2.5610316), Const(2.2132402), Const(-0.6435727)]), 2, 1e-6, None),
+        ("fir-5", Filter(sq, [Const(0.2)] * 5, []), 2, 0.0, None),
+    ]
+    n = 256 + 48 * 512 + 300
+    for name, w, passes, tol, seed in cases:
+        serial, i0 = render(w, n, monkeypatch, 0, seed=seed)
+        assert i0.split_passes == passes, (name, i0.split_passes)
+        ref = oracle(w, n, seed=seed)
+        assert np.abs(serial - ref).max() <= 1e-4, name
+        for s in (2, 16):
+            got, info = render(w, n, monkeypatch, s, seed=seed)
+            assert info.split_rounds >= 1, name
+            d = float(np.abs(got - serial).max())
+            assert d <= tol, (name, s, d)
+            assert np.abs(got - ref).max() <= 1e-4, (name, s)
+
+
+def test_clock_under_a_filter(monkeypatch):
+    """filter_1_1 of benches/tracker_benches.rs:19-34: a one-pole filter over Time — the clock's position is
+    analytic, the ramp's running average is an affine map like any other."""
+    w = Filter(Time(), [Const(0.5)], [Const(-0.5)])
+    n = 43 * 1024
+    serial, _ = render(w, n, monkeypatch, 0)
+    got, info = render(w, n, monkeypatch, 8)
+    assert info.split_rounds >= 1
+    assert np.abs(got - serial).max() <= 1e-6 * max(1.0, float(np.abs(serial).max()))
+    assert np.abs(got - oracle(w, n)).max() <= 1e-4
+
+
+def test_streams_continue_across_split_calls(monkeypatch):
+    """The last segment's final state is the voice's state: a split call, a serial call and another split call
+    are one stream."""
+    from tuun_b200.workloads import fm_filter_params, fm_filter_voice
+    w = fm_filter_voice()
+    params = fm_filter_params([49157, 34061, 16389 + 256 * 9])   # cutoffs >= 632 Hz: noise gain < 40
+    n = 3 * 20000
+    serial, _ = render(w, n, monkeypatch, 0, params=params, voices=3)
+    got, info = render(w, n, monkeypatch, 8, params=params, voices=3, calls=[20000, 1000, 19000, 20000])
+    assert info.split_passes == 3 and info.split_rounds >= 3
+    assert np.abs(got - serial).max() <= 1e-5   # the 503 Hz low-pass of the third voice has noise gain 38
+    assert np.abs(got - oracle(w, n, params=params, voices=3)).max() <= 1e-4
+
+
+def test_long_single_voice_splits_by_itself(monkeypatch):
+    """Config 4's shape: one voice x 60 s.  No knob: the call is split because one warp would render it alone."""
+    from tuun_b200.generator import Program
+    monkeypatch.delenv("TUUN_B200_SPLIT", raising=False)
+    sq = Alt(Sine(Const(TAU * f32(220.0)), Const(0.0)), Const(1.0), Const(-1.0))
+    w = lpf(sq, 0.707, 2000.0)
+    n = 60 * SR
+    p = Program(w, SR)
+    out = np.zeros((1, n), dtype=np.float32)
+    lens = p.render(out)
+    assert lens[0] == n
+    info = p.info
+    assert info.split_rounds >= 1 and info.split_segments >= 256
+    ref = oracle(w, n)
+    e = np.abs(out - ref)
+    assert e.max() <= 1e-4
+    assert e[:, -SR:].max() <= 2 * e[:, :SR].max() + 1e-6   # no drift over the minute

@@ -47,6 +47,10 @@ class TbProgramInfo(ctypes.Structure):
         ("lane_min_voices", ctypes.c_uint32),
         ("lane_capacity", ctypes.c_uint32),
         ("lane_fm_capacity", ctypes.c_uint32),
+        ("split_passes", ctypes.c_uint32),
+        ("split_segments", ctypes.c_uint32),
+        ("split_seg_samples", ctypes.c_uint64),
+        ("split_rounds", ctypes.c_uint64),
     ]
 
 

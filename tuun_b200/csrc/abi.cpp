@@ -14,6 +14,7 @@
 #include "../../include/tuun_b200.h"
 #include "lower.h"
 #include "program.h"
+#include "split.h"
 
 extern "C" size_t tb_kernel_smem_bytes(uint32_t n_code, uint32_t n_slots, uint32_t aux_words,
                                        uint32_t n_cval, uint32_t state_words, uint32_t steady_ok,
@@ -100,6 +101,18 @@ struct tb_program {
     uint64_t launches = 0;
     uint64_t noise_seed = 0x7475756E2545F491ull, noise_first_voice = 0;  // tb_seed_noise
     uint32_t fast_mode = 2;  // FAST-class sines: 1 = f32 polynomial, 2 = MUFU (TUUN_B200_FAST_SINES)
+    // time-axis split (split.cu): per-segment state blocks and scratch, grown on demand
+    tb_split_entry* d_split = nullptr;
+    uint32_t* d_vs = nullptr;
+    uint32_t* d_vi = nullptr;
+    unsigned long long* d_vlen = nullptr;
+    size_t vstate_cap = 0;          // virtual voices the three buffers hold
+    float* d_split_cval = nullptr;
+    unsigned long long* d_split_inc = nullptr;
+    size_t split_real_cap = 0;      // real voices the two scratch tables hold
+    uint64_t split_rounds = 0;      // split renders so far (tb_program_info)
+    uint32_t split_last_segments = 0;
+    uint64_t split_last_seg_samples = 0;
 
     ~tb_program() {
         cudaSetDevice(device);
@@ -107,6 +120,7 @@ struct tb_program {
         cudaFree(d_filt); cudaFree(d_fixed); cudaFree(d_pool); cudaFree(d_state); cudaFree(d_params);
         cudaFree(d_len); cudaFree(d_done); cudaFree(d_mix); cudaFree(d_stage[0]); cudaFree(d_stage[1]);
         cudaFree(d_lane_code); cudaFree(d_lane_aux); cudaFree(d_lane_queue);
+        cudaFree(d_split); cudaFree(d_vs); cudaFree(d_vi); cudaFree(d_vlen); cudaFree(d_split_cval); cudaFree(d_split_inc);
         if (h_fault) cudaFreeHost(h_fault);
         for (auto& e : lane_ev) {
             if (e[0]) cudaEventDestroy(e[0]);
@@ -307,8 +321,8 @@ int launch_lanes(tb_program* p, tb_launch& B) {
 // < TB_LS samples of a call that do not fill a lane tile; a stream that is past its first tile goes
 // straight to the lane kernel (a caller streaming 1024-sample blocks pays one launch per block).
 // State blocks are shared, so all launches continue one stream.
-int launch_generate(tb_program* p, const tb_launch& L, uint64_t pos) {
-    const bool big = p->lane_smem != 0 && L.n_voices >= p->lane_min_voices && L.out != nullptr;
+int launch_generate_seq(tb_program* p, const tb_launch& L, uint64_t pos) {
+    const bool big = p->lane_smem != 0 && L.n_voices >= p->lane_min_voices && (L.out != nullptr || L.state_only);
     if (!big) return launch(p, L);
     // The fused-FM-voice kernel starts a stream itself (the filter's read-ahead, run_fm_voice) and takes
     // the samples that do not fill a tile: one launch for the whole call.  (A root Fin keeps its general
@@ -356,6 +370,185 @@ int launch_generate(tb_program* p, const tb_launch& L, uint64_t pos) {
         T.mid_call = 1;
         if ((rc = launch(p, T))) return rc;
     }
+    return TB_OK;
+}
+
+// ---- time-axis split (split.cu) -------------------------------------------------------------------
+// Few voices and many samples: a voice is one warp (or one thread), so a 60-second render of one voice
+// would leave the device idle.  A steady program's state obeys associative laws over time (program.h
+// tb_split_entry), so the call is cut into S = 2^k segments per voice, rendered side by side as V S
+// "virtual voices" of the same kernels: `split_passes - 1` summary passes (final states only, no samples
+// stored), each followed by a scan over the segments that makes one more level of state right, then the
+// pass that writes the samples.  Phase sums are exact (u64), so sines are the samples of the unsplit render;
+// filter histories come out of an f64 scan and differ from the serial f32 recurrence by its round-off noise.
+struct SplitPlan {
+    uint32_t s_log2 = 0;
+    uint64_t seg = 0;
+};
+int n_sm_of_device() {
+    static int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0)
+            n_sm = 148;
+    }
+    return n_sm;
+}
+// Segments for a call of n samples over V voices whose stream is past its first tile; false: render serially.
+// TUUN_B200_SPLIT: "0" never, "S" always S segments (a power of two) when the call is long enough, unset:
+// when the batch is small enough that the passes pay (V <= warps the device holds / (2 passes)).
+bool plan_split(const tb_program* p, const tb_launch& L, uint64_t n, SplitPlan* plan) {
+    if (p->low.split_passes == 0 || !p->d_split || L.out == nullptr || L.done != nullptr || L.mode != 0 || L.vsplit_log2 != 0)
+        return false;
+    const uint64_t V = L.n_voices;
+    const uint64_t cap = (uint64_t)n_sm_of_device() * 16;  // resident warps of the warp-per-voice kernel
+    const char* env = std::getenv("TUUN_B200_SPLIT");
+    uint64_t want = 0, min_seg = TB_TILE_S;
+    if (env) {
+        want = std::strtoull(env, nullptr, 10);
+        if (want < 2) return false;
+    } else {
+        if (n < 16384 || V * 2 * p->low.split_passes > cap) return false;
+        want = 2 * cap / V;
+        min_seg = 2 * TB_TILE_S;
+        // enough voice-samples for the lane-per-voice kernels (2.4 x the rate on FM voices): 4 lane_min_voices
+        // virtual voices of at least 4096 samples
+        if (p->lane_smem != 0 && p->lane_min_voices > 0 && V * (n / 4096) >= 4ull * p->lane_min_voices) {
+            want = (4ull * p->lane_min_voices + V - 1) / V;
+            min_seg = 4096;
+        }
+    }
+    uint32_t k = 0;
+    while ((2ull << k) <= want && k < 20) k++;         // S = 2^k <= want
+    while (k > 0 && (n >> k) < min_seg) k--;           // segments of at least min_seg samples
+    if (k == 0) return false;
+    const uint64_t seg = (n >> k) / TB_TILE_S * TB_TILE_S;  // whole steady tiles: segments start where the
+    if (seg == 0) return false;                             // unsplit render's tiles start
+    if (V << k > 0x7fffffffull) return false;
+    plan->s_log2 = k;
+    plan->seg = seg;
+    return true;
+}
+int ensure_split_buffers(tb_program* p, uint64_t n_virtual, uint32_t n_real) {
+    if (n_virtual > p->vstate_cap) {
+        cudaFree(p->d_vs); cudaFree(p->d_vi); cudaFree(p->d_vlen);
+        p->d_vs = p->d_vi = nullptr;
+        p->d_vlen = nullptr;
+        p->vstate_cap = 0;
+        const size_t bytes = (size_t)n_virtual * p->low.state_words * 4;
+        CU(cudaMalloc(reinterpret_cast<void**>(&p->d_vs), bytes));
+        CU(cudaMalloc(reinterpret_cast<void**>(&p->d_vi), bytes));
+        CU(cudaMalloc(reinterpret_cast<void**>(&p->d_vlen), (size_t)n_virtual * 8));
+        p->vstate_cap = n_virtual;
+    }
+    if (n_real > p->split_real_cap) {
+        cudaFree(p->d_split_cval); cudaFree(p->d_split_inc);
+        p->d_split_cval = nullptr;
+        p->d_split_inc = nullptr;
+        p->split_real_cap = 0;
+        CU(cudaMalloc(reinterpret_cast<void**>(&p->d_split_cval), (size_t)n_real * std::max<size_t>(p->low.cexpr.size(), 1) * 4));
+        CU(cudaMalloc(reinterpret_cast<void**>(&p->d_split_inc), (size_t)n_real * std::max<size_t>(p->low.split.size(), 1) * 8));
+        p->split_real_cap = n_real;
+    }
+    return TB_OK;
+}
+// One round: S seg samples of every voice of L (stream primed), rows at L.out.
+int render_split_round(tb_program* p, const tb_launch& L, const SplitPlan& plan, uint64_t pos) {
+    const uint32_t V = L.n_voices;
+    const uint64_t nv = (uint64_t)V << plan.s_log2;
+    int rc = ensure_split_buffers(p, nv, V);
+    if (rc) return rc;
+    tb_split_args A;
+    std::memset(&A, 0, sizeof(A));
+    A.cexpr = p->d_cexpr;
+    A.n_cval = (uint32_t)p->low.cexpr.size();
+    A.entries = p->d_split;
+    A.n_entries = (uint32_t)p->low.split.size();
+    A.filt = p->d_filt;
+    A.params = L.params;
+    A.n_params = L.n_params;
+    A.sample_rate = p->sample_rate;
+    A.state_words = p->low.state_words;
+    A.n_real = V;
+    A.s_log2 = plan.s_log2;
+    A.seg = plan.seg;
+    A.real_state = L.state;
+    A.vi = p->d_vi;
+    A.vs = p->d_vs;
+    A.cval = p->d_split_cval;
+    A.inc = p->d_split_inc;
+    cudaError_t e = tb_split_seed(&A, p->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "tb_split_seed");
+    p->launches += 2;
+    const size_t state_bytes = (size_t)nv * p->low.state_words * 4;
+    for (uint32_t pass = 1; pass <= p->low.split_passes; pass++) {
+        const bool last = pass == p->low.split_passes;
+        CU(cudaMemcpyAsync(p->d_vs, p->d_vi, state_bytes, cudaMemcpyDeviceToDevice, p->stream));
+        tb_launch B = L;
+        B.state = p->d_vs;
+        B.n_voices = (uint32_t)nv;
+        B.n_samples = plan.seg;
+        B.vsplit_log2 = plan.s_log2;
+        B.vseg = plan.seg;
+        B.out = last ? L.out : nullptr;
+        B.state_only = last ? 0 : 1;
+        B.out_len = p->d_vlen;
+        B.accumulate = 0;
+        B.mid_call = 1;
+        B.done = nullptr;
+        if ((rc = launch_generate_seq(p, B, std::max<uint64_t>(pos, TB_TILE)))) return rc;
+        if (!last) {
+            e = tb_split_fix(&A, pass, p->stream);
+            if (e != cudaSuccess) return cuda_fail(e, "tb_split_fix");
+            p->launches++;
+        }
+    }
+    e = tb_split_finish(&A, L.state, L.out_len, plan.seg << plan.s_log2, L.accumulate ? 1 : 0, p->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "tb_split_finish");
+    p->launches++;
+    p->split_rounds++;
+    return TB_OK;
+}
+
+// A generate launch: split in time when that pays (rounds of S segments until what is left is short), else
+// — and for the head tile of a stream and the rest — the serial form.
+int launch_generate(tb_program* p, const tb_launch& L, uint64_t pos) {
+    SplitPlan plan;
+    if (p->low.split_passes == 0 || !plan_split(p, L, L.n_samples, &plan)) return launch_generate_seq(p, L, pos);
+    tb_launch R = L;  // what is left of the call
+    int rc = TB_OK;
+    if (!p->pos_known) return launch_generate_seq(p, L, pos);
+    if (pos < (uint64_t)TB_TILE && !p->low.filt.empty()) {
+        // the first tile of a stream: filter pre-reads (generator.rs:234-252) on the general interpreter.  (A
+        // program without filters is steady from its first sample, and so are its segments.)
+        tb_launch H = L;
+        H.n_samples = TB_TILE;
+        if ((rc = launch_generate_seq(p, H, pos))) return rc;
+        R.out = L.out + TB_TILE;
+        R.n_samples = L.n_samples - TB_TILE;
+        R.accumulate = 1;
+        R.mid_call = 1;
+        R.call_pos = L.call_pos + TB_TILE;
+        pos += TB_TILE;
+    }
+    bool first = true;
+    while (R.n_samples > 0 && plan_split(p, R, R.n_samples, &plan)) {
+        if (first) {  // tb_program_info: the round that covers most of the call
+            p->split_last_segments = 1u << plan.s_log2;
+            p->split_last_seg_samples = plan.seg;
+            first = false;
+        }
+        if ((rc = render_split_round(p, R, plan, pos))) return rc;
+        const uint64_t done = plan.seg << plan.s_log2;
+        R.out += done;
+        R.n_samples -= done;
+        R.accumulate = 1;
+        R.mid_call = 1;
+        R.call_pos += done;
+        pos += done;
+    }
+    if (R.n_samples > 0) return launch_generate_seq(p, R, pos);
     return TB_OK;
 }
 
@@ -496,6 +689,7 @@ int tb_program_create(const tb_node* nodes, uint32_t n_nodes, const int32_t* lis
         return bail(rc);
     if (!size_cta(p->low, &p->warps, &p->smem))
         return bail(set_error(TB_ERR_UNSUPPORTED, "program needs more shared memory than one CTA has"));
+    if (p->low.split_passes > 0 && (rc = upload(p->low.split, &p->d_split))) return bail(rc);
     // The lane-per-voice kernels (lanes.cuh): for batches large enough that one thread per voice fills
     // the device.  TUUN_B200_LANES=0 disables it; TUUN_B200_LANE_MIN_VOICES moves the threshold.
     const char* le = std::getenv("TUUN_B200_LANES");
@@ -565,6 +759,10 @@ int tb_lower_check(const tb_node* nodes, uint32_t n_nodes, const int32_t* lists,
         info->lane_min_voices = 0;
         info->lane_capacity = 0;
         info->lane_fm_capacity = 0;
+        info->split_passes = low.split_passes;
+        info->split_segments = 0;
+        info->split_seg_samples = 0;
+        info->split_rounds = 0;
     }
     return TB_OK;
 }
@@ -585,6 +783,10 @@ int tb_program_get_info(const tb_program* p, tb_program_info* info) {
     info->lane_min_voices = p->lane_min_voices;
     info->lane_capacity = p->lane_capacity;
     info->lane_fm_capacity = p->lane_fm_capacity;
+    info->split_passes = p->d_split ? p->low.split_passes : 0;
+    info->split_segments = p->split_last_segments;
+    info->split_seg_samples = p->split_last_seg_samples;
+    info->split_rounds = p->split_rounds;
     return TB_OK;
 }
 

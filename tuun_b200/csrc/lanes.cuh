@@ -704,7 +704,13 @@ struct RowStore {
     size_t off;            // samples already stored
     bool fast, vec_ok;
     float* mix;            // mixdown without rows (tb_launch::mix_partial): this warp's row of partial sums
+    uint32_t sl2;          // time-axis split (tb_launch::vsplit_log2): rows are segments of the real voices' rows
+    size_t vseg;
 };
+// First sample (of this launch) of virtual voice vv's row.
+__device__ __forceinline__ float* row_of(const RowStore& R, uint32_t vv) {
+    return R.out + (size_t)(vv >> R.sl2) * R.stride + (size_t)(vv & ((1u << R.sl2) - 1u)) * R.vseg;
+}
 #ifndef TB_ST
 #define TB_ST 2
 #endif
@@ -731,7 +737,18 @@ __device__ __forceinline__ void store_pair(RowStore& R, int l) {
     __syncwarp();
     float* d = R.out + (size_t)(R.v0 + (l >> 3)) * R.stride + R.off + (size_t)(l & 7) * 4;
     const size_t step = 4 * R.stride;
-    if (R.fast) {  // all 32 rows of the warp exist and are 16-byte aligned
+    if (R.sl2 != 0) {  // segments of real voices' rows (abi.cpp render_split_round)
+        if (R.out) {
+            UNROLL for (int i = 0; i < 8; i++) {
+                const uint32_t vv = R.v0 + (uint32_t)(l >> 3) + 4u * i;
+                if (vv < R.n_voices) {
+                    float* q = row_of(R, vv) + R.off + (size_t)(l & 7) * 4;
+                    if (R.vec_ok) st_row(reinterpret_cast<float4*>(q), v[i]);
+                    else put4(q, v[i], false);
+                }
+            }
+        }
+    } else if (R.fast) {  // all 32 rows of the warp exist and are 16-byte aligned
         UNROLL for (int i = 0; i < 8; i++) st_row(reinterpret_cast<float4*>(d + i * step), v[i]);
     } else if (R.out) {
         UNROLL for (int i = 0; i < 8; i++)
@@ -745,11 +762,11 @@ __device__ __forceinline__ void store_single(RowStore& R, int l, int half) {
     const float4* src = R.tbase + (4 * half + (l & 3)) * AS + (l >> 2);
     UNROLL for (int i = 0; i < 4; i++) v[i] = src[8 * i];
     __syncwarp();
-    float* d = R.out + (size_t)(R.v0 + (l >> 2)) * R.stride + R.off + (size_t)(l & 3) * 4;
-    const size_t step = 8 * R.stride;
     if (R.out) {
-        UNROLL for (int i = 0; i < 4; i++)
-            if (R.v0 + (uint32_t)(l >> 2) + 8u * i < R.n_voices) put4(d + i * step, v[i], R.vec_ok);
+        UNROLL for (int i = 0; i < 4; i++) {
+            const uint32_t vv = R.v0 + (uint32_t)(l >> 2) + 8u * i;
+            if (vv < R.n_voices) put4(row_of(R, vv) + R.off + (size_t)(l & 3) * 4, v[i], R.vec_ok);
+        }
     }
     R.off += LS;
 }
@@ -903,12 +920,11 @@ __device__ __forceinline__ void store_partial(RowStore& R, int l, int half, int 
     UNROLL for (int i = 0; i < 4; i++) v[i] = src[8 * i];
     __syncwarp();
     if (R.out) {
-        float* d = R.out + (size_t)(R.v0 + (l >> 2)) * R.stride + R.off + (size_t)(l & 3) * 4;
-        const size_t step = 8 * R.stride;
         const int e0 = (l & 3) * 4;
         UNROLL for (int i = 0; i < 4; i++) {
-            if (R.v0 + (uint32_t)(l >> 2) + 8u * i < R.n_voices) {
-                float* q = d + i * step;
+            const uint32_t vv = R.v0 + (uint32_t)(l >> 2) + 8u * i;
+            if (vv < R.n_voices) {
+                float* q = row_of(R, vv) + R.off + (size_t)(l & 3) * 4;
                 if (e0 + 0 < rem) q[0] = v[i].x;
                 if (e0 + 1 < rem) q[1] = v[i].y;
                 if (e0 + 2 < rem) q[2] = v[i].z;
@@ -1094,7 +1110,7 @@ __device__ __forceinline__ void lanes_body(const tb_launch& P, uint32_t group, u
     if (active) {
         // ld.cg: with the work queue the block was last written by another CTA, possibly on another SM
         for (uint32_t k = 0; k < P.state_words; k++) stw(M, (int)(P.n_cval + k), __ldcg(gstate + k));
-        setup_lane(P, M, P.params ? P.params + (size_t)voice * P.n_params : nullptr);
+        setup_lane(P, M, P.params ? P.params + (size_t)(voice >> P.vsplit_log2) * P.n_params : nullptr);
         // Every filter must hold its full history (generator.rs:234-252): the host renders the
         // first tile of a stream with the general interpreter before it comes here.
         bool ready = true;
@@ -1126,6 +1142,8 @@ __device__ __forceinline__ void lanes_body(const tb_launch& P, uint32_t group, u
     R.vec_ok = (reinterpret_cast<uintptr_t>(P.out) & 15) == 0 && (P.out_stride & 3) == 0;
     R.fast = R.vec_ok && P.out != nullptr && v0 + 32u <= P.n_voices;
     R.mix = MIX ? P.mix_partial + (size_t)(v0 >> 5) * P.mix_stride + s0 : nullptr;
+    R.sl2 = P.vsplit_log2;
+    R.vseg = (size_t)P.vseg;
     const bool warp_live = __any_sync(FULL, active);
     const uint32_t code_s = (uint32_t)__cvta_generic_to_shared(code);
     const u64 n_tiles = ns / (u64)LS;
@@ -1154,8 +1172,8 @@ __device__ __forceinline__ void lanes_body(const tb_launch& P, uint32_t group, u
             for (u64 t = 0; t < n_tiles; t++) {
                 if (active) {
                     M.A = abase + (t & 1) * 4 * AS;
-                    if (P.fast_mode == 2) run_lane_tile<2>(P, code_s, M, voice, sk);
-                    else run_lane_tile<1>(P, code_s, M, voice, sk);
+                    if (P.fast_mode == 2) run_lane_tile<2>(P, code_s, M, voice >> P.vsplit_log2, sk);
+                    else run_lane_tile<1>(P, code_s, M, voice >> P.vsplit_log2, sk);
                 }
                 tile_done<MIX>(R, l, t, n_tiles);
             }

@@ -1004,6 +1004,51 @@ struct Lowerer {
     }
 
 
+    // ---- time-axis split plan (program.h tb_split_entry) ---------------------------------------------
+    // Walks the tree the steady stream was emitted from.  Returns the first render pass in which node i's
+    // output is right in every segment (1 = the first pass), recording one entry per stateful node.
+    int split_level(int i) {
+        const tb_node& n = nodes[i];
+        switch (n.kind) {
+            case TB_CONST: return 1;
+            case TB_TIME:
+            case TB_NOISE:
+                out.split.push_back(tb_split_entry{SP_POS, (uint32_t)state_off[i], 0u, 0});
+                return 1;
+            case TB_MARKED:
+            case TB_CAPTURED: return split_level(n.a);
+            case TB_BINARY: {
+                const int la = split_level(n.a);
+                return const_of(n.b) >= 0 ? la : std::max(la, split_level(n.b));
+            }
+            case TB_ALT: {
+                int lv = split_level(n.a);
+                if (const_of(n.b) < 0) lv = std::max(lv, split_level(n.b));
+                if (const_of(n.c) < 0) lv = std::max(lv, split_level(n.c));
+                return lv;
+            }
+            case TB_SINE: {
+                const int cf = const_of(n.a), cp = const_of(n.b);
+                int lv = 1;
+                if (cf >= 0) {
+                    out.split.push_back(tb_split_entry{SP_SINE_CONST, (uint32_t)state_off[i], 0u, cf});
+                } else {
+                    const int lf = split_level(n.a);  // the increments are right in pass lf: the sum after it
+                    out.split.push_back(tb_split_entry{SP_SINE_VAR, (uint32_t)state_off[i], (uint32_t)lf, 0});
+                    lv = lf + 1;
+                }
+                if (cp < 0) lv = std::max(lv, split_level(n.b));
+                return lv;
+            }
+            case TB_FILTER: {
+                const int li = split_level(n.a);
+                out.split.push_back(tb_split_entry{SP_FILTER, (uint32_t)state_off[i], (uint32_t)li, filt_idx[i]});
+                return li + 1;
+            }
+            default: return 1 << 20;  // not reached: emit_steady took the tree
+        }
+    }
+
     // ---- lane-per-voice plan (lanes.cuh) -------------------------------------------------------------
     // The ST_* stream again, with every operand rewritten for a thread that keeps its own voice in
     // its own column of shared memory (program.h): constants at W[0, n_cval), the state block at
@@ -1231,6 +1276,13 @@ struct Lowerer {
                 emit(ST_END);
                 out.steady_ok = out.lane_clk ? 0 : 1;  // clocked words: lane kernels only
                 lane_steady_root = true;
+                if (out.steady_ok) {
+                    const int passes = split_level(root);
+                    bool ok = passes <= 8;
+                    for (const tb_split_entry& e : out.split) ok = ok && (int)e.state_off >= 0;
+                    if (ok) out.split_passes = (uint32_t)passes;
+                    else out.split.clear();
+                }
             } else {
                 out.lane_clk = 0;
                 out.code.resize(code0);

@@ -30,6 +30,9 @@ struct Lowered {
     uint32_t lane_w_words = 0, lane_q_units = 0, lane_slots = 0;
     uint32_t lane_clk = 0;      // the steady stream uses the clocked words (Reset): lane kernels only
     int32_t lane_fin_goe = -1;  // root Fin with an analytic length over a steady tree: its goe entry, else -1
+    // time-axis split plan (program.h tb_split_entry); split_passes = 0 when the program does not qualify
+    std::vector<tb_split_entry> split;
+    uint32_t split_passes = 0;
     int status = 0;
     std::string error;
 };

@@ -214,6 +214,29 @@ struct tb_goe {
     uint32_t step_off;    // into the goe step table: pairs (sign, cval index): value -= / += cval
 };
 
+// Time-axis split (split.cu, abi.cpp render_split): a steady program's carried state at ANY sample offset
+// follows from per-segment summaries, so one voice can be rendered as S independent segments ("virtual
+// voices") once every segment knows its initial state.  One entry per stateful node of the steady stream:
+//   SP_POS         Time / Noise position: + 1 per sample                                   (analytic)
+//   SP_SINE_CONST  Sine with a constant rate: accumulator + inc * n, exact in 2^-64 turns  (analytic)
+//   SP_SINE_VAR    Sine with a rate waveform: the accumulator is a sum of increments — a segment's
+//                  (final - initial) accumulator is its summary, exclusive prefix sums give the starts
+//                  (u64, exact and associative: bit-identical to the unsplit render)
+//   SP_FILTER      constant-coefficient Filter: the state (K-1 inputs, J outputs) obeys
+//                  X' = M^L X + z, so z = final - M^L initial is a segment's summary and a scan of affine
+//                  maps over the segments gives the starts (f64; differs from the serial f32 recurrence
+//                  by its round-off noise)
+// `level` = the render pass after which the entry's summary is right (its inputs were rendered from
+// right states in that pass); analytic entries have level 0.  A program needs `split_passes` passes, the
+// last of which writes the samples.
+enum tb_split_kind : uint32_t { SP_POS = 0, SP_SINE_CONST = 1, SP_SINE_VAR = 2, SP_FILTER = 3 };
+struct tb_split_entry {
+    uint32_t kind;
+    uint32_t state_off;  // first word of the node's state block
+    uint32_t level;
+    int32_t a;           // SP_SINE_CONST: cval of the rate; SP_FILTER: filter table index
+};
+
 struct tb_filter_tab {
     uint32_t K, J;
     uint32_t all_const;    // every coefficient literally Const (generator.rs:428-440)
@@ -280,4 +303,10 @@ struct tb_launch {
     uint32_t accumulate;   // out_len[v] += (chunked host-output renders) instead of =
     uint32_t exact_fb;     // constant-coefficient feedback by the serial recurrence instead of the scan
     uint8_t* done;         // [n_voices] or NULL: voices that already returned short in this call
+    // time-axis split: `n_voices` counts virtual voices; virtual voice vv is segment (vv & (2^vsplit_log2 - 1))
+    // of real voice (vv >> vsplit_log2): parameters, noise streams and the output row belong to the real
+    // voice, the row starts vseg samples further per segment; state and out_len are per virtual voice.
+    uint32_t vsplit_log2;  // 0: every voice is a real voice
+    uint64_t vseg;         // samples per segment
+    uint32_t state_only;   // render for the final state alone (a summary pass): out == NULL is not "mixdown"
 };

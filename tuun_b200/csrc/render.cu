@@ -1505,7 +1505,10 @@ tb_render_kernel(const tb_launch P) {
     const size_t per_warp = per_warp_slots + aux_b + cval_b + state_b + slen_b + svm_b;
     unsigned char* base = smem_raw + off + per_warp * warp;
     WarpMem M;
-    M.voice = voice;
+    // time-axis split (program.h tb_launch::vsplit_log2): `voice` is a virtual voice — a segment of a real one
+    const uint32_t rvoice = voice >> P.vsplit_log2;
+    const uint32_t vseg_i = voice & ((1u << P.vsplit_log2) - 1u);
+    M.voice = rvoice;
     M.slots = reinterpret_cast<float*>(base); base += per_warp_slots;
     M.aux = reinterpret_cast<u64*>(base); base += aux_b;
     M.cval = reinterpret_cast<float*>(base); base += cval_b;
@@ -1522,7 +1525,7 @@ tb_render_kernel(const tb_launch P) {
 
     uint32_t* gstate = P.state + (size_t)voice * P.state_words;
     for (uint32_t t = l; t < P.state_words; t += 32) M.state[t] = gstate[t];
-    setup_voice(P, M, P.params ? P.params + (size_t)voice * P.n_params : nullptr, sk);
+    setup_voice(P, M, P.params ? P.params + (size_t)rvoice * P.n_params : nullptr, sk);
 
     int ctl[TB_CTL_DEPTH];
     float acc[C];
@@ -1532,7 +1535,7 @@ tb_render_kernel(const tb_launch P) {
     cx.vm = 0xffu;
     u64 total = 0;
     if (P.mode == 0) {
-        float* row = P.out ? P.out + (size_t)voice * P.out_stride : nullptr;
+        float* row = P.out ? P.out + (size_t)rvoice * P.out_stride + (size_t)vseg_i * P.vseg : nullptr;
         const bool vec_ok = row && ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
         const uint32_t code_s = (uint32_t)__cvta_generic_to_shared(code);
         // Whole tiles take the steady path once every filter holds its full history

@@ -51,6 +51,13 @@ def fm_filter_voice() -> Waveform:
                   [Const(0.0, param=6), Const(0.0, param=7)])
 
 
+def fm_pair_voice() -> Waveform:
+    """The carrier of config 5 without its filter (same parameter table): against the oracle its error is the
+    phase error itself."""
+    mod = Sine(Const(1.0, param=0), Const(PI / F(2.0)))
+    return Sine(add(mul(mod, Const(1.0, param=1)), Const(1.0, param=2)), Const(0.0))
+
+
 def fm_filter_params(voice_ids, sample_rate=44100) -> np.ndarray:
     """The sweep of SURVEY §8(d) config 5, all in f32: fc = 55*2^(5*(v%256)/256),
     I = 10*((v>>8)%16)/16, D in {0.5,1,2,3}[(v>>12)%4], fm = D/2*fc, cut = 200*40^(((v>>14)%4)/4),
