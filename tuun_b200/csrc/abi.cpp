@@ -322,7 +322,8 @@ int launch_lanes(tb_program* p, tb_launch& B) {
 // straight to the lane kernel (a caller streaming 1024-sample blocks pays one launch per block).
 // State blocks are shared, so all launches continue one stream.
 int launch_generate_seq(tb_program* p, const tb_launch& L, uint64_t pos) {
-    const bool big = p->lane_smem != 0 && L.n_voices >= p->lane_min_voices && (L.out != nullptr || L.state_only);
+    const bool big = p->lane_smem != 0 && L.n_voices >= p->lane_min_voices && (L.out != nullptr || L.state_only) &&
+                     !(L.vsplit > 1 && L.vsplit_log2 == 0);  // the lane kernels take 2^k segments per voice only
     if (!big) return launch(p, L);
     // The fused-FM-voice kernel starts a stream itself (the filter's read-ahead, run_fm_voice) and takes
     // the samples that do not fill a tile: one launch for the whole call.  (A root Fin keeps its general
@@ -382,8 +383,8 @@ int launch_generate_seq(tb_program* p, const tb_launch& L, uint64_t pos) {
 // pass that writes the samples.  Phase sums are exact (u64), so sines are the samples of the unsplit render;
 // filter histories come out of an f64 scan and differ from the serial f32 recurrence by its round-off noise.
 struct SplitPlan {
-    uint32_t s_log2 = 0;
-    uint64_t seg = 0;
+    uint32_t n_seg = 0;   // S
+    uint64_t seg = 0;     // samples per segment, a multiple of the steady tile
 };
 int n_sm_of_device() {
     static int n_sm = 0;
@@ -396,37 +397,43 @@ int n_sm_of_device() {
     return n_sm;
 }
 // Segments for a call of n samples over V voices whose stream is past its first tile; false: render serially.
-// TUUN_B200_SPLIT: "0" never, "S" always S segments (a power of two) when the call is long enough, unset:
-// when the batch is small enough that the passes pay (V <= warps the device holds / (2 passes)).
+// TUUN_B200_SPLIT: "0" never, "S" about S segments when the call is long enough, unset: when the batch is small
+// enough that the passes pay (V <= warps the device holds / (2 passes)).  Segments are whole steady tiles, so
+// they start where the unsplit render's tiles start; what does not fill S segments is left to the caller
+// (another round, or the serial form).
 bool plan_split(const tb_program* p, const tb_launch& L, uint64_t n, SplitPlan* plan) {
-    if (p->low.split_passes == 0 || !p->d_split || L.out == nullptr || L.done != nullptr || L.mode != 0 || L.vsplit_log2 != 0)
+    if (p->low.split_passes == 0 || !p->d_split || L.out == nullptr || L.done != nullptr || L.mode != 0 || L.vsplit > 1)
         return false;
     const uint64_t V = L.n_voices;
     const uint64_t cap = (uint64_t)n_sm_of_device() * 16;  // resident warps of the warp-per-voice kernel
     const char* env = std::getenv("TUUN_B200_SPLIT");
     uint64_t want = 0, min_seg = TB_TILE_S;
+    bool lanes = false;
     if (env) {
         want = std::strtoull(env, nullptr, 10);
         if (want < 2) return false;
     } else {
-        if (n < 16384 || V * 2 * p->low.split_passes > cap) return false;
+        if (n < 4096 || V * 2 * p->low.split_passes > cap) return false;
         want = 2 * cap / V;
-        min_seg = 2 * TB_TILE_S;
         // enough voice-samples for the lane-per-voice kernels (2.4 x the rate on FM voices): 4 lane_min_voices
         // virtual voices of at least 4096 samples
         if (p->lane_smem != 0 && p->lane_min_voices > 0 && V * (n / 4096) >= 4ull * p->lane_min_voices) {
             want = (4ull * p->lane_min_voices + V - 1) / V;
             min_seg = 4096;
+            lanes = true;
         }
     }
-    uint32_t k = 0;
-    while ((2ull << k) <= want && k < 20) k++;         // S = 2^k <= want
-    while (k > 0 && (n >> k) < min_seg) k--;           // segments of at least min_seg samples
-    if (k == 0) return false;
-    const uint64_t seg = (n >> k) / TB_TILE_S * TB_TILE_S;  // whole steady tiles: segments start where the
-    if (seg == 0) return false;                             // unsplit render's tiles start
-    if (V << k > 0x7fffffffull) return false;
-    plan->s_log2 = k;
+    uint64_t seg = n / want / TB_TILE_S * TB_TILE_S;                    // at least `want` segments ...
+    seg = std::max<uint64_t>(seg, min_seg);                            // ... of at least min_seg samples
+    uint64_t S = n / seg;
+    // The lane kernels address segment rows by shift and mask: a batch that will take them gets 2^k segments.
+    if (lanes || (p->lane_smem != 0 && V * S >= p->lane_min_voices)) {
+        uint64_t k = 0;
+        while ((2ull << k) <= S) k++;
+        S = 1ull << k;
+    }
+    if (S < 2 || V * S > 0x7fffffffull) return false;
+    plan->n_seg = (uint32_t)S;
     plan->seg = seg;
     return true;
 }
@@ -456,7 +463,7 @@ int ensure_split_buffers(tb_program* p, uint64_t n_virtual, uint32_t n_real) {
 // One round: S seg samples of every voice of L (stream primed), rows at L.out.
 int render_split_round(tb_program* p, const tb_launch& L, const SplitPlan& plan, uint64_t pos) {
     const uint32_t V = L.n_voices;
-    const uint64_t nv = (uint64_t)V << plan.s_log2;
+    const uint64_t nv = (uint64_t)V * plan.n_seg;
     int rc = ensure_split_buffers(p, nv, V);
     if (rc) return rc;
     tb_split_args A;
@@ -471,7 +478,7 @@ int render_split_round(tb_program* p, const tb_launch& L, const SplitPlan& plan,
     A.sample_rate = p->sample_rate;
     A.state_words = p->low.state_words;
     A.n_real = V;
-    A.s_log2 = plan.s_log2;
+    A.n_seg = plan.n_seg;
     A.seg = plan.seg;
     A.real_state = L.state;
     A.vi = p->d_vi;
@@ -489,7 +496,10 @@ int render_split_round(tb_program* p, const tb_launch& L, const SplitPlan& plan,
         B.state = p->d_vs;
         B.n_voices = (uint32_t)nv;
         B.n_samples = plan.seg;
-        B.vsplit_log2 = plan.s_log2;
+        B.vsplit = plan.n_seg;
+        B.vsplit_log2 = 0;
+        while ((1u << B.vsplit_log2) < plan.n_seg) B.vsplit_log2++;
+        if ((1u << B.vsplit_log2) != plan.n_seg) B.vsplit_log2 = 0;
         B.vseg = plan.seg;
         B.out = last ? L.out : nullptr;
         B.state_only = last ? 0 : 1;
@@ -504,7 +514,7 @@ int render_split_round(tb_program* p, const tb_launch& L, const SplitPlan& plan,
             p->launches++;
         }
     }
-    e = tb_split_finish(&A, L.state, L.out_len, plan.seg << plan.s_log2, L.accumulate ? 1 : 0, p->stream);
+    e = tb_split_finish(&A, L.state, L.out_len, plan.seg * plan.n_seg, L.accumulate ? 1 : 0, p->stream);
     if (e != cudaSuccess) return cuda_fail(e, "tb_split_finish");
     p->launches++;
     p->split_rounds++;
@@ -535,12 +545,12 @@ int launch_generate(tb_program* p, const tb_launch& L, uint64_t pos) {
     bool first = true;
     while (R.n_samples > 0 && plan_split(p, R, R.n_samples, &plan)) {
         if (first) {  // tb_program_info: the round that covers most of the call
-            p->split_last_segments = 1u << plan.s_log2;
+            p->split_last_segments = plan.n_seg;
             p->split_last_seg_samples = plan.seg;
             first = false;
         }
         if ((rc = render_split_round(p, R, plan, pos))) return rc;
-        const uint64_t done = plan.seg << plan.s_log2;
+        const uint64_t done = plan.seg * plan.n_seg;
         R.out += done;
         R.n_samples -= done;
         R.accumulate = 1;

@@ -303,10 +303,11 @@ struct tb_launch {
     uint32_t accumulate;   // out_len[v] += (chunked host-output renders) instead of =
     uint32_t exact_fb;     // constant-coefficient feedback by the serial recurrence instead of the scan
     uint8_t* done;         // [n_voices] or NULL: voices that already returned short in this call
-    // time-axis split: `n_voices` counts virtual voices; virtual voice vv is segment (vv & (2^vsplit_log2 - 1))
-    // of real voice (vv >> vsplit_log2): parameters, noise streams and the output row belong to the real
-    // voice, the row starts vseg samples further per segment; state and out_len are per virtual voice.
-    uint32_t vsplit_log2;  // 0: every voice is a real voice
+    // time-axis split: `n_voices` counts virtual voices; virtual voice vv is segment (vv % vsplit) of real
+    // voice (vv / vsplit): parameters, noise streams and the output row belong to the real voice, the row
+    // starts vseg samples further per segment; state and out_len are per virtual voice.
+    uint32_t vsplit;       // segments per voice; 0 or 1: every voice is a real voice
+    uint32_t vsplit_log2;  // log2(vsplit) when it is a power of two (the lane kernels take only those), else 0
     uint64_t vseg;         // samples per segment
     uint32_t state_only;   // render for the final state alone (a summary pass): out == NULL is not "mixdown"
 };

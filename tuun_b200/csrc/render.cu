@@ -1506,8 +1506,9 @@ tb_render_kernel(const tb_launch P) {
     unsigned char* base = smem_raw + off + per_warp * warp;
     WarpMem M;
     // time-axis split (program.h tb_launch::vsplit_log2): `voice` is a virtual voice — a segment of a real one
-    const uint32_t rvoice = voice >> P.vsplit_log2;
-    const uint32_t vseg_i = voice & ((1u << P.vsplit_log2) - 1u);
+    const uint32_t vsplit = P.vsplit > 1u ? P.vsplit : 1u;
+    const uint32_t rvoice = voice / vsplit;
+    const uint32_t vseg_i = voice - rvoice * vsplit;
     M.voice = rvoice;
     M.slots = reinterpret_cast<float*>(base); base += per_warp_slots;
     M.aux = reinterpret_cast<u64*>(base); base += aux_b;

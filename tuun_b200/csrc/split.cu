@@ -13,7 +13,7 @@
 //                   exact and associative, the result does not depend on S — and a scan of affine
 //                   maps X' = M^L X + z for Filter histories (f64);
 //   tb_split_finish hands the last segment's final state back to the voice.
-// One warp per real voice; S is a power of two.
+// One warp per real voice.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -61,8 +61,8 @@ __global__ void split_prepare_kernel(const tb_split_args A) {
 // Per virtual voice: the real voice's state, analytic entries advanced to the segment's first sample.
 __global__ void split_seed_kernel(const tb_split_args A) {
     const uint32_t vv = blockIdx.x * blockDim.x + threadIdx.x;
-    if (vv >= (A.n_real << A.s_log2)) return;
-    const uint32_t v = vv >> A.s_log2, s = vv & ((1u << A.s_log2) - 1u);
+    if (vv >= A.n_real * A.n_seg) return;
+    const uint32_t v = vv / A.n_seg, s = vv - v * A.n_seg;
     const uint32_t* src = A.real_state + (size_t)v * A.state_words;
     uint32_t* dst = A.vi + (size_t)vv * A.state_words;
     for (uint32_t k = 0; k < A.state_words; k++) dst[k] = src[k];
@@ -102,8 +102,8 @@ __global__ void __launch_bounds__(32) split_fix_kernel(const tb_split_args A, ui
     __shared__ double tmp[2][MAXD * MAXD];
     const uint32_t v = blockIdx.x;
     const int l = threadIdx.x;
-    const uint32_t S = 1u << A.s_log2;
-    const size_t vv0 = (size_t)v << A.s_log2;
+    const uint32_t S = A.n_seg;
+    const size_t vv0 = (size_t)v * S;
     for (uint32_t k = 0; k < A.n_entries; k++) {
         const tb_split_entry e = A.entries[k];
         if (e.level != level) continue;
@@ -215,7 +215,7 @@ __global__ void split_finish_kernel(const tb_split_args A, uint32_t* real_state,
                                     unsigned long long n, int accumulate) {
     const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= A.n_real) return;
-    const uint32_t* src = A.vs + (((size_t)v << A.s_log2) + ((1u << A.s_log2) - 1u)) * A.state_words;
+    const uint32_t* src = A.vs + ((size_t)v * A.n_seg + (A.n_seg - 1u)) * A.state_words;
     uint32_t* dst = real_state + (size_t)v * A.state_words;
     for (uint32_t k = 0; k < A.state_words; k++) dst[k] = src[k];
     if (out_len) out_len[v] = (accumulate ? out_len[v] : 0ull) + n;
@@ -225,7 +225,7 @@ __global__ void split_finish_kernel(const tb_split_args A, uint32_t* real_state,
 
 extern "C" cudaError_t tb_split_seed(const tb_split_args* A, cudaStream_t stream) {
     split_prepare_kernel<<<(A->n_real + 127) / 128, 128, 0, stream>>>(*A);
-    const uint32_t nv = A->n_real << A->s_log2;
+    const uint32_t nv = A->n_real * A->n_seg;
     split_seed_kernel<<<(nv + 127) / 128, 128, 0, stream>>>(*A);
     return cudaGetLastError();
 }

@@ -15,10 +15,10 @@ struct tb_split_args {
     uint32_t n_params;
     uint32_t sample_rate, state_words;
     uint32_t n_real;      // real voices
-    uint32_t s_log2;      // log2 of the segments per voice
+    uint32_t n_seg;       // segments per voice (S)
     uint64_t seg;         // samples per segment
     const uint32_t* real_state;  // [n_real][state_words]
-    uint32_t* vi;         // [n_real << s_log2][state_words]: initial state of every segment
+    uint32_t* vi;         // [n_real * n_seg][state_words]: initial state of every segment
     uint32_t* vs;         // same shape: the state the render kernels advance (final state after a pass)
     float* cval;          // [n_real][n_cval] scratch: the voices' constant tables
     unsigned long long* inc;  // [n_real][n_entries] scratch: per-sample advance of the analytic entries
