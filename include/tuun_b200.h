@@ -164,6 +164,18 @@ int tb_seed_noise(tb_program* p, uint64_t seed, uint64_t first_voice);
 /* waveform::set_state(root, State::Initial) for every voice (waveform.rs:322). */
 int tb_reset(tb_program* p);
 
+/*
+ * waveform::substitute(&mut w, &mark_id, &Const(value)) (waveform.rs:396-462), mid-stream: the contents
+ * of every Marked node whose id is `mark_id` become Const(value); every other node keeps its state and the
+ * stream continues ("it picks up where it would have been", generator.rs:1398-1463 — which is why Fin
+ * advances both of its children).  This is the form the reference itself uses: slider and amplitude values
+ * are Marked constants replaced by constants (player.rs:110, :265-288).  `*n_replaced` (may be NULL) receives
+ * the number of Marked nodes changed; 0 is not an error (substitute replaces "zero or more parts").
+ * TB_ERR_UNSUPPORTED when a matching Marked node holds anything but a Const (the tree would change shape;
+ * create a new program for that), or when the new value changes how the tree lowers.
+ */
+int tb_substitute(tb_program* p, uint32_t mark_id, float value, uint32_t* n_replaced);
+
 /* Stream the render is enqueued on (a cudaStream_t), for callers that time with events. */
 void* tb_stream(tb_program* p);
 /* Run subsequent renders of this program on a caller-owned cudaStream_t. */

@@ -242,6 +242,12 @@ public:
         return len;
     }
     void reset() { check(tb_reset(h_)); }  // waveform::set_state(root, Initial)
+    // waveform::substitute(&mut w, &mark_id, &Const(value)) (waveform.rs:396): returns the nodes replaced
+    uint32_t substitute(uint32_t mark_id, float value) {
+        uint32_t n = 0;
+        check(tb_substitute(h_, mark_id, value, &n));
+        return n;
+    }
     tb_program_info info() const {
         tb_program_info i{};
         check(tb_program_get_info(h_, &i));

@@ -78,6 +78,7 @@ extern "C" {
         flags: u32,
     ) -> c_int;
     pub fn tb_reset(p: *mut TbProgram) -> c_int;
+    pub fn tb_substitute(p: *mut TbProgram, mark_id: u32, value: f32, n_replaced: *mut u32) -> c_int;
     pub fn tb_stream(p: *mut TbProgram) -> *mut c_void;
     pub fn tb_set_stream(p: *mut TbProgram, cuda_stream: *mut c_void) -> c_int;
     pub fn tb_seed_noise(p: *mut TbProgram, seed: u64, first_voice: u64) -> c_int;
@@ -233,6 +234,14 @@ impl B200Waveform {
     /// `waveform::set_state(w, State::Initial)`
     pub fn reset(&mut self) -> Result<(), Error> {
         check(unsafe { tb_reset(self.handle) })
+    }
+
+    /// `waveform::substitute(&mut w, &mark_id, &Const(value))` (waveform.rs:396): the number of `Marked`
+    /// nodes whose contents were replaced.  The stream continues from the carried state.
+    pub fn substitute_const(&mut self, mark_id: u32, value: f32) -> Result<u32, Error> {
+        let mut n: u32 = 0;
+        check(unsafe { tb_substitute(self.handle, mark_id, value, &mut n) })?;
+        Ok(n)
     }
 }
 

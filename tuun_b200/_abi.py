@@ -27,7 +27,7 @@ TB_NO_VOICE_OUT = 4
 # every symbol include/tuun_b200.h declares
 EXPORTS = [
     "tb_program_create", "tb_program_destroy", "tb_render", "tb_render_mix", "tb_length", "tb_reset",
-    "tb_seed_noise", "tb_stream", "tb_set_stream", "tb_program_get_info", "tb_lane_kernel_times", "tb_lower_check", "tb_last_error", "tb_abi_version",
+    "tb_seed_noise", "tb_substitute", "tb_stream", "tb_set_stream", "tb_program_get_info", "tb_lane_kernel_times", "tb_lower_check", "tb_last_error", "tb_abi_version",
 ]
 
 
@@ -88,6 +88,8 @@ def lib():
     L.tb_length.argtypes = [P, P, u32, u32, u64, P, u32]
     L.tb_seed_noise.restype = ctypes.c_int
     L.tb_seed_noise.argtypes = [P, u64, u64]
+    L.tb_substitute.restype = ctypes.c_int
+    L.tb_substitute.argtypes = [P, u32, ctypes.c_float, ctypes.POINTER(u32)]
     L.tb_reset.restype = ctypes.c_int
     L.tb_reset.argtypes = [P]
     L.tb_stream.restype = P

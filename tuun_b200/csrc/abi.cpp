@@ -57,6 +57,10 @@ int upload(const std::vector<T>& v, T** dst) {
 
 struct tb_program {
     tb::Lowered low;
+    std::vector<tb_node> nodes;   // the op list as given (tb_substitute re-lowers it)
+    std::vector<int32_t> lists;
+    uint64_t fixed_len = 0;
+    bool fast_sines = true;
     uint32_t sample_rate = 0;
     int device = 0;
     tb_insn* d_code = nullptr;
@@ -642,6 +646,10 @@ int tb_program_create(const tb_node* nodes, uint32_t n_nodes, const int32_t* lis
         delete p;
         return set_error(rc, msg);
     }
+    p->nodes.assign(nodes, nodes + n_nodes);
+    if (lists && n_lists) p->lists.assign(lists, lists + n_lists);
+    p->fixed_len = fixed_len;
+    p->fast_sines = fast;
     if (std::getenv("TUUN_B200_DEBUG")) {
         std::fprintf(stderr, "[tuun_b200] lane_ok %u: W %u words, Q %u units, %u slots\n", p->low.lane_ok,
                      p->low.lane_w_words, p->low.lane_q_units, p->low.lane_slots);
@@ -816,6 +824,50 @@ int tb_seed_noise(tb_program* p, uint64_t seed, uint64_t first_voice) {
     if (!p) return set_error(TB_ERR_INVALID, "NULL program");
     p->noise_seed = seed;
     p->noise_first_voice = first_voice;
+    return TB_OK;
+}
+
+int tb_substitute(tb_program* p, uint32_t mark_id, float value, uint32_t* n_replaced) {
+    if (!p) return set_error(TB_ERR_INVALID, "NULL program");
+    if (n_replaced) *n_replaced = 0;
+    std::vector<tb_node> nodes = p->nodes;
+    uint32_t hits = 0;
+    for (const tb_node& m : p->nodes) {
+        if (m.kind != TB_MARKED || m.mark_id != mark_id) continue;
+        if (m.a < 0 || (size_t)m.a >= nodes.size() || nodes[m.a].kind != TB_CONST)
+            return set_error(TB_ERR_UNSUPPORTED, "tb_substitute: the Marked node holds a waveform that is not a Const");
+        nodes[m.a].value = value;
+        nodes[m.a].param_slot = -1;  // the new waveform is the same constant for every voice
+        hits++;
+    }
+    if (n_replaced) *n_replaced = hits;
+    if (hits == 0) return TB_OK;
+    // Same tree shape, another literal: lower again and require the same program around the constant table
+    // (a literal can decide the lowering only through is_const's Append(c, c) arm, generator.rs:597-603).
+    tb::Lowered low;
+    int rc = tb::lower(nodes.data(), (uint32_t)nodes.size(), p->lists.data(), (uint32_t)p->lists.size(), p->fixed_len,
+                       p->fast_sines, low);
+    if (rc != TB_OK) return set_error(rc, low.error);
+    const tb::Lowered& o = p->low;
+    const bool same = low.code.size() == o.code.size() && low.cexpr.size() == o.cexpr.size() &&
+                      low.state_words == o.state_words && low.aux.size() == o.aux.size() && low.n_slots == o.n_slots &&
+                      low.lane_code.size() == o.lane_code.size() && low.lane_aux.size() == o.lane_aux.size() &&
+                      low.split.size() == o.split.size() && low.goe.size() == o.goe.size() &&
+                      low.goe_steps.size() == o.goe_steps.size() && low.filt.size() == o.filt.size() &&
+                      (low.code.empty() || std::memcmp(low.code.data(), o.code.data(), low.code.size() * sizeof(tb_insn)) == 0);
+    if (!same) return set_error(TB_ERR_UNSUPPORTED, "tb_substitute: the new value changes how the tree lowers");
+    CU(cudaSetDevice(p->device));
+    // Renders enqueued so far read the old table: the copy is ordered behind them on the program's stream.
+    CU(cudaStreamSynchronize(p->stream));
+    if (!low.cexpr.empty())
+        CU(cudaMemcpy(p->d_cexpr, low.cexpr.data(), low.cexpr.size() * sizeof(tb_cexpr), cudaMemcpyHostToDevice));
+    // keep what tb_program_create adjusted after lowering (diagnostic switches)
+    low.steady_ok = o.steady_ok;
+    low.lane_ok = o.lane_ok;
+    low.lane_fin_goe = o.lane_fin_goe;
+    low.lane_clk = o.lane_clk;
+    p->low = std::move(low);
+    p->nodes.swap(nodes);
     return TB_OK;
 }
 

@@ -80,6 +80,13 @@ class Program:
         """tb_seed_noise: the seed of the per-node, per-voice Noise streams (generator.rs:113-118)."""
         _abi.check(_abi.lib().tb_seed_noise(self._h, ctypes.c_uint64(seed), ctypes.c_uint64(first_voice)))
 
+    def substitute(self, mark_id: int, value: float) -> int:
+        """waveform::substitute(&mut w, &mark_id, &Const(value)) (waveform.rs:396): every Marked node with this
+        id now holds Const(value); the stream continues.  Returns the number of nodes replaced."""
+        n = ctypes.c_uint32(0)
+        _abi.check(_abi.lib().tb_substitute(self._h, mark_id, ctypes.c_float(value), ctypes.byref(n)))
+        return int(n.value)
+
     def reset(self):
         """waveform::set_state(root, Initial) for every voice (waveform.rs:322)."""
         _abi.check(_abi.lib().tb_reset(self._h))
