@@ -176,6 +176,36 @@ int tb_reset(tb_program* p);
  */
 int tb_substitute(tb_program* p, uint32_t mark_id, float value, uint32_t* n_replaced);
 
+/*
+ * Time-segment sharding over several GPUs (one process per GPU): few voices, long renders.  A steady
+ * program's carried state (generator.rs:12-35) has an associative form over time — positions, sums of phase
+ * increments, affine maps of filter histories — so the next n_segments * seg_samples samples of every voice
+ * can be rendered as n_segments segments by different devices: rank r renders segments [seg_lo, seg_hi) of
+ * every voice; after each pass the ranks exchange the segments' final states (a few dozen bytes per stateful
+ * node and segment: one all-gather over NVLink) and every rank runs the same scan over them.
+ *
+ *     tb_segments_begin(p, params, .., n_voices, n_segments, seg_samples, flags, &n_passes)
+ *     for pass in 1 ..= n_passes:
+ *         tb_segments_pass(p, pass, seg_lo, seg_hi, out, stride, TB_OUT_DEVICE)    // rows only on the last pass
+ *         all-gather the state blocks of [seg_lo, seg_hi) (tb_segments_states)     // caller: NCCL / MPI / nothing
+ *         if pass < n_passes: tb_segments_fix(p, pass)
+ *     tb_segments_end(p)                       // the stream continues behind the last segment on every rank
+ *
+ * Every rank holds the same program, voices and stream position (call tb_render for the first 256 samples
+ * of a stream on every rank: filters read ahead on their first call).  seg_samples is a multiple of 512.
+ * States: a device array of n_voices * n_segments blocks of *bytes_per_segment bytes, block (v, s) at index
+ * v * n_segments + s.  On the last pass `out` receives the rows of the rank's own segments:
+ * out[v * out_stride + (s - seg_lo) * seg_samples + i].  With one rank and [0, n_segments) this is what
+ * tb_render does by itself for few voices.  TB_ERR_UNSUPPORTED: the program is not steady.
+ */
+int tb_segments_begin(tb_program* p, const float* params, uint32_t n_params, uint32_t n_voices,
+                      uint32_t n_segments, uint64_t seg_samples, uint32_t flags, uint32_t* n_passes);
+int tb_segments_pass(tb_program* p, uint32_t pass, uint32_t seg_lo, uint32_t seg_hi, float* out,
+                     uint64_t out_stride, uint32_t flags);
+int tb_segments_states(tb_program* p, void** states, uint64_t* bytes_per_segment);
+int tb_segments_fix(tb_program* p, uint32_t pass);
+int tb_segments_end(tb_program* p);
+
 /* Stream the render is enqueued on (a cudaStream_t), for callers that time with events. */
 void* tb_stream(tb_program* p);
 /* Run subsequent renders of this program on a caller-owned cudaStream_t. */

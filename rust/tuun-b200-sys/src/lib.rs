@@ -79,6 +79,16 @@ extern "C" {
     ) -> c_int;
     pub fn tb_reset(p: *mut TbProgram) -> c_int;
     pub fn tb_substitute(p: *mut TbProgram, mark_id: u32, value: f32, n_replaced: *mut u32) -> c_int;
+    pub fn tb_segments_begin(
+        p: *mut TbProgram, params: *const f32, n_params: u32, n_voices: u32, n_segments: u32, seg_samples: u64,
+        flags: u32, n_passes: *mut u32,
+    ) -> c_int;
+    pub fn tb_segments_pass(
+        p: *mut TbProgram, pass: u32, seg_lo: u32, seg_hi: u32, out: *mut f32, out_stride: u64, flags: u32,
+    ) -> c_int;
+    pub fn tb_segments_states(p: *mut TbProgram, states: *mut *mut core::ffi::c_void, bytes_per_segment: *mut u64) -> c_int;
+    pub fn tb_segments_fix(p: *mut TbProgram, pass: u32) -> c_int;
+    pub fn tb_segments_end(p: *mut TbProgram) -> c_int;
     pub fn tb_stream(p: *mut TbProgram) -> *mut c_void;
     pub fn tb_set_stream(p: *mut TbProgram, cuda_stream: *mut c_void) -> c_int;
     pub fn tb_seed_noise(p: *mut TbProgram, seed: u64, first_voice: u64) -> c_int;

@@ -87,3 +87,68 @@ def test_two_rank_mixdown_over_gloo():
     assert (lens == np.asarray(ref_lens)).all() and len(lens) == n_voices
     # two partial sums instead of one running sum: f32 re-association, bounded by a few ulps of the mix
     assert np.max(np.abs(mix - serial)) <= 4e-6 * n_voices
+
+
+# ---- time-segment sharding: the exchange step of tb_segments_* (sharding.exchange_segment_states) ----
+def test_segment_plans():
+    from tuun_b200.sharding import plan_segments, segment_range
+    for world in (1, 2, 4, 8):
+        for n in (600 * SR, 60 * SR, 10 * SR, 65536):
+            S, seg = plan_segments(n, world)
+            assert S % world == 0 and seg % 512 == 0 and seg >= 512 and S * seg <= n
+            assert n - S * seg < S * 512                      # what is left for the serial tail
+            parts = [segment_range(S, r, world) for r in range(world)]
+            assert parts[0][0] == 0 and parts[-1][1] == S
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+            assert len({hi - lo for lo, hi in parts}) == 1    # equal shares: one plain all-gather
+    assert plan_segments(16 * 2048 + 100, 8, per_rank=2) == (16, 2048)
+    with pytest.raises(ValueError):
+        segment_range(10, 0, 4)
+    with pytest.raises(ValueError):
+        plan_segments(1000, 8)
+
+
+def _state_block(v, s, words):
+    """What a rank writes for segment s of voice v in this test: a pattern that names the block."""
+    return (np.arange(words, dtype=np.int64) * 7 + v * 1000003 + s * 101).astype(np.int32)
+
+
+def _seg_worker(rank, world, port, V, S, words, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+
+    from tuun_b200.sharding import exchange_segment_states, segment_range
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lo, hi = segment_range(S, rank, world)
+        states = torch.full((V, S, words), -1, dtype=torch.int32)   # what other ranks own is stale here
+        for v in range(V):
+            for s in range(lo, hi):
+                states[v, s] = torch.from_numpy(_state_block(v, s, words))
+        exchange_segment_states(states, lo, hi)
+        q.put((rank, states.numpy().copy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_segment_state_exchange_over_gloo():
+    """After a pass every rank holds the final states of its own time range of every voice; the all-gather must
+    leave EVERY rank with all [voice, segment] blocks in place (the scan over segments then runs redundantly
+    and identically on every rank)."""
+    import torch.multiprocessing as mp
+    V, S, words, world = 3, 8, 11, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_seg_worker, args=(r, world, port, V, S, words, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = np.stack([np.stack([_state_block(v, s, words) for s in range(S)]) for v in range(V)])
+    for r in range(world):
+        np.testing.assert_array_equal(got[r], want)

@@ -27,7 +27,8 @@ TB_NO_VOICE_OUT = 4
 # every symbol include/tuun_b200.h declares
 EXPORTS = [
     "tb_program_create", "tb_program_destroy", "tb_render", "tb_render_mix", "tb_length", "tb_reset",
-    "tb_seed_noise", "tb_substitute", "tb_stream", "tb_set_stream", "tb_program_get_info", "tb_lane_kernel_times", "tb_lower_check", "tb_last_error", "tb_abi_version",
+    "tb_seed_noise", "tb_substitute", "tb_segments_begin", "tb_segments_pass", "tb_segments_states", "tb_segments_fix",
+    "tb_segments_end", "tb_stream", "tb_set_stream", "tb_program_get_info", "tb_lane_kernel_times", "tb_lower_check", "tb_last_error", "tb_abi_version",
 ]
 
 
@@ -90,6 +91,16 @@ def lib():
     L.tb_seed_noise.argtypes = [P, u64, u64]
     L.tb_substitute.restype = ctypes.c_int
     L.tb_substitute.argtypes = [P, u32, ctypes.c_float, ctypes.POINTER(u32)]
+    L.tb_segments_begin.restype = ctypes.c_int
+    L.tb_segments_begin.argtypes = [P, P, u32, u32, u32, u64, u32, ctypes.POINTER(u32)]
+    L.tb_segments_pass.restype = ctypes.c_int
+    L.tb_segments_pass.argtypes = [P, u32, u32, u32, P, u64, u32]
+    L.tb_segments_states.restype = ctypes.c_int
+    L.tb_segments_states.argtypes = [P, ctypes.POINTER(P), ctypes.POINTER(u64)]
+    L.tb_segments_fix.restype = ctypes.c_int
+    L.tb_segments_fix.argtypes = [P, u32]
+    L.tb_segments_end.restype = ctypes.c_int
+    L.tb_segments_end.argtypes = [P]
     L.tb_reset.restype = ctypes.c_int
     L.tb_reset.argtypes = [P]
     L.tb_stream.restype = P

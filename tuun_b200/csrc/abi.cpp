@@ -114,6 +114,10 @@ struct tb_program {
     float* d_split_cval = nullptr;
     unsigned long long* d_split_inc = nullptr;
     size_t split_real_cap = 0;      // real voices the two scratch tables hold
+    tb_split_args split_args = {};  // the split in progress (split_begin .. split_finish)
+    uint32_t seg_voices = 0;        // tb_segments_begin .. tb_segments_end: voices of the sharded render, 0 = none
+    const float* seg_params = nullptr;
+    uint32_t seg_n_params = 0;
     uint64_t split_rounds = 0;      // split renders so far (tb_program_info)
     uint32_t split_last_segments = 0;
     uint64_t split_last_seg_samples = 0;
@@ -327,7 +331,8 @@ int launch_lanes(tb_program* p, tb_launch& B) {
 // State blocks are shared, so all launches continue one stream.
 int launch_generate_seq(tb_program* p, const tb_launch& L, uint64_t pos) {
     const bool big = p->lane_smem != 0 && L.n_voices >= p->lane_min_voices && (L.out != nullptr || L.state_only) &&
-                     !(L.vsplit > 1 && L.vsplit_log2 == 0);  // the lane kernels take 2^k segments per voice only
+                     !(L.vsplit > 1 && L.vsplit_log2 == 0) &&  // the lane kernels take 2^k segments per voice only
+                     !(L.vsplit == 1 && L.vsplit_total > 1);   // (a launch of one segment per voice: warp kernel)
     if (!big) return launch(p, L);
     // The fused-FM-voice kernel starts a stream itself (the filter's read-ahead, run_fm_voice) and takes
     // the samples that do not fill a tile: one launch for the whole call.  (A root Fin keeps its general
@@ -464,13 +469,16 @@ int ensure_split_buffers(tb_program* p, uint64_t n_virtual, uint32_t n_real) {
     }
     return TB_OK;
 }
-// One round: S seg samples of every voice of L (stream primed), rows at L.out.
-int render_split_round(tb_program* p, const tb_launch& L, const SplitPlan& plan, uint64_t pos) {
+// The steps of a split render.  split_begin seeds the initial state of every segment; split_pass renders the
+// segments [seg_lo, seg_hi) of every voice from them (pass = 1 .. split_passes; only the last one stores
+// samples, at out_base[v * stride + s * seg + i]); split_fix makes the entries of level `pass` right from the
+// final states of ALL segments; split_finish hands the last segment's final state back to the voice.
+int split_begin(tb_program* p, const tb_launch& L, const SplitPlan& plan) {
     const uint32_t V = L.n_voices;
     const uint64_t nv = (uint64_t)V * plan.n_seg;
     int rc = ensure_split_buffers(p, nv, V);
     if (rc) return rc;
-    tb_split_args A;
+    tb_split_args& A = p->split_args;
     std::memset(&A, 0, sizeof(A));
     A.cexpr = p->d_cexpr;
     A.n_cval = (uint32_t)p->low.cexpr.size();
@@ -492,35 +500,55 @@ int render_split_round(tb_program* p, const tb_launch& L, const SplitPlan& plan,
     cudaError_t e = tb_split_seed(&A, p->stream);
     if (e != cudaSuccess) return cuda_fail(e, "tb_split_seed");
     p->launches += 2;
-    const size_t state_bytes = (size_t)nv * p->low.state_words * 4;
-    for (uint32_t pass = 1; pass <= p->low.split_passes; pass++) {
-        const bool last = pass == p->low.split_passes;
-        CU(cudaMemcpyAsync(p->d_vs, p->d_vi, state_bytes, cudaMemcpyDeviceToDevice, p->stream));
-        tb_launch B = L;
-        B.state = p->d_vs;
-        B.n_voices = (uint32_t)nv;
-        B.n_samples = plan.seg;
-        B.vsplit = plan.n_seg;
-        B.vsplit_log2 = 0;
-        while ((1u << B.vsplit_log2) < plan.n_seg) B.vsplit_log2++;
-        if ((1u << B.vsplit_log2) != plan.n_seg) B.vsplit_log2 = 0;
-        B.vseg = plan.seg;
-        B.out = last ? L.out : nullptr;
-        B.state_only = last ? 0 : 1;
-        B.out_len = p->d_vlen;
-        B.accumulate = 0;
-        B.mid_call = 1;
-        B.done = nullptr;
-        if ((rc = launch_generate_seq(p, B, std::max<uint64_t>(pos, TB_TILE)))) return rc;
-        if (!last) {
-            e = tb_split_fix(&A, pass, p->stream);
-            if (e != cudaSuccess) return cuda_fail(e, "tb_split_fix");
-            p->launches++;
-        }
-    }
-    e = tb_split_finish(&A, L.state, L.out_len, plan.seg * plan.n_seg, L.accumulate ? 1 : 0, p->stream);
+    return TB_OK;
+}
+int split_pass(tb_program* p, const tb_launch& L, uint32_t pass, uint32_t seg_lo, uint32_t seg_hi, float* out_base,
+               uint64_t pos) {
+    const tb_split_args& A = p->split_args;
+    const bool last = pass == p->low.split_passes;
+    const size_t state_bytes = (size_t)A.n_real * A.n_seg * p->low.state_words * 4;
+    CU(cudaMemcpyAsync(p->d_vs, p->d_vi, state_bytes, cudaMemcpyDeviceToDevice, p->stream));
+    tb_launch B = L;
+    B.state = p->d_vs;
+    B.n_voices = A.n_real * (seg_hi - seg_lo);
+    B.n_samples = A.seg;
+    B.vsplit = seg_hi - seg_lo;
+    B.vsplit_total = A.n_seg;
+    B.vseg_lo = seg_lo;
+    B.vsplit_log2 = 0;
+    while ((1u << B.vsplit_log2) < B.vsplit) B.vsplit_log2++;
+    if ((1u << B.vsplit_log2) != B.vsplit) B.vsplit_log2 = 0;
+    if (B.vsplit == 1) B.vsplit_log2 = 0;
+    B.vseg = A.seg;
+    B.out = last ? out_base : nullptr;
+    B.state_only = last ? 0 : 1;
+    B.out_len = p->d_vlen;
+    B.accumulate = 0;
+    B.mid_call = 1;
+    B.done = nullptr;
+    return launch_generate_seq(p, B, std::max<uint64_t>(pos, TB_TILE));
+}
+int split_fix(tb_program* p, uint32_t pass) {
+    cudaError_t e = tb_split_fix(&p->split_args, pass, p->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "tb_split_fix");
+    p->launches++;
+    return TB_OK;
+}
+int split_finish(tb_program* p, uint32_t* real_state, unsigned long long* out_len, uint64_t n, bool accumulate) {
+    cudaError_t e = tb_split_finish(&p->split_args, real_state, out_len, n, accumulate ? 1 : 0, p->stream);
     if (e != cudaSuccess) return cuda_fail(e, "tb_split_finish");
     p->launches++;
+    return TB_OK;
+}
+// One round: S seg samples of every voice of L (stream primed), rows at L.out.
+int render_split_round(tb_program* p, const tb_launch& L, const SplitPlan& plan, uint64_t pos) {
+    int rc = split_begin(p, L, plan);
+    if (rc) return rc;
+    for (uint32_t pass = 1; pass <= p->low.split_passes; pass++) {
+        if ((rc = split_pass(p, L, pass, 0, plan.n_seg, L.out, pos))) return rc;
+        if (pass < p->low.split_passes && (rc = split_fix(p, pass))) return rc;
+    }
+    if ((rc = split_finish(p, L.state, L.out_len, plan.seg * plan.n_seg, L.accumulate != 0))) return rc;
     p->split_rounds++;
     return TB_OK;
 }
@@ -868,6 +896,89 @@ int tb_substitute(tb_program* p, uint32_t mark_id, float value, uint32_t* n_repl
     low.lane_clk = o.lane_clk;
     p->low = std::move(low);
     p->nodes.swap(nodes);
+    return TB_OK;
+}
+
+// ---- time-segment sharding across GPUs (include/tuun_b200.h) ------------------------------------------
+int tb_segments_begin(tb_program* p, const float* params, uint32_t n_params, uint32_t n_voices, uint32_t n_segments,
+                      uint64_t seg_samples, uint32_t flags, uint32_t* n_passes) {
+    if (!p) return set_error(TB_ERR_INVALID, "NULL program");
+    if (p->low.split_passes == 0 || !p->d_split)
+        return set_error(TB_ERR_UNSUPPORTED, "tb_segments_begin: not a steady program (state has no associative form)");
+    if (n_voices == 0 || n_segments < 1 || seg_samples == 0 || seg_samples % TB_TILE_S != 0)
+        return set_error(TB_ERR_INVALID, "tb_segments_begin: seg_samples must be a positive multiple of 512");
+    if ((uint64_t)n_voices * n_segments > 0x7fffffffull) return set_error(TB_ERR_INVALID, "too many segments");
+    CU(cudaSetDevice(p->device));
+    int rc = ensure_voices(p, n_voices);
+    if (rc) return rc;
+    if (!p->pos_known || (!p->low.filt.empty() && p->stream_pos < (uint64_t)TB_TILE))
+        return set_error(TB_ERR_STATE, "tb_segments_begin: render the first 256 samples of the stream with tb_render first "
+                                       "(filters read ahead on their first call, generator.rs:234-252)");
+    const float* d_params = nullptr;
+    if ((rc = stage_params(p, params, n_params, n_voices, flags, &d_params))) return rc;
+    tb_launch L;
+    fill_launch(p, &L);
+    L.params = d_params;
+    L.n_params = n_params;
+    L.n_voices = n_voices;
+    SplitPlan plan;
+    plan.n_seg = n_segments;
+    plan.seg = seg_samples;
+    if ((rc = split_begin(p, L, plan))) return rc;
+    p->seg_voices = n_voices;
+    p->seg_params = d_params;
+    p->seg_n_params = n_params;
+    if (n_passes) *n_passes = p->low.split_passes;
+    return TB_OK;
+}
+
+int tb_segments_pass(tb_program* p, uint32_t pass, uint32_t seg_lo, uint32_t seg_hi, float* out, uint64_t out_stride,
+                     uint32_t flags) {
+    if (!p || p->seg_voices == 0) return set_error(TB_ERR_STATE, "tb_segments_pass without tb_segments_begin");
+    const tb_split_args& A = p->split_args;
+    if (pass < 1 || pass > p->low.split_passes || seg_lo >= seg_hi || seg_hi > A.n_seg)
+        return set_error(TB_ERR_INVALID, "tb_segments_pass: bad pass or segment range");
+    const bool last = pass == p->low.split_passes;
+    if (last && (!out || !(flags & TB_OUT_DEVICE)))
+        return set_error(TB_ERR_INVALID, "tb_segments_pass: the last pass needs device rows (TB_OUT_DEVICE)");
+    if (last && out_stride < (uint64_t)(seg_hi - seg_lo) * A.seg) return set_error(TB_ERR_INVALID, "out_stride too small");
+    CU(cudaSetDevice(p->device));
+    tb_launch L;
+    fill_launch(p, &L);
+    L.params = p->seg_params;
+    L.n_params = p->seg_n_params;
+    L.n_voices = p->seg_voices;
+    L.out_stride = out_stride;
+    // rows are addressed by the segment's number within the voice: segment seg_lo starts at out[v * stride]
+    float* base = last ? out - (size_t)seg_lo * A.seg : nullptr;
+    return split_pass(p, L, pass, seg_lo, seg_hi, base, p->stream_pos);
+}
+
+int tb_segments_states(tb_program* p, void** states, uint64_t* bytes_per_segment) {
+    if (!p || p->seg_voices == 0) return set_error(TB_ERR_STATE, "tb_segments_states without tb_segments_begin");
+    if (states) *states = p->d_vs;
+    if (bytes_per_segment) *bytes_per_segment = (uint64_t)p->low.state_words * 4;
+    return TB_OK;
+}
+
+int tb_segments_fix(tb_program* p, uint32_t pass) {
+    if (!p || p->seg_voices == 0) return set_error(TB_ERR_STATE, "tb_segments_fix without tb_segments_begin");
+    if (pass < 1 || pass >= p->low.split_passes) return set_error(TB_ERR_INVALID, "tb_segments_fix: no such summary pass");
+    CU(cudaSetDevice(p->device));
+    return split_fix(p, pass);
+}
+
+int tb_segments_end(tb_program* p) {
+    if (!p || p->seg_voices == 0) return set_error(TB_ERR_STATE, "tb_segments_end without tb_segments_begin");
+    CU(cudaSetDevice(p->device));
+    const uint64_t n = p->split_args.seg * p->split_args.n_seg;
+    int rc = split_finish(p, p->d_state, nullptr, n, false);
+    if (rc) return rc;
+    p->stream_pos += n;
+    p->seg_voices = 0;
+    p->split_rounds++;
+    p->split_last_segments = p->split_args.n_seg;
+    p->split_last_seg_samples = p->split_args.seg;
     return TB_OK;
 }
 

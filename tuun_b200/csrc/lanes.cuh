@@ -704,12 +704,12 @@ struct RowStore {
     size_t off;            // samples already stored
     bool fast, vec_ok;
     float* mix;            // mixdown without rows (tb_launch::mix_partial): this warp's row of partial sums
-    uint32_t sl2;          // time-axis split (tb_launch::vsplit_log2): rows are segments of the real voices' rows
+    uint32_t sl2, seg_lo;  // time-axis split (tb_launch::vsplit_log2, vseg_lo): rows are segments of the real voices' rows
     size_t vseg;
 };
 // First sample (of this launch) of virtual voice vv's row.
 __device__ __forceinline__ float* row_of(const RowStore& R, uint32_t vv) {
-    return R.out + (size_t)(vv >> R.sl2) * R.stride + (size_t)(vv & ((1u << R.sl2) - 1u)) * R.vseg;
+    return R.out + (size_t)(vv >> R.sl2) * R.stride + (size_t)(R.seg_lo + (vv & ((1u << R.sl2) - 1u))) * R.vseg;
 }
 #ifndef TB_ST
 #define TB_ST 2
@@ -1106,7 +1106,11 @@ __device__ __forceinline__ void lanes_body(const tb_launch& P, uint32_t group, u
     sk.flimit = (float)(TB_FM_TURNS * TB_TAU * (double)P.sample_rate);  // tighter than render.cu's 100: see pd_make
     sk.plimit = 600.0f;
 
-    uint32_t* gstate = P.state + (size_t)voice * P.state_words;
+    // the voice's state block; with the time-axis split (tb_launch::vsplit*) that of its segment
+    const size_t vidx = P.vsplit_total > 1u ? (size_t)(voice >> P.vsplit_log2) * P.vsplit_total + P.vseg_lo +
+                                            (voice & ((1u << P.vsplit_log2) - 1u))
+                                      : (size_t)voice;
+    uint32_t* gstate = P.state + vidx * P.state_words;
     if (active) {
         // ld.cg: with the work queue the block was last written by another CTA, possibly on another SM
         for (uint32_t k = 0; k < P.state_words; k++) stw(M, (int)(P.n_cval + k), __ldcg(gstate + k));
@@ -1143,6 +1147,7 @@ __device__ __forceinline__ void lanes_body(const tb_launch& P, uint32_t group, u
     R.fast = R.vec_ok && P.out != nullptr && v0 + 32u <= P.n_voices;
     R.mix = MIX ? P.mix_partial + (size_t)(v0 >> 5) * P.mix_stride + s0 : nullptr;
     R.sl2 = P.vsplit_log2;
+    R.seg_lo = P.vseg_lo;
     R.vseg = (size_t)P.vseg;
     const bool warp_live = __any_sync(FULL, active);
     const uint32_t code_s = (uint32_t)__cvta_generic_to_shared(code);
@@ -1183,7 +1188,7 @@ __device__ __forceinline__ void lanes_body(const tb_launch& P, uint32_t group, u
     if (active) {
         finish_lane(P, M, ns);
         u64 mine = ns;  // samples of this unit that belong to the voice
-        const u64 before = (accumulate && P.out_len) ? __ldcg(P.out_len + voice) : 0ull;
+        const u64 before = (accumulate && P.out_len) ? __ldcg(P.out_len + vidx) : 0ull;
         if (P.lane_fin_goe >= 0) {
             // Root Fin (generator.rs:133-168): the inner tree was rendered for the whole unit (the tail of a
             // finished voice's row is undefined by contract, generator.rs:76-95); what counts is how far the
@@ -1209,7 +1214,7 @@ __device__ __forceinline__ void lanes_body(const tb_launch& P, uint32_t group, u
             mine = rem < ns ? rem : ns;
         }
         for (uint32_t k = 0; k < P.state_words; k++) gstate[k] = ldw(M, (int)(P.n_cval + k));
-        if (P.out_len) P.out_len[voice] = before + mine;
+        if (P.out_len) P.out_len[vidx] = before + mine;
     }
 }
 

@@ -306,8 +306,13 @@ struct tb_launch {
     // time-axis split: `n_voices` counts virtual voices; virtual voice vv is segment (vv % vsplit) of real
     // voice (vv / vsplit): parameters, noise streams and the output row belong to the real voice, the row
     // starts vseg samples further per segment; state and out_len are per virtual voice.
-    uint32_t vsplit;       // segments per voice; 0 or 1: every voice is a real voice
+    // A launch may cover a RANGE of a voice's segments (time sharding over GPUs: every rank renders its own
+    // range): segment sl of the launch is segment vseg_lo + sl of the voice, whose state block is number
+    // v * vsplit_total + vseg_lo + sl.
+    uint32_t vsplit;       // segments per voice in this launch; 0 or 1: every voice is a real voice
     uint32_t vsplit_log2;  // log2(vsplit) when it is a power of two (the lane kernels take only those), else 0
+    uint32_t vsplit_total; // segments per voice in all (>= vseg_lo + vsplit)
+    uint32_t vseg_lo;      // first segment of this launch
     uint64_t vseg;         // samples per segment
     uint32_t state_only;   // render for the final state alone (a summary pass): out == NULL is not "mixdown"
 };

@@ -1508,7 +1508,8 @@ tb_render_kernel(const tb_launch P) {
     // time-axis split (program.h tb_launch::vsplit_log2): `voice` is a virtual voice — a segment of a real one
     const uint32_t vsplit = P.vsplit > 1u ? P.vsplit : 1u;
     const uint32_t rvoice = voice / vsplit;
-    const uint32_t vseg_i = voice - rvoice * vsplit;
+    const uint32_t vseg_i = P.vseg_lo + (voice - rvoice * vsplit);  // segment of the voice
+    const size_t vidx = P.vsplit_total > 1u ? (size_t)rvoice * P.vsplit_total + vseg_i : (size_t)voice;  // state block
     M.voice = rvoice;
     M.slots = reinterpret_cast<float*>(base); base += per_warp_slots;
     M.aux = reinterpret_cast<u64*>(base); base += aux_b;
@@ -1524,7 +1525,7 @@ tb_render_kernel(const tb_launch P) {
     sk.flimit = (float)(100.0 * TB_TAU * (double)P.sample_rate);
     sk.plimit = 600.0f;
 
-    uint32_t* gstate = P.state + (size_t)voice * P.state_words;
+    uint32_t* gstate = P.state + vidx * P.state_words;
     for (uint32_t t = l; t < P.state_words; t += 32) M.state[t] = gstate[t];
     setup_voice(P, M, P.params ? P.params + (size_t)rvoice * P.n_params : nullptr, sk);
 
@@ -1647,7 +1648,7 @@ tb_render_kernel(const tb_launch P) {
     __syncwarp();
     for (uint32_t t = l; t < P.state_words; t += 32) gstate[t] = M.state[t];
     if (l == 0) {
-        if (P.out_len) P.out_len[voice] = (P.accumulate ? P.out_len[voice] : 0ull) + total;
+        if (P.out_len) P.out_len[vidx] = (P.accumulate ? P.out_len[vidx] : 0ull) + total;
         if (P.done && total < P.n_samples) P.done[voice] = 1;
     }
 }
