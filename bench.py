@@ -43,6 +43,10 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-mix", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the secondary records: strong scaling, time sharding, exact sines, per-config table")
+    ap.add_argument("--shard-voices", type=int, default=64, help="voices of the time-sharded render (x --shard-seconds)")
+    ap.add_argument("--shard-seconds", type=float, default=600.0)
     return ap.parse_args()
 
 
@@ -163,6 +167,151 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def timed_steps(step, steps, stream, barrier, world):
+    """`steps` calls of step() bracketed by CUDA events on `stream`; device milliseconds, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    barrier()
+    for a, b in evs:
+        a.record(stream)
+        step()
+        b.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    ms = float(sum(a.elapsed_time(b) for a, b in evs))
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def strong_record(args, world, rank, local, n_samples, barrier, peak):
+    """north_star's own shape: the 65,536-voice batch DIVIDED over the ranks (contiguous voice ranges, no
+    data-path collective).  Reported next to the weak-scaling `value`; efficiency is value / (N x the N = 1 value)."""
+    import torch
+    from tuun_b200.generator import Program
+    from tuun_b200.sharding import voice_range
+    from tuun_b200.workloads import fm_filter_params, fm_filter_voice
+    lo, hi = voice_range(args.voices, rank, world)
+    params = torch.from_numpy(fm_filter_params(np.arange(lo, hi))).cuda()
+    prog = Program(fm_filter_voice(), SAMPLE_RATE, device=local)
+    stream = torch.cuda.ExternalStream(prog.stream, device=local)
+    out = torch.empty((hi - lo, n_samples), dtype=torch.float32, device="cuda")
+
+    def step():
+        prog.reset()
+        prog.render(out, params=params)
+
+    for _ in range(3):
+        step()
+    steps = max(3, args.steps)
+    ms = timed_steps(step, steps, stream, barrier, world)
+    info = prog.info
+    value = args.voices * n_samples * steps / (ms * 1e-3)
+    kernel = ("tb_render_lanes_fm_kernel" if info.lane_launches and info.lane_fm_capacity
+              else "tb_render_lanes_kernel" if info.lane_launches else "tb_render_kernel")
+    return {"value": value, "unit": UNIT, "ms_per_step": ms / steps, "voices": args.voices,
+            "voices_per_gpu": hi - lo, "kernel": kernel, "split_segments": int(info.split_segments),
+            "hbm_frac_per_gpu": 4.0 * (hi - lo) * n_samples / (ms / steps * 1e-3) / 1e9 / peak,
+            "scaling": "strong: total work fixed at the 65,536-voice batch"}
+
+
+def time_shard_record(args, world, rank, local, barrier, peak):
+    """Few voices, a long render: --shard-voices FM + low-pass voices x --shard-seconds, every rank rendering its
+    own TIME range of every voice (tb_segments_*: one all-gather of the segments' state blocks per pass over
+    NCCL).  At N = 1 this is what tb_render does by itself for a small batch."""
+    import torch
+    from tuun_b200.generator import Program
+    from tuun_b200.sharding import plan_segments, render_time_sharded
+    from tuun_b200.workloads import fm_filter_params, fm_filter_sample_ids, fm_filter_voice
+    V = args.shard_voices
+    n = int(round(args.shard_seconds * SAMPLE_RATE))
+    head = 256
+    S, seg = plan_segments(n - head, world, per_rank=512)
+    params = torch.from_numpy(fm_filter_params(fm_filter_sample_ids(V))).cuda()
+    prog = Program(fm_filter_voice(), SAMPLE_RATE, device=local)
+    stream = torch.cuda.ExternalStream(prog.stream, device=local)
+    head_out = torch.empty((V, head), dtype=torch.float32, device="cuda")
+    out = torch.empty((V, S // world * seg), dtype=torch.float32, device="cuda")
+    passes = [0]
+
+    def step():
+        prog.reset()
+        prog.render(head_out, params=params)          # the first tile of the stream: every rank, serial
+        passes[0] = render_time_sharded(prog, out, V, S, seg, rank, world, params=params)
+        stream.wait_stream(torch.cuda.current_stream())
+
+    for _ in range(2):
+        step()
+    steps = 3
+    ms = timed_steps(step, steps, stream, barrier, world)
+    samples = head + S * seg
+    value = V * samples * steps / (ms * 1e-3)
+    words = prog.info.state_words
+    return {"value": value, "unit": UNIT, "ms_per_step": ms / steps, "voices": V, "samples_per_voice": samples,
+            "segments": S, "segment_samples": seg, "passes": passes[0],
+            "exchange_bytes_per_pass_per_rank": int(V * (S // world) * words * 4),
+            "hbm_frac_per_gpu": 4.0 * V * samples / world / (ms / steps * 1e-3) / 1e9 / peak,
+            "sharding": "time: rank r renders segments [r S/N, (r+1) S/N) of every voice; states all-gathered per pass"}
+
+
+def exact_sines_record(args, local, n_local, n_samples, params_d, out, peak):
+    """The same batch with every sine in the EXACT class (TUUN_B200_FAST_SINES=0: f64 polynomial on the 64-bit
+    phase, the f32 the reference's libm sin rounds to on 99.98 % of samples) — what the FAST-class carrier
+    (MUFU.SIN on 23 phase bits, the default) buys, and the error of both against the oracle on a sample."""
+    import torch
+    from oracle.binding import OracleProgram
+    from tuun_b200.generator import Program
+    from tuun_b200.workloads import fm_filter_params, fm_filter_cover_ids, fm_filter_voice
+    os.environ["TUUN_B200_FAST_SINES"] = "0"
+    try:
+        prog = Program(fm_filter_voice(), SAMPLE_RATE, device=local)
+    finally:
+        del os.environ["TUUN_B200_FAST_SINES"]
+    stream = torch.cuda.ExternalStream(prog.stream, device=local)
+
+    def step():
+        prog.reset()
+        prog.render(out, params=params_d)
+
+    step()
+    step()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record(stream)
+    for _ in range(2):
+        step()
+    b.record(stream)
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / 2
+    info = prog.info
+    # error of both classes on 64 covering voices x 2 s (the full-length comparison is tests/test_gpu_cfg5_full.py)
+    ids = fm_filter_cover_ids(1)[::4]
+    pr = fm_filter_params(ids)
+    n_err = 2 * SAMPLE_RATE
+    ref, _, _, _ = OracleProgram(fm_filter_voice(), SAMPLE_RATE).render_batch(pr, len(ids), n_err, threads=os.cpu_count() or 1)
+    errs = {}
+    for name, env in (("exact", "0"), ("fast", None)):
+        if env is not None:
+            os.environ["TUUN_B200_FAST_SINES"] = env
+        os.environ["TUUN_B200_LANE_MIN_VOICES"] = "1"
+        try:
+            q = Program(fm_filter_voice(), SAMPLE_RATE, device=local)
+            got = np.zeros((len(ids), n_err), dtype=np.float32)
+            q.render(got, params=pr)
+        finally:
+            os.environ.pop("TUUN_B200_FAST_SINES", None)
+            os.environ.pop("TUUN_B200_LANE_MIN_VOICES", None)
+        errs[name] = float(np.abs(got - ref).max())
+    value = n_local * n_samples / (ms * 1e-3)
+    return {"value": value, "unit": UNIT, "ms_per_step": ms, "hbm_frac": 4.0 * value / 1e9 / peak,
+            "kernel": "tb_render_lanes_kernel" if info.lane_launches else "tb_render_kernel",
+            "max_abs_err_vs_oracle": errs["exact"], "fast_class_max_abs_err_vs_oracle": errs["fast"],
+            "err_sample": f"{len(ids)} voices covering every index / ratio / cutoff class x {n_err} samples, lane kernels",
+            "note": "TUUN_B200_FAST_SINES=0: both sines of a voice by the f64 polynomial"}
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -272,7 +421,19 @@ def main():
         if tj.get("kernel", "tb_render_kernel") == kernel:
             traffic = float(tj["dram_bytes_per_voice_sample"]) * n_local * lane_samples
             traffic_src = tj["source"]
+    # pure-store stream over the same rows, same run: cudaMemsetAsync, best of 3, CUDA events
+    store_gbs = 0.0
+    for _ in range(3):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out.zero_()
+        b.record()
+        torch.cuda.synchronize()
+        store_gbs = max(store_gbs, out.numel() * 4 / (a.elapsed_time(b) * 1e-3) / 1e9)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "store_peak": store_gbs, "frac_of_store_peak": achieved / store_gbs if store_gbs else None,
+                "store_peak_how": "cudaMemsetAsync over this run's output rows, best of 3 (a pure-store stream; `peak` is a "
+                                  "read+write copy)",
                 "traffic": traffic, "traffic_source": traffic_src, "kernel": kernel,
                 "share_of_step": dominant_share,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
@@ -310,7 +471,24 @@ def main():
         et = torch.tensor([e1 - e0], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(et, op=dist.ReduceOp.MAX)
+        # the ceiling of that path: the same rows device -> pinned host by plain copies, all ranks at once
+        dev_win = out[:grp]
+        barrier()
+        c0 = time.perf_counter()
+        for a in range(0, n_local, grp):
+            host[: min(grp, n_local - a)].copy_(dev_win[: min(grp, n_local - a)], non_blocking=True)
+        torch.cuda.synchronize()
+        c1 = time.perf_counter()
+        ct = torch.tensor([c1 - c0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ct, op=dist.ReduceOp.MAX)
+        d2h_gbs = n_local * n_samples * 4 / float(ct.item()) / 1e9
+        e2e_rate = n_total * n_samples * e2e_steps / float(et.item())
         e2e = {"value": n_total * n_samples * e2e_steps / float(et.item()), "unit": UNIT,
+               "d2h_ceiling_gbs_per_gpu": d2h_gbs,
+               "frac_of_d2h_ceiling": (e2e_rate / world * 4 / 1e9) / d2h_gbs if d2h_gbs else None,
+               "d2h_ceiling_how": "the same rows copied device -> the same pinned window with cudaMemcpyAsync alone, all ranks "
+                                  "at once, same run",
                "h2d_bytes_per_step": int(n_local * 8 * 4), "d2h_bytes_per_step": int(n_local * n_samples * 4 + n_local * 8),
                "voices": n_total, "steps": e2e_steps, "host_window_rows": grp,
                "path": "tb_render with pinned host rows: voice groups rendered into 2 device staging buffers, "
@@ -345,12 +523,60 @@ def main():
         mt = torch.tensor([m1 - m0], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(mt, op=dist.ReduceOp.MAX)
+        # the same with a HOST consumer of the mix (the reference-shaped contract of tracker.rs:597-642: one mono
+        # buffer leaves): H2D of the parameter table from pinned memory and D2H of [n_samples] floats inside the timed region
+        mix_h = torch.empty(n_samples, dtype=torch.float32, pin_memory=True)
+        params_pin = torch.from_numpy(params_h).pin_memory()
+        params_dev = torch.empty_like(params_d)
+
+        def mix_e2e_step():
+            params_dev.copy_(params_pin, non_blocking=True)
+            mstream.wait_stream(torch.cuda.current_stream())
+            prog_m.reset()
+            prog_m.render_mix(mix_d, n_local, params=params_dev)
+            done_ev.record(mstream)
+            torch.cuda.current_stream().wait_event(done_ev)
+            if world > 1:
+                reduce_mix(mix_d, dst=0)
+            if rank == 0:
+                mix_h.copy_(mix_d, non_blocking=True)
+            torch.cuda.synchronize()
+
+        mix_e2e_step()
+        barrier()
+        x0 = time.perf_counter()
+        for _ in range(msteps):
+            mix_e2e_step()
+        barrier()
+        x1 = time.perf_counter()
+        xt = torch.tensor([x1 - x0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(xt, op=dist.ReduceOp.MAX)
         mixdown = {"value": n_total * n_samples * msteps / float(mt.item()), "unit": UNIT,
+                   "e2e": {"value": n_total * n_samples * msteps / float(xt.item()), "unit": UNIT,
+                           "h2d_bytes_per_step": int(n_local * 8 * 4), "d2h_bytes_per_step": int(n_samples * 4),
+                           "path": "pinned parameter table -> device, tb_render_mix, NCCL reduce, mix -> pinned host"},
                    "ms_per_step": 1e3 * float(mt.item()) / msteps, "nccl_reduce_bytes": int(n_samples * 4) if world > 1 else 0,
                    "mode": "tb_render_mix(TB_NO_VOICE_OUT | TB_OUT_DEVICE) per rank (voices summed on the chip inside the lane "
                            "kernel, per-warp partial rows added in order), then ncclReduce(sum,f32) to rank 0"}
         del prog_m
 
+    # secondary records (none of them inside `value`)
+    extras = {}
+    if not args.no_extras:
+        if world == 1:
+            extras["exact_sines"] = exact_sines_record(args, local, n_local, n_samples, params_d, out, peak)
+        del out
+        torch.cuda.empty_cache()
+        if world > 1 and args.scaling == "weak":
+            extras["strong"] = strong_record(args, world, rank, local, n_samples, barrier, peak)
+        extras["time_shard"] = time_shard_record(args, world, rank, local, barrier, peak)
+        if rank == 0 and world == 1:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import config_bench
+            extras["configs"] = config_bench.run(reps=3, hbm_gbs=peak)
+            extras["configs_note"] = ("one voice each (the reference's own bench shape), wall clock of tb_render with device rows "
+                                      "against the CPU port on one core in 1024-sample blocks; see tools/config_bench.py")
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -359,6 +585,7 @@ def main():
                 "data": "synthetic", "config": config(args, n_samples, world), "clocks": clocks,
                 "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e, "mixdown": mixdown,
                 "wall_ms_per_step": float(tmax[1].item()) / args.steps, "lengths_ok": lens_ok}
+        line.update(extras)
         if not args.no_cpu:
             cb, _ = cpu_baseline(args, n_samples, args.cpu_seconds, os.cpu_count() or 1)
             line["cpu_baseline"] = cb

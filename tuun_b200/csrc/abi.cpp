@@ -286,7 +286,7 @@ int launch_lanes(tb_program* p, tb_launch& B) {
     const uint32_t groups = (B.n_voices + TB_LANE_THREADS - 1) / TB_LANE_THREADS;
     const bool fm = fm_kernel_applies(p, B.n_voices);
     const char* qe = std::getenv("TUUN_B200_LANE_QUEUE");  // diagnostics: "0" never, "1" always
-    const bool want = !fm && (qe ? qe[0] == '1' : groups > p->lane_capacity);
+    const bool want = !fm && B.vsplit_total <= 1 && (qe ? qe[0] == '1' : groups > p->lane_capacity);
     B.lane_queue = nullptr;
     if (want && B.n_samples >= 4 * 2 * TB_LS) {
         // 16 segments (or fewer, of at least 1024 samples): the last wave of units wastes < 1/16 of the time

@@ -14,6 +14,10 @@ tb_render_lanes_mix_kernel(const tb_launch P) { lanes_body<true, false>(P, block
 
 extern "C" void tb_lanes_queue_kernels(const void** plain, const void** mix);  // lanes_queue.cu
 extern "C" void tb_lanes_fm_kernels(const void** plain, const void** mix);     // lanes_fm.cu
+extern "C" void tb_lanes_split_kernels(const void** plain);                    // lanes_split.cu
+extern "C" void tb_lanes_fm_split_kernels(const void** plain);                 // lanes_fm_split.cu
+extern "C" void tb_lanes_split_run(const tb_launch* P, uint32_t grid, size_t smem, cudaStream_t stream);
+extern "C" void tb_lanes_fm_split_run(const tb_launch* P, uint32_t grid, size_t smem, cudaStream_t stream);
 extern "C" void tb_lanes_queue_run(const tb_launch* P, uint32_t grid, size_t smem, cudaStream_t stream);
 extern "C" void tb_lanes_fm_run(const tb_launch* P, uint32_t grid, size_t smem, cudaStream_t stream);
 
@@ -27,9 +31,11 @@ extern "C" size_t tb_lanes_smem_bytes(uint32_t n_lane_code, uint32_t w_words, ui
 extern "C" cudaError_t tb_lanes_launch(const tb_launch* P, size_t smem, int kind, cudaStream_t stream) {
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
-        const void* ks[6] = {(const void*)tb_render_lanes_kernel, (const void*)tb_render_lanes_mix_kernel};
+        const void* ks[8] = {(const void*)tb_render_lanes_kernel, (const void*)tb_render_lanes_mix_kernel};
         tb_lanes_queue_kernels(&ks[2], &ks[3]);
         tb_lanes_fm_kernels(&ks[4], &ks[5]);
+        tb_lanes_split_kernels(&ks[6]);
+        tb_lanes_fm_split_kernels(&ks[7]);
         for (const void* k : ks) {
             cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
@@ -37,7 +43,11 @@ extern "C" cudaError_t tb_lanes_launch(const tb_launch* P, size_t smem, int kind
         configured = smem;
     }
     const uint32_t groups = (P->n_voices + LT - 1) / LT;
-    if (kind == 1) tb_lanes_queue_run(P, std::min(groups * P->lane_segs, P->lane_grid), smem, stream);
+    const bool vsplit = P->vsplit_total > 1;  // virtual voices (time-axis split): the kernels of lanes_*split.cu; no mixdown
+    if (vsplit && P->mix_partial) return cudaErrorInvalidValue;
+    if (vsplit && kind == 2) tb_lanes_fm_split_run(P, groups, smem, stream);
+    else if (vsplit) tb_lanes_split_run(P, groups, smem, stream);
+    else if (kind == 1) tb_lanes_queue_run(P, std::min(groups * P->lane_segs, P->lane_grid), smem, stream);
     else if (kind == 2) tb_lanes_fm_run(P, groups, smem, stream);
     else if (P->mix_partial) tb_render_lanes_mix_kernel<<<groups, LT, smem, stream>>>(*P);
     else tb_render_lanes_kernel<<<groups, LT, smem, stream>>>(*P);

@@ -30,6 +30,11 @@
 #ifndef TB_LANE_MIN_BLOCKS
 #define TB_LANE_MIN_BLOCKS 7
 #endif
+// Time-axis split (program.h tb_launch::vsplit*): the kernels that take launches of virtual voices are compiled
+// apart (lanes_split.cu, lanes_fm_split.cu) so that the plain ones keep their code, registers and schedule.
+#ifndef TB_LANES_VSPLIT
+#define TB_LANES_VSPLIT 0
+#endif
 
 namespace {
 
@@ -709,6 +714,7 @@ struct RowStore {
 };
 // First sample (of this launch) of virtual voice vv's row.
 __device__ __forceinline__ float* row_of(const RowStore& R, uint32_t vv) {
+    if (!TB_LANES_VSPLIT) return R.out + (size_t)vv * R.stride;
     return R.out + (size_t)(vv >> R.sl2) * R.stride + (size_t)(R.seg_lo + (vv & ((1u << R.sl2) - 1u))) * R.vseg;
 }
 #ifndef TB_ST
@@ -737,7 +743,7 @@ __device__ __forceinline__ void store_pair(RowStore& R, int l) {
     __syncwarp();
     float* d = R.out + (size_t)(R.v0 + (l >> 3)) * R.stride + R.off + (size_t)(l & 7) * 4;
     const size_t step = 4 * R.stride;
-    if (R.sl2 != 0) {  // segments of real voices' rows (abi.cpp render_split_round)
+    if (TB_LANES_VSPLIT) {  // segments of real voices' rows (abi.cpp split_pass)
         if (R.out) {
             UNROLL for (int i = 0; i < 8; i++) {
                 const uint32_t vv = R.v0 + (uint32_t)(l >> 3) + 4u * i;
@@ -1107,14 +1113,15 @@ __device__ __forceinline__ void lanes_body(const tb_launch& P, uint32_t group, u
     sk.plimit = 600.0f;
 
     // the voice's state block; with the time-axis split (tb_launch::vsplit*) that of its segment
-    const size_t vidx = P.vsplit_total > 1u ? (size_t)(voice >> P.vsplit_log2) * P.vsplit_total + P.vseg_lo +
-                                            (voice & ((1u << P.vsplit_log2) - 1u))
-                                      : (size_t)voice;
+    const size_t vidx = TB_LANES_VSPLIT ? (size_t)(voice >> P.vsplit_log2) * P.vsplit_total + P.vseg_lo +
+                                              (voice & ((1u << P.vsplit_log2) - 1u))
+                                        : (size_t)voice;
+    const uint32_t rvoice = TB_LANES_VSPLIT ? voice >> P.vsplit_log2 : voice;  // parameters and noise streams
     uint32_t* gstate = P.state + vidx * P.state_words;
     if (active) {
         // ld.cg: with the work queue the block was last written by another CTA, possibly on another SM
         for (uint32_t k = 0; k < P.state_words; k++) stw(M, (int)(P.n_cval + k), __ldcg(gstate + k));
-        setup_lane(P, M, P.params ? P.params + (size_t)(voice >> P.vsplit_log2) * P.n_params : nullptr);
+        setup_lane(P, M, P.params ? P.params + (size_t)rvoice * P.n_params : nullptr);
         // Every filter must hold its full history (generator.rs:234-252): the host renders the
         // first tile of a stream with the general interpreter before it comes here.
         bool ready = true;
@@ -1146,9 +1153,9 @@ __device__ __forceinline__ void lanes_body(const tb_launch& P, uint32_t group, u
     R.vec_ok = (reinterpret_cast<uintptr_t>(P.out) & 15) == 0 && (P.out_stride & 3) == 0;
     R.fast = R.vec_ok && P.out != nullptr && v0 + 32u <= P.n_voices;
     R.mix = MIX ? P.mix_partial + (size_t)(v0 >> 5) * P.mix_stride + s0 : nullptr;
-    R.sl2 = P.vsplit_log2;
-    R.seg_lo = P.vseg_lo;
-    R.vseg = (size_t)P.vseg;
+    R.sl2 = TB_LANES_VSPLIT ? P.vsplit_log2 : 0u;
+    R.seg_lo = TB_LANES_VSPLIT ? P.vseg_lo : 0u;
+    R.vseg = TB_LANES_VSPLIT ? (size_t)P.vseg : 0;
     const bool warp_live = __any_sync(FULL, active);
     const uint32_t code_s = (uint32_t)__cvta_generic_to_shared(code);
     const u64 n_tiles = ns / (u64)LS;
@@ -1177,8 +1184,8 @@ __device__ __forceinline__ void lanes_body(const tb_launch& P, uint32_t group, u
             for (u64 t = 0; t < n_tiles; t++) {
                 if (active) {
                     M.A = abase + (t & 1) * 4 * AS;
-                    if (P.fast_mode == 2) run_lane_tile<2>(P, code_s, M, voice >> P.vsplit_log2, sk);
-                    else run_lane_tile<1>(P, code_s, M, voice >> P.vsplit_log2, sk);
+                    if (P.fast_mode == 2) run_lane_tile<2>(P, code_s, M, rvoice, sk);
+                    else run_lane_tile<1>(P, code_s, M, rvoice, sk);
                 }
                 tile_done<MIX>(R, l, t, n_tiles);
             }
