@@ -819,13 +819,55 @@ __device__ __forceinline__ void tile_done(RowStore& R, int l, u64 t, u64 n_tiles
 // Nyquist rate is half a turn): every increment goes through the integer conversion instead.
 //   p: the carrier phase in 2^-44 turns (bits above 43 are ignored and may hold anything).
 //   CAP: also report in p_cap the phase before sample `cap` (the phase after `cap` samples of the tile).
+// The modulator's rotations held in REGISTERS for the whole launch (TB_FM_ROT_REGS, the default): the tile
+// loop's loads of the 9-entry table from shared memory queue behind the conversions and MUFU sines in the
+// memory-I/O pipe, and the products that consume them were the largest single stall of the loop (26 % of its
+// samples, ncu source view, profiles/r2_*).  Five entries suffice when the tile is built in two levels: the
+// pair (sin, cos) at samples 4 and 12 by a rotation of -+4 steps from the centre, then every other sample as
+// (sub-centre) +- k steps, k = 1..3, sample 0 as sample 4 - 4 steps: 30 f64 operations a tile against 27,
+// no loads.  Rounding errors of the extra level are ~1e-16, as before far below the f32 result's 6e-8.
+#ifndef TB_FM_ROT_REGS
+#define TB_FM_ROT_REGS 1
+#endif
+struct FmRot {
+    double c1, s1, c2, s2, c3, s3, c4, s4, c16, s16;
+};
+__device__ __forceinline__ FmRot fm_rot_load(const double2* rot) {
+    FmRot r;
+    double2 t;
+    t = rot[(size_t)0 * LT]; r.c1 = t.x; r.s1 = t.y;
+    t = rot[(size_t)1 * LT]; r.c2 = t.x; r.s2 = t.y;
+    t = rot[(size_t)2 * LT]; r.c3 = t.x; r.s3 = t.y;
+    t = rot[(size_t)3 * LT]; r.c4 = t.x; r.s4 = t.y;
+    t = rot[(size_t)(LS / 2) * LT]; r.c16 = t.x; r.s16 = t.y;
+    return r;
+}
 template <bool SLOW, bool CAP = false>
-__device__ __forceinline__ void fm_carrier_tile(float (&car)[LS], double& S, double& Cq, const double2* rot, u64 mm,
-                                                u64 cc, u64& p, const SineK& sk, int cap = 0, u64* p_cap = nullptr) {
+__device__ __forceinline__ void fm_carrier_tile(float (&car)[LS], double& S, double& Cq, const double2* rot, const FmRot& rr,
+                                                u64 mm, u64 cc, u64& p, const SineK& sk, int cap = 0, u64* p_cap = nullptr) {
     float f[LS];
 #if TB_ABL == 4
     UNROLL for (int j = 0; j < LS; j++) f[j] = TB_D2F(S) + j;
+#elif TB_FM_ROT_REGS
+    (void)rot;
+    {
+        f[8] = TB_D2F(S);
+        const double cs4 = Cq * rr.s4, ss4 = S * rr.s4;
+        const double Sa = fma(S, rr.c4, -cs4), Sb = fma(S, rr.c4, cs4);     // sin at samples 4 and 12
+        const double Ca = fma(Cq, rr.c4, ss4), Cb = fma(Cq, rr.c4, -ss4);   // cos there
+        f[4] = TB_D2F(Sa);
+        f[12] = TB_D2F(Sb);
+        double b;
+        b = Ca * rr.s1; f[5] = TB_D2F(fma(Sa, rr.c1, b)); f[3] = TB_D2F(fma(Sa, rr.c1, -b));
+        b = Cb * rr.s1; f[13] = TB_D2F(fma(Sb, rr.c1, b)); f[11] = TB_D2F(fma(Sb, rr.c1, -b));
+        b = Ca * rr.s2; f[6] = TB_D2F(fma(Sa, rr.c2, b)); f[2] = TB_D2F(fma(Sa, rr.c2, -b));
+        b = Cb * rr.s2; f[14] = TB_D2F(fma(Sb, rr.c2, b)); f[10] = TB_D2F(fma(Sb, rr.c2, -b));
+        b = Ca * rr.s3; f[7] = TB_D2F(fma(Sa, rr.c3, b)); f[1] = TB_D2F(fma(Sa, rr.c3, -b));
+        b = Cb * rr.s3; f[15] = TB_D2F(fma(Sb, rr.c3, b)); f[9] = TB_D2F(fma(Sb, rr.c3, -b));
+        f[0] = TB_D2F(fma(Sa, rr.c4, -(Ca * rr.s4)));
+    }
 #else
+    (void)rr;
     f[LS / 2] = TB_D2F(S);
     UNROLL for (int k = 1; k < LS / 2; k++) {
         const double2 r = rot[(size_t)(k - 1) * LT];
@@ -838,9 +880,14 @@ __device__ __forceinline__ void fm_carrier_tile(float (&car)[LS], double& S, dou
         f[0] = TB_D2F(fma(S, r.x, -(Cq * r.y)));
     }
 #endif
+#if TB_FM_ROT_REGS
+    const double S2 = fma(S, rr.c16, Cq * rr.s16);
+    Cq = fma(Cq, rr.c16, -(S * rr.s16));
+#else
     const double2 r16 = rot[(size_t)(LS / 2) * LT];
     const double S2 = fma(S, r16.x, Cq * r16.y);
     Cq = fma(Cq, r16.x, -(S * r16.y));
+#endif
     S = S2;
     UNROLL for (int j = 0; j < LS; j += 2) unpk2(add2(mul2(pk2(f[j], f[j + 1]), mm), cc), f[j], f[j + 1]);
     if (SLOW) {
@@ -996,19 +1043,21 @@ __device__ __forceinline__ void run_fm_voice(const tb_insn* code, LaneMem& M, co
             F.p2 = __fmul_rn(F.a2, F.y2);
         }
     }
+    FmRot rr = {};
+    if (active) rr = fm_rot_load(rot);
     float car[LS];
     UNROLL for (int j = 0; j < LS; j++) car[j] = 0.0f;
     if (!TAIL) {
         for (u64 t = 0; t < n_tiles; t++) {
             if (active) {
-                fm_carrier_tile<SLOW>(car, S, Cq, rot, mm, cc, p, sk);
+                fm_carrier_tile<SLOW>(car, S, Cq, rot, rr, mm, cc, p, sk);
                 M.A = abase + (t & 1) * 4 * AS;
                 lacc_store(M, car);
             }
             tile_done<MIX>(R, l, t, n_tiles);
         }
     } else if (n_tiles > 0) {
-        if (active) fm_carrier_tile<SLOW>(car, S, Cq, rot, mm, cc, p, sk);
+        if (active) fm_carrier_tile<SLOW>(car, S, Cq, rot, rr, mm, cc, p, sk);
         for (u64 t = 1; t < n_tiles; t++) {
             if (active) {
                 float y[LS], nxt[LS];
@@ -1017,7 +1066,7 @@ __device__ __forceinline__ void run_fm_voice(const tb_insn* code, LaneMem& M, co
 #else
                 biquad_tile(y, car, F);                                   // tile t-1 leaves ...
 #endif
-                fm_carrier_tile<SLOW>(nxt, S, Cq, rot, mm, cc, p, sk);    // ... while tile t is made
+                fm_carrier_tile<SLOW>(nxt, S, Cq, rot, rr, mm, cc, p, sk);    // ... while tile t is made
                 M.A = abase + ((t - 1) & 1) * 4 * AS;
                 lacc_store(M, y);
                 UNROLL for (int j = 0; j < LS; j++) car[j] = nxt[j];
@@ -1038,7 +1087,7 @@ __device__ __forceinline__ void run_fm_voice(const tb_insn* code, LaneMem& M, co
         const int half = (int)(n_tiles & 1);
         if (active) {
             u64 p_rem = p;
-            fm_carrier_tile<SLOW, true>(car, S, Cq, rot, mm, cc, p, sk, rem, &p_rem);
+            fm_carrier_tile<SLOW, true>(car, S, Cq, rot, rr, mm, cc, p, sk, rem, &p_rem);
             p = p_rem;
             float y[LS];
             if (TAIL) {
