@@ -154,3 +154,45 @@ def test_long_single_voice_splits_by_itself(monkeypatch):
     e = np.abs(out - ref)
     assert e.max() <= 1e-4
     assert e[:, -SR:].max() <= 2 * e[:, :SR].max() + 1e-6   # no drift over the minute
+
+
+def test_reset_oscillators_split(monkeypatch):
+    """sawtooth / pulse / triangle of lib/v0/std.tuun are a Reset over a clock (Appendix B of SURVEY.md): a segment
+    needs the class of the trigger's last sample and the run's local clock at its start — a copy and a "last set"
+    scan over the segments (split.cu SP_RESET_SIGN / SP_CLK).  Edges must land on the same samples."""
+    from tuun_b200.builder import Std, pipe, to_waveform, filter_
+    from tuun_b200.optimizer import optimize
+    s = Std()
+    f43 = filter_([0.2, 0.3, 0.2, 0.1], [-0.5, 0.2, -0.1])
+    cases = [("sawtooth", s.sawtooth(220), 2), ("pulse", s.pulse(0.3, 110), 2), ("triangle", s.triangle(55), 2),
+             ("pulse-filter_4_3", pipe(s.pulse(0.5, 110), f43), 3)]
+    n = 256 + 64 * 512 + 77
+    for name, v, passes in cases:
+        w = optimize(to_waveform(v))
+        serial, i0 = render(w, n, monkeypatch, 0)
+        assert i0.split_passes == passes, (name, i0.split_passes)
+        ref = oracle(w, n)
+        assert np.abs(serial - ref).max() <= 1e-4, name
+        for sgm in (4, 64):
+            got, info = render(w, n, monkeypatch, sgm)
+            assert info.split_rounds >= 1, name
+            bad = np.abs(got - ref) > 1e-4
+            assert not bad.any(), (name, sgm, int(bad.sum()), np.nonzero(bad[0])[0][:5])
+            assert np.abs(got - serial).max() <= 2e-6, (name, sgm)
+
+
+def test_pulse_modulated_fm_splits_by_itself(monkeypatch):
+    """fm-variations.tuunp:22 (config 3): a pulse — Reset, Alt — driving the frequency of a carrier: the Reset's
+    clock, then the carrier's phase sum, then the samples (three passes), 10 s of one voice."""
+    from tuun_b200 import workloads as W
+    from tuun_b200.generator import Program
+    monkeypatch.delenv("TUUN_B200_SPLIT", raising=False)
+    name, w = W.cfg3_fm_variations()[10]
+    assert name == "pulse-fm"
+    n = 441000
+    p = Program(w, SR)
+    out = np.zeros((1, n), dtype=np.float32)
+    assert p.render(out)[0] == n
+    assert p.info.split_rounds >= 1 and p.info.split_passes == 3
+    e = np.abs(out - oracle(w, n))
+    assert e.max() <= 1e-4 and e[:, -SR:].max() <= 2 * e[:, :SR].max() + 1e-6

@@ -330,7 +330,9 @@ int launch_lanes(tb_program* p, tb_launch& B) {
 // straight to the lane kernel (a caller streaming 1024-sample blocks pays one launch per block).
 // State blocks are shared, so all launches continue one stream.
 int launch_generate_seq(tb_program* p, const tb_launch& L, uint64_t pos) {
-    const bool big = p->lane_smem != 0 && L.n_voices >= p->lane_min_voices && (L.out != nullptr || L.state_only) &&
+    // (a split pass of a program with clocked words — a Reset in the steady stream — has no other kernel to run on)
+    const bool clk_split = p->low.lane_clk != 0 && L.vsplit_total > 1;
+    const bool big = p->lane_smem != 0 && (L.n_voices >= p->lane_min_voices || clk_split) && (L.out != nullptr || L.state_only) &&
                      !(L.vsplit > 1 && L.vsplit_log2 == 0) &&  // the lane kernels take 2^k segments per voice only
                      !(L.vsplit == 1 && L.vsplit_total > 1);   // (a launch of one segment per voice: warp kernel)
     if (!big) return launch(p, L);
@@ -416,25 +418,44 @@ bool plan_split(const tb_program* p, const tb_launch& L, uint64_t n, SplitPlan* 
     const uint64_t V = L.n_voices;
     const uint64_t cap = (uint64_t)n_sm_of_device() * 16;  // resident warps of the warp-per-voice kernel
     const char* env = std::getenv("TUUN_B200_SPLIT");
-    uint64_t want = 0, min_seg = TB_TILE_S;
-    bool lanes = false;
+    uint64_t want = 0, min_seg = TB_TILE_S, grain = TB_TILE_S;
+    const bool clk = p->low.lane_clk != 0;  // clocked words (a Reset in the steady stream): lane kernels only
+    if (clk && p->lane_smem == 0) return false;
+    bool lanes = clk;
+    bool one_wave = false;
+    if (clk) {  // one thread per segment, tiles of 16 samples (the serial lane path tiles the stream from sample 256 too)
+        min_seg = 128;
+        grain = 2 * TB_LS;
+    }
     if (env) {
         want = std::strtoull(env, nullptr, 10);
         if (want < 2) return false;
+    } else if (clk) {
+        if (n < 4096 || V * 2 * p->low.split_passes > cap) return false;
+        want = 32 * cap / V;
     } else {
         if (n < 4096 || V * 2 * p->low.split_passes > cap) return false;
-        want = 2 * cap / V;
+        want = cap / V;     // one resident wave of warps: a second, partial wave costs a whole segment's time
+        one_wave = true;
         // enough voice-samples for the lane-per-voice kernels (2.4 x the rate on FM voices): 4 lane_min_voices
         // virtual voices of at least 4096 samples
         if (p->lane_smem != 0 && p->lane_min_voices > 0 && V * (n / 4096) >= 4ull * p->lane_min_voices) {
             want = (4ull * p->lane_min_voices + V - 1) / V;
             min_seg = 4096;
             lanes = true;
+            one_wave = false;
         }
     }
-    uint64_t seg = n / want / TB_TILE_S * TB_TILE_S;                    // at least `want` segments ...
-    seg = std::max<uint64_t>(seg, min_seg);                            // ... of at least min_seg samples
+    // at least `want` segments (one_wave: at most) of whole tiles, none shorter than min_seg
+    uint64_t seg = one_wave ? ((n + want - 1) / want + grain - 1) / grain * grain : n / want / grain * grain;
+    seg = std::max<uint64_t>(seg, min_seg);
     uint64_t S = n / seg;
+    // split.cu scans a voice's segments with one warp: beyond a few thousand the scan would take longer than the
+    // passes (measured: 16,384 segments of a filtered pulse, 9 ms against 3.9 ms with 4,096)
+    if (S > 4096) {
+        S = 4096;
+        seg = n / S / grain * grain;
+    }
     // The lane kernels address segment rows by shift and mask: a batch that will take them gets 2^k segments.
     if (lanes || (p->lane_smem != 0 && V * S >= p->lane_min_voices)) {
         uint64_t k = 0;
@@ -561,9 +582,11 @@ int launch_generate(tb_program* p, const tb_launch& L, uint64_t pos) {
     tb_launch R = L;  // what is left of the call
     int rc = TB_OK;
     if (!p->pos_known) return launch_generate_seq(p, L, pos);
-    if (pos < (uint64_t)TB_TILE && !p->low.filt.empty()) {
+    if (pos < (uint64_t)TB_TILE && (!p->low.filt.empty() || p->low.lane_clk)) {
         // the first tile of a stream: filter pre-reads (generator.rs:234-252) on the general interpreter.  (A
-        // program without filters is steady from its first sample, and so are its segments.)
+        // program without filters is steady from its first sample, and so are its segments — except under a
+        // Reset: its trigger starts at phase 0 exactly, where the sign decides the first restart
+        // (generator.rs:296) and must come from the exact phase, not from a rotated sin / cos pair.)
         tb_launch H = L;
         H.n_samples = TB_TILE;
         if ((rc = launch_generate_seq(p, H, pos))) return rc;

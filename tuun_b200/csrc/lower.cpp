@@ -1007,14 +1007,29 @@ struct Lowerer {
     // ---- time-axis split plan (program.h tb_split_entry) ---------------------------------------------
     // Walks the tree the steady stream was emitted from.  Returns the first render pass in which node i's
     // output is right in every segment (1 = the first pass), recording one entry per stateful node.
+    int split_clk_level = -1;  // >= 0 inside a Reset: the pass in which its trigger is right
     int split_level(int i) {
         const tb_node& n = nodes[i];
         switch (n.kind) {
             case TB_CONST: return 1;
             case TB_TIME:
-            case TB_NOISE:
+                if (split_clk_level >= 0) {  // the run's own clock
+                    out.split.push_back(tb_split_entry{SP_CLK, (uint32_t)state_off[i], (uint32_t)split_clk_level, -1});
+                    return split_clk_level + 1;
+                }
                 out.split.push_back(tb_split_entry{SP_POS, (uint32_t)state_off[i], 0u, 0});
                 return 1;
+            case TB_NOISE:  // not restarted by a Reset
+                out.split.push_back(tb_split_entry{SP_POS, (uint32_t)state_off[i], 0u, 0});
+                return 1;
+            case TB_RESET: {
+                const int lt = split_level(n.a);
+                out.split.push_back(tb_split_entry{SP_RESET_SIGN, (uint32_t)state_off[i], (uint32_t)lt, 0});
+                split_clk_level = lt;
+                const int li = split_level(n.b);
+                split_clk_level = -1;
+                return std::max(lt + 1, li);
+            }
             case TB_MARKED:
             case TB_CAPTURED: return split_level(n.a);
             case TB_BINARY: {
@@ -1030,6 +1045,10 @@ struct Lowerer {
             case TB_SINE: {
                 const int cf = const_of(n.a), cp = const_of(n.b);
                 int lv = 1;
+                if (split_clk_level >= 0) {  // constant rate and phase (emit_steady): accumulator = rate x local clock
+                    out.split.push_back(tb_split_entry{SP_CLK, (uint32_t)state_off[i], (uint32_t)split_clk_level, cf});
+                    return split_clk_level + 1;
+                }
                 if (cf >= 0) {
                     out.split.push_back(tb_split_entry{SP_SINE_CONST, (uint32_t)state_off[i], 0u, cf});
                 } else {
@@ -1276,7 +1295,7 @@ struct Lowerer {
                 emit(ST_END);
                 out.steady_ok = out.lane_clk ? 0 : 1;  // clocked words: lane kernels only
                 lane_steady_root = true;
-                if (out.steady_ok) {
+                {   // clocked words run on the lane kernels only: lane_ok decides below whether the plan stands
                     const int passes = split_level(root);
                     bool ok = passes <= 8;
                     for (const tb_split_entry& e : out.split) ok = ok && (int)e.state_off >= 0;
@@ -1304,6 +1323,10 @@ struct Lowerer {
         out.lane_ok = ((out.steady_ok || out.lane_fin_goe >= 0 || lane_steady_root) && build_lane_plan()) ? 1u : 0u;
         if (!out.lane_ok) {
             out.lane_fin_goe = -1;
+            if (out.lane_clk) {  // a split of clocked words needs the lane kernels
+                out.split.clear();
+                out.split_passes = 0;
+            }
             out.lane_clk = 0;
         }
         out.n_nodes = n_nodes;

@@ -229,12 +229,18 @@ struct tb_goe {
 // `level` = the render pass after which the entry's summary is right (its inputs were rendered from
 // right states in that pass); analytic entries have level 0.  A program needs `split_passes` passes, the
 // last of which writes the samples.
-enum tb_split_kind : uint32_t { SP_POS = 0, SP_SINE_CONST = 1, SP_SINE_VAR = 2, SP_FILTER = 3 };
+//   SP_RESET_SIGN  Reset (generator.rs:273-318): the class of the trigger's last sample — a segment starts from the
+//                  class its predecessor ended in (a copy, right once the trigger is)
+//   SP_CLK         a clocked node under a Reset (Time, or a Sine with constant rate and phase, whose state is the
+//                  run's local clock x its rate, lanes.cuh ST_TIME_CLK / ST_SINE_CLK): a segment either restarts
+//                  the clock — its final value is then absolute — or advances it by rate x L.  Which of the two
+//                  happened shows in (final - initial); a "last set" scan over the segments gives the starts.
+enum tb_split_kind : uint32_t { SP_POS = 0, SP_SINE_CONST = 1, SP_SINE_VAR = 2, SP_FILTER = 3, SP_RESET_SIGN = 4, SP_CLK = 5 };
 struct tb_split_entry {
     uint32_t kind;
     uint32_t state_off;  // first word of the node's state block
     uint32_t level;
-    int32_t a;           // SP_SINE_CONST: cval of the rate; SP_FILTER: filter table index
+    int32_t a;           // SP_SINE_CONST: cval of the rate; SP_FILTER: filter table index; SP_CLK: cval of the rate, -1 = Time
 };
 
 struct tb_filter_tab {

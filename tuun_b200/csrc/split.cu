@@ -52,8 +52,9 @@ __global__ void split_prepare_kernel(const tb_split_args A) {
     for (uint32_t k = 0; k < A.n_entries; k++) {
         const tb_split_entry e = A.entries[k];
         u64 inc = 0;
-        if (e.kind == SP_POS) inc = 1ull;
-        else if (e.kind == SP_SINE_CONST) inc = turns_to_fx_slow((double)cv[e.a] / (TB_TAU * (double)A.sample_rate));
+        if (e.kind == SP_POS || (e.kind == SP_CLK && e.a < 0)) inc = 1ull;
+        else if (e.kind == SP_SINE_CONST || e.kind == SP_CLK)
+            inc = turns_to_fx_slow((double)cv[e.a] / (TB_TAU * (double)A.sample_rate));
         A.inc[(size_t)v * A.n_entries + k] = inc;
     }
 }
@@ -124,6 +125,45 @@ __global__ void __launch_bounds__(32) split_fix_kernel(const tb_split_args A, ui
                 if (l == 0 && c0 > 0) stu64(A.vi + (vv0 + s) * A.state_words, e.state_off, carry);
                 if (l < 31 && s + 1 < S) stu64(A.vi + (vv0 + s + 1) * A.state_words, e.state_off, carry + incl);
                 carry += __shfl_sync(FULL, incl, 31);
+                __syncwarp();
+            }
+        } else if (e.kind == SP_RESET_SIGN) {
+            // the class of the last trigger sample carries over (the sign word does not depend on where it started)
+            for (uint32_t s = 1 + l; s < S; s += 32)
+                A.vi[(vv0 + s) * A.state_words + e.state_off] = A.vs[(vv0 + s - 1) * A.state_words + e.state_off];
+            __syncwarp();
+        } else if (e.kind == SP_CLK) {
+            // A segment that restarted its clock ends at an absolute value; one that did not added rate x L to what
+            // it started from.  Inclusive "last set" scan: (set, value) o (set', value') = set' ? (1, value')
+            // : (set, value + value').
+            const u64 step = A.inc[(size_t)v * A.n_entries + k] * A.seg;
+            u64 carry = ldu64(A.vi + vv0 * A.state_words, e.state_off);  // the clock at the start of the chunk
+            for (uint32_t c0 = 0; c0 < S; c0 += 32) {
+                const uint32_t s = c0 + l;
+                u64 val = 0;
+                bool set = false;
+                if (s < S) {
+                    const size_t o = (vv0 + s) * A.state_words;
+                    const u64 f = ldu64(A.vs + o, e.state_off), i0 = ldu64(A.vi + o, e.state_off);
+                    set = (f - i0) != step;
+                    val = set ? f : step;
+                }
+                if (l == 0 && !set) {  // the chunk's first segment continues the carried clock
+                    val += carry;
+                    set = true;
+                }
+                UNROLL for (int d = 1; d < 32; d <<= 1) {
+                    const u64 pv = __shfl_up_sync(FULL, val, d);
+                    const bool ps = __shfl_up_sync(FULL, set ? 1 : 0, d) != 0;
+                    if (l >= d && !set) {
+                        val += pv;
+                        set = ps;
+                    }
+                }
+                __syncwarp();
+                if (l == 0 && c0 > 0) stu64(A.vi + (vv0 + s) * A.state_words, e.state_off, carry);
+                if (l < 31 && s + 1 < S) stu64(A.vi + (vv0 + s + 1) * A.state_words, e.state_off, val);
+                carry = __shfl_sync(FULL, val, 31);
                 __syncwarp();
             }
         } else if (e.kind == SP_FILTER) {
