@@ -579,7 +579,7 @@ static int build(tbo_program* p) {
             case TB_TIME:
             case TB_NOISE: break;
             case TB_FIXED:
-                if (s.fixed_off + s.fixed_len > p->pool.size()) return TB_ERR_INVALID;
+                if (s.fixed_len > p->pool.size() || s.fixed_off > p->pool.size() - s.fixed_len) return TB_ERR_INVALID;  // no u64 wrap
                 w->fixed = p->pool.data() + s.fixed_off;
                 w->fixed_len = s.fixed_len;
                 break;

@@ -131,3 +131,30 @@ def test_nesting_is_checked_against_the_kernel_control_stack():
     with pytest.raises(_abi.TuunB200Error) as e:
         lower_check(chain(400))
     assert e.value.status == _abi.TB_ERR_UNSUPPORTED and "nested too deeply" in e.value.message
+
+
+def test_op_list_must_be_a_tree_and_fixed_ranges_must_not_wrap():
+    """tb_lower_check (no device): a node with two parents, an unreachable node, a Fixed range that wraps u64."""
+    import ctypes
+    import numpy as np
+    from tuun_b200 import _abi
+    from tuun_b200.waveform import BinaryPointOp, Const, Fixed, Operator, Sine, flatten
+    L = _abi.lib()
+    info = _abi.TbProgramInfo()
+
+    def check(ops, fixed_len=None):
+        lists = np.asarray(ops.lists, dtype=np.int32)
+        lp = lists.ctypes.data_as(ctypes.c_void_p) if lists.size else None
+        return L.tb_lower_check(ops.nodes, ops.n_nodes, lp, len(ops.lists),
+                                len(ops.fixed_pool) if fixed_len is None else fixed_len, ctypes.byref(info))
+
+    ops = flatten(BinaryPointOp(Operator.Add, Sine(Const(440.0), Const(0.0)), Const(1.0)))
+    assert check(ops) == _abi.TB_OK
+    shared = flatten(BinaryPointOp(Operator.Add, Sine(Const(440.0), Const(0.0)), Const(1.0)))
+    shared.nodes[shared.n_nodes - 1].b = shared.nodes[shared.n_nodes - 1].a      # the sine twice, the constant orphaned
+    assert check(shared) == _abi.TB_ERR_INVALID
+    assert b"parent" in L.tb_last_error() or b"reachable" in L.tb_last_error()
+    fx = flatten(Fixed([1.0, 2.0, 3.0]))
+    assert check(fx) == _abi.TB_OK
+    fx.nodes[0].fixed_off = 2 ** 64 - 2                                            # off + len wraps to 1 <= 3
+    assert check(fx) == _abi.TB_ERR_INVALID

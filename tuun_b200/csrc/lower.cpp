@@ -84,7 +84,16 @@ struct Lowerer {
     // ---- validation -------------------------------------------------------------------
     void validate() {
         if (!nodes || n_nodes == 0) fail(TB_ERR_INVALID, "empty op list");
-        auto child_ok = [&](int32_t c, uint32_t self) { return c >= 0 && (uint32_t)c < self; };
+        if (!lists && n_lists > 0) fail(TB_ERR_INVALID, "lists is NULL but n_lists > 0");
+        // A Waveform owns each child exactly once (Box, waveform.rs:23-100): the op list must be a TREE rooted in its last
+        // node.  A node with two parents would share one state block between them, an unreachable one is not part of
+        // the waveform at all.
+        std::vector<uint32_t> parents(n_nodes, 0);
+        auto child_ok = [&](int32_t c, uint32_t self) {
+            if (c < 0 || (uint32_t)c >= self) return false;
+            parents[c]++;
+            return true;
+        };
         for (uint32_t i = 0; i < n_nodes; i++) {
             const tb_node& n = nodes[i];
             if (n.reserved != 0) fail(TB_ERR_INVALID, "tb_node.reserved must be 0");
@@ -95,7 +104,7 @@ struct Lowerer {
                     break;
                 case TB_TIME:
                 case TB_NOISE: break;
-                case TB_FIXED: ok = n.fixed_off + n.fixed_len <= pool_len; break;
+                case TB_FIXED: ok = n.fixed_len <= pool_len && n.fixed_off <= pool_len - n.fixed_len; break;  // no u64 wrap
                 case TB_FIN:
                 case TB_APPEND:
                 case TB_SINE:
@@ -115,6 +124,11 @@ struct Lowerer {
             }
             if (!ok) fail(TB_ERR_INVALID, "malformed node " + std::to_string(i));
         }
+        for (uint32_t i = 0; i + 1 < n_nodes; i++)
+            if (parents[i] != 1)
+                fail(TB_ERR_INVALID, "node " + std::to_string(i) + (parents[i] == 0 ? " is not reachable from the root"
+                                                                                     : " has more than one parent") +
+                                         ": the op list must be a tree (one node per Waveform variant instance)");
     }
 
     // ---- is_const (generator.rs:574-612), evaluated per voice through the cexpr table ----

@@ -10,10 +10,15 @@ callback — so the only deterministic part is `generate(buffer_start, out)`; th
 function on a virtual clock that advances by exactly one buffer per callback.
 
 What runs on the GPU: every waveform is rendered WHOLE when it is activated (one tb_render launch;
-streaming it segment by segment would be one tiny launch per waveform per segment).  Because the
-reference generator is block-size invariant (its own tests run chunks of 1/2/4/8), handing out
-consecutive slices of that render is what the per-segment `generate` calls would have produced,
-and discarding a prefix is the late-start catch-up (tracker.rs:509-531).  The adds stay in
+streaming it segment by segment would be one tiny launch per waveform per segment).  The reference
+generator is block-size invariant for the trees the reference itself tests that way (chunks of
+1/2/4/8, generator.rs:1284-1351), so handing out consecutive slices of that render is what the
+per-segment `generate` calls would have produced — with two exceptions the reference's code has and its
+tests do not reach: a Fin whose length is a rendered, non-monotonic waveform is re-polled per call
+(generator.rs:672-687), and a finite input under a Filter; such trees come out as
+ONE-call renders here.  Discarding a prefix is the late-start catch-up (tracker.rs:509-531), except that
+the reference still writes the discarded prefix of a Captured node to its file.  A waveform that has not
+ended after `max_seconds` is cut there with a RuntimeWarning.  The adds stay in
 activation order, each rounded, exactly like `out[filled + j] += tmp[j]` (tracker.rs:617-619).
 
 Times are integer nanoseconds with Rust's `Duration` conversions (from_secs_f32 rounds to nearest,
@@ -118,6 +123,10 @@ class OfflineTracker:
 
     def _activate(self, pending: _Pending, segment_start: int) -> _Active:
         samples = self._render(pending.waveform, self.max_samples)
+        if len(samples) >= self.max_samples:
+            import warnings
+            warnings.warn(f"waveform {pending.id} has not ended after {self.max_samples} samples (max_seconds): cut there",
+                          RuntimeWarning, stacklevel=2)
         a = _Active(pending.id, pending.start, samples)
         caps: Dict[str, Waveform] = {}
         _captured_subtrees(pending.waveform, caps)
@@ -133,7 +142,8 @@ class OfflineTracker:
             else:
                 a.captures[stem] = self._render(sub, max(1, len(samples)))[:len(samples)]
         if pending.start < segment_start:  # late start: generate and discard (tracker.rs:509-531)
-            delta = int(np.round(F(as_secs_f32(segment_start - pending.start) * F(self.sample_rate))))
+            # f32::round (tracker.rs:517) rounds halves away from zero; np.round would round them to even
+            delta = int(np.floor(np.float64(F(as_secs_f32(segment_start - pending.start) * F(self.sample_rate))) + 0.5))
             a.cursor = min(delta, len(samples))
         return a
 
