@@ -19,6 +19,7 @@ TAU = f32(2 * math.pi)
 
 def program(w, monkeypatch, lanes=True):
     from tuun_b200.generator import Program
+    monkeypatch.setenv("TUUN_B200_SPLIT", "0")  # these tests count launches of the serial forms (split: test_gpu_split.py)
     if lanes:
         monkeypatch.setenv("TUUN_B200_LANES", "1")
         monkeypatch.setenv("TUUN_B200_LANE_MIN_VOICES", "1")

@@ -488,6 +488,8 @@ __device__ __forceinline__ void run_lane_tile(const tb_launch& P, uint32_t code_
                 // before this tile", encoded -1 - j, which every clocked node adds to its own carried position.
                 lacc_load(M, acc);
                 bool neg = ldw(M, in.a) == 0u;
+                // second state word: the class of the first sample seen since it was last cleared (split.cu SP_CLK)
+                if (ldw(M, in.a + 1) == 0u) stw(M, in.a + 1, acc[0] >= 0.0f ? 2u : 1u);
                 int o = -1;
                 float clk[LS];
                 UNROLL for (int j = 0; j < LS; j++) {

@@ -496,7 +496,7 @@ struct Lowerer {
                 break;
             }
             case TB_RESET: {
-                const int st = state_of(i, 1);
+                const int st = state_of(i, 2);
                 emit_gen(n.a);
                 // All runs of a tile at once (the segmented form) when the inner tree allows it; else run by run,
                 // the way the reference does it (generator.rs:288-316): the inner tree's generate code over the
@@ -618,7 +618,7 @@ struct Lowerer {
                 emit(n.op == TB_MERGE ? L_MAX : L_MIN);
                 break;
             case TB_RESET:
-                (void)state_of(i, 1);
+                (void)state_of(i, 2);
                 emit_len(n.a);
                 break;
             case TB_ALT:
@@ -800,7 +800,7 @@ struct Lowerer {
                 break;
             }
             case TB_RESET: {
-                const int st = state_of(i, 1);
+                const int st = state_of(i, 2);
                 emit_seg(n.a);
                 const int s = alloc_slot();
                 emit(S_RESET_BEGIN, st, s);
@@ -919,7 +919,7 @@ struct Lowerer {
                 if (!emit_steady(n.a)) return false;
                 const int s = s_alloc();
                 if (s > 0xff) return false;
-                emit(ST_RESET_CLK, state_of(i, 1), s);
+                emit(ST_RESET_CLK, state_of(i, 2), s);
                 s_last = -1;
                 clk_slot = s;
                 const bool ok = emit_steady(n.b);
@@ -1022,24 +1022,26 @@ struct Lowerer {
     // Walks the tree the steady stream was emitted from.  Returns the first render pass in which node i's
     // output is right in every segment (1 = the first pass), recording one entry per stateful node.
     int split_clk_level = -1;  // >= 0 inside a Reset: the pass in which its trigger is right
+    int split_clk_reset = -1;  // ... and the state block of that Reset
     int split_level(int i) {
         const tb_node& n = nodes[i];
         switch (n.kind) {
             case TB_CONST: return 1;
             case TB_TIME:
                 if (split_clk_level >= 0) {  // the run's own clock
-                    out.split.push_back(tb_split_entry{SP_CLK, (uint32_t)state_off[i], (uint32_t)split_clk_level, -1});
+                    out.split.push_back(tb_split_entry{SP_CLK, (uint32_t)state_off[i], (uint32_t)split_clk_level, -1, split_clk_reset});
                     return split_clk_level + 1;
                 }
-                out.split.push_back(tb_split_entry{SP_POS, (uint32_t)state_off[i], 0u, 0});
+                out.split.push_back(tb_split_entry{SP_POS, (uint32_t)state_off[i], 0u, 0, 0});
                 return 1;
             case TB_NOISE:  // not restarted by a Reset
-                out.split.push_back(tb_split_entry{SP_POS, (uint32_t)state_off[i], 0u, 0});
+                out.split.push_back(tb_split_entry{SP_POS, (uint32_t)state_off[i], 0u, 0, 0});
                 return 1;
             case TB_RESET: {
                 const int lt = split_level(n.a);
-                out.split.push_back(tb_split_entry{SP_RESET_SIGN, (uint32_t)state_off[i], (uint32_t)lt, 0});
+                out.split.push_back(tb_split_entry{SP_RESET_SIGN, (uint32_t)state_off[i], (uint32_t)lt, 0, 0});
                 split_clk_level = lt;
+                split_clk_reset = state_off[i];
                 const int li = split_level(n.b);
                 split_clk_level = -1;
                 return std::max(lt + 1, li);
@@ -1060,14 +1062,14 @@ struct Lowerer {
                 const int cf = const_of(n.a), cp = const_of(n.b);
                 int lv = 1;
                 if (split_clk_level >= 0) {  // constant rate and phase (emit_steady): accumulator = rate x local clock
-                    out.split.push_back(tb_split_entry{SP_CLK, (uint32_t)state_off[i], (uint32_t)split_clk_level, cf});
+                    out.split.push_back(tb_split_entry{SP_CLK, (uint32_t)state_off[i], (uint32_t)split_clk_level, cf, split_clk_reset});
                     return split_clk_level + 1;
                 }
                 if (cf >= 0) {
-                    out.split.push_back(tb_split_entry{SP_SINE_CONST, (uint32_t)state_off[i], 0u, cf});
+                    out.split.push_back(tb_split_entry{SP_SINE_CONST, (uint32_t)state_off[i], 0u, cf, 0});
                 } else {
                     const int lf = split_level(n.a);  // the increments are right in pass lf: the sum after it
-                    out.split.push_back(tb_split_entry{SP_SINE_VAR, (uint32_t)state_off[i], (uint32_t)lf, 0});
+                    out.split.push_back(tb_split_entry{SP_SINE_VAR, (uint32_t)state_off[i], (uint32_t)lf, 0, 0});
                     lv = lf + 1;
                 }
                 if (cp < 0) lv = std::max(lv, split_level(n.b));
@@ -1075,7 +1077,7 @@ struct Lowerer {
             }
             case TB_FILTER: {
                 const int li = split_level(n.a);
-                out.split.push_back(tb_split_entry{SP_FILTER, (uint32_t)state_off[i], (uint32_t)li, filt_idx[i]});
+                out.split.push_back(tb_split_entry{SP_FILTER, (uint32_t)state_off[i], (uint32_t)li, filt_idx[i], 0});
                 return li + 1;
             }
             default: return 1 << 20;  // not reached: emit_steady took the tree

@@ -235,12 +235,16 @@ struct tb_goe {
 //                  run's local clock x its rate, lanes.cuh ST_TIME_CLK / ST_SINE_CLK): a segment either restarts
 //                  the clock — its final value is then absolute — or advances it by rate x L.  Which of the two
 //                  happened shows in (final - initial); a "last set" scan over the segments gives the starts.
+//                  (A restart on a segment's very first sample depends on the class the segment STARTED from, which
+//                  was a guess in that pass: the Reset's second state word records the class of the first sample a
+//                  launch saw, which lets the scan undo a spurious restart there or supply a missed one.)
 enum tb_split_kind : uint32_t { SP_POS = 0, SP_SINE_CONST = 1, SP_SINE_VAR = 2, SP_FILTER = 3, SP_RESET_SIGN = 4, SP_CLK = 5 };
 struct tb_split_entry {
     uint32_t kind;
     uint32_t state_off;  // first word of the node's state block
     uint32_t level;
     int32_t a;           // SP_SINE_CONST: cval of the rate; SP_FILTER: filter table index; SP_CLK: cval of the rate, -1 = Time
+    int32_t b;           // SP_CLK: state block of the Reset whose clock it is
 };
 
 struct tb_filter_tab {

@@ -72,6 +72,8 @@ __global__ void split_seed_kernel(const tb_split_args A) {
         const tb_split_entry e = A.entries[k];
         if (e.kind == SP_POS || e.kind == SP_SINE_CONST)
             stu64(dst, e.state_off, ldu64(dst, e.state_off) + A.inc[(size_t)v * A.n_entries + k] * n);
+        else if (e.kind == SP_RESET_SIGN)
+            dst[e.state_off + 1] = 0u;  // "class of the first sample seen": recorded anew by every pass
     }
 }
 
@@ -105,9 +107,11 @@ __global__ void __launch_bounds__(32) split_fix_kernel(const tb_split_args A, ui
     const int l = threadIdx.x;
     const uint32_t S = A.n_seg;
     const size_t vv0 = (size_t)v * S;
+    // (SP_CLK reads the sign words the segments STARTED from: SP_RESET_SIGN overwrites them in a second round)
+    for (uint32_t round = 0; round < 2; round++)
     for (uint32_t k = 0; k < A.n_entries; k++) {
         const tb_split_entry e = A.entries[k];
-        if (e.level != level) continue;
+        if (e.level != level || (e.kind == SP_RESET_SIGN) != (round == 1)) continue;
         if (e.kind == SP_SINE_VAR) {
             // accumulator at the start of segment s = accumulator of the voice + the increments of segments < s
             u64 carry = ldu64(A.vi + vv0 * A.state_words, e.state_off);
@@ -145,8 +149,22 @@ __global__ void __launch_bounds__(32) split_fix_kernel(const tb_split_args A, ui
                 if (s < S) {
                     const size_t o = (vv0 + s) * A.state_words;
                     const u64 f = ldu64(A.vs + o, e.state_off), i0 = ldu64(A.vi + o, e.state_off);
-                    set = (f - i0) != step;
-                    val = set ? f : step;
+                    // a restart on the first sample: what the pass saw (from the class it was started with) and
+                    // what is true (from the class the previous segment really ended in)
+                    const bool first_nonneg = A.vs[o + e.b + 1] == 2u;
+                    const bool guess_neg = A.vi[o + e.b] == 0u;
+                    const bool true_neg = s == 0 ? guess_neg : A.vs[o - A.state_words + e.b] == 0u;
+                    const bool saw0 = guess_neg && first_nonneg, true0 = true_neg && first_nonneg;
+                    if (true0) {         // the clock restarted on the first sample: the final value is absolute —
+                        set = true;      // what the pass computed if it saw that restart or a later one, else L steps
+                        val = (saw0 || (f - i0) != step) ? f : step;
+                    } else if (saw0) {   // spurious: undone, unless a later restart made the final value absolute anyway
+                        set = f != step;
+                        val = set ? f : step;
+                    } else {
+                        set = (f - i0) != step;
+                        val = set ? f : step;
+                    }
                 }
                 if (l == 0 && !set) {  // the chunk's first segment continues the carried clock
                     val += carry;
