@@ -1,5 +1,5 @@
 """Config 5 (BASELINE.json: 65,536 FM + low-pass voices x 10 s) at its OWN length, through the kernel
-the bench times: the default kernel selection (a batch of >= 10,656 voices takes tb_render_lanes_fm_kernel),
+the bench times: the default kernel selection (a batch of > 12,288 voices takes tb_render_lanes_fm_kernel, whole),
 device rows, 441,000 samples in one call — compared with the CPU oracle (generator.rs:86-515 restated) on
 512 voices that cover every modulation index, ratio, cutoff and Q of the sweep.
 
@@ -43,7 +43,8 @@ def test_cfg5_full_length_default_kernel():
     N = 441000
     cover = fm_filter_cover_ids(2)                       # 512 voices: every (I, D, cut) class twice, every Q
     assert 49230 not in cover
-    ids = np.concatenate([cover, [49230], fm_filter_sample_ids(10752 - 513, first=1)])
+    # 12,352 voices: above the batch size (12,288) below which tb_render would cut the voices in time as well
+    ids = np.concatenate([cover, [49230], fm_filter_sample_ids(12352 - 513, first=1)])
     V, C = len(ids), 513
     w = fm_filter_voice()
     params = fm_filter_params(ids)

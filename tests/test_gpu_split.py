@@ -196,3 +196,45 @@ def test_pulse_modulated_fm_splits_by_itself(monkeypatch):
     assert p.info.split_rounds >= 1 and p.info.split_passes == 3
     e = np.abs(out - oracle(w, n))
     assert e.max() <= 1e-4 and e[:, -SR:].max() <= 2 * e[:, :SR].max() + 1e-6
+
+
+def test_fm_batch_split_with_filter_warm_up(monkeypatch):
+    """The form strong scaling takes (65,536 voices over 8 GPUs leave 8,192 each: too few to fill the lane kernel):
+    every voice in S segments, the carrier's phase sums from a pass that computes nothing else, the biquad's history
+    from a warm-up before each segment (abi.cpp render_split_fm).  Forced on a small batch here; voices cover every
+    filter shape, including the slowest-forgetting one (200 Hz, Q = 2: 3,500 samples of warm-up)."""
+    import torch
+    from tuun_b200.generator import Program
+    from tuun_b200.workloads import fm_filter_cover_ids, fm_filter_params, fm_filter_tolerance, fm_filter_voice
+    w = fm_filter_voice()
+    ids = fm_filter_cover_ids(1)[::2]            # 128 voices
+    params = fm_filter_params(ids)
+    V, n = len(ids), 256 + 4 * 40000 + 100
+    monkeypatch.setenv("TUUN_B200_LANE_MIN_VOICES", "1")
+    monkeypatch.setenv("TUUN_B200_SPLIT_FM", "0")
+    serial = np.zeros((V, n), dtype=np.float32)
+    Program(w, SR).render(serial, params=params)
+    monkeypatch.setenv("TUUN_B200_SPLIT_FM", "4")
+    p = Program(w, SR)
+    got = torch.zeros((V, n), dtype=torch.float32, device="cuda")
+    lens = np.zeros(V, dtype=np.uint64)
+    p.render(got, params=params, out_len=lens)
+    info = p.info
+    assert (lens == n).all() and info.split_rounds == 1 and info.split_segments == 4 and info.split_seg_samples == 40000
+    got = got.cpu().numpy()
+    ref, _, _, _ = OracleProgram(w, SR).render_batch(params, V, n, threads=8)
+    tol = fm_filter_tolerance(params, 1e-4)
+    assert (np.abs(got - ref).max(axis=1) <= tol).all()
+    assert (np.abs(serial - ref).max(axis=1) <= tol).all()
+    d = np.abs(got - serial).max(axis=1)
+    from tuun_b200.workloads import biquad_noise_gain
+    g = biquad_noise_gain(params[:, 6], params[:, 7])
+    assert (d <= 6e-7 * np.maximum(g, 5.0)).all(), float((d / np.maximum(g, 5.0)).max())   # the filter's own round-off noise
+    assert float(np.median(d)) <= 2e-6
+    # and the stream continues: the next (serial) call of both programs agrees the same way
+    monkeypatch.setenv("TUUN_B200_SPLIT_FM", "0")
+    nxt = np.zeros((V, 3000), dtype=np.float32)
+    p.render(nxt, params=params)
+    o = OracleProgram(w, SR)
+    ref2, _, _, _ = o.render_batch(params, V, n + 3000, threads=8)
+    assert (np.abs(nxt - ref2[:, n:]).max(axis=1) <= tol).all()

@@ -111,6 +111,12 @@ struct tb_program {
     uint32_t* d_vi = nullptr;
     unsigned long long* d_vlen = nullptr;
     size_t vstate_cap = 0;          // virtual voices the three buffers hold
+    uint32_t* d_vw = nullptr;       // fused FM voice: warm-up states, carrier snapshots, longest warm-up needed
+    unsigned long long* d_snap = nullptr;
+    uint32_t* d_warm_need = nullptr;
+    size_t vwarm_cap = 0;
+    uint64_t split_fm_rounds = 0;   // of split_rounds, those of the FM form (summary of phase sums + filter warm-up)
+    uint64_t split_last_warm = 0;
     float* d_split_cval = nullptr;
     unsigned long long* d_split_inc = nullptr;
     size_t split_real_cap = 0;      // real voices the two scratch tables hold
@@ -129,6 +135,7 @@ struct tb_program {
         cudaFree(d_len); cudaFree(d_done); cudaFree(d_mix); cudaFree(d_stage[0]); cudaFree(d_stage[1]);
         cudaFree(d_lane_code); cudaFree(d_lane_aux); cudaFree(d_lane_queue);
         cudaFree(d_split); cudaFree(d_vs); cudaFree(d_vi); cudaFree(d_vlen); cudaFree(d_split_cval); cudaFree(d_split_inc);
+        cudaFree(d_vw); cudaFree(d_snap); cudaFree(d_warm_need);
         if (h_fault) cudaFreeHost(h_fault);
         for (auto& e : lane_ev) {
             if (e[0]) cudaEventDestroy(e[0]);
@@ -333,8 +340,9 @@ int launch_generate_seq(tb_program* p, const tb_launch& L, uint64_t pos) {
     // (a split pass of a program with clocked words — a Reset in the steady stream — has no other kernel to run on)
     const bool clk_split = p->low.lane_clk != 0 && L.vsplit_total > 1;
     const bool big = p->lane_smem != 0 && (L.n_voices >= p->lane_min_voices || clk_split) && (L.out != nullptr || L.state_only) &&
-                     !(L.vsplit > 1 && L.vsplit_log2 == 0) &&  // the lane kernels take 2^k segments per voice only
-                     !(L.vsplit == 1 && L.vsplit_total > 1);   // (a launch of one segment per voice: warp kernel)
+                     (L.fm_sums ||                              // (the summary kernel stores no rows: any number of segments)
+                      (!(L.vsplit > 1 && L.vsplit_log2 == 0) &&  // the lane kernels take 2^k segments per voice only
+                       !(L.vsplit == 1 && L.vsplit_total > 1))); // (a launch of one segment per voice: warp kernel)
     if (!big) return launch(p, L);
     // The fused-FM-voice kernel starts a stream itself (the filter's read-ahead, run_fm_voice) and takes
     // the samples that do not fill a tile: one launch for the whole call.  (A root Fin keeps its general
@@ -523,16 +531,25 @@ int split_begin(tb_program* p, const tb_launch& L, const SplitPlan& plan) {
     p->launches += 2;
     return TB_OK;
 }
+struct PassOpt {
+    bool fm_sums = false;      // fused FM voice: phase sums only, snapshot after snap_at samples (split.h)
+    uint64_t snap_at = 0;
+    uint32_t* states = nullptr;  // render these state blocks in place (no copy from d_vi) for `samples` samples
+    uint64_t samples = 0;
+};
 int split_pass(tb_program* p, const tb_launch& L, uint32_t pass, uint32_t seg_lo, uint32_t seg_hi, float* out_base,
-               uint64_t pos) {
+               uint64_t pos, const PassOpt& opt = PassOpt()) {
     const tb_split_args& A = p->split_args;
     const bool last = pass == p->low.split_passes;
     const size_t state_bytes = (size_t)A.n_real * A.n_seg * p->low.state_words * 4;
-    CU(cudaMemcpyAsync(p->d_vs, p->d_vi, state_bytes, cudaMemcpyDeviceToDevice, p->stream));
+    if (!opt.states) CU(cudaMemcpyAsync(p->d_vs, p->d_vi, state_bytes, cudaMemcpyDeviceToDevice, p->stream));
     tb_launch B = L;
-    B.state = p->d_vs;
+    B.state = opt.states ? opt.states : p->d_vs;
     B.n_voices = A.n_real * (seg_hi - seg_lo);
-    B.n_samples = A.seg;
+    B.n_samples = opt.states ? opt.samples : A.seg;
+    B.fm_sums = opt.fm_sums ? 1u : 0u;
+    B.vsnap = opt.fm_sums ? A.snap : nullptr;
+    B.vsnap_at = opt.snap_at;
     B.vsplit = seg_hi - seg_lo;
     B.vsplit_total = A.n_seg;
     B.vseg_lo = seg_lo;
@@ -574,44 +591,156 @@ int render_split_round(tb_program* p, const tb_launch& L, const SplitPlan& plan,
     return TB_OK;
 }
 
+// ---- a batch of fused FM voices with a biquad, too small to fill the lane kernel (strong scaling: 65,536 voices over 8
+// GPUs are 8,192 each, 1.7 warps an SM) ---------------------------------------------------------------------------------
+// The general split would render such a batch three times.  Here the two summaries are cheap: (1) the carrier's phase
+// sums come from a pass that computes nothing else (run_fm_sums: a third of a tile's instructions), and (2) the
+// biquad's history at a segment's start comes from a warm-up — `warm` samples before the segment, from zero history,
+// long enough for the filter to forget it (split.cu split_fm_need_kernel) — instead of a pass over the whole
+// segment and an affine scan.  Sines stay bit-identical to the serial render (exact phase sums); the filter differs
+// by < 1e-11 of its state plus, like any change of partition, its own round-off noise.
+bool plan_split_fm(const tb_program* p, const tb_launch& L, uint64_t n, SplitPlan* plan) {
+    if (p->low.split_passes != 3 || !p->d_split || p->lane_fm_capacity == 0 || L.out == nullptr || L.done != nullptr ||
+        L.mode != 0 || L.vsplit_total > 1 || p->low.filt.size() != 1)
+        return false;
+    const char* env = std::getenv("TUUN_B200_SPLIT_FM");  // "0": never; "S": S segments whatever the batch
+    uint64_t S = 0;
+    const uint64_t V = L.n_voices;
+    if (env) {
+        S = std::strtoull(env, nullptr, 10);
+        if (S < 2) return false;
+    } else {
+        if (std::getenv("TUUN_B200_SPLIT")) return false;          // the general form was asked for (or none)
+        if (V < 64 || V > 12288 || n < 65536) return false;         // small batches: the general form; large ones fill the device
+        S = 65536 / V;
+    }
+    uint64_t k = 0;
+    while ((2ull << k) <= S) k++;
+    S = 1ull << k;
+    if (S > 4096) S = 4096;
+    while (S >= 2 && n / S < 32768) S >>= 1;                        // room for the warm-up (a few thousand samples)
+    if (S < 2) return false;
+    plan->n_seg = (uint32_t)S;
+    plan->seg = n / S / (2 * TB_LS) * (2 * TB_LS);
+    return true;
+}
+int ensure_warm_buffers(tb_program* p, uint64_t nv) {
+    if (nv > p->vwarm_cap) {
+        cudaFree(p->d_vw); cudaFree(p->d_snap);
+        p->d_vw = nullptr;
+        p->d_snap = nullptr;
+        p->vwarm_cap = 0;
+        CU(cudaMalloc(reinterpret_cast<void**>(&p->d_vw), (size_t)nv * p->low.state_words * 4));
+        CU(cudaMalloc(reinterpret_cast<void**>(&p->d_snap), (size_t)nv * 8));
+        p->vwarm_cap = nv;
+    }
+    if (!p->d_warm_need) CU(cudaMalloc(reinterpret_cast<void**>(&p->d_warm_need), 4));
+    return TB_OK;
+}
+// Returns TB_OK and *done = true when the round was rendered; *done = false: not applicable after all (a filter
+// that does not forget fast enough), nothing was changed.
+int render_split_fm(tb_program* p, const tb_launch& L, const SplitPlan& plan, uint64_t pos, bool* done) {
+    *done = false;
+    int rc = split_begin(p, L, plan);
+    if (rc) return rc;
+    tb_split_args& A = p->split_args;
+    if ((rc = ensure_warm_buffers(p, (uint64_t)A.n_real * A.n_seg))) return rc;
+    A.vw = p->d_vw;
+    A.snap = p->d_snap;
+    A.warm_need = p->d_warm_need;
+    A.fm_carrier = A.fm_filter = -1;
+    for (size_t k = 0; k < p->low.split.size(); k++) {
+        if (p->low.split[k].kind == SP_SINE_VAR) A.fm_carrier = (int32_t)k;
+        if (p->low.split[k].kind == SP_FILTER) A.fm_filter = (int32_t)k;
+    }
+    if (A.fm_carrier < 0 || A.fm_filter < 0) return TB_OK;
+    CU(cudaMemsetAsync(p->d_warm_need, 0, 4, p->stream));
+    cudaError_t e = tb_split_fm_need(&A, p->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "tb_split_fm_need");
+    uint32_t need = 0;
+    CU(cudaMemcpyAsync(&need, p->d_warm_need, 4, cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    p->launches++;
+    uint64_t warm = ((uint64_t)need + TB_LS - 1) / TB_LS * TB_LS;
+    if (need == 0xffffffffu || warm * 4 > plan.seg) return TB_OK;   // the warm-up would not be a small fraction
+    A.warm = warm;
+    // 1: phase sums (and the snapshot where the next segment's warm-up starts), then the exact starts
+    PassOpt sums;
+    sums.fm_sums = true;
+    sums.snap_at = plan.seg - warm;
+    if ((rc = split_pass(p, L, 1, 0, plan.n_seg - 1, nullptr, pos, sums))) return rc;  // nobody starts behind the last segment
+    if ((rc = split_fix(p, 1))) return rc;
+    // 2: the filters' histories by warm-up
+    e = tb_split_fm_warm_seed(&A, p->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "tb_split_fm_warm_seed");
+    PassOpt wp;
+    wp.states = p->d_vw;
+    wp.samples = warm;
+    if ((rc = split_pass(p, L, 2, 0, plan.n_seg, nullptr, pos, wp))) return rc;
+    e = tb_split_fm_adopt(&A, p->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "tb_split_fm_adopt");
+    p->launches += 2;
+    // 3: the samples
+    if ((rc = split_pass(p, L, 3, 0, plan.n_seg, L.out, pos))) return rc;
+    if ((rc = split_finish(p, L.state, L.out_len, plan.seg * plan.n_seg, L.accumulate != 0))) return rc;
+    p->split_rounds++;
+    p->split_fm_rounds++;
+    p->split_last_warm = warm;
+    *done = true;
+    return TB_OK;
+}
+
 // A generate launch: split in time when that pays (rounds of S segments until what is left is short), else
 // — and for the head tile of a stream and the rest — the serial form.
 int launch_generate(tb_program* p, const tb_launch& L, uint64_t pos) {
+    if (p->low.split_passes == 0 || !p->pos_known) return launch_generate_seq(p, L, pos);
+    // The first tile of a stream stays on the serial form: filter pre-reads (generator.rs:234-252).  (A program
+    // without filters is steady from its first sample, and so are its segments — except under a Reset: its trigger
+    // starts at phase 0 exactly, where the sign decides the first restart (generator.rs:296) and must come from the
+    // exact phase, not from a rotated sin / cos pair.)
+    const bool need_head = pos < (uint64_t)TB_TILE && (!p->low.filt.empty() || p->low.lane_clk);
+    const uint64_t head = need_head ? (uint64_t)TB_TILE : 0;
+    if (L.n_samples <= head) return launch_generate_seq(p, L, pos);
     SplitPlan plan;
-    if (p->low.split_passes == 0 || !plan_split(p, L, L.n_samples, &plan)) return launch_generate_seq(p, L, pos);
+    const bool fm = plan_split_fm(p, L, L.n_samples - head, &plan);
+    if (!fm && !plan_split(p, L, L.n_samples - head, &plan)) return launch_generate_seq(p, L, pos);
     tb_launch R = L;  // what is left of the call
     int rc = TB_OK;
-    if (!p->pos_known) return launch_generate_seq(p, L, pos);
-    if (pos < (uint64_t)TB_TILE && (!p->low.filt.empty() || p->low.lane_clk)) {
-        // the first tile of a stream: filter pre-reads (generator.rs:234-252) on the general interpreter.  (A
-        // program without filters is steady from its first sample, and so are its segments — except under a
-        // Reset: its trigger starts at phase 0 exactly, where the sign decides the first restart
-        // (generator.rs:296) and must come from the exact phase, not from a rotated sin / cos pair.)
-        tb_launch H = L;
-        H.n_samples = TB_TILE;
-        if ((rc = launch_generate_seq(p, H, pos))) return rc;
-        R.out = L.out + TB_TILE;
-        R.n_samples = L.n_samples - TB_TILE;
+    auto advance = [&](uint64_t n) {
+        R.out += n;
+        R.n_samples -= n;
         R.accumulate = 1;
         R.mid_call = 1;
-        R.call_pos = L.call_pos + TB_TILE;
-        pos += TB_TILE;
+        R.call_pos += n;
+        pos += n;
+    };
+    if (need_head) {
+        tb_launch H = L;
+        H.n_samples = head;
+        if ((rc = launch_generate_seq(p, H, pos))) return rc;
+        advance(head);
     }
     bool first = true;
-    while (R.n_samples > 0 && plan_split(p, R, R.n_samples, &plan)) {
-        if (first) {  // tb_program_info: the round that covers most of the call
+    auto note = [&]() {  // tb_program_info: the round that covers most of the call
+        if (first) {
             p->split_last_segments = plan.n_seg;
             p->split_last_seg_samples = plan.seg;
             first = false;
         }
+    };
+    if (fm) {
+        bool done = false;
+        if ((rc = render_split_fm(p, R, plan, pos, &done))) return rc;
+        if (done) {
+            note();
+            advance(plan.seg * plan.n_seg);
+        }
+        return R.n_samples > 0 ? launch_generate_seq(p, R, pos) : TB_OK;
+    }
+    while (R.n_samples > 0 && plan_split(p, R, R.n_samples, &plan)) {
+        note();
         if ((rc = render_split_round(p, R, plan, pos))) return rc;
-        const uint64_t done = plan.seg * plan.n_seg;
-        R.out += done;
-        R.n_samples -= done;
-        R.accumulate = 1;
-        R.mid_call = 1;
-        R.call_pos += done;
-        pos += done;
+        advance(plan.seg * plan.n_seg);
     }
     if (R.n_samples > 0) return launch_generate_seq(p, R, pos);
     return TB_OK;

@@ -15,7 +15,7 @@ tb_render_lanes_mix_kernel(const tb_launch P) { lanes_body<true, false>(P, block
 extern "C" void tb_lanes_queue_kernels(const void** plain, const void** mix);  // lanes_queue.cu
 extern "C" void tb_lanes_fm_kernels(const void** plain, const void** mix);     // lanes_fm.cu
 extern "C" void tb_lanes_split_kernels(const void** plain);                    // lanes_split.cu
-extern "C" void tb_lanes_fm_split_kernels(const void** plain);                 // lanes_fm_split.cu
+extern "C" void tb_lanes_fm_split_kernels(const void** plain, const void** sums);  // lanes_fm_split.cu
 extern "C" void tb_lanes_split_run(const tb_launch* P, uint32_t grid, size_t smem, cudaStream_t stream);
 extern "C" void tb_lanes_fm_split_run(const tb_launch* P, uint32_t grid, size_t smem, cudaStream_t stream);
 extern "C" void tb_lanes_queue_run(const tb_launch* P, uint32_t grid, size_t smem, cudaStream_t stream);
@@ -31,11 +31,11 @@ extern "C" size_t tb_lanes_smem_bytes(uint32_t n_lane_code, uint32_t w_words, ui
 extern "C" cudaError_t tb_lanes_launch(const tb_launch* P, size_t smem, int kind, cudaStream_t stream) {
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
-        const void* ks[8] = {(const void*)tb_render_lanes_kernel, (const void*)tb_render_lanes_mix_kernel};
+        const void* ks[9] = {(const void*)tb_render_lanes_kernel, (const void*)tb_render_lanes_mix_kernel};
         tb_lanes_queue_kernels(&ks[2], &ks[3]);
         tb_lanes_fm_kernels(&ks[4], &ks[5]);
         tb_lanes_split_kernels(&ks[6]);
-        tb_lanes_fm_split_kernels(&ks[7]);
+        tb_lanes_fm_split_kernels(&ks[7], &ks[8]);
         for (const void* k : ks) {
             cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;

@@ -713,6 +713,7 @@ struct RowStore {
     float* mix;            // mixdown without rows (tb_launch::mix_partial): this warp's row of partial sums
     uint32_t sl2, seg_lo;  // time-axis split (tb_launch::vsplit_log2, vseg_lo): rows are segments of the real voices' rows
     size_t vseg;
+    const unsigned long long* rowoff;  // ... whose first samples (offsets from `out`, in floats) sit in a table, one per row of the warp
 };
 // First sample (of this launch) of virtual voice vv's row.
 __device__ __forceinline__ float* row_of(const RowStore& R, uint32_t vv) {
@@ -746,11 +747,15 @@ __device__ __forceinline__ void store_pair(RowStore& R, int l) {
     float* d = R.out + (size_t)(R.v0 + (l >> 3)) * R.stride + R.off + (size_t)(l & 7) * 4;
     const size_t step = 4 * R.stride;
     if (TB_LANES_VSPLIT) {  // segments of real voices' rows (abi.cpp split_pass)
-        if (R.out) {
+        if (R.fast) {  // all 32 rows of the warp exist and are 16-byte aligned
+            const unsigned long long* ro = R.rowoff + (l >> 3);
+            float* base = R.out + R.off + (size_t)(l & 7) * 4;
+            UNROLL for (int i = 0; i < 8; i++) st_row(reinterpret_cast<float4*>(base + ro[4 * i]), v[i]);
+        } else if (R.out) {
             UNROLL for (int i = 0; i < 8; i++) {
-                const uint32_t vv = R.v0 + (uint32_t)(l >> 3) + 4u * i;
-                if (vv < R.n_voices) {
-                    float* q = row_of(R, vv) + R.off + (size_t)(l & 7) * 4;
+                const uint32_t r = (uint32_t)(l >> 3) + 4u * i;
+                if (R.v0 + r < R.n_voices) {
+                    float* q = R.out + R.rowoff[r] + R.off + (size_t)(l & 7) * 4;
                     if (R.vec_ok) st_row(reinterpret_cast<float4*>(q), v[i]);
                     else put4(q, v[i], false);
                 }
@@ -844,7 +849,8 @@ __device__ __forceinline__ FmRot fm_rot_load(const double2* rot) {
     t = rot[(size_t)(LS / 2) * LT]; r.c16 = t.x; r.s16 = t.y;
     return r;
 }
-template <bool SLOW, bool CAP = false>
+//   PHASE_ONLY: the summary pass of a time-axis split (run_fm_sums) wants the phase after the tile, not its sines.
+template <bool SLOW, bool CAP = false, bool PHASE_ONLY = false>
 __device__ __forceinline__ void fm_carrier_tile(float (&car)[LS], double& S, double& Cq, const double2* rot, const FmRot& rr,
                                                 u64 mm, u64 cc, u64& p, const SineK& sk, int cap = 0, u64* p_cap = nullptr) {
     float f[LS];
@@ -900,8 +906,20 @@ __device__ __forceinline__ void fm_carrier_tile(float (&car)[LS], double& S, dou
             p += freq_to_inc(f[j + 1], sk) >> 20;
             if (CAP && j == cap) *p_cap = t0;
             if (CAP && j + 1 == cap) *p_cap = t1;
-            sin_m23x2(p44_m23(t0), p44_m23(t1), car[j], car[j + 1]);
+            if (!PHASE_ONLY) sin_m23x2(p44_m23(t0), p44_m23(t1), car[j], car[j + 1]);
         }
+        return;
+    }
+    if (PHASE_ONLY) {
+        // Only the phase after the tile is wanted: the 16 increments are rounded to the grid independently (the same
+        // integers the running DFMA below adds: the sum of an integer and f * kscale rounds to that integer plus
+        // rint(f * kscale); a tie would need f * kscale to be a half-integer exactly, which its 77-bit product with
+        // 2^44 / (2 pi sample_rate) never is) and added as integers — no serial chain of 16 DFMAs.
+        u64 sum = 0;
+        // (f as a double by integer instructions: this pass is bound by the conversion unit, the ALU is idle)
+        UNROLL for (int j = 0; j < LS; j++)
+            sum += (u64)__double_as_longlong(fma(f32_to_f64_alu(f[j]), sk.kscale, 6755399441055744.0));
+        p += sum;  // the magic bits above the 44 phase bits are dropped by whoever reads p
         return;
     }
     // One DFMA per sample adds f * kscale to the running phase and rounds the sum to 2^-44 turns (pd_make).
@@ -916,7 +934,7 @@ __device__ __forceinline__ void fm_carrier_tile(float (&car)[LS], double& S, dou
 #if TB_ABL == 2
         car[j] = __uint_as_float(pd_m23(T0)); car[j + 1] = __uint_as_float(pd_m23(T1));
 #else
-        sin_m23x2(pd_m23(T0), pd_m23(T1), car[j], car[j + 1]);
+        if (!PHASE_ONLY) sin_m23x2(pd_m23(T0), pd_m23(T1), car[j], car[j + 1]);
 #endif
     }
     p = pd_bits(Pd);
@@ -1121,10 +1139,37 @@ __device__ __forceinline__ void run_fm_voice(const tb_insn* code, LaneMem& M, co
     }
 }
 
+// The summary pass of a time-axis split of a fused FM voice (abi.cpp render_split_fm): only the carrier's phase
+// sum matters — the modulator's tile, the affine map and the phase steps; no sines, no filter, no rows (a third of
+// the full tile's instructions).  After `snap_tile` tiles the accumulator so far is recorded in *snap: the phase
+// at the point where the NEXT segment's filter warm-up starts.
+template <bool SLOW>
+__device__ __forceinline__ void run_fm_sums(const tb_insn* code, LaneMem& M, const SineK& sk, bool active, u64 n_tiles,
+                                            u64 snap_tile, unsigned long long* snap) {
+    if (!active) return;
+    const tb_insn w0 = code[0], w1 = code[1];
+    const double2* rot = reinterpret_cast<const double2*>(M.Q + (size_t)((w0.op >> 8) & 0xffu) * LT);
+    double S = ldd(M, w0.a), Cq = ldd(M, w0.a + 2);
+    const float m = ldf(M, w1.a), c = ldf(M, w1.b);
+    const u64 mm = pk2(m, m), cc = pk2(c, c);
+    const u64 acc0 = ld64(M, w0.b);
+    const u64 p_start = (acc0 + ld64(M, w0.c)) >> 20;
+    u64 p = p_start;
+    const FmRot rr = fm_rot_load(rot);
+    float car[LS];
+    for (u64 t = 0; t < n_tiles; t++) {
+        if (t == snap_tile && snap) *snap = acc0 + ((p - p_start) << 20);
+        fm_carrier_tile<SLOW, false, true>(car, S, Cq, rot, rr, mm, cc, p, sk);
+    }
+    if (n_tiles == snap_tile && snap) *snap = acc0 + ((p - p_start) << 20);
+    st64(M, w0.b, acc0 + ((p - p_start) << 20));
+}
+
 // One unit of work: the 64 voices of `group`, samples [s0, s0 + ns) of the launch (multiples of TB_LS).
+//   SUMS: the summary kernel of lanes_fm_split.cu (run_fm_sums).
 //   FM_ONLY: the kernels of lanes_fm.cu, launched by the host only for a program that is one fused FM
 //   voice (run_fm_voice; no interpreter in the kernel).
-template <bool MIX, bool FM_ONLY>
+template <bool MIX, bool FM_ONLY, bool SUMS = false>
 __device__ __forceinline__ void lanes_body(const tb_launch& P, uint32_t group, u64 s0, u64 ns, bool accumulate) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int t = threadIdx.x, l = t & 31, warp = t >> 5;
@@ -1164,10 +1209,10 @@ __device__ __forceinline__ void lanes_body(const tb_launch& P, uint32_t group, u
     sk.plimit = 600.0f;
 
     // the voice's state block; with the time-axis split (tb_launch::vsplit*) that of its segment
-    const size_t vidx = TB_LANES_VSPLIT ? (size_t)(voice >> P.vsplit_log2) * P.vsplit_total + P.vseg_lo +
-                                              (voice & ((1u << P.vsplit_log2) - 1u))
-                                        : (size_t)voice;
-    const uint32_t rvoice = TB_LANES_VSPLIT ? voice >> P.vsplit_log2 : voice;  // parameters and noise streams
+    // (the summary kernel stores no rows and takes any number of segments: its launches leave out the last one)
+    const uint32_t rvoice = !TB_LANES_VSPLIT ? voice : (SUMS ? voice / P.vsplit : voice >> P.vsplit_log2);  // parameters, noise
+    const uint32_t vseg_i = !TB_LANES_VSPLIT ? 0u : P.vseg_lo + (SUMS ? voice - rvoice * P.vsplit : voice & ((1u << P.vsplit_log2) - 1u));
+    const size_t vidx = TB_LANES_VSPLIT ? (size_t)rvoice * P.vsplit_total + vseg_i : (size_t)voice;
     uint32_t* gstate = P.state + vidx * P.state_words;
     if (active) {
         // ld.cg: with the work queue the block was last written by another CTA, possibly on another SM
@@ -1202,11 +1247,18 @@ __device__ __forceinline__ void lanes_body(const tb_launch& P, uint32_t group, u
     R.off = 0;
     // Rows that are not 16-byte aligned (odd strides) take four scalar stores per lane instead.
     R.vec_ok = (reinterpret_cast<uintptr_t>(P.out) & 15) == 0 && (P.out_stride & 3) == 0;
-    R.fast = R.vec_ok && P.out != nullptr && v0 + 32u <= P.n_voices;
+    R.fast = R.vec_ok && P.out != nullptr && v0 + 32u <= P.n_voices && (!TB_LANES_VSPLIT || (P.vseg & 3) == 0);
     R.mix = MIX ? P.mix_partial + (size_t)(v0 >> 5) * P.mix_stride + s0 : nullptr;
     R.sl2 = TB_LANES_VSPLIT ? P.vsplit_log2 : 0u;
     R.seg_lo = TB_LANES_VSPLIT ? P.vseg_lo : 0u;
     R.vseg = TB_LANES_VSPLIT ? (size_t)P.vseg : 0;
+    R.rowoff = nullptr;
+#if TB_LANES_VSPLIT
+    __shared__ unsigned long long rowoff_s[LT];  // the CTA's rows: offset of each one's first sample of this launch
+    rowoff_s[t] = (unsigned long long)rvoice * P.out_stride + (unsigned long long)vseg_i * P.vseg;
+    __syncthreads();
+    R.rowoff = rowoff_s + warp * 32;
+#endif
     const bool warp_live = __any_sync(FULL, active);
     const uint32_t code_s = (uint32_t)__cvta_generic_to_shared(code);
     const u64 n_tiles = ns / (u64)LS;
@@ -1221,7 +1273,11 @@ __device__ __forceinline__ void lanes_body(const tb_launch& P, uint32_t group, u
     }
     const int rem = (int)(ns % (u64)LS);  // only the fused FM voice is launched with samples beyond whole tiles
     if (warp_live || (MIX && v0 < P.n_voices)) {  // a warp without a live voice still owes its (zero) partial sums
-        if (fm_program) {
+        if (fm_program && SUMS) {
+            unsigned long long* snap = P.vsnap ? P.vsnap + vidx : nullptr;
+            if (!fm_slow) run_fm_sums<false>(code, M, sk, active, n_tiles, P.vsnap_at / (u64)LS, snap);
+            else run_fm_sums<true>(code, M, sk, active, n_tiles, P.vsnap_at / (u64)LS, snap);
+        } else if (fm_program) {
             const bool tail = code[1].c >= 0;
             if (!fm_slow) {
                 if (tail) run_fm_voice<true, MIX, false>(code, M, sk, R, active, l, n_tiles, rem, prime);

@@ -13,7 +13,15 @@
 extern "C" __global__ void __maxnreg__(TB_FM_MAXNREG)
 tb_render_lanes_fm_split_kernel(const tb_launch P) { lanes_body<false, true>(P, blockIdx.x, 0, P.n_samples, P.accumulate != 0); }
 
-extern "C" void tb_lanes_fm_split_kernels(const void** plain) { *plain = (const void*)tb_render_lanes_fm_split_kernel; }
+// The summary pass (lanes.cuh run_fm_sums): phase sums only.
+extern "C" __global__ void __maxnreg__(TB_FM_MAXNREG)
+tb_render_lanes_fm_sums_kernel(const tb_launch P) { lanes_body<false, true, true>(P, blockIdx.x, 0, P.n_samples, P.accumulate != 0); }
+
+extern "C" void tb_lanes_fm_split_kernels(const void** plain, const void** sums) {
+    *plain = (const void*)tb_render_lanes_fm_split_kernel;
+    *sums = (const void*)tb_render_lanes_fm_sums_kernel;
+}
 extern "C" void tb_lanes_fm_split_run(const tb_launch* P, uint32_t grid, size_t smem, cudaStream_t stream) {
-    tb_render_lanes_fm_split_kernel<<<grid, LT, smem, stream>>>(*P);
+    if (P->fm_sums) tb_render_lanes_fm_sums_kernel<<<grid, LT, smem, stream>>>(*P);
+    else tb_render_lanes_fm_split_kernel<<<grid, LT, smem, stream>>>(*P);
 }

@@ -325,4 +325,7 @@ struct tb_launch {
     uint32_t vseg_lo;      // first segment of this launch
     uint64_t vseg;         // samples per segment
     uint32_t state_only;   // render for the final state alone (a summary pass): out == NULL is not "mixdown"
+    uint32_t fm_sums;      // fused FM voice, summary pass: the carrier's phase sum alone (lanes.cuh run_fm_sums)
+    unsigned long long* vsnap;  // ... which records the accumulator after vsnap_at samples in vsnap[state block]
+    uint64_t vsnap_at;
 };

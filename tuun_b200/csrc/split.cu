@@ -268,6 +268,59 @@ __global__ void __launch_bounds__(32) split_fix_kernel(const tb_split_args A, ui
     }
 }
 
+// ---- fused FM voice with a biquad: filter histories by warm-up (abi.cpp render_split_fm) ---------------------
+// How many samples until a biquad's zero-input response has decayed below 1e-11 of where it started: the filter's
+// history at a segment's start then follows, to f32 precision, from rendering that many samples before it from
+// ZERO history — no summary pass over the whole segment.  Poles of 1 + a1 z^-1 + a2 z^-2; the bound leaves room
+// for the 1 / sin(pole angle) a resonant pair's response carries (35 for a 200 Hz pair at 44.1 kHz).
+__global__ void split_fm_need_kernel(const tb_split_args A) {
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= A.n_real) return;
+    const tb_filter_tab* ft = &A.filt[A.entries[A.fm_filter].a];
+    const float* cv = A.cval + (size_t)v * A.n_cval;
+    const double a1 = (double)cv[~ft->coef[ft->K]], a2 = (double)cv[~ft->coef[ft->K + 1]];
+    const double disc = a1 * a1 - 4.0 * a2;
+    double r;
+    if (disc < 0.0) r = sqrt(a2);
+    else r = 0.5 * (fabs(a1) + sqrt(disc));
+    uint32_t need = 0xffffffffu;
+    if (r < 0.9999 && r == r) need = r <= 1e-3 ? 16u : (uint32_t)ceil(log(1e-11) / log(r));
+    atomicMax(A.warm_need, need);
+}
+// The state a segment's warm-up starts from, `warm` samples before the segment: positions and constant-rate sines
+// moved back analytically, the carrier's accumulator = (true start of the PREVIOUS segment) + (what that segment
+// had added `seg - warm` samples in, from the summary pass's snapshot), the filter with zero history.
+__global__ void split_fm_warm_seed_kernel(const tb_split_args A) {
+    const uint32_t vv = blockIdx.x * blockDim.x + threadIdx.x;
+    if (vv >= A.n_real * A.n_seg) return;
+    const uint32_t v = vv / A.n_seg, s = vv - v * A.n_seg;
+    const uint32_t* src = A.vi + (size_t)vv * A.state_words;
+    uint32_t* dst = A.vw + (size_t)vv * A.state_words;
+    for (uint32_t k = 0; k < A.state_words; k++) dst[k] = src[k];
+    if (s == 0) return;  // the first segment starts from the voice's own state: its warm-up result is not used
+    for (uint32_t k = 0; k < A.n_entries; k++) {
+        const tb_split_entry e = A.entries[k];
+        if (e.kind == SP_POS || e.kind == SP_SINE_CONST)
+            stu64(dst, e.state_off, ldu64(dst, e.state_off) - A.inc[(size_t)v * A.n_entries + k] * A.warm);
+    }
+    const tb_split_entry ec = A.entries[A.fm_carrier], ef = A.entries[A.fm_filter];
+    const u64 guess = ldu64(A.real_state + (size_t)v * A.state_words, ec.state_off);  // what every segment of the summary pass started from
+    const u64 prev_start = ldu64(A.vi + (size_t)(vv - 1) * A.state_words, ec.state_off);
+    stu64(dst, ec.state_off, prev_start + (A.snap[vv - 1] - guess));
+    const tb_filter_tab* ft = &A.filt[ef.a];
+    for (uint32_t k = 0; k < ft->K - 1 + ft->J; k++) dst[ef.state_off + 2 + k] = 0u;
+}
+// The warm-up's final filter history is the segment's initial one.
+__global__ void split_fm_adopt_kernel(const tb_split_args A) {
+    const uint32_t vv = blockIdx.x * blockDim.x + threadIdx.x;
+    if (vv >= A.n_real * A.n_seg) return;
+    if (vv % A.n_seg == 0) return;
+    const tb_split_entry ef = A.entries[A.fm_filter];
+    const tb_filter_tab* ft = &A.filt[ef.a];
+    for (uint32_t k = 0; k < ft->K - 1 + ft->J; k++)
+        A.vi[(size_t)vv * A.state_words + ef.state_off + 2 + k] = A.vw[(size_t)vv * A.state_words + ef.state_off + 2 + k];
+}
+
 // The voice's state is the final state of its last segment; out_len (+)= what the split rendered.
 __global__ void split_finish_kernel(const tb_split_args A, uint32_t* real_state, unsigned long long* out_len,
                                     unsigned long long n, int accumulate) {
@@ -289,6 +342,20 @@ extern "C" cudaError_t tb_split_seed(const tb_split_args* A, cudaStream_t stream
 }
 extern "C" cudaError_t tb_split_fix(const tb_split_args* A, uint32_t level, cudaStream_t stream) {
     split_fix_kernel<<<A->n_real, 32, 0, stream>>>(*A, level);
+    return cudaGetLastError();
+}
+extern "C" cudaError_t tb_split_fm_need(const tb_split_args* A, cudaStream_t stream) {
+    split_fm_need_kernel<<<(A->n_real + 127) / 128, 128, 0, stream>>>(*A);
+    return cudaGetLastError();
+}
+extern "C" cudaError_t tb_split_fm_warm_seed(const tb_split_args* A, cudaStream_t stream) {
+    const uint32_t nv = A->n_real * A->n_seg;
+    split_fm_warm_seed_kernel<<<(nv + 127) / 128, 128, 0, stream>>>(*A);
+    return cudaGetLastError();
+}
+extern "C" cudaError_t tb_split_fm_adopt(const tb_split_args* A, cudaStream_t stream) {
+    const uint32_t nv = A->n_real * A->n_seg;
+    split_fm_adopt_kernel<<<(nv + 127) / 128, 128, 0, stream>>>(*A);
     return cudaGetLastError();
 }
 extern "C" cudaError_t tb_split_finish(const tb_split_args* A, uint32_t* real_state, unsigned long long* out_len,
