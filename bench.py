@@ -222,6 +222,7 @@ def time_shard_record(args, world, rank, local, barrier, peak):
     own TIME range of every voice (tb_segments_*: one all-gather of the segments' state blocks per pass over
     NCCL).  At N = 1 this is what tb_render does by itself for a small batch."""
     import torch
+    import torch.distributed as dist
     from tuun_b200.generator import Program
     from tuun_b200.sharding import plan_segments, render_time_sharded
     from tuun_b200.workloads import fm_filter_params, fm_filter_sample_ids, fm_filter_voice
@@ -249,9 +250,27 @@ def time_shard_record(args, world, rank, local, barrier, peak):
     samples = head + S * seg
     value = V * samples * steps / (ms * 1e-3)
     words = prog.info.state_words
+    # what this rank rendered against the same voices rendered serially (no split of any kind) on this rank
+    os.environ["TUUN_B200_SPLIT"] = "0"
+    try:
+        ser = Program(fm_filter_voice(), SAMPLE_RATE, device=local)
+        full = torch.empty((V, samples), dtype=torch.float32, device="cuda")
+        ser.render(full, params=params)
+        torch.cuda.synchronize()
+    finally:
+        del os.environ["TUUN_B200_SPLIT"]
+    lo = head + rank * (S // world) * seg
+    diff = (full[:, lo:lo + (S // world) * seg] - out).abs().amax(dim=1)
+    dmax = torch.tensor([float(diff.max()), float(diff.median())], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(dmax, op=dist.ReduceOp.MAX)
+    del full, ser
     return {"value": value, "unit": UNIT, "ms_per_step": ms / steps, "voices": V, "samples_per_voice": samples,
             "segments": S, "segment_samples": seg, "passes": passes[0],
             "exchange_bytes_per_pass_per_rank": int(V * (S // world) * words * 4),
+            "max_abs_diff_vs_serial": float(dmax[0].item()), "median_voice_diff_vs_serial": float(dmax[1].item()),
+            "diff_note": "every rank's time range against the same 64 voices rendered serially on that rank (max over ranks); "
+                         "the difference is the biquads' round-off noise (affine scan vs serial recurrence)",
             "hbm_frac_per_gpu": 4.0 * V * samples / world / (ms / steps * 1e-3) / 1e9 / peak,
             "sharding": "time: rank r renders segments [r S/N, (r+1) S/N) of every voice; states all-gathered per pass"}
 
@@ -328,6 +347,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the renderer has no CPU path")
     torch.cuda.set_device(local)
+    from tuun_b200.sharding import bind_to_gpu_numa
+    numa = bind_to_gpu_numa(local) if world > 1 else {"numa_node": None}
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_samples = int(round(args.seconds * SAMPLE_RATE))
@@ -490,7 +511,7 @@ def main():
                "d2h_ceiling_how": "the same rows copied device -> the same pinned window with cudaMemcpyAsync alone, all ranks "
                                   "at once, same run",
                "h2d_bytes_per_step": int(n_local * 8 * 4), "d2h_bytes_per_step": int(n_local * n_samples * 4 + n_local * 8),
-               "voices": n_total, "steps": e2e_steps, "host_window_rows": grp,
+               "voices": n_total, "steps": e2e_steps, "host_window_rows": grp, "numa": numa,
                "path": "tb_render with pinned host rows: voice groups rendered into 2 device staging buffers, "
                        "each group leaves with one cudaMemcpyAsync on a second stream while the next renders"}
         del host, host_np, prog_h

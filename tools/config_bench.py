@@ -31,7 +31,11 @@ def shapes():
            ("cfg2 harmonica x4", W.cfg2_harmonica(4), 100000)]
     out += [("cfg3 " + name, w, 441000) for name, w in W.cfg3_fm_variations()]
     out += [("cfg4 " + name, w, 60 * SR) for name, w in W.cfg4_filters()]
-    out += [("bench " + name, w, blocks * 1024) for name, w, blocks in W.tracker_benches()]
+    tb = W.tracker_benches()
+    out += [("bench " + name, w, blocks * 1024) for name, w, blocks in tb]
+    # the criterion shapes run for 1 s (43 blocks): a render that short is mostly launch latency on a GPU, so the
+    # two constant-coefficient ones are also shown at config 4's length
+    out += [("bench " + name + " x 60 s", w, 60 * SR) for name, w, _ in tb if name in ("filter_1_1", "filter_4_3")]
     return out
 
 

@@ -236,6 +236,49 @@ __device__ __forceinline__ void iir_serial_exact(float (&acc)[C], const float (&
     }
 }
 
+// Feedback with coefficient WAVEFORMS (generator.rs:467-507: one value per output sample; filter_1_1_linear of
+// benches/tracker_benches.rs:36-67): the same lane-after-lane recurrence, every lane holding its own samples of
+// every coefficient in registers.  (The general form below — one lane walking the tile through shared memory —
+// remains for more than four feedback taps.)
+template <int J>
+__device__ __forceinline__ void iir_serial_varying(float (&acc)[C], const float (&u)[C], const float (&a)[J][C],
+                                                   const float* hy, int w0, int out_len) {
+    const int l = lane_id();
+    float s[J];
+    UNROLL for (int jj = 0; jj < J; jj++) s[jj] = hy[J - 1 - jj];
+    UNROLL for (int j = 0; j < C; j++) acc[j] = u[j];
+    _Pragma("unroll 1") for (int L = 0; L < 32; L++) {
+        if (l == L) {
+            UNROLL for (int j = 0; j < C; j++) {
+                const int i = l * C + j;
+                if (i >= w0 && i < w0 + out_len) {
+                    float y = u[j];
+                    UNROLL for (int jj = 0; jj < J; jj++) y = __fsub_rn(y, __fmul_rn(a[jj][j], s[jj]));
+                    UNROLL for (int jj = J - 1; jj > 0; jj--) s[jj] = s[jj - 1];
+                    s[0] = y;
+                    acc[j] = y;
+                }
+            }
+        }
+        UNROLL for (int jj = 0; jj < J; jj++) s[jj] = __shfl_sync(FULL, s[jj], L);
+    }
+}
+template <int J>
+__device__ __forceinline__ void iir_varying(const WarpMem& M, const tb_filter_tab* ft, float (&acc)[C], const float (&u)[C],
+                                            const float* hy, int w0, int out_len) {
+    float a[J][C];
+    UNROLL for (int jj = 0; jj < J; jj++) {
+        const int oj = ft->coef[ft->K + jj];
+        if (oj < 0) {
+            const float c = M.cval[~oj];
+            UNROLL for (int j = 0; j < C; j++) a[jj][j] = c;
+        } else {
+            slot_load(M.slots, oj, a[jj]);
+        }
+    }
+    iir_serial_varying<J>(acc, u, a, hy, w0, out_len);
+}
+
 // Full-tile fast path of the constant-coefficient filter: window = whole tile, history complete,
 // nothing finishing.  Same arithmetic as filter_run below without any per-sample window test.
 template <int J>
@@ -437,8 +480,16 @@ __device__ void filter_run(const tb_launch& P, const WarpMem& M, Ctx& cx, float 
             case 3: iir_scan_const<3>(acc, u, a, mp, hy, w0, out_len); break;
             default: iir_scan_const<4>(acc, u, a, mp, hy, w0, out_len); break;
         }
+    } else if (J <= TB_MAX_J) {
+        // Time-varying feedback coefficients: the recurrence lane after lane, coefficients in registers.
+        switch (J) {
+            case 1: iir_varying<1>(M, ft, acc, u, hy, w0, out_len); break;
+            case 2: iir_varying<2>(M, ft, acc, u, hy, w0, out_len); break;
+            case 3: iir_varying<3>(M, ft, acc, u, hy, w0, out_len); break;
+            default: iir_varying<4>(M, ft, acc, u, hy, w0, out_len); break;
+        }
     } else {
-        // Time-varying feedback coefficients: serial recurrence by lane 0 over the tile.
+        // ... with more than four taps: serial recurrence by lane 0 over the tile, through shared memory.
         float* us = M.slots + (size_t)ft->u_slot * TILE;
         slot_store(M.slots, ft->u_slot, u);
         __syncwarp();

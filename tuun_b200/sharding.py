@@ -201,3 +201,34 @@ def render_time_sharded(program, out_local, n_voices: int, n_segments: int, seg_
             ts.fix(k)
     ts.end()
     return ts.passes
+
+
+def bind_to_gpu_numa(local_rank: int) -> dict:
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (Linux sysfs), BEFORE it allocates pinned
+    host buffers: pinned pages are then first-touched on that node and device-to-host copies do not cross the
+    socket interconnect.  With 8 ranks draining rows over PCIe at once the host side is the bottleneck
+    (bench.py e2e).  Returns what it found; a missing sysfs entry or a single-node box leaves the affinity alone."""
+    import os
+    info = {"numa_node": None, "cpus": None}
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        info["numa_node"] = node
+        if node < 0:
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info["cpus"] = len(allowed)
+    except Exception as e:  # noqa: BLE001 — best effort: the render does not depend on it
+        info["error"] = str(e)[:80]
+    return info
