@@ -238,6 +238,11 @@ typedef struct tb_program_info {
     uint32_t split_segments;  /* S of the first (largest) round of the most recent split call; 0: no call was split yet */
     uint64_t split_seg_samples; /* samples per segment of that round */
     uint64_t split_rounds;    /* split rounds so far */
+    /* a root sequence — Append(Fin{len, a}, Append(Fin{len', b}, ..)) with analytic, voice-independent lengths: what
+       `<[a, b, ..]>` evaluates to — is held as one program per part, each rendered where it starts */
+    uint32_t sequence_parts;  /* 0: the tree is one program */
+    uint32_t reserved0;
+    uint64_t sequence_renders; /* generate launches that went part by part */
 } tb_program_info;
 int tb_program_get_info(const tb_program* p, tb_program_info* info);
 

@@ -53,6 +53,9 @@ pub struct TbProgramInfo {
     pub split_segments: u32,
     pub split_seg_samples: u64,
     pub split_rounds: u64,
+    pub sequence_parts: u32,
+    pub reserved0: u32,
+    pub sequence_renders: u64,
 }
 
 pub const TB_OUT_DEVICE: u32 = 1;

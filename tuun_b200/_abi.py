@@ -52,6 +52,9 @@ class TbProgramInfo(ctypes.Structure):
         ("split_segments", ctypes.c_uint32),
         ("split_seg_samples", ctypes.c_uint64),
         ("split_rounds", ctypes.c_uint64),
+        ("sequence_parts", ctypes.c_uint32),
+        ("reserved0", ctypes.c_uint32),
+        ("sequence_renders", ctypes.c_uint64),
     ]
 
 

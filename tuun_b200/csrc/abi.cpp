@@ -23,6 +23,8 @@ extern "C" cudaError_t tb_kernel_launch(const tb_launch* P, size_t smem, uint32_
 extern "C" size_t tb_lanes_smem_bytes(uint32_t n_lane_code, uint32_t w_words, uint32_t q_units, uint32_t slots);
 extern "C" cudaError_t tb_lanes_launch(const tb_launch* P, size_t smem, int kind, cudaStream_t stream);
 extern "C" cudaError_t tb_lanes_occupancy(size_t smem, int kind, int* blocks_per_sm, int* n_sm);
+extern "C" cudaError_t tb_len_set(unsigned long long* out_len, uint32_t n, unsigned long long add, int accumulate,
+                                  cudaStream_t stream);
 extern "C" cudaError_t tb_mix_launch(const float* rows, uint64_t stride, const unsigned long long* lens,
                                      uint32_t n_voices, uint64_t n_samples, uint64_t t0, float* mix,
                                      int accumulate, cudaStream_t stream);
@@ -57,6 +59,7 @@ int upload(const std::vector<T>& v, T** dst) {
 
 struct tb_program {
     tb::Lowered low;
+    std::vector<uint32_t> noise_ids;  // a part of a sequence: the numbers of its nodes in the whole tree
     std::vector<tb_node> nodes;   // the op list as given (tb_substitute re-lowers it)
     std::vector<int32_t> lists;
     uint64_t fixed_len = 0;
@@ -105,6 +108,13 @@ struct tb_program {
     uint64_t launches = 0;
     uint64_t noise_seed = 0x7475756E2545F491ull, noise_first_voice = 0;  // tb_seed_noise
     uint32_t fast_mode = 2;  // FAST-class sines: 1 = f32 polynomial, 2 = MUFU (TUUN_B200_FAST_SINES)
+    // A root sequence (lower.h sequence_parts): every part is a program of its own, rendered where it starts.
+    std::vector<tb_program*> part_prog;
+    std::vector<uint64_t> part_len;   // samples; ~0 for the last part
+    uint64_t seq_renders = 0;         // generate launches that went part by part
+    static constexpr int kSeqStreams = 16;  // the parts of one call are independent streams: rendered side by side
+    cudaStream_t seq_stream[kSeqStreams] = {};
+    cudaEvent_t seq_fork = nullptr, seq_join[kSeqStreams] = {};
     // time-axis split (split.cu): per-segment state blocks and scratch, grown on demand
     tb_split_entry* d_split = nullptr;
     uint32_t* d_vs = nullptr;
@@ -129,7 +139,13 @@ struct tb_program {
     uint64_t split_last_seg_samples = 0;
 
     ~tb_program() {
+        for (tb_program* q : part_prog) delete q;
         cudaSetDevice(device);
+        for (int i = 0; i < kSeqStreams; i++) {
+            if (seq_stream[i]) cudaStreamDestroy(seq_stream[i]);
+            if (seq_join[i]) cudaEventDestroy(seq_join[i]);
+        }
+        if (seq_fork) cudaEventDestroy(seq_fork);
         cudaFree(d_code); cudaFree(d_cexpr); cudaFree(d_aux); cudaFree(d_goe); cudaFree(d_goe_steps);
         cudaFree(d_filt); cudaFree(d_fixed); cudaFree(d_pool); cudaFree(d_state); cudaFree(d_params);
         cudaFree(d_len); cudaFree(d_done); cudaFree(d_mix); cudaFree(d_stage[0]); cudaFree(d_stage[1]);
@@ -692,7 +708,73 @@ int render_split_fm(tb_program* p, const tb_launch& L, const SplitPlan& plan, ui
 
 // A generate launch: split in time when that pays (rounds of S segments until what is left is short), else
 // — and for the head tile of a stream and the rest — the serial form.
+int launch_generate(tb_program* p, const tb_launch& L, uint64_t pos);
+// A root sequence, part by part: part k is a stream of its own that starts at sample start_k = len_0 + .. + len_(k-1) of
+// the voice's stream (the second arm of an Append starts from Initial state, generator.rs:169-188), so the samples
+// [pos, pos + n) of the call belong to the parts they overlap, each rendered by its own (much smaller) program from
+// its own carried state.  `pos` is the same for every voice: the lengths are analytic and voice-independent.
+int launch_sequence(tb_program* p, const tb_launch& L, uint64_t pos) {
+    const uint64_t v0 = (uint64_t)(L.state - p->d_state) / p->low.state_words;  // first voice of this launch in the batch
+    // the parts this call overlaps
+    struct Piece { size_t k; uint64_t a, b, start; };
+    std::vector<Piece> pieces;
+    uint64_t start = 0;
+    for (size_t k = 0; k < p->part_prog.size(); k++) {
+        const uint64_t len = p->part_len[k];
+        const uint64_t end = len == ~0ull ? ~0ull : start + len;
+        const uint64_t a = std::max(pos, start), b = std::min(pos + L.n_samples, end);
+        if (a < b) pieces.push_back(Piece{k, a, b, start});
+        if (end == ~0ull || end >= pos + L.n_samples) break;
+        start = end;
+    }
+    if (pieces.empty()) return TB_OK;
+    int rc = TB_OK;
+    // Every part but the last one of the call fills its share whole (its Fin cannot end early), so out_len is what lies in
+    // front of the last one plus what that one generates: set the former here, let the last part add.
+    if (L.out_len) {
+        cudaError_t e = tb_len_set(L.out_len, L.n_voices, pieces.back().a - pos, L.accumulate ? 1 : 0, p->stream);
+        if (e != cudaSuccess) return cuda_fail(e, "tb_len_set");
+        p->launches++;
+    }
+    CU(cudaEventRecord(p->seq_fork, p->stream));  // parameters staged, earlier renders done
+    bool used[tb_program::kSeqStreams] = {};
+    for (const Piece& pc : pieces) {
+        tb_program* q = p->part_prog[pc.k];
+        const int si = (int)(pc.k % tb_program::kSeqStreams);
+        q->noise_seed = p->noise_seed;
+        q->noise_first_voice = p->noise_first_voice;
+        if (!used[si]) CU(cudaStreamWaitEvent(q->stream, p->seq_fork, 0));
+        used[si] = true;
+        if ((rc = ensure_voices(q, p->n_voices))) return rc;
+        tb_launch Q;
+        fill_launch(q, &Q);
+        Q.params = L.params;
+        Q.n_params = L.n_params;
+        Q.n_voices = L.n_voices;
+        Q.voice_base = L.voice_base;
+        Q.state = q->d_state + v0 * q->low.state_words;
+        Q.out = L.out ? L.out + (pc.a - pos) : nullptr;
+        Q.out_stride = L.out_stride;
+        Q.out_len = &pc == &pieces.back() ? L.out_len : nullptr;
+        Q.done = L.done;
+        Q.mode = 0;
+        Q.n_samples = pc.b - pc.a;
+        Q.accumulate = 1;
+        Q.mid_call = (L.mid_call && pc.a == pos) ? 1u : 0u;
+        Q.call_pos = L.call_pos + (pc.a - pos);
+        if ((rc = launch_generate(q, Q, pc.a - pc.start))) return rc;
+    }
+    for (int si = 0; si < tb_program::kSeqStreams; si++) {
+        if (!used[si]) continue;
+        CU(cudaEventRecord(p->seq_join[si], p->seq_stream[si]));
+        CU(cudaStreamWaitEvent(p->stream, p->seq_join[si], 0));
+    }
+    p->seq_renders++;
+    return TB_OK;
+}
+
 int launch_generate(tb_program* p, const tb_launch& L, uint64_t pos) {
+    if (!p->part_prog.empty() && p->pos_known && L.mode == 0) return launch_sequence(p, L, pos);
     if (p->low.split_passes == 0 || !p->pos_known) return launch_generate_seq(p, L, pos);
     // The first tile of a stream stays on the serial form: filter pre-reads (generator.rs:234-252).  (A program
     // without filters is steady from its first sample, and so are its segments — except under a Reset: its trigger
@@ -808,9 +890,61 @@ extern "C" {
 uint32_t tb_abi_version(void) { return TB_ABI_VERSION; }
 const char* tb_last_error(void) { return g_error.c_str(); }
 
+static int create_program(const tb_node* nodes, uint32_t n_nodes, const int32_t* lists, uint32_t n_lists,
+                          const float* fixed_pool, uint64_t fixed_len, uint32_t sample_rate, int device,
+                          tb_program** out_program, const uint32_t* noise_ids, bool allow_sequence);
+
 int tb_program_create(const tb_node* nodes, uint32_t n_nodes, const int32_t* lists, uint32_t n_lists,
                       const float* fixed_pool, uint64_t fixed_len, uint32_t sample_rate, int device,
                       tb_program** out_program) {
+    return create_program(nodes, n_nodes, lists, n_lists, fixed_pool, fixed_len, sample_rate, device, out_program, nullptr,
+                          true);
+}
+
+// The subtree rooted at `root` as an op list of its own (children before parents, Filter lists re-based); ids[i] =
+// index the new node i had in the whole list (the number of its Noise stream).
+static void extract_subtree(const std::vector<tb_node>& nodes, const std::vector<int32_t>& lists, int root,
+                            std::vector<tb_node>& sub, std::vector<int32_t>& sub_lists, std::vector<uint32_t>& ids) {
+    std::vector<char> in(nodes.size(), 0);
+    std::vector<int> stack{root};
+    while (!stack.empty()) {
+        const int i = stack.back();
+        stack.pop_back();
+        if (in[i]) continue;
+        in[i] = 1;
+        const tb_node& n = nodes[i];
+        for (int c : {n.a, n.b, n.c})
+            if (c >= 0 && n.kind != TB_CONST && n.kind != TB_TIME && n.kind != TB_NOISE && n.kind != TB_FIXED) stack.push_back(c);
+        if (n.kind == TB_FILTER)
+            for (uint32_t j = 0; j < n.ff_count + n.fb_count; j++) stack.push_back(lists[n.list_off + j]);
+    }
+    std::vector<int> map(nodes.size(), -1);
+    sub.clear();
+    sub_lists.clear();
+    ids.clear();
+    for (int i = 0; i <= root; i++) {
+        if (!in[i]) continue;
+        tb_node n = nodes[i];
+        const bool leaf = n.kind == TB_CONST || n.kind == TB_TIME || n.kind == TB_NOISE || n.kind == TB_FIXED;
+        if (!leaf) {
+            if (n.a >= 0) n.a = map[n.a];
+            if (n.b >= 0) n.b = map[n.b];
+            if (n.c >= 0) n.c = map[n.c];
+        }
+        if (n.kind == TB_FILTER) {
+            const uint32_t off = (uint32_t)sub_lists.size();
+            for (uint32_t j = 0; j < n.ff_count + n.fb_count; j++) sub_lists.push_back(map[lists[n.list_off + j]]);
+            n.list_off = off;
+        }
+        map[i] = (int)sub.size();
+        sub.push_back(n);
+        ids.push_back((uint32_t)i);
+    }
+}
+
+static int create_program(const tb_node* nodes, uint32_t n_nodes, const int32_t* lists, uint32_t n_lists,
+                          const float* fixed_pool, uint64_t fixed_len, uint32_t sample_rate, int device,
+                          tb_program** out_program, const uint32_t* noise_ids, bool allow_sequence) {
     if (!out_program) return set_error(TB_ERR_INVALID, "out_program is NULL");
     *out_program = nullptr;
     if (!nodes || n_nodes == 0) return set_error(TB_ERR_INVALID, "empty op list");
@@ -820,12 +954,13 @@ int tb_program_create(const tb_node* nodes, uint32_t n_nodes, const int32_t* lis
     if (!p) return set_error(TB_ERR_NOMEM, "out of host memory");
     const char* fs = std::getenv("TUUN_B200_FAST_SINES");
     const bool fast = !(fs && fs[0] == '0');
-    int rc = tb::lower(nodes, n_nodes, lists, n_lists, fixed_len, fast, p->low);
+    int rc = tb::lower(nodes, n_nodes, lists, n_lists, fixed_len, fast, p->low, noise_ids);
     if (rc != TB_OK) {
         std::string msg = p->low.error;
         delete p;
         return set_error(rc, msg);
     }
+    if (noise_ids) p->noise_ids.assign(noise_ids, noise_ids + n_nodes);
     p->nodes.assign(nodes, nodes + n_nodes);
     if (lists && n_lists) p->lists.assign(lists, lists + n_lists);
     p->fixed_len = fixed_len;
@@ -923,6 +1058,46 @@ int tb_program_create(const tb_node* nodes, uint32_t n_nodes, const int32_t* lis
             cudaGetLastError();
         }
     }
+    // A root sequence: one program per part (TUUN_B200_SEQ=0: the whole tree as one program, as for any other tree).
+    const char* sq = std::getenv("TUUN_B200_SEQ");
+    std::vector<tb::SeqPart> parts;
+    if (allow_sequence && !(sq && sq[0] == '0') &&
+        tb::sequence_parts(nodes, n_nodes, lists, n_lists, fixed_len, sample_rate, parts)) {
+        bool ok = true;
+        for (const tb::SeqPart& sp : parts) {
+            std::vector<tb_node> sub;
+            std::vector<int32_t> sub_lists;
+            std::vector<uint32_t> ids;
+            extract_subtree(p->nodes, p->lists, sp.root, sub, sub_lists, ids);
+            tb_program* q = nullptr;
+            if (create_program(sub.data(), (uint32_t)sub.size(), sub_lists.data(), (uint32_t)sub_lists.size(), fixed_pool,
+                               fixed_len, sample_rate, device, &q, ids.data(), false) != TB_OK) {
+                ok = false;
+                break;
+            }
+            cudaStreamSynchronize(q->stream);
+            if (q->own_stream) cudaStreamDestroy(q->stream);
+            q->own_stream = false;
+            const int si = (int)(p->part_prog.size() % tb_program::kSeqStreams);
+            if (!p->seq_stream[si] &&
+                (cudaStreamCreateWithFlags(&p->seq_stream[si], cudaStreamNonBlocking) != cudaSuccess ||
+                 cudaEventCreateWithFlags(&p->seq_join[si], cudaEventDisableTiming) != cudaSuccess)) {
+                delete q;
+                ok = false;
+                break;
+            }
+            q->stream = p->seq_stream[si];  // parts are independent streams: the ones a call overlaps render side by side
+            p->part_prog.push_back(q);
+            p->part_len.push_back(sp.len);
+        }
+        if (ok && cudaEventCreateWithFlags(&p->seq_fork, cudaEventDisableTiming) != cudaSuccess) ok = false;
+        if (!ok) {  // some part the device path does not take: the whole tree as one program, like before
+            for (tb_program* q : p->part_prog) delete q;
+            p->part_prog.clear();
+            p->part_len.clear();
+            g_error.clear();
+        }
+    }
     *out_program = p;
     return TB_OK;
 }
@@ -961,6 +1136,9 @@ int tb_lower_check(const tb_node* nodes, uint32_t n_nodes, const int32_t* lists,
         info->split_segments = 0;
         info->split_seg_samples = 0;
         info->split_rounds = 0;
+        info->sequence_parts = 0;
+        info->reserved0 = 0;
+        info->sequence_renders = 0;
     }
     return TB_OK;
 }
@@ -977,6 +1155,10 @@ int tb_program_get_info(const tb_program* p, tb_program_info* info) {
     info->n_params = p->low.n_params;
     info->kernel_launches = p->launches;
     info->lane_launches = p->lane_launches;
+    for (const tb_program* q : p->part_prog) {  // a sequence: what its parts launched
+        info->kernel_launches += q->launches;
+        info->lane_launches += q->lane_launches;
+    }
     info->lane_smem_bytes = (uint32_t)p->lane_smem;
     info->lane_min_voices = p->lane_min_voices;
     info->lane_capacity = p->lane_capacity;
@@ -985,6 +1167,10 @@ int tb_program_get_info(const tb_program* p, tb_program_info* info) {
     info->split_segments = p->split_last_segments;
     info->split_seg_samples = p->split_last_seg_samples;
     info->split_rounds = p->split_rounds;
+    info->sequence_parts = (uint32_t)p->part_prog.size();
+    info->reserved0 = 0;
+    info->sequence_renders = p->seq_renders;
+    for (const tb_program* q : p->part_prog) info->split_rounds += q->split_rounds;
     return TB_OK;
 }
 
@@ -997,7 +1183,7 @@ int tb_set_stream(tb_program* p, void* cuda_stream) {
     if (p->own_stream) cudaStreamDestroy(p->stream);
     p->stream = (cudaStream_t)cuda_stream;
     p->own_stream = false;
-    return TB_OK;
+    return TB_OK;  // (the parts of a sequence keep their own streams, forked from and joined to this one)
 }
 
 int tb_seed_noise(tb_program* p, uint64_t seed, uint64_t first_voice) {
@@ -1026,7 +1212,7 @@ int tb_substitute(tb_program* p, uint32_t mark_id, float value, uint32_t* n_repl
     // (a literal can decide the lowering only through is_const's Append(c, c) arm, generator.rs:597-603).
     tb::Lowered low;
     int rc = tb::lower(nodes.data(), (uint32_t)nodes.size(), p->lists.data(), (uint32_t)p->lists.size(), p->fixed_len,
-                       p->fast_sines, low);
+                       p->fast_sines, low, p->noise_ids.empty() ? nullptr : p->noise_ids.data());
     if (rc != TB_OK) return set_error(rc, low.error);
     const tb::Lowered& o = p->low;
     const bool same = low.code.size() == o.code.size() && low.cexpr.size() == o.cexpr.size() &&
@@ -1048,6 +1234,10 @@ int tb_substitute(tb_program* p, uint32_t mark_id, float value, uint32_t* n_repl
     low.lane_clk = o.lane_clk;
     p->low = std::move(low);
     p->nodes.swap(nodes);
+    for (tb_program* q : p->part_prog) {  // the parts of a sequence hold copies of their subtrees
+        uint32_t n = 0;
+        if ((rc = tb_substitute(q, mark_id, value, &n))) return rc;
+    }
     return TB_OK;
 }
 
@@ -1143,6 +1333,10 @@ int tb_reset(tb_program* p) {
     p->fresh = true;
     p->stream_pos = 0;
     p->pos_known = true;
+    for (tb_program* q : p->part_prog) {
+        int rc = tb_reset(q);
+        if (rc) return rc;
+    }
     return TB_OK;
 }
 
@@ -1345,6 +1539,46 @@ int tb_length(tb_program* p, const float* params, uint32_t n_params, uint32_t n_
     L.n_samples = max;
     L.out_len = p->d_len;
     L.mode = 1;
+    if (!p->part_prog.empty() && p->pos_known) {
+        // A root sequence (launch_sequence): length(Append(a, b), max) advances a, then b by what is left
+        // (generator.rs:705-722) — part by part, like generate.
+        uint64_t start = 0;
+        const uint64_t pos = p->stream_pos;
+        bool first = true;
+        for (size_t k = 0; k < p->part_prog.size(); k++) {
+            const uint64_t plen = p->part_len[k];
+            const uint64_t end = plen == ~0ull ? ~0ull : start + plen;
+            const uint64_t a = std::max(pos, start), b = std::min(pos + max, end);
+            if (a < b) {
+                tb_program* q = p->part_prog[k];
+                if ((rc = ensure_voices(q, n_voices))) return rc;
+                tb_launch Q;
+                fill_launch(q, &Q);
+                Q.params = d_params;
+                Q.n_params = n_params;
+                Q.n_voices = n_voices;
+                Q.n_samples = b - a;
+                Q.out_len = p->d_len;
+                Q.mode = 1;
+                Q.accumulate = first ? 0u : 1u;
+                q->pos_known = false;
+                // (on the part's own stream, ordered between what the program's stream did before and does next)
+                CU(cudaEventRecord(p->seq_fork, p->stream));
+                CU(cudaStreamWaitEvent(q->stream, p->seq_fork, 0));
+                if ((rc = launch(q, Q))) return rc;
+                const int si = (int)(k % tb_program::kSeqStreams);
+                CU(cudaEventRecord(p->seq_join[si], q->stream));
+                CU(cudaStreamWaitEvent(p->stream, p->seq_join[si], 0));
+                first = false;
+            }
+            if (end == ~0ull || end >= pos + max) break;
+            start = end;
+        }
+        p->stream_pos += max;
+        CU(cudaMemcpyAsync(len, p->d_len, (size_t)n_voices * 8, cudaMemcpyDeviceToHost, p->stream));
+        CU(cudaStreamSynchronize(p->stream));
+        return TB_OK;
+    }
     p->pos_known = false;  // length() advances positions by per-node amounts (generator.rs:620-782)
     if ((rc = launch(p, L))) return rc;
     CU(cudaMemcpyAsync(len, p->d_len, (size_t)n_voices * 8, cudaMemcpyDeviceToHost, p->stream));

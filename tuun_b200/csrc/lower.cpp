@@ -12,6 +12,7 @@
 #include "lower.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
@@ -28,6 +29,9 @@ struct Lowerer {
     uint64_t pool_len;
     Lowered& out;
     bool fast_sines;
+    const uint32_t* noise_ids = nullptr;  // node -> number of its Noise stream (a part of a sequence keeps the numbers
+                                          // its nodes have in the whole tree, lower.h sequence_parts); NULL: the index
+    int noise_id(int i) const { return noise_ids ? (int)noise_ids[i] : i; }
 
     std::vector<int> const_memo;   // node -> cval index, -2 = not computed, -1 = not const
     std::vector<int> state_off;    // node -> offset of its state block (or -1)
@@ -336,7 +340,7 @@ struct Lowerer {
             case TB_CONST: produced(emit(G_CONST, const_of(i))); break;
             case TB_TIME: produced(emit(G_TIME, state_of(i, 2))); break;
             case TB_FIXED: produced(emit(G_FIXED, state_of(i, 2), fixed_table(i))); break;
-            case TB_NOISE: produced(emit(G_NOISE, state_of(i, 2), i)); break;
+            case TB_NOISE: produced(emit(G_NOISE, state_of(i, 2), noise_id(i))); break;
             case TB_MARKED:
             case TB_CAPTURED: emit_gen(n.a); break;
             case TB_BINARY: {
@@ -821,7 +825,7 @@ struct Lowerer {
             case TB_NOISE:
                 if (seg_gated > 0)
                     fail(TB_ERR_UNSUPPORTED, "Noise under a Fin, an Append or a finite operand inside a Reset");
-                emit(S_NOISE, state_of(i, 2), i);
+                emit(S_NOISE, state_of(i, 2), noise_id(i));
                 break;
             case TB_FILTER: fail(TB_ERR_UNSUPPORTED, "Filter inside a Reset");
             case TB_APPEND: {
@@ -928,7 +932,7 @@ struct Lowerer {
                 out.lane_clk = 1;
                 return ok;
             }
-            case TB_NOISE: s_produced(emit(ST_NOISE, state_of(i, 2), i)); return true;
+            case TB_NOISE: s_produced(emit(ST_NOISE, state_of(i, 2), noise_id(i))); return true;
             case TB_MARKED:
             case TB_CAPTURED: return emit_steady(n.a);
             case TB_BINARY: {
@@ -1351,10 +1355,66 @@ struct Lowerer {
 
 }  // namespace
 
+// The parts of a root sequence (lower.h).
+bool sequence_parts(const tb_node* nodes, uint32_t n_nodes, const int32_t* lists, uint32_t n_lists, uint64_t pool_len,
+                    uint32_t sample_rate, std::vector<SeqPart>& parts) {
+    parts.clear();
+    Lowered tmp;
+    Lowerer L(nodes, n_nodes, lists, n_lists, pool_len, tmp, true);
+    try {
+        L.validate();
+        L.const_memo.assign(n_nodes, -2);
+        L.state_off.assign(n_nodes, -1);
+        L.state_len.assign(n_nodes, 0);
+        L.fixed_idx.assign(n_nodes, -1);
+        L.filt_idx.assign(n_nodes, -1);
+        L.sensitive.assign(n_nodes, 0);
+        // the leaves of the root's tree of Appends, in order (Marked / Captured are pass-throughs, generator.rs:344-358)
+        std::vector<int> leaves;
+        std::function<void(int)> collect = [&](int i) {
+            int c = i;
+            while (nodes[c].kind == TB_MARKED || nodes[c].kind == TB_CAPTURED) c = nodes[c].a;
+            if (nodes[c].kind == TB_APPEND) {
+                collect(nodes[c].a);
+                collect(nodes[c].b);
+            } else {
+                leaves.push_back(i);  // with its wrappers
+            }
+        };
+        collect((int)n_nodes - 1);
+        if (leaves.size() < 2 || leaves.size() > 256) return false;
+        int cur = leaves.back();
+        for (size_t q = 0; q + 1 < leaves.size(); q++) {
+            int a = leaves[q];
+            while (nodes[a].kind == TB_MARKED || nodes[a].kind == TB_CAPTURED) a = nodes[a].a;
+            if (nodes[a].kind != TB_FIN || !L.never_ends(nodes[a].b)) return false;
+            const int gi = L.build_goe(nodes[a].a);
+            const tb_goe g = tmp.goe[gi];
+            if (g.term != GOE_TIME || g.through_append) return false;
+            float value = 0.0f;  // greater_or_equals_at (generator.rs:787-862), the arithmetic of the kernels' goe_eval
+            for (uint32_t k = 0; k < g.n_steps; k++) {
+                const tb_cexpr& e = tmp.cexpr[tmp.goe_steps[g.step_off + 2 * k + 1]];
+                if (e.kind != CE_LIT) return false;  // a per-voice length: the parts would start at per-voice offsets
+                value = tmp.goe_steps[g.step_off + 2 * k] > 0 ? value + e.value : value - e.value;
+            }
+            const float t = std::ceil(value * (float)sample_rate);
+            if (!(t >= 1.0f) || t >= 9.0e15f) return false;
+            parts.push_back(SeqPart{leaves[q], (uint64_t)t});
+        }
+        if (parts.empty()) return false;
+        parts.push_back(SeqPart{cur, ~0ull});
+        return true;
+    } catch (int) {
+        parts.clear();
+        return false;
+    }
+}
+
 int lower(const tb_node* nodes, uint32_t n_nodes, const int32_t* lists, uint32_t n_lists,
-          uint64_t pool_len, bool fast_sines, Lowered& out) {
+          uint64_t pool_len, bool fast_sines, Lowered& out, const uint32_t* noise_ids) {
     out = Lowered();
     Lowerer L(nodes, n_nodes, lists, n_lists, pool_len, out, fast_sines);
+    L.noise_ids = noise_ids;
     try {
         L.run();
     } catch (int status) {

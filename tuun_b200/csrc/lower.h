@@ -37,8 +37,23 @@ struct Lowered {
     std::string error;
 };
 
-// Returns TB_OK or a negative tb_status (out.error holds the reason).
+// Returns TB_OK or a negative tb_status (out.error holds the reason).  noise_ids (may be NULL): node -> number of
+// its Noise stream, for an op list that is a part of a larger tree.
 int lower(const tb_node* nodes, uint32_t n_nodes, const int32_t* lists, uint32_t n_lists,
-          uint64_t pool_len, bool fast_sines, Lowered& out);
+          uint64_t pool_len, bool fast_sines, Lowered& out, const uint32_t* noise_ids = nullptr);
+
+// A root SEQUENCE — a tree of Appends (nested either way, under Marked / Captured wrappers) whose leaves are
+// Fin{len_0, a_0}, Fin{len_1, a_1}, ..., rest: what `<[a, b, c]>`, `a \ b` and Player::beats_waveform evaluate to
+// (builtins.rs:208-299, optimizer.rs:212-229, player.rs:232-260) — with Fin lengths that are analytic and the same
+// for every voice (Time +- literal constants, generator.rs:787-862) over waveforms that cannot end earlier.  The second
+// arm of an Append starts from its own Initial state (generator.rs:169-188), so every part is an independent stream
+// that begins at a known sample: parts[i] = {root node of the part (the Fin with its wrappers; the rest for the last
+// one), its length in samples (~0 for the last)}.  False when the root is no such sequence (or has more than 256 parts).
+struct SeqPart {
+    int root;
+    uint64_t len;
+};
+bool sequence_parts(const tb_node* nodes, uint32_t n_nodes, const int32_t* lists, uint32_t n_lists, uint64_t pool_len,
+                    uint32_t sample_rate, std::vector<SeqPart>& parts);
 
 }  // namespace tb

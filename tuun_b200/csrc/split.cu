@@ -334,6 +334,19 @@ __global__ void split_finish_kernel(const tb_split_args A, uint32_t* real_state,
 
 }  // namespace
 
+// out_len[v] = (accumulate ? out_len[v] : 0) + add  (abi.cpp launch_sequence)
+namespace {
+__global__ void len_set_kernel(unsigned long long* out_len, uint32_t n, unsigned long long add, int accumulate) {
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v < n) out_len[v] = (accumulate ? out_len[v] : 0ull) + add;
+}
+}  // namespace
+extern "C" cudaError_t tb_len_set(unsigned long long* out_len, uint32_t n, unsigned long long add, int accumulate,
+                                  cudaStream_t stream) {
+    len_set_kernel<<<(n + 127) / 128, 128, 0, stream>>>(out_len, n, add, accumulate);
+    return cudaGetLastError();
+}
+
 extern "C" cudaError_t tb_split_seed(const tb_split_args* A, cudaStream_t stream) {
     split_prepare_kernel<<<(A->n_real + 127) / 128, 128, 0, stream>>>(*A);
     const uint32_t nv = A->n_real * A->n_seg;
