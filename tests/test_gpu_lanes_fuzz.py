@@ -123,3 +123,48 @@ def test_random_steady_tree(monkeypatch, seed):
         scale = np.maximum(1.0, np.max(np.abs(ref), axis=1, keepdims=True))  # tolerance relative to the voice's peak
         bad = int(np.count_nonzero(d / scale > 2e-4))
         assert bad <= 6, (seed, lanes, bad, float(d.max()), str(w)[:200])
+
+
+@pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("TUUN_FUZZ_SEEDS", "36"))))
+def test_random_steady_tree_split_in_time(monkeypatch, seed):
+    """The same random steady trees with every voice cut into segments (TUUN_B200_SPLIT forced: split.cu): phase
+    prefix sums, affine scans of filter histories, Reset clocks — against the oracle, through both kernel families
+    (a handful of voices: warp kernel; TUUN_B200_LANE_MIN_VOICES=1: lane kernels, 2^k segments), in two calls."""
+    from tuun_b200.generator import Program, lower_check
+    g = Gen(1000 + seed)
+    w = g.tree(3)
+    info = lower_check(w)
+    if info.split_passes == 0:
+        pytest.skip("not a steady program")
+    V, N1, N2 = 5, 256 + 512 * 9 + 37, 512 * 5 + 100
+    rng = np.random.default_rng(seed)
+    params = np.stack([TAU * rng.uniform(30, 2500, V), TAU * rng.uniform(0.5, 40, V), rng.uniform(-1, 1, V),
+                       rng.uniform(0.1, 2, V)], axis=1).astype(np.float32)
+    ref = np.zeros((V, N1 + N2), dtype=np.float32)
+    o = OracleProgram(w, SR)
+    for v in range(V):
+        o.initialize_state()
+        o.seed_noise(77, v)
+        o.set_params(params[v])
+        ref[v] = o.render(N1 + N2)
+    scale = np.maximum(1.0, np.max(np.abs(ref), axis=1, keepdims=True))
+    for lanes, segs in ((False, 7), (True, 4)):
+        if lanes and info.lane_smem_bytes == 0:
+            continue
+        monkeypatch.setenv("TUUN_B200_LANES", "1" if lanes else "0")
+        monkeypatch.setenv("TUUN_B200_LANE_MIN_VOICES", "1")
+        monkeypatch.setenv("TUUN_B200_SPLIT", str(segs))
+        p = Program(w, SR)
+        p.seed_noise(77, 0)
+        a = np.zeros((V, N1), dtype=np.float32)
+        b = np.zeros((V, N2), dtype=np.float32)
+        l1 = p.render(a, params=params)
+        l2 = p.render(b, params=params)
+        assert (l1 == N1).all() and (l2 == N2).all()
+        if not lanes and info.tile == 256:
+            assert p.info.split_rounds == 0      # clocked words (a Reset): split only on the lane kernels
+            continue
+        assert p.info.split_rounds >= 2, (seed, lanes)
+        d = np.abs(np.concatenate([a, b], axis=1) - ref)
+        bad = int(np.count_nonzero(d / scale > 2e-4))
+        assert bad <= 6, (seed, lanes, bad, float(d.max()), str(w)[:200])
