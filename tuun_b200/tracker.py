@@ -9,8 +9,10 @@ activation order, and retires waveforms that return short.  Its clock is the wal
 callback — so the only deterministic part is `generate(buffer_start, out)`; this module mirrors that
 function on a virtual clock that advances by exactly one buffer per callback.
 
-What runs on the GPU: every waveform is rendered WHOLE when it is activated (one tb_render launch;
-streaming it segment by segment would be one tiny launch per waveform per segment).  The reference
+What runs on the GPU: every waveform is rendered WHOLE when it is activated (`Generator::length` for
+its extent, then one tb_render of exactly that many samples; one program per waveform object, so a
+repeating waveform is re-rendered, not re-lowered; streaming it segment by segment would be one tiny
+launch per waveform per segment).  The reference
 generator is block-size invariant for the trees the reference itself tests that way (chunks of
 1/2/4/8, generator.rs:1284-1351), so handing out consecutive slices of that render is what the
 per-segment `generate` calls would have produced — with two exceptions the reference's code has and its
@@ -100,15 +102,24 @@ class OfflineTracker:
         self.now = 0                        # ns: start of the next buffer
         self.captured: Dict[str, List[np.ndarray]] = {}
         self.launches = 0
+        self._keep: List[Waveform] = []
 
     def _gpu_render(self, device):
+        programs: Dict[int, object] = {}   # one program per waveform object: a repeating waveform is re-rendered, not re-lowered
+
         def render(w: Waveform, n: int) -> np.ndarray:
             from .generator import Program
-            p = Program(w, self.sample_rate, device=device)
-            out = np.zeros((1, n), dtype=np.float32)
-            got = int(p.render(out)[0])
-            self.launches += int(p.info.kernel_launches)
-            p.close()
+            p = programs.get(id(w))
+            if p is None:
+                p = programs[id(w)] = Program(w, self.sample_rate, device=device)
+                self._keep.append(w)  # id() stays unique while the waveform is alive
+            before = int(p.info.kernel_launches)
+            p.reset()
+            length = int(p.lengths(1, n)[0])   # Generator::length: how much there is (at most n), no samples
+            p.reset()
+            out = np.zeros((1, max(length, 1)), dtype=np.float32)
+            got = int(p.render(out[:, :length])[0]) if length else 0
+            self.launches += int(p.info.kernel_launches) - before
             return out[0, :got]
 
         return render
