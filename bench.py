@@ -209,7 +209,9 @@ def strong_record(args, world, rank, local, n_samples, barrier, peak):
     ms = timed_steps(step, steps, stream, barrier, world)
     info = prog.info
     value = args.voices * n_samples * steps / (ms * 1e-3)
-    kernel = ("tb_render_lanes_fm_kernel" if info.lane_launches and info.lane_fm_capacity
+    kernel = ("tb_render_lanes_fm_split_kernel after tb_render_lanes_fm_sums_kernel (every voice cut in time: phase-sum pass, "
+              "filter warm-up, samples)" if info.lane_launches and info.lane_fm_capacity and info.split_rounds
+              else "tb_render_lanes_fm_kernel" if info.lane_launches and info.lane_fm_capacity
               else "tb_render_lanes_kernel" if info.lane_launches else "tb_render_kernel")
     return {"value": value, "unit": UNIT, "ms_per_step": ms / steps, "voices": args.voices,
             "voices_per_gpu": hi - lo, "kernel": kernel, "split_segments": int(info.split_segments),
