@@ -355,10 +355,7 @@ int launch_lanes(tb_program* p, tb_launch& B) {
 int launch_generate_seq(tb_program* p, const tb_launch& L, uint64_t pos) {
     // (a split pass of a program with clocked words — a Reset in the steady stream — has no other kernel to run on)
     const bool clk_split = p->low.lane_clk != 0 && L.vsplit_total > 1;
-    const bool big = p->lane_smem != 0 && (L.n_voices >= p->lane_min_voices || clk_split) && (L.out != nullptr || L.state_only) &&
-                     (L.fm_sums ||                              // (the summary kernel stores no rows: any number of segments)
-                      (!(L.vsplit > 1 && L.vsplit_log2 == 0) &&  // the lane kernels take 2^k segments per voice only
-                       !(L.vsplit == 1 && L.vsplit_total > 1))); // (a launch of one segment per voice: warp kernel)
+    const bool big = p->lane_smem != 0 && (L.n_voices >= p->lane_min_voices || clk_split) && (L.out != nullptr || L.state_only);
     if (!big) return launch(p, L);
     // The fused-FM-voice kernel starts a stream itself (the filter's read-ahead, run_fm_voice) and takes
     // the samples that do not fill a tile: one launch for the whole call.  (A root Fin keeps its general
@@ -480,12 +477,7 @@ bool plan_split(const tb_program* p, const tb_launch& L, uint64_t n, SplitPlan* 
         S = 4096;
         seg = n / S / grain * grain;
     }
-    // The lane kernels address segment rows by shift and mask: a batch that will take them gets 2^k segments.
-    if (lanes || (p->lane_smem != 0 && V * S >= p->lane_min_voices)) {
-        uint64_t k = 0;
-        while ((2ull << k) <= S) k++;
-        S = 1ull << k;
-    }
+    (void)lanes;
     if (S < 2 || V * S > 0x7fffffffull) return false;
     plan->n_seg = (uint32_t)S;
     plan->seg = seg;
@@ -569,10 +561,6 @@ int split_pass(tb_program* p, const tb_launch& L, uint32_t pass, uint32_t seg_lo
     B.vsplit = seg_hi - seg_lo;
     B.vsplit_total = A.n_seg;
     B.vseg_lo = seg_lo;
-    B.vsplit_log2 = 0;
-    while ((1u << B.vsplit_log2) < B.vsplit) B.vsplit_log2++;
-    if ((1u << B.vsplit_log2) != B.vsplit) B.vsplit_log2 = 0;
-    if (B.vsplit == 1) B.vsplit_log2 = 0;
     B.vseg = A.seg;
     B.out = last ? out_base : nullptr;
     B.state_only = last ? 0 : 1;

@@ -711,14 +711,13 @@ struct RowStore {
     size_t off;            // samples already stored
     bool fast, vec_ok;
     float* mix;            // mixdown without rows (tb_launch::mix_partial): this warp's row of partial sums
-    uint32_t sl2, seg_lo;  // time-axis split (tb_launch::vsplit_log2, vseg_lo): rows are segments of the real voices' rows
-    size_t vseg;
-    const unsigned long long* rowoff;  // ... whose first samples (offsets from `out`, in floats) sit in a table, one per row of the warp
+    const unsigned long long* rowoff;  // time-axis split (tb_launch::vsplit*): rows are segments of the real voices' rows,
+                                       // whose first samples (offsets from `out`, in floats) sit in a table, one per row of the warp
 };
 // First sample (of this launch) of virtual voice vv's row.
 __device__ __forceinline__ float* row_of(const RowStore& R, uint32_t vv) {
     if (!TB_LANES_VSPLIT) return R.out + (size_t)vv * R.stride;
-    return R.out + (size_t)(vv >> R.sl2) * R.stride + (size_t)(R.seg_lo + (vv & ((1u << R.sl2) - 1u))) * R.vseg;
+    return R.out + R.rowoff[vv - R.v0];
 }
 #ifndef TB_ST
 #define TB_ST 2
@@ -1209,9 +1208,8 @@ __device__ __forceinline__ void lanes_body(const tb_launch& P, uint32_t group, u
     sk.plimit = 600.0f;
 
     // the voice's state block; with the time-axis split (tb_launch::vsplit*) that of its segment
-    // (the summary kernel stores no rows and takes any number of segments: its launches leave out the last one)
-    const uint32_t rvoice = !TB_LANES_VSPLIT ? voice : (SUMS ? voice / P.vsplit : voice >> P.vsplit_log2);  // parameters, noise
-    const uint32_t vseg_i = !TB_LANES_VSPLIT ? 0u : P.vseg_lo + (SUMS ? voice - rvoice * P.vsplit : voice & ((1u << P.vsplit_log2) - 1u));
+    const uint32_t rvoice = !TB_LANES_VSPLIT ? voice : voice / (P.vsplit ? P.vsplit : 1u);  // parameters, noise streams
+    const uint32_t vseg_i = !TB_LANES_VSPLIT ? 0u : P.vseg_lo + (voice - rvoice * P.vsplit);
     const size_t vidx = TB_LANES_VSPLIT ? (size_t)rvoice * P.vsplit_total + vseg_i : (size_t)voice;
     uint32_t* gstate = P.state + vidx * P.state_words;
     if (active) {
@@ -1249,9 +1247,6 @@ __device__ __forceinline__ void lanes_body(const tb_launch& P, uint32_t group, u
     R.vec_ok = (reinterpret_cast<uintptr_t>(P.out) & 15) == 0 && (P.out_stride & 3) == 0;
     R.fast = R.vec_ok && P.out != nullptr && v0 + 32u <= P.n_voices && (!TB_LANES_VSPLIT || (P.vseg & 3) == 0);
     R.mix = MIX ? P.mix_partial + (size_t)(v0 >> 5) * P.mix_stride + s0 : nullptr;
-    R.sl2 = TB_LANES_VSPLIT ? P.vsplit_log2 : 0u;
-    R.seg_lo = TB_LANES_VSPLIT ? P.vseg_lo : 0u;
-    R.vseg = TB_LANES_VSPLIT ? (size_t)P.vseg : 0;
     R.rowoff = nullptr;
 #if TB_LANES_VSPLIT
     __shared__ unsigned long long rowoff_s[LT];  // the CTA's rows: offset of each one's first sample of this launch

@@ -320,7 +320,6 @@ struct tb_launch {
     // range): segment sl of the launch is segment vseg_lo + sl of the voice, whose state block is number
     // v * vsplit_total + vseg_lo + sl.
     uint32_t vsplit;       // segments per voice in this launch; 0 or 1: every voice is a real voice
-    uint32_t vsplit_log2;  // log2(vsplit) when it is a power of two (the lane kernels take only those), else 0
     uint32_t vsplit_total; // segments per voice in all (>= vseg_lo + vsplit)
     uint32_t vseg_lo;      // first segment of this launch
     uint64_t vseg;         // samples per segment

@@ -1556,7 +1556,7 @@ tb_render_kernel(const tb_launch P) {
     const size_t per_warp = per_warp_slots + aux_b + cval_b + state_b + slen_b + svm_b;
     unsigned char* base = smem_raw + off + per_warp * warp;
     WarpMem M;
-    // time-axis split (program.h tb_launch::vsplit_log2): `voice` is a virtual voice — a segment of a real one
+    // time-axis split (program.h tb_launch::vsplit*): `voice` is a virtual voice — a segment of a real one
     const uint32_t vsplit = P.vsplit > 1u ? P.vsplit : 1u;
     const uint32_t rvoice = voice / vsplit;
     const uint32_t vseg_i = P.vseg_lo + (voice - rvoice * vsplit);  // segment of the voice
