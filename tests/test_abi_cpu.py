@@ -158,3 +158,27 @@ def test_op_list_must_be_a_tree_and_fixed_ranges_must_not_wrap():
     assert check(fx) == _abi.TB_OK
     fx.nodes[0].fixed_off = 2 ** 64 - 2                                            # off + len wraps to 1 <= 3
     assert check(fx) == _abi.TB_ERR_INVALID
+
+
+def test_lowering_plans_without_a_device():
+    """tb_lower_check reports what a render would do with a tree: time-axis split passes (0: not a steady program) and
+    the parts of a root sequence."""
+    from tuun_b200 import workloads as W
+    from tuun_b200.generator import lower_check
+    from tuun_b200.builder import Std, to_waveform
+    from tuun_b200.optimizer import optimize
+    assert lower_check(W.fm_filter_voice()).split_passes == 3          # modulator analytic, carrier sums, filter, samples
+    assert lower_check(W.fm_pair_voice()).split_passes == 2
+    assert lower_check(W.cfg1_from_source()).split_passes == 0         # a note that ends: not steady
+    progs = dict(W.cfg4_filters())
+    assert lower_check(progs["square220-lpf"]).split_passes == 2
+    assert lower_check(progs["square-cascade"]).split_passes == 4      # one more pass per filter in the chain
+    assert lower_check(progs["pulse-filter_4_3"]).split_passes == 3    # Reset clocks, then the filter
+    assert lower_check(progs["noise-lpf"]).split_passes == 0           # a Fixed buffer can end
+    s = Std()
+    assert lower_check(optimize(to_waveform(s.sawtooth(220)))).split_passes == 2
+    seq = lower_check(W.cfg2_harmonica(4))
+    assert seq.sequence_parts == 4 and seq.split_passes == 0
+    marks = [w for name, w, _ in W.tracker_benches() if name == "marks_4_40"][0]
+    assert lower_check(marks).sequence_parts == 160                    # left-nested Appends of Marked sequences
+    assert lower_check(W.fm_filter_voice()).sequence_parts == 0

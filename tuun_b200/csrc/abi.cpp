@@ -615,7 +615,7 @@ bool plan_split_fm(const tb_program* p, const tb_launch& L, uint64_t n, SplitPla
         if (S < 2) return false;
     } else {
         if (std::getenv("TUUN_B200_SPLIT")) return false;          // the general form was asked for (or none)
-        if (V < 64 || V > 12288 || n < 65536) return false;         // small batches: the general form; large ones fill the device
+        if (V > 12288 || n < 65536) return false;                   // large batches fill the device as they are
         S = 65536 / V;
     }
     uint64_t k = 0;
@@ -624,6 +624,9 @@ bool plan_split_fm(const tb_program* p, const tb_launch& L, uint64_t n, SplitPla
     if (S > 4096) S = 4096;
     while (S >= 2 && n / S < 32768) S >>= 1;                        // room for the warm-up (a few thousand samples)
     if (S < 2) return false;
+    // a warm-up needs long segments, so a handful of voices cannot be cut finely enough to fill the lane kernel this
+    // way: they take the general form (three passes, segments of any length)
+    if (!env && V * S < 16384) return false;
     plan->n_seg = (uint32_t)S;
     plan->seg = n / S / (2 * TB_LS) * (2 * TB_LS);
     return true;
@@ -1124,7 +1127,8 @@ int tb_lower_check(const tb_node* nodes, uint32_t n_nodes, const int32_t* lists,
         info->split_segments = 0;
         info->split_seg_samples = 0;
         info->split_rounds = 0;
-        info->sequence_parts = 0;
+        std::vector<tb::SeqPart> parts;  // (lengths at 44.1 kHz: whether the root is a sequence does not depend on the rate)
+        info->sequence_parts = tb::sequence_parts(nodes, n_nodes, lists, n_lists, fixed_len, 44100, parts) ? (uint32_t)parts.size() : 0u;
         info->reserved0 = 0;
         info->sequence_renders = 0;
     }
