@@ -711,6 +711,8 @@ struct RowStore {
     size_t off;            // samples already stored
     bool fast, vec_ok;
     float* mix;            // mixdown without rows (tb_launch::mix_partial): this warp's row of partial sums
+    float* dfast;          // fast path: this lane's 16 bytes of its first row at the current offset, and 4 rows further on:
+    size_t step4;          // kept in registers so that the loop neither re-derives them nor reloads the stride (LDC)
     const unsigned long long* rowoff;  // time-axis split (tb_launch::vsplit*): rows are segments of the real voices' rows,
                                        // whose first samples (offsets from `out`, in floats) sit in a table, one per row of the warp
 };
@@ -761,7 +763,12 @@ __device__ __forceinline__ void store_pair(RowStore& R, int l) {
             }
         }
     } else if (R.fast) {  // all 32 rows of the warp exist and are 16-byte aligned
-        UNROLL for (int i = 0; i < 8; i++) st_row(reinterpret_cast<float4*>(d + i * step), v[i]);
+        float* q = R.dfast;
+        UNROLL for (int i = 0; i < 8; i++) {
+            st_row(reinterpret_cast<float4*>(q), v[i]);
+            q += R.step4;
+        }
+        R.dfast += 2 * LS;
     } else if (R.out) {
         UNROLL for (int i = 0; i < 8; i++)
             if (R.v0 + (uint32_t)(l >> 3) + 4u * i < R.n_voices) put4(d + i * step, v[i], R.vec_ok);
@@ -1077,7 +1084,11 @@ __device__ __forceinline__ void run_fm_voice(const tb_insn* code, LaneMem& M, co
         }
     } else if (n_tiles > 0) {
         if (active) fm_carrier_tile<SLOW>(car, S, Cq, rot, rr, mm, cc, p, sk);
-        for (u64 t = 1; t < n_tiles; t++) {
+        // (a 32-bit down-counter and a parity bit: with `t < n_tiles` as the condition the compiler re-derives n_tiles
+        // from the launch parameters in constant memory every iteration — an LDC whose latency showed as 5 % of the
+        // loop's stall samples)
+        uint32_t odd = 0;  // parity of the tile that leaves
+        for (uint32_t left = (uint32_t)(n_tiles - 1); left != 0; left--) {
             if (active) {
                 float y[LS], nxt[LS];
 #if TB_ABL == 1
@@ -1086,13 +1097,15 @@ __device__ __forceinline__ void run_fm_voice(const tb_insn* code, LaneMem& M, co
                 biquad_tile(y, car, F);                                   // tile t-1 leaves ...
 #endif
                 fm_carrier_tile<SLOW>(nxt, S, Cq, rot, rr, mm, cc, p, sk);    // ... while tile t is made
-                M.A = abase + ((t - 1) & 1) * 4 * AS;
+                M.A = abase + odd * 4 * AS;
                 lacc_store(M, y);
                 UNROLL for (int j = 0; j < LS; j++) car[j] = nxt[j];
             }
 #if TB_ABL != 5
-            tile_done<MIX>(R, l, t - 1, n_tiles);
+            if (MIX) mix_tile(R, l, (int)odd);
+            else if (odd) store_pair(R, l);
 #endif
+            odd ^= 1u;
         }
         if (active) {
             float y[LS];
@@ -1248,6 +1261,8 @@ __device__ __forceinline__ void lanes_body(const tb_launch& P, uint32_t group, u
     R.fast = R.vec_ok && P.out != nullptr && v0 + 32u <= P.n_voices && (!TB_LANES_VSPLIT || (P.vseg & 3) == 0);
     R.mix = MIX ? P.mix_partial + (size_t)(v0 >> 5) * P.mix_stride + s0 : nullptr;
     R.rowoff = nullptr;
+    R.step4 = 4 * (size_t)P.out_stride;
+    R.dfast = R.fast ? R.out + (size_t)(v0 + (uint32_t)(l >> 3)) * R.stride + (size_t)(l & 7) * 4 : nullptr;
 #if TB_LANES_VSPLIT
     __shared__ unsigned long long rowoff_s[LT];  // the CTA's rows: offset of each one's first sample of this launch
     rowoff_s[t] = (unsigned long long)rvoice * P.out_stride + (unsigned long long)vseg_i * P.vseg;
