@@ -146,3 +146,27 @@ def test_length_in_the_middle_of_a_sequence(monkeypatch):
     # the same calls on the tree as ONE program
     one, l1, i1 = gpu(w, 12000, blocks=[3000, 4000, 5000], length_at=(3000, 4000), env={"TUUN_B200_SEQ": "0"}, monkeypatch=monkeypatch)
     assert i1.sequence_parts == 0 and np.abs(one[0, 7000:] - r2).max() <= 2e-6
+
+
+def test_a_tune_of_three_hundred_notes(monkeypatch):
+    """As one program such a sequence needs a control stack deeper than the interpreter has (about 120 notes:
+    TB_ERR_UNSUPPORTED); part by part it is 300 small programs."""
+    from tuun_b200._abi import TB_ERR_UNSUPPORTED, TuunB200Error
+    from tuun_b200.generator import Program, lower_check
+    rng = np.random.default_rng(9)
+    notes = [Fin(add(Time(), Const(-f32(0.01))), BinaryPointOp(Operator.Merge, Sine(Const(f32(2 * np.pi * f)), Const(0.0)), Const(0.0)))
+             for f in rng.uniform(200, 2000, 300)]
+    w = notes[-1]
+    for x in reversed(notes[:-1]):
+        w = Append(x, w)
+    assert lower_check(w).sequence_parts == 300
+    n = 300 * 441
+    ref, rl = oracle_rows(w, n + 50)
+    assert rl[0] == n
+    got, l, info = gpu(w, n + 50)
+    assert info.sequence_parts == 300 and l[0] == n
+    close(got, ref, rl, tol=2e-6)
+    monkeypatch.setenv("TUUN_B200_SEQ", "0")
+    with pytest.raises(TuunB200Error) as e:
+        Program(w, SR)
+    assert e.value.status == TB_ERR_UNSUPPORTED

@@ -112,6 +112,7 @@ struct tb_program {
     std::vector<tb_program*> part_prog;
     std::vector<uint64_t> part_len;   // samples; ~0 for the last part
     uint64_t seq_renders = 0;         // generate launches that went part by part
+    bool seq_only = false;            // the tree lowers only part by part (as one program it is nested too deeply): `low` is a stand-in
     static constexpr int kSeqStreams = 16;  // the parts of one call are independent streams: rendered side by side
     cudaStream_t seq_stream[kSeqStreams] = {};
     cudaEvent_t seq_fork = nullptr, seq_join[kSeqStreams] = {};
@@ -766,6 +767,7 @@ int launch_sequence(tb_program* p, const tb_launch& L, uint64_t pos) {
 
 int launch_generate(tb_program* p, const tb_launch& L, uint64_t pos) {
     if (!p->part_prog.empty() && p->pos_known && L.mode == 0) return launch_sequence(p, L, pos);
+    if (p->seq_only) return set_error(TB_ERR_UNSUPPORTED, "this tree renders only part by part");
     if (p->low.split_passes == 0 || !p->pos_known) return launch_generate_seq(p, L, pos);
     // The first tile of a stream stays on the serial form: filter pre-reads (generator.rs:234-252).  (A program
     // without filters is steady from its first sample, and so are its segments — except under a Reset: its trigger
@@ -946,8 +948,25 @@ static int create_program(const tb_node* nodes, uint32_t n_nodes, const int32_t*
     const char* fs = std::getenv("TUUN_B200_FAST_SINES");
     const bool fast = !(fs && fs[0] == '0');
     int rc = tb::lower(nodes, n_nodes, lists, n_lists, fixed_len, fast, p->low, noise_ids);
+    std::string whole_error;
+    if (rc == TB_ERR_UNSUPPORTED && allow_sequence) {
+        // A long tune nests deeper than the interpreter's control stack as ONE program, but lowers part by part: the
+        // program then has no whole-tree form at all (`low` becomes a stand-in with one state word).
+        std::vector<tb::SeqPart> probe;
+        const char* sq0 = std::getenv("TUUN_B200_SEQ");
+        if (!(sq0 && sq0[0] == '0') && tb::sequence_parts(nodes, n_nodes, lists, n_lists, fixed_len, sample_rate, probe)) {
+            whole_error = p->low.error;
+            tb_node zero;
+            std::memset(&zero, 0, sizeof(zero));
+            zero.kind = TB_CONST;
+            zero.a = zero.b = zero.c = -1;
+            zero.param_slot = -1;
+            rc = tb::lower(&zero, 1, nullptr, 0, 0, fast, p->low, nullptr);
+            p->seq_only = rc == TB_OK;
+        }
+    }
     if (rc != TB_OK) {
-        std::string msg = p->low.error;
+        std::string msg = whole_error.empty() ? p->low.error : whole_error;
         delete p;
         return set_error(rc, msg);
     }
@@ -1086,8 +1105,12 @@ static int create_program(const tb_node* nodes, uint32_t n_nodes, const int32_t*
             for (tb_program* q : p->part_prog) delete q;
             p->part_prog.clear();
             p->part_len.clear();
-            g_error.clear();
+            if (!p->seq_only) g_error.clear();
         }
+    }
+    if (p->seq_only && p->part_prog.empty()) {  // no whole-tree form and no parts: what the whole tree said
+        delete p;
+        return set_error(TB_ERR_UNSUPPORTED, whole_error);
     }
     *out_program = p;
     return TB_OK;
@@ -1101,6 +1124,38 @@ int tb_lower_check(const tb_node* nodes, uint32_t n_nodes, const int32_t* lists,
     tb::Lowered low;
     const char* fs = std::getenv("TUUN_B200_FAST_SINES");
     int rc = tb::lower(nodes, n_nodes, lists, n_lists, fixed_len, !(fs && fs[0] == '0'), low);
+    if (rc == TB_ERR_UNSUPPORTED) {
+        // part by part (create_program): every part must lower; the geometry reported is that of the largest one
+        std::vector<tb::SeqPart> parts;
+        const char* sq0 = std::getenv("TUUN_B200_SEQ");
+        std::string whole = low.error;
+        if (!(sq0 && sq0[0] == '0') && tb::sequence_parts(nodes, n_nodes, lists, n_lists, fixed_len, 44100, parts)) {
+            std::vector<tb_node> all(nodes, nodes + n_nodes);
+            std::vector<int32_t> all_lists(lists, lists + (lists ? n_lists : 0));
+            tb::Lowered best;
+            bool ok = true;
+            for (const tb::SeqPart& sp : parts) {
+                std::vector<tb_node> sub;
+                std::vector<int32_t> sub_lists;
+                std::vector<uint32_t> ids;
+                extract_subtree(all, all_lists, sp.root, sub, sub_lists, ids);
+                tb::Lowered one;
+                if (tb::lower(sub.data(), (uint32_t)sub.size(), sub_lists.data(), (uint32_t)sub_lists.size(), fixed_len,
+                              !(fs && fs[0] == '0'), one, ids.data()) != TB_OK) {
+                    ok = false;
+                    break;
+                }
+                if (one.code.size() >= best.code.size()) best = one;
+            }
+            if (ok) {
+                low = best;
+                low.n_nodes = n_nodes;
+                rc = TB_OK;
+            } else {
+                low.error = whole;
+            }
+        }
+    }
     if (rc != TB_OK) return set_error(rc, low.error);
     uint32_t warps = 0;
     size_t smem = 0;
@@ -1200,6 +1255,15 @@ int tb_substitute(tb_program* p, uint32_t mark_id, float value, uint32_t* n_repl
     }
     if (n_replaced) *n_replaced = hits;
     if (hits == 0) return TB_OK;
+    if (p->seq_only) {  // no whole-tree program to lower again: the parts hold the subtrees
+        p->nodes.swap(nodes);
+        for (tb_program* q : p->part_prog) {
+            uint32_t n = 0;
+            int rcq = tb_substitute(q, mark_id, value, &n);
+            if (rcq) return rcq;
+        }
+        return TB_OK;
+    }
     // Same tree shape, another literal: lower again and require the same program around the constant table
     // (a literal can decide the lowering only through is_const's Append(c, c) arm, generator.rs:597-603).
     tb::Lowered low;

@@ -1382,7 +1382,7 @@ bool sequence_parts(const tb_node* nodes, uint32_t n_nodes, const int32_t* lists
             }
         };
         collect((int)n_nodes - 1);
-        if (leaves.size() < 2 || leaves.size() > 256) return false;
+        if (leaves.size() < 2 || leaves.size() > 4096) return false;
         int cur = leaves.back();
         for (size_t q = 0; q + 1 < leaves.size(); q++) {
             int a = leaves[q];

@@ -48,7 +48,7 @@ int lower(const tb_node* nodes, uint32_t n_nodes, const int32_t* lists, uint32_t
 // for every voice (Time +- literal constants, generator.rs:787-862) over waveforms that cannot end earlier.  The second
 // arm of an Append starts from its own Initial state (generator.rs:169-188), so every part is an independent stream
 // that begins at a known sample: parts[i] = {root node of the part (the Fin with its wrappers; the rest for the last
-// one), its length in samples (~0 for the last)}.  False when the root is no such sequence (or has more than 256 parts).
+// one), its length in samples (~0 for the last)}.  False when the root is no such sequence (or has more than 4096 parts).
 struct SeqPart {
     int root;
     uint64_t len;
