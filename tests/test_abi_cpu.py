@@ -119,18 +119,23 @@ def test_lane_plan_of_the_headline_voice():
 
 
 def test_nesting_is_checked_against_the_kernel_control_stack():
-    """A sequence is a right-nested Append chain (optimizer.rs:212-229): two control-stack words per note."""
+    """A sequence is a right-nested Append chain (optimizer.rs:212-229): two control-stack words per note when it has to
+    be ONE program — per-voice note lengths here (a root sequence of voice-independent lengths lowers part by part and
+    has no such limit: lower.h sequence_parts)."""
     from tuun_b200.generator import lower_check
     from tuun_b200.waveform import Append, Fin, add
-    def chain(notes):
+    def chain(notes, per_voice):
         w = Const(0.0)
         for k in range(notes):
-            w = Append(Fin(add(Time(), Const(-0.01)), Sine(Const(2000.0 + k), Const(0.0))), w)
+            length = Const(-0.01, param=0) if per_voice else Const(-0.01)
+            w = Append(Fin(add(Time(), length), Sine(Const(2000.0 + k), Const(0.0))), w)
         return w
-    assert lower_check(chain(100)).n_code_words > 0
+    assert lower_check(chain(100, True)).n_code_words > 0
     with pytest.raises(_abi.TuunB200Error) as e:
-        lower_check(chain(400))
+        lower_check(chain(400, True))
     assert e.value.status == _abi.TB_ERR_UNSUPPORTED and "nested too deeply" in e.value.message
+    info = lower_check(chain(400, False))
+    assert info.sequence_parts == 401 and info.n_code_words > 0
 
 
 def test_op_list_must_be_a_tree_and_fixed_ranges_must_not_wrap():
