@@ -241,7 +241,7 @@ typedef struct tb_program_info {
     /* a root sequence — Append(Fin{len, a}, Append(Fin{len', b}, ..)) with analytic, voice-independent lengths: what
        `<[a, b, ..]>` evaluates to — is held as one program per part, each rendered where it starts */
     uint32_t sequence_parts;  /* 0: the tree is one program */
-    uint32_t reserved0;
+    uint32_t split_fm_rounds; /* of split_rounds: those in the form for fused FM voices (phase-sum pass, filter warm-up, samples) */
     uint64_t sequence_renders; /* generate launches that went part by part */
 } tb_program_info;
 int tb_program_get_info(const tb_program* p, tb_program_info* info);

@@ -54,7 +54,7 @@ pub struct TbProgramInfo {
     pub split_seg_samples: u64,
     pub split_rounds: u64,
     pub sequence_parts: u32,
-    pub reserved0: u32,
+    pub split_fm_rounds: u32,
     pub sequence_renders: u64,
 }
 

@@ -16,11 +16,15 @@ SR = 44100
 TAU = f32(2 * math.pi)
 
 
-def two_rank_render(w, params, V, S, seg, monkeypatch, tail=1000):
+def two_rank_render(w, params, V, S, seg, monkeypatch, tail=1000, fm_form=False):
     import torch
     from tuun_b200.generator import Program
     from tuun_b200.sharding import TimeShard, segment_range
-    monkeypatch.setenv("TUUN_B200_SPLIT", "0")      # the serial reference and the heads: no split of their own
+    if fm_form:   # the cheaper form for fused FM voices (phase-sum pass, filter warm-up): same protocol for the caller
+        monkeypatch.setenv("TUUN_B200_SPLIT_FM", "0")
+        monkeypatch.setenv("TUUN_B200_LANE_MIN_VOICES", "1")
+    else:
+        monkeypatch.setenv("TUUN_B200_SPLIT", "0")  # the serial reference and the heads: no split of their own
     head = 256
     n = head + S * seg
     serial = np.zeros((V, n + tail), dtype=np.float32)
@@ -32,7 +36,11 @@ def two_rank_render(w, params, V, S, seg, monkeypatch, tail=1000):
         p.render(h, params=params)
         heads.append(h)
     outs = [torch.zeros((V, S // 2 * seg), dtype=torch.float32, device="cuda") for _ in ranks]
+    if fm_form:
+        monkeypatch.setenv("TUUN_B200_SPLIT_FM", "1")
     shards = [TimeShard(p, V, S, seg, *segment_range(S, r, 2), params=params) for r, p in enumerate(ranks)]
+    if fm_form:
+        monkeypatch.setenv("TUUN_B200_SPLIT_FM", "0")
     assert shards[0].passes == shards[1].passes
     for k in range(1, shards[0].passes + 1):
         for ts, o in zip(shards, outs):
@@ -55,6 +63,7 @@ def two_rank_render(w, params, V, S, seg, monkeypatch, tail=1000):
         t = np.zeros((V, tail), dtype=np.float32)
         p.render(t, params=params)
         tails.append(t)
+    assert (ranks[0].info.split_fm_rounds == 1) == fm_form
     return serial, got, tails, shards[0].passes
 
 
@@ -74,6 +83,27 @@ def test_two_ranks_render_one_stream_fm_filter(monkeypatch):
         o.initialize_state()
         o.set_params(params[v])
         assert np.abs(got[v] - o.render(n)).max() <= 1e-4
+
+
+def test_two_ranks_fm_form(monkeypatch):
+    """The same protocol when the library takes the cheaper form for fused FM voices (what the time_shard record of
+    bench.py runs: 64 voices x 512 segments per rank): pass 1 phase sums only — the snapshot for the warm-ups rides in
+    the exchanged state blocks —, pass 2 the filters' warm-ups, local to each rank, pass 3 the samples."""
+    from tuun_b200.workloads import biquad_noise_gain, fm_filter_cover_ids, fm_filter_params, fm_filter_tolerance, fm_filter_voice
+    w = fm_filter_voice()
+    ids = fm_filter_cover_ids(1)[::8]            # 32 voices, every cutoff and Q
+    params = fm_filter_params(ids)
+    V, S, seg = len(ids), 4, 16384               # the slowest filter needs 3,500 samples of warm-up: a quarter of a segment
+    serial, got, tails, passes = two_rank_render(w, params, V, S, seg, monkeypatch, fm_form=True)
+    assert passes == 3
+    n = got.shape[1]
+    g = np.maximum(biquad_noise_gain(params[:, 6], params[:, 7]), 5.0)
+    assert (np.abs(got - serial[:, :n]).max(axis=1) <= 6e-7 * g).all()
+    for t in tails:
+        assert (np.abs(t - serial[:, n:]).max(axis=1) <= 6e-7 * g).all()
+    o = OracleProgram(w, SR)
+    ref, _, _, _ = o.render_batch(params, V, n, threads=8)
+    assert (np.abs(got - ref).max(axis=1) <= fm_filter_tolerance(params, 1e-4)).all()
 
 
 def test_two_ranks_sines_are_bit_identical(monkeypatch):

@@ -221,6 +221,7 @@ def test_fm_batch_split_with_filter_warm_up(monkeypatch):
     p.render(got, params=params, out_len=lens)
     info = p.info
     assert (lens == n).all() and info.split_rounds == 1 and info.split_segments == 4 and info.split_seg_samples == 40000
+    assert info.split_fm_rounds == 1
     got = got.cpu().numpy()
     ref, _, _, _ = OracleProgram(w, SR).render_batch(params, V, n, threads=8)
     tol = fm_filter_tolerance(params, 1e-4)

@@ -53,7 +53,7 @@ class TbProgramInfo(ctypes.Structure):
         ("split_seg_samples", ctypes.c_uint64),
         ("split_rounds", ctypes.c_uint64),
         ("sequence_parts", ctypes.c_uint32),
-        ("reserved0", ctypes.c_uint32),
+        ("split_fm_rounds", ctypes.c_uint32),
         ("sequence_renders", ctypes.c_uint64),
     ]
 

@@ -133,6 +133,7 @@ struct tb_program {
     size_t split_real_cap = 0;      // real voices the two scratch tables hold
     tb_split_args split_args = {};  // the split in progress (split_begin .. split_finish)
     uint32_t seg_voices = 0;        // tb_segments_begin .. tb_segments_end: voices of the sharded render, 0 = none
+    bool seg_fm = false;            // ... in the form of render_split_fm (phase-sum pass, filter warm-up, samples)
     const float* seg_params = nullptr;
     uint32_t seg_n_params = 0;
     uint64_t split_rounds = 0;      // split renders so far (tb_program_info)
@@ -645,14 +646,14 @@ int ensure_warm_buffers(tb_program* p, uint64_t nv) {
     if (!p->d_warm_need) CU(cudaMalloc(reinterpret_cast<void**>(&p->d_warm_need), 4));
     return TB_OK;
 }
-// Returns TB_OK and *done = true when the round was rendered; *done = false: not applicable after all (a filter
-// that does not forget fast enough), nothing was changed.
-int render_split_fm(tb_program* p, const tb_launch& L, const SplitPlan& plan, uint64_t pos, bool* done) {
-    *done = false;
-    int rc = split_begin(p, L, plan);
-    if (rc) return rc;
+// After split_begin: the warm-up the batch's filters need (split.cu split_fm_need_kernel), in A.warm; *ok = false when
+// the form does not apply (a filter that does not forget fast enough: the warm-up would not be a small fraction of a
+// segment).  Synchronises the stream once.
+int prepare_split_fm(tb_program* p, uint64_t seg, bool* ok) {
+    *ok = false;
     tb_split_args& A = p->split_args;
-    if ((rc = ensure_warm_buffers(p, (uint64_t)A.n_real * A.n_seg))) return rc;
+    int rc = ensure_warm_buffers(p, (uint64_t)A.n_real * A.n_seg);
+    if (rc) return rc;
     A.vw = p->d_vw;
     A.snap = p->d_snap;
     A.warm_need = p->d_warm_need;
@@ -669,9 +670,23 @@ int render_split_fm(tb_program* p, const tb_launch& L, const SplitPlan& plan, ui
     CU(cudaMemcpyAsync(&need, p->d_warm_need, 4, cudaMemcpyDeviceToHost, p->stream));
     CU(cudaStreamSynchronize(p->stream));
     p->launches++;
-    uint64_t warm = ((uint64_t)need + TB_LS - 1) / TB_LS * TB_LS;
-    if (need == 0xffffffffu || warm * 4 > plan.seg) return TB_OK;   // the warm-up would not be a small fraction
+    const uint64_t warm = ((uint64_t)need + TB_LS - 1) / TB_LS * TB_LS;
+    if (need == 0xffffffffu || warm * 4 > seg) return TB_OK;
     A.warm = warm;
+    *ok = true;
+    return TB_OK;
+}
+// Returns TB_OK and *done = true when the round was rendered; *done = false: not applicable after all, nothing was changed.
+int render_split_fm(tb_program* p, const tb_launch& L, const SplitPlan& plan, uint64_t pos, bool* done) {
+    *done = false;
+    int rc = split_begin(p, L, plan);
+    if (rc) return rc;
+    tb_split_args& A = p->split_args;
+    bool ok = false;
+    if ((rc = prepare_split_fm(p, plan.seg, &ok))) return rc;
+    if (!ok) return TB_OK;
+    const uint64_t warm = A.warm;
+    cudaError_t e = cudaSuccess;
     // 1: phase sums (and the snapshot where the next segment's warm-up starts), then the exact starts
     PassOpt sums;
     sums.fm_sums = true;
@@ -1184,7 +1199,7 @@ int tb_lower_check(const tb_node* nodes, uint32_t n_nodes, const int32_t* lists,
         info->split_rounds = 0;
         std::vector<tb::SeqPart> parts;  // (lengths at 44.1 kHz: whether the root is a sequence does not depend on the rate)
         info->sequence_parts = tb::sequence_parts(nodes, n_nodes, lists, n_lists, fixed_len, 44100, parts) ? (uint32_t)parts.size() : 0u;
-        info->reserved0 = 0;
+        info->split_fm_rounds = 0;
         info->sequence_renders = 0;
     }
     return TB_OK;
@@ -1215,7 +1230,7 @@ int tb_program_get_info(const tb_program* p, tb_program_info* info) {
     info->split_seg_samples = p->split_last_seg_samples;
     info->split_rounds = p->split_rounds;
     info->sequence_parts = (uint32_t)p->part_prog.size();
-    info->reserved0 = 0;
+    info->split_fm_rounds = (uint32_t)p->split_fm_rounds;
     info->sequence_renders = p->seq_renders;
     for (const tb_program* q : p->part_prog) info->split_rounds += q->split_rounds;
     return TB_OK;
@@ -1323,6 +1338,16 @@ int tb_segments_begin(tb_program* p, const float* params, uint32_t n_params, uin
     plan.n_seg = n_segments;
     plan.seg = seg_samples;
     if ((rc = split_begin(p, L, plan))) return rc;
+    // A batch of fused FM voices with a biquad takes the cheaper form of render_split_fm: pass 1 = phase sums only,
+    // pass 2 = the filters' warm-ups (local to every rank), pass 3 = the samples; same protocol for the caller.
+    p->seg_fm = false;
+    const char* fe = std::getenv("TUUN_B200_SPLIT_FM");
+    if (p->low.split_passes == 3 && p->lane_fm_capacity != 0 && p->low.filt.size() == 1 && !(fe && fe[0] == '0') &&
+        !std::getenv("TUUN_B200_SPLIT") && ((fe && fe[0] != '0') || (uint64_t)n_voices * n_segments >= 16384)) {
+        bool ok = false;
+        if ((rc = prepare_split_fm(p, seg_samples, &ok))) return rc;
+        p->seg_fm = ok;
+    }
     p->seg_voices = n_voices;
     p->seg_params = d_params;
     p->seg_n_params = n_params;
@@ -1349,6 +1374,18 @@ int tb_segments_pass(tb_program* p, uint32_t pass, uint32_t seg_lo, uint32_t seg
     L.out_stride = out_stride;
     // rows are addressed by the segment's number within the voice: segment seg_lo starts at out[v * stride]
     float* base = last ? out - (size_t)seg_lo * A.seg : nullptr;
+    if (p->seg_fm && pass == 1) {  // phase sums (the snapshot rides in the state blocks: lanes.cuh run_fm_sums)
+        PassOpt sums;
+        sums.fm_sums = true;
+        sums.snap_at = A.seg - A.warm;
+        return split_pass(p, L, 1, seg_lo, seg_hi, nullptr, p->stream_pos, sums);
+    }
+    if (p->seg_fm && pass == 2) {  // the warm-ups of this rank's segments, from the states tb_segments_fix(1) made
+        PassOpt wp;
+        wp.states = p->d_vw;
+        wp.samples = A.warm;
+        return split_pass(p, L, 2, seg_lo, seg_hi, nullptr, p->stream_pos, wp);
+    }
     return split_pass(p, L, pass, seg_lo, seg_hi, base, p->stream_pos);
 }
 
@@ -1363,6 +1400,19 @@ int tb_segments_fix(tb_program* p, uint32_t pass) {
     if (!p || p->seg_voices == 0) return set_error(TB_ERR_STATE, "tb_segments_fix without tb_segments_begin");
     if (pass < 1 || pass >= p->low.split_passes) return set_error(TB_ERR_INVALID, "tb_segments_fix: no such summary pass");
     CU(cudaSetDevice(p->device));
+    if (p->seg_fm) {
+        cudaError_t e = cudaSuccess;
+        if (pass == 1) {  // exact carrier starts, then the states every warm-up starts from
+            int rc = split_fix(p, 1);
+            if (rc) return rc;
+            e = tb_split_fm_warm_seed(&p->split_args, p->stream);
+        } else {          // the warm-ups' final filter histories are the segments' initial ones
+            e = tb_split_fm_adopt(&p->split_args, p->stream);
+        }
+        if (e != cudaSuccess) return cuda_fail(e, "tb_segments_fix");
+        p->launches++;
+        return TB_OK;
+    }
     return split_fix(p, pass);
 }
 
@@ -1375,6 +1425,7 @@ int tb_segments_end(tb_program* p) {
     p->stream_pos += n;
     p->seg_voices = 0;
     p->split_rounds++;
+    if (p->seg_fm) p->split_fm_rounds++;
     p->split_last_segments = p->split_args.n_seg;
     p->split_last_seg_samples = p->split_args.seg;
     return TB_OK;

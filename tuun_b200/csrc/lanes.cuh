@@ -1154,7 +1154,9 @@ __device__ __forceinline__ void run_fm_voice(const tb_insn* code, LaneMem& M, co
 // The summary pass of a time-axis split of a fused FM voice (abi.cpp render_split_fm): only the carrier's phase
 // sum matters — the modulator's tile, the affine map and the phase steps; no sines, no filter, no rows (a third of
 // the full tile's instructions).  After `snap_tile` tiles the accumulator so far is recorded in *snap: the phase
-// at the point where the NEXT segment's filter warm-up starts.
+// at the point where the NEXT segment's filter warm-up starts — and, when the voice has a filter, in the first two
+// words of its history in the state block as well (nothing reads a filter's history after a summary pass), so that
+// the snapshot travels with the state blocks the ranks of a time-sharded render exchange.
 template <bool SLOW>
 __device__ __forceinline__ void run_fm_sums(const tb_insn* code, LaneMem& M, const SineK& sk, bool active, u64 n_tiles,
                                             u64 snap_tile, unsigned long long* snap) {
@@ -1169,11 +1171,14 @@ __device__ __forceinline__ void run_fm_sums(const tb_insn* code, LaneMem& M, con
     u64 p = p_start;
     const FmRot rr = fm_rot_load(rot);
     float car[LS];
+    u64 snapped = acc0;
     for (u64 t = 0; t < n_tiles; t++) {
-        if (t == snap_tile && snap) *snap = acc0 + ((p - p_start) << 20);
+        if (t == snap_tile) snapped = acc0 + ((p - p_start) << 20);
         fm_carrier_tile<SLOW, false, true>(car, S, Cq, rot, rr, mm, cc, p, sk);
     }
-    if (n_tiles == snap_tile && snap) *snap = acc0 + ((p - p_start) << 20);
+    if (n_tiles == snap_tile) snapped = acc0 + ((p - p_start) << 20);
+    if (snap) *snap = snapped;
+    if (w1.c >= 0) st64(M, w1.c + 2, snapped);
     st64(M, w0.b, acc0 + ((p - p_start) << 20));
 }
 

@@ -306,7 +306,9 @@ __global__ void split_fm_warm_seed_kernel(const tb_split_args A) {
     const tb_split_entry ec = A.entries[A.fm_carrier], ef = A.entries[A.fm_filter];
     const u64 guess = ldu64(A.real_state + (size_t)v * A.state_words, ec.state_off);  // what every segment of the summary pass started from
     const u64 prev_start = ldu64(A.vi + (size_t)(vv - 1) * A.state_words, ec.state_off);
-    stu64(dst, ec.state_off, prev_start + (A.snap[vv - 1] - guess));
+    // (the snapshot of the summary pass sits in the first two history words of the previous segment's final state)
+    const u64 snap = ldu64(A.vs + (size_t)(vv - 1) * A.state_words, ef.state_off + 2);
+    stu64(dst, ec.state_off, prev_start + (snap - guess));
     const tb_filter_tab* ft = &A.filt[ef.a];
     for (uint32_t k = 0; k < ft->K - 1 + ft->J; k++) dst[ef.state_off + 2 + k] = 0u;
 }
