@@ -231,7 +231,8 @@ def time_shard_record(args, world, rank, local, barrier, peak):
     V = args.shard_voices
     n = int(round(args.shard_seconds * SAMPLE_RATE))
     head = 256
-    S, seg = plan_segments(n - head, world, per_rank=512)
+    # segments of at least 16,384 samples (room for the filters' warm-up: the cheaper form of the split), at most 512 a rank
+    S, seg = plan_segments(n - head, world, per_rank=max(32, min(512, (n - head) // (world * 16384))))
     params = torch.from_numpy(fm_filter_params(fm_filter_sample_ids(V))).cuda()
     prog = Program(fm_filter_voice(), SAMPLE_RATE, device=local)
     stream = torch.cuda.ExternalStream(prog.stream, device=local)
