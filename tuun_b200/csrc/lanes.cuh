@@ -1,4 +1,5 @@
-// lanes.cuh — the lane-per-voice kernels (lanes.cu, lanes_queue.cu, lanes_fm.cu): large batches of steady-state voices.
+// lanes.cuh — the lane-per-voice kernels (lanes.cu, lanes_queue.cu, lanes_fm.cu; lanes_split.cu and lanes_fm_split.cu for
+// the segments of a time-axis split): large batches of steady-state voices.
 //
 // render.cu gives every voice a warp and turns the reference's sequential state into warp scans.
 // With tens of thousands of voices in one call the batch itself is the parallel axis: here ONE
@@ -17,9 +18,11 @@
 // The program is the ST_* stream of the steady-state interpreter (steady.cuh) with operands
 // rewritten and common chains fused by lower.cpp (build_lane_plan, fuse_lane_fm); state blocks are
 // those of the other kernels, so launches of either kind continue one stream.  The host (abi.cpp
-// launch_generate) renders the first general tile of a stream and the < 16 samples of a call that
+// launch_generate_seq) renders the first general tile of a stream and the < 16 samples of a call that
 // do not fill a tile with tb_render_kernel — except for a program that is one fused FM voice, whose
-// loop (run_fm_voice) starts the stream and takes those samples itself.
+// loop (run_fm_voice) starts the stream and takes those samples itself.  A thread may also own ONE
+// SEGMENT of a voice (TB_LANES_VSPLIT: abi.cpp split_pass): parameters, noise streams and the row
+// belong to the voice, the state block to the segment.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -214,7 +214,7 @@ struct tb_goe {
     uint32_t step_off;    // into the goe step table: pairs (sign, cval index): value -= / += cval
 };
 
-// Time-axis split (split.cu, abi.cpp render_split): a steady program's carried state at ANY sample offset
+// Time-axis split (split.cu, abi.cpp render_split_round): a steady program's carried state at ANY sample offset
 // follows from per-segment summaries, so one voice can be rendered as S independent segments ("virtual
 // voices") once every segment knows its initial state.  One entry per stateful node of the steady stream:
 //   SP_POS         Time / Noise position: + 1 per sample                                   (analytic)

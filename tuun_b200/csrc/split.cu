@@ -1,4 +1,4 @@
-// split.cu — time-axis split of a steady program (program.h tb_split_entry; abi.cpp render_split).
+// split.cu — time-axis split of a steady program (program.h tb_split_entry; abi.cpp render_split_round, render_split_fm).
 //
 // The reference streams a waveform block by block and keeps the cursor in the tree's own State
 // (generator.rs:12-35, :76-85).  For a steady program every piece of that state is either a
