@@ -138,9 +138,10 @@ int tb_render(tb_program* p, const float* params, uint32_t n_params, uint32_t n_
  * out[v][i] for i < out_len[v], in f32.  With rows (`out` given) the adds run in voice index order
  * exactly like the tracker's serial `out[j] += tmp[j]` (tracker.rs:617-619).  With TB_NO_VOICE_OUT
  * (`out` may be NULL) a large steady batch never materialises its rows: each warp of the lane kernel
- * adds its 32 voices on the chip — two blocks of 16 in voice order, then the two blocks — and the
- * per-warp partial rows are added in warp order; the first 256-271 samples of a stream are mixed in
- * plain voice order.  That is the same sum RE-ASSOCIATED in blocks of 16 / 32 voices: deterministic,
+ * adds its 32 voices on the chip in voice order and the per-warp partial rows are added in warp
+ * order (programs other than a single fused FM voice: the first 256-271 samples of a stream are
+ * rendered by the general kernel and mixed in plain voice order).  That is the same sum
+ * RE-ASSOCIATED in blocks of 32 voices ((v0 + .. + v31) + (v32 + .. + v63) + ..): deterministic,
  * equal to the serial order within f32 re-association (|difference| <= a few ulp of the mix x
  * log2(voices)), not bit-identical to it.  Callers that need the tracker's exact order pass rows.
  * `mix` holds n_samples floats, is overwritten, and lives where `out` lives (TB_OUT_DEVICE).

@@ -215,40 +215,27 @@ def test_default_threshold_keeps_small_batches_on_the_warp_kernel(monkeypatch):
 
 
 def test_mixdown_on_chip(monkeypatch):
-    """tb_render_mix without rows on a large steady batch: the head tile is mixed in voice order, the
-    lane part is summed on the chip in blocks — 16 voices serially, two blocks per warp, warps in
-    order — and never written as rows.  Checked bit for bit against that order applied to the rows
-    the same kernels render, and against the oracle's serial mix within the per-voice tolerance."""
+    """tb_render_mix without rows on a large steady batch: the voices are summed on the chip in blocks — the 32
+    voices of a warp in voice order, warps in order — and never written as rows (the fused-FM-voice kernel takes the
+    whole call, from the stream's first sample to the samples that do not fill a tile).  Checked bit for bit against
+    that order applied to the rows the same kernel renders, and against the oracle's serial mix within the
+    per-voice tolerance."""
     V, N = 1000, 256 + 16 * 50
     w, params = cfg5(V)
     rows = np.zeros((V, N), dtype=np.float32)
-    # rows rendered the way the mixdown renders: general head tile, then lane tiles (without its own kernel the
-    # fused voice runs inside the interpreter kernel, behind a general head like any other program)
-    monkeypatch.setenv("TUUN_B200_LANE_FM_KERNEL", "0")
     program(w, monkeypatch).render(rows, params=params)
-    monkeypatch.delenv("TUUN_B200_LANE_FM_KERNEL")
     p = program(w, monkeypatch)
     mix = np.full(N, np.inf, dtype=np.float32)
     lens = p.render_mix(mix, V, params=params)
-    assert p.info.lane_launches == 1 and (lens == N).all()
-    want = np.zeros(N, dtype=np.float32)
-    for v in range(V):
-        want[:256] += rows[v, :256]
-    padded = np.zeros((1024, N - 256), dtype=np.float32)
-    padded[:V] = rows[:, 256:]
+    assert p.info.lane_launches == 1 and p.info.kernel_launches == 2 and (lens == N).all()   # the lane kernel + one tb_mix_kernel
+    padded = np.zeros((1024, N), dtype=np.float32)
+    padded[:V] = rows
+    want = None
     for wi in range(0, 1024, 32):
-        lo = np.zeros(N - 256, dtype=np.float32)
-        hi = np.zeros(N - 256, dtype=np.float32)
-        lo += padded[wi]
-        hi += padded[wi + 16]
-        for v in range(1, 16):
-            lo += padded[wi + v]
-            hi += padded[wi + 16 + v]
-        part = lo + hi
-        if wi == 0:
-            want[256:] = part
-        else:
-            want[256:] += part
+        part = padded[wi].copy()
+        for v in range(1, 32):
+            part += padded[wi + v]
+        want = part if want is None else want + part
     np.testing.assert_array_equal(mix, want)
     # ragged length, device mix buffer, against the oracle
     import torch

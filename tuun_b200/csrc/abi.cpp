@@ -841,11 +841,15 @@ int launch_generate(tb_program* p, const tb_launch& L, uint64_t pos) {
 // it is summed over the 32 voices of each warp inside the lane kernel (lanes.cuh mix_tile) and the
 // per-warp partial rows are added in warp order.  No voice row of the lane part ever reaches memory.
 int render_mix_lanes(tb_program* p, const tb_launch& L, float* d_mix, uint64_t pos) {
-    uint64_t head = (p->pos_known && pos >= (uint64_t)TB_TILE) ? 0 : TB_TILE;  // see launch_generate
-    head += (L.n_samples - head) % TB_LS;
+    // The fused-FM-voice kernel starts a stream itself and takes the samples that do not fill a tile (as for rows,
+    // launch_generate_seq): one lane launch for the whole call, no general head.
+    const bool fm_whole = fm_kernel_applies(p, L.n_voices) && p->pos_known && L.n_samples >= TB_LS;
+    uint64_t head = fm_whole ? 0 : ((p->pos_known && pos >= (uint64_t)TB_TILE) ? 0 : TB_TILE);  // see launch_generate_seq
+    if (!fm_whole) head += (L.n_samples - head) % TB_LS;
     const uint64_t bulk = L.n_samples - head;
+    const uint64_t stride = (bulk + TB_LS - 1) / TB_LS * TB_LS;  // partial rows hold whole tiles
     const uint64_t n_warps = (L.n_voices + 31) / 32;
-    const size_t need = std::max<size_t>((size_t)L.n_voices * head, (size_t)n_warps * bulk);
+    const size_t need = std::max<size_t>((size_t)L.n_voices * head, (size_t)n_warps * stride);
     if (need > p->stage_cap) {
         for (int i = 0; i < 2; i++) {
             cudaFree(p->d_stage[i]);
@@ -875,9 +879,9 @@ int render_mix_lanes(tb_program* p, const tb_launch& L, float* d_mix, uint64_t p
     B.accumulate = head ? 1 : L.accumulate;
     B.done = nullptr;
     B.mix_partial = p->d_stage[1];
-    B.mix_stride = bulk;
+    B.mix_stride = stride;
     if ((rc = launch_lanes(p, B))) return rc;
-    e = tb_mix_launch(p->d_stage[1], bulk, nullptr, (uint32_t)n_warps, bulk, 0, d_mix + head, 0, p->stream);
+    e = tb_mix_launch(p->d_stage[1], stride, nullptr, (uint32_t)n_warps, bulk, 0, d_mix + head, 0, p->stream);
     if (e != cudaSuccess) return cuda_fail(e, "tb_mix_kernel launch");
     p->launches++;
     return TB_OK;

@@ -792,18 +792,28 @@ __device__ __forceinline__ void store_single(RowStore& R, int l, int half) {
     }
     R.off += LS;
 }
-// Mixdown without rows (tb_render_mix with TB_NO_VOICE_OUT): instead of leaving, the tile is summed over
-// the warp's 32 voices on the chip — lane l adds sample (l & 15) of voices 16 (l >> 4) .. +15 in voice
-// order, the two halves are added, and 64 bytes of partial sums go to the warp's row of
-// tb_launch::mix_partial.  tb_mix_kernel then adds the rows of all warps in warp order: the tracker's
-// serial `out[j] += tmp[j]` (tracker.rs:617-619) re-associated in blocks of 16 voices.
+// Mixdown without rows (tb_render_mix with TB_NO_VOICE_OUT): instead of leaving, every pair of tiles is summed over
+// the warp's 32 voices on the chip — lane l adds sample l of the pair (32 samples) over voices 0 .. 31 IN VOICE
+// ORDER (with the chunk stride of AS units the 32 lanes of a load touch 32 different banks) — and 128 bytes of
+// partial sums go to the warp's row of tb_launch::mix_partial.  tb_mix_kernel then adds the rows of all warps in
+// warp order: the tracker's serial `out[j] += tmp[j]` (tracker.rs:617-619) re-associated in blocks of 32 voices.
+__device__ __forceinline__ void mix_pair(RowStore& R, int l) {
+    __syncwarp();
+    const int half = l >> 4, smp = l & 15;
+    const float* a = reinterpret_cast<const float*>(R.tbase + (4 * half + (smp >> 2)) * AS) + (smp & 3);
+    float s = a[0];
+    UNROLL for (int v = 1; v < 32; v++) s = __fadd_rn(s, a[4 * v]);
+    __syncwarp();
+    R.mix[R.off + l] = s;
+    R.off += 2 * LS;
+}
+// An odd last tile (in half `half` of the buffer): the same sums, sixteen lanes at work.
 __device__ __forceinline__ void mix_tile(RowStore& R, int l, int half) {
     __syncwarp();
     const int smp = l & 15;
-    const float* a = reinterpret_cast<const float*>(R.tbase + (4 * half + (smp >> 2)) * AS + 16 * (l >> 4)) + (smp & 3);
+    const float* a = reinterpret_cast<const float*>(R.tbase + (4 * half + (smp >> 2)) * AS) + (smp & 3);
     float s = a[0];
-    UNROLL for (int v = 1; v < 16; v++) s = __fadd_rn(s, a[4 * v]);
-    s = __fadd_rn(s, __shfl_down_sync(FULL, s, 16));
+    UNROLL for (int v = 1; v < 32; v++) s = __fadd_rn(s, a[4 * v]);
     __syncwarp();
     if (l < 16) R.mix[R.off + l] = s;
     R.off += LS;
@@ -811,9 +821,13 @@ __device__ __forceinline__ void mix_tile(RowStore& R, int l, int half) {
 // Tile number t (from 0) of the launch has just been written to its half of the buffer.
 template <bool MIX>
 __device__ __forceinline__ void tile_done(RowStore& R, int l, u64 t, u64 n_tiles) {
-    if (MIX) mix_tile(R, l, (int)(t & 1));
-    else if (t & 1) store_pair(R, l);
-    else if (t + 1 == n_tiles) store_single(R, l, 0);
+    if (t & 1) {
+        if (MIX) mix_pair(R, l);
+        else store_pair(R, l);
+    } else if (t + 1 == n_tiles) {
+        if (MIX) mix_tile(R, l, 0);
+        else store_single(R, l, 0);
+    }
 }
 
 // ---- a program that is ONE fused FM voice ----------------------------------------------------------
@@ -1105,8 +1119,10 @@ __device__ __forceinline__ void run_fm_voice(const tb_insn* code, LaneMem& M, co
                 UNROLL for (int j = 0; j < LS; j++) car[j] = nxt[j];
             }
 #if TB_ABL != 5
-            if (MIX) mix_tile(R, l, (int)odd);
-            else if (odd) store_pair(R, l);
+            if (odd) {
+                if (MIX) mix_pair(R, l);
+                else store_pair(R, l);
+            }
 #endif
             odd ^= 1u;
         }
@@ -1118,7 +1134,7 @@ __device__ __forceinline__ void run_fm_voice(const tb_insn* code, LaneMem& M, co
         }
         tile_done<MIX>(R, l, n_tiles - 1, n_tiles);
     }
-    if (!MIX && rem > 0) {  // the samples that do not fill a tile (rows only: the on-chip mixdown gets whole tiles)
+    if (rem > 0) {  // the samples that do not fill a tile
         const int half = (int)(n_tiles & 1);
         if (active) {
             u64 p_rem = p;
@@ -1140,7 +1156,10 @@ __device__ __forceinline__ void run_fm_voice(const tb_insn* code, LaneMem& M, co
             M.A = abase + half * 4 * AS;
             lacc_store(M, y);
         }
-        store_partial(R, l, half, rem);
+        // (mixdown: a whole tile of sums is written, of which the caller reads the first `rem`: the partial rows are
+        // padded to whole tiles)
+        if (MIX) mix_tile(R, l, half);
+        else store_partial(R, l, half, rem);
     }
     M.A = abase;
     if (active) {  // registers -> state block; finish_lane advances the modulator's accumulator
