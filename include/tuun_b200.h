@@ -244,6 +244,9 @@ typedef struct tb_program_info {
     uint32_t sequence_parts;  /* 0: the tree is one program */
     uint32_t split_fm_rounds; /* of split_rounds: those in the form for fused FM voices (phase-sum pass, filter warm-up, samples) */
     uint64_t sequence_renders; /* generate launches that went part by part */
+    uint32_t lane_fm_ws_capacity; /* 32-voice CTAs of the fused-FM-voice kernel's two-warps-a-voice form the device holds at once; 0: not applicable */
+    uint32_t reserved0;
+    uint64_t fm_ws_launches;  /* of lane_launches: those of that form (tb_render_lanes_fm_ws_kernel) */
 } tb_program_info;
 int tb_program_get_info(const tb_program* p, tb_program_info* info);
 

@@ -56,6 +56,9 @@ pub struct TbProgramInfo {
     pub sequence_parts: u32,
     pub split_fm_rounds: u32,
     pub sequence_renders: u64,
+    pub lane_fm_ws_capacity: u32,
+    pub reserved0: u32,
+    pub fm_ws_launches: u64,
 }
 
 pub const TB_OUT_DEVICE: u32 = 1;

@@ -55,6 +55,9 @@ class TbProgramInfo(ctypes.Structure):
         ("sequence_parts", ctypes.c_uint32),
         ("split_fm_rounds", ctypes.c_uint32),
         ("sequence_renders", ctypes.c_uint64),
+        ("lane_fm_ws_capacity", ctypes.c_uint32),
+        ("reserved0", ctypes.c_uint32),
+        ("fm_ws_launches", ctypes.c_uint64),
     ]
 
 

@@ -23,6 +23,10 @@ extern "C" cudaError_t tb_kernel_launch(const tb_launch* P, size_t smem, uint32_
 extern "C" size_t tb_lanes_smem_bytes(uint32_t n_lane_code, uint32_t w_words, uint32_t q_units, uint32_t slots);
 extern "C" cudaError_t tb_lanes_launch(const tb_launch* P, size_t smem, int kind, cudaStream_t stream);
 extern "C" cudaError_t tb_lanes_occupancy(size_t smem, int kind, int* blocks_per_sm, int* n_sm);
+// lanes_fm_ws.cu: the fused FM voice as a phase warp and a tone warp per 32 voices
+extern "C" size_t tb_lanes_fm_ws_smem_bytes(uint32_t n_lane_code, uint32_t w_words, uint32_t q_units, uint32_t slots);
+extern "C" void tb_lanes_fm_ws_run(const tb_launch* P, size_t smem, cudaStream_t stream);
+extern "C" cudaError_t tb_lanes_fm_ws_occupancy(size_t smem, int* blocks_per_sm);
 extern "C" cudaError_t tb_len_set(unsigned long long* out_len, uint32_t n, unsigned long long add, int accumulate,
                                   cudaStream_t stream);
 extern "C" cudaError_t tb_mix_launch(const float* rows, uint64_t stride, const unsigned long long* lens,
@@ -80,6 +84,10 @@ struct tb_program {
     uint32_t lane_min_voices = 0;   // batches at least this large take it
     uint32_t lane_capacity = 0;     // CTAs of the lane interpreter kernels the device holds at once
     uint32_t lane_fm_capacity = 0;  // same for the fused-FM-voice kernel; 0: the program is not one fused FM voice
+    uint32_t lane_fm_ws_capacity = 0;  // 32-voice CTAs of its two-warps-a-voice form (lanes_fm_ws.cu) the device holds; 0: not applicable
+    size_t lane_fm_ws_smem = 0;
+    uint32_t lane_fm_ws_min_voices = 0;
+    uint64_t fm_ws_launches = 0;
     uint32_t* d_lane_queue = nullptr;  // work queue of the persistent form (program.h tb_launch::lane_queue)
     size_t lane_queue_cap = 0;
     uint32_t* h_fault = nullptr;    // mapped pinned counter written by the lane kernel
@@ -271,6 +279,7 @@ void fill_launch(const tb_program* p, tb_launch* L) {
     L->fault = p->d_fault;
     L->lane_fin_goe = p->low.lane_fin_goe;
     L->lane_clk = p->low.lane_clk;
+    L->lane_kscale = 17592186044416.0 / (6.283185307179586476925286766559 * (double)p->sample_rate);
 }
 
 int launch(tb_program* p, const tb_launch& L) {
@@ -310,6 +319,9 @@ bool fm_kernel_applies(const tb_program* p, uint32_t n_voices) {
 int launch_lanes(tb_program* p, tb_launch& B) {
     const uint32_t groups = (B.n_voices + TB_LANE_THREADS - 1) / TB_LANE_THREADS;
     const bool fm = fm_kernel_applies(p, B.n_voices);
+    // ... as a phase warp and a tone warp per 32 voices when the device holds all those CTAs at once (lanes_fm_ws.cu)
+    const bool fm_ws = fm && p->lane_fm_ws_capacity != 0 && (B.n_voices + 31u) / 32u <= p->lane_fm_ws_capacity &&
+                       B.vsplit_total <= 1 && B.n_voices >= p->lane_fm_ws_min_voices;
     const char* qe = std::getenv("TUUN_B200_LANE_QUEUE");  // diagnostics: "0" never, "1" always
     const bool want = !fm && B.vsplit_total <= 1 && (qe ? qe[0] == '1' : groups > p->lane_capacity);
     B.lane_queue = nullptr;
@@ -340,7 +352,14 @@ int launch_lanes(tb_program* p, tb_launch& B) {
         CU(cudaEventCreate(&ev[1]));
     }
     CU(cudaEventRecord(ev[0], p->stream));
-    cudaError_t e = tb_lanes_launch(&B, p->lane_smem, fm ? 2 : (B.lane_queue ? 1 : 0), p->stream);
+    cudaError_t e = cudaSuccess;
+    if (fm_ws) {
+        tb_lanes_fm_ws_run(&B, p->lane_fm_ws_smem, p->stream);
+        e = cudaGetLastError();
+        p->fm_ws_launches++;
+    } else {
+        e = tb_lanes_launch(&B, p->lane_smem, fm ? 2 : (B.lane_queue ? 1 : 0), p->stream);
+    }
     if (e != cudaSuccess) return cuda_fail(e, "lane kernel launch");
     CU(cudaEventRecord(ev[1], p->stream));
     p->launches++;
@@ -960,7 +979,7 @@ static int create_program(const tb_node* nodes, uint32_t n_nodes, const int32_t*
     if (!out_program) return set_error(TB_ERR_INVALID, "out_program is NULL");
     *out_program = nullptr;
     if (!nodes || n_nodes == 0) return set_error(TB_ERR_INVALID, "empty op list");
-    if (sample_rate == 0) return set_error(TB_ERR_INVALID, "sample_rate must be > 0");
+    if (sample_rate == 0 || sample_rate >= 0x80000000u) return set_error(TB_ERR_INVALID, "sample_rate must be > 0 and below 2^31");
     if (fixed_len > 0 && !fixed_pool) return set_error(TB_ERR_INVALID, "fixed_pool is NULL");
     tb_program* p = new (std::nothrow) tb_program();
     if (!p) return set_error(TB_ERR_NOMEM, "out of host memory");
@@ -1076,6 +1095,19 @@ static int create_program(const tb_node* nodes, uint32_t n_nodes, const int32_t*
                 (lc[0].op >> 24) == TB_SINE_FAST && p->fast_mode == 2 && !(fe && fe[0] == '0')) {
                 int fb = 0, fs = 0;
                 if (tb_lanes_occupancy(ls, 2, &fb, &fs) == cudaSuccess && fb > 0) p->lane_fm_capacity = (uint32_t)(fb * fs);
+                // Two warps a voice (lanes_fm_ws.cu): a filter tail, no root Fin; its ring lies over 8 Q units.
+                const char* we = std::getenv("TUUN_B200_FM_WS");  // diagnostics: "0" keeps one thread a voice
+                const size_t ws = tb_lanes_fm_ws_smem_bytes((uint32_t)lc.size(), p->low.lane_w_words, p->low.lane_q_units,
+                                                            p->low.lane_slots);
+                int wb = 0;
+                if (p->lane_fm_capacity != 0 && lc[1].c >= 0 && p->low.lane_fin_goe < 0 && p->low.filt.size() == 1 &&
+                    p->low.lane_q_units + 4 * p->low.lane_slots >= 8 && ws <= 48 * 1024 && !(we && we[0] == '0') &&
+                    tb_lanes_fm_ws_occupancy(ws, &wb) == cudaSuccess && wb > 0) {
+                    p->lane_fm_ws_capacity = (uint32_t)(wb * fs);
+                    p->lane_fm_ws_smem = ws;
+                    const char* wm = std::getenv("TUUN_B200_FM_WS_MIN_VOICES");
+                    p->lane_fm_ws_min_voices = wm ? (uint32_t)std::strtoul(wm, nullptr, 10) : 0u;
+                }
             }
             // Default threshold: a little over one CTA per SM.  Measured on config 5: the lane kernel takes
             // the same time for 9,472 and 18,944 voices (one warp per scheduler, latency bound: 3.7e11 and
@@ -1197,6 +1229,8 @@ int tb_lower_check(const tb_node* nodes, uint32_t n_nodes, const int32_t* lists,
         info->lane_min_voices = 0;
         info->lane_capacity = 0;
         info->lane_fm_capacity = 0;
+        info->lane_fm_ws_capacity = 0;
+        info->fm_ws_launches = 0;
         info->split_passes = low.split_passes;
         info->split_segments = 0;
         info->split_seg_samples = 0;
@@ -1229,6 +1263,8 @@ int tb_program_get_info(const tb_program* p, tb_program_info* info) {
     info->lane_min_voices = p->lane_min_voices;
     info->lane_capacity = p->lane_capacity;
     info->lane_fm_capacity = p->lane_fm_capacity;
+    info->lane_fm_ws_capacity = p->lane_fm_ws_capacity;
+    info->fm_ws_launches = p->fm_ws_launches;
     info->split_passes = p->d_split ? p->low.split_passes : 0;
     info->split_segments = p->split_last_segments;
     info->split_seg_samples = p->split_last_seg_samples;

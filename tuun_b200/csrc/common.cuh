@@ -67,6 +67,7 @@ struct SineK {
     double inv_turn;  // 1 / (TAU * sample_rate)
     float flimit;     // |f| below which the magic-number conversion is exact
     float plimit;
+    uint32_t one23;   // lanes.cuh pd_m23: the bits of 1.0f in a register the compiler cannot see through
 };
 
 // rint(x) for |x| < 2^51 through the 1.5*2^52 trick; result shifted to 2^-64-turn units, so whole

@@ -168,6 +168,15 @@ __device__ __forceinline__ u64 pd_bits(double Pd) { return (u64)__double_as_long
 __device__ __forceinline__ uint32_t pd_m23(double Pd) {
     return (__funnelshift_l((uint32_t)__double2loint(Pd), (uint32_t)__double2hiint(Pd), 11) & 0x007fffffu) | 0x3f800000u;
 }
+// The same in two instructions instead of three: `(x & 0x007fffff) | 0x3f800000` with both masks as literals is two
+// LOP3s (the instruction holds one immediate); with 1.0f's bits in a register (SineK::one23, made from a launch
+// parameter so that neither compiler folds it back) it is one.  16 instructions of 352 a tile in the FM voice loop.
+__device__ __forceinline__ uint32_t pd_m23(double Pd, uint32_t one) {
+    const uint32_t x = __funnelshift_l((uint32_t)__double2loint(Pd), (uint32_t)__double2hiint(Pd), 11);
+    uint32_t r;
+    asm("lop3.b32 %0, %1, 0x007fffff, %2, 0xEA;" : "=r"(r) : "r"(x), "r"(one));
+    return r;
+}
 __device__ __forceinline__ uint32_t p44_m23(u64 p44) { return ((uint32_t)(p44 >> 21) & 0x007fffffu) | 0x3f800000u; }
 __device__ __forceinline__ float sin_m23(uint32_t m) { return __sinf(fmaf(__uint_as_float(m), TB_SIN23_A, TB_SIN23_B)); }
 __device__ __forceinline__ void sin_m23x2(uint32_t m0, uint32_t m1, float& s0, float& s1) {
@@ -873,7 +882,9 @@ __device__ __forceinline__ FmRot fm_rot_load(const double2* rot) {
     return r;
 }
 //   PHASE_ONLY: the summary pass of a time-axis split (run_fm_sums) wants the phase after the tile, not its sines.
-template <bool SLOW, bool CAP = false, bool PHASE_ONLY = false>
+//   RAW: car[] receives the bit patterns 1.m of the sines' arguments (pd_m23) instead of the sines — the producer
+//   warp of the warp-specialised kernel (lanes_fm_ws.cu) hands those to the warp that owns MUFU and the filter.
+template <bool SLOW, bool CAP = false, bool PHASE_ONLY = false, bool RAW = false>
 __device__ __forceinline__ void fm_carrier_tile(float (&car)[LS], double& S, double& Cq, const double2* rot, const FmRot& rr,
                                                 u64 mm, u64 cc, u64& p, const SineK& sk, int cap = 0, u64* p_cap = nullptr) {
     float f[LS];
@@ -929,7 +940,8 @@ __device__ __forceinline__ void fm_carrier_tile(float (&car)[LS], double& S, dou
             p += freq_to_inc(f[j + 1], sk) >> 20;
             if (CAP && j == cap) *p_cap = t0;
             if (CAP && j + 1 == cap) *p_cap = t1;
-            if (!PHASE_ONLY) sin_m23x2(p44_m23(t0), p44_m23(t1), car[j], car[j + 1]);
+            if (RAW) { car[j] = __uint_as_float(p44_m23(t0)); car[j + 1] = __uint_as_float(p44_m23(t1)); }
+            else if (!PHASE_ONLY) sin_m23x2(p44_m23(t0), p44_m23(t1), car[j], car[j + 1]);
         }
         return;
     }
@@ -957,7 +969,8 @@ __device__ __forceinline__ void fm_carrier_tile(float (&car)[LS], double& S, dou
 #if TB_ABL == 2
         car[j] = __uint_as_float(pd_m23(T0)); car[j + 1] = __uint_as_float(pd_m23(T1));
 #else
-        if (!PHASE_ONLY) sin_m23x2(pd_m23(T0), pd_m23(T1), car[j], car[j + 1]);
+        if (RAW) { car[j] = __uint_as_float(pd_m23(T0, sk.one23)); car[j + 1] = __uint_as_float(pd_m23(T1, sk.one23)); }
+        else if (!PHASE_ONLY) sin_m23x2(pd_m23(T0, sk.one23), pd_m23(T1, sk.one23), car[j], car[j + 1]);
 #endif
     }
     p = pd_bits(Pd);
@@ -1246,6 +1259,7 @@ __device__ __forceinline__ void lanes_body(const tb_launch& P, uint32_t group, u
     sk.inv_turn = 1.0 / (TB_TAU * (double)P.sample_rate);
     sk.flimit = (float)(TB_FM_TURNS * TB_TAU * (double)P.sample_rate);  // tighter than render.cu's 100: see pd_make
     sk.plimit = 600.0f;
+    sk.one23 = 0x3f800000u | (P.sample_rate >> 31);  // (sample rates stay below 2^31: tb_program_create)
 
     // the voice's state block; with the time-axis split (tb_launch::vsplit*) that of its segment
     const uint32_t rvoice = !TB_LANES_VSPLIT ? voice : voice / (P.vsplit ? P.vsplit : 1u);  // parameters, noise streams

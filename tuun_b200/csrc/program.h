@@ -327,4 +327,6 @@ struct tb_launch {
     uint32_t fm_sums;      // fused FM voice, summary pass: the carrier's phase sum alone (lanes.cuh run_fm_sums)
     unsigned long long* vsnap;  // ... which records the accumulator after vsnap_at samples in vsnap[state block]
     uint64_t vsnap_at;
+    double lane_kscale;    // 2^44 / (TAU * sample_rate) (common.cuh SineK::kscale), made by the host: an operand straight out of
+                           // the constant bank instead of two registers of the warps that live on 64 (lanes_fm_ws.cu)
 };
