@@ -211,6 +211,7 @@ def strong_record(args, world, rank, local, n_samples, barrier, peak):
     value = args.voices * n_samples * steps / (ms * 1e-3)
     kernel = ("tb_render_lanes_fm_split_kernel after tb_render_lanes_fm_sums_kernel (every voice cut in time: phase-sum pass, "
               "filter warm-up, samples)" if info.lane_launches and info.lane_fm_capacity and info.split_rounds
+              else "tb_render_lanes_fm_ws_kernel" if info.lane_launches and info.fm_ws_launches
               else "tb_render_lanes_fm_kernel" if info.lane_launches and info.lane_fm_capacity
               else "tb_render_lanes_kernel" if info.lane_launches else "tb_render_kernel")
     return {"value": value, "unit": UNIT, "ms_per_step": ms / steps, "voices": args.voices,
@@ -421,7 +422,8 @@ def main():
     lane_ms = prog.lane_kernel_times(args.steps) if info.lane_launches else np.zeros(0)
     if len(lane_ms):
         groups = (n_local + 63) // 64
-        kernel = ("tb_render_lanes_fm_kernel" if info.lane_fm_capacity and groups <= info.lane_fm_capacity
+        kernel = ("tb_render_lanes_fm_ws_kernel" if info.fm_ws_launches
+                  else "tb_render_lanes_fm_kernel" if info.lane_fm_capacity and groups <= info.lane_fm_capacity
                   else "tb_render_lanes_queue_kernel" if groups > info.lane_capacity else "tb_render_lanes_kernel")
         # the fused-FM-voice kernel renders the whole call in one launch; the interpreter kernels leave the first
         # 256-sample tile and the < 16 samples past the last lane tile to the general kernel

@@ -483,6 +483,51 @@ def test_fm_voice_kernel_edges(monkeypatch):
     assert np.max(np.abs(out[3] - ref[3])) <= 1e-3
 
 
+def test_fm_ws_matches_single_thread_kernel(monkeypatch):
+    """The fused FM voice as a phase warp and a tone warp per 32 voices (lanes_fm_ws.cu, the default when the device
+    holds all those CTAs at once) against the one-thread-a-voice form (lanes_fm.cu, TUUN_B200_FM_WS=0): the same
+    operations in the same order on both sides of the hand-over, so rows, lengths, carried state (later calls of the
+    same stream) and the on-chip mixdown are bit-identical — over ragged batch sizes (a last CTA with dead lanes),
+    call lengths around tile pairs, a slow-conversion voice, and rows that are only 8-byte aligned."""
+    import torch
+    from tuun_b200.workloads import fm_filter_params, fm_filter_sample_ids, fm_filter_voice
+    w = fm_filter_voice()
+
+    def run(ws, V, calls, mix=False, wild=False):
+        monkeypatch.setenv("TUUN_B200_FM_WS", "1" if ws else "0")
+        p = program(w, monkeypatch)
+        prm = fm_filter_params(fm_filter_sample_ids(V))
+        if wild:
+            prm[min(3, V - 1), 1] = 6.0e7
+        params = torch.from_numpy(prm).cuda()
+        outs = []
+        for n in calls:
+            if mix:
+                m = torch.zeros((n,), dtype=torch.float32, device="cuda")
+                p.render_mix(m, V, params=params)
+                outs.append(m.cpu().numpy())
+            else:
+                out = torch.full((V, n), float("inf"), dtype=torch.float32, device="cuda")
+                lens = p.render(out, params=params, out_len=np.zeros(V, dtype=np.uint64))
+                assert (lens == n).all()
+                outs.append(out.cpu().numpy())
+        return outs, int(p.info.fm_ws_launches), int(p.info.lane_launches)
+
+    for V, calls, wild in [(64, [4096, 1000], False), (100, [4101, 16, 31, 777], False), (33, [17, 15, 16, 48, 64], False),
+                           (2049, [2048 + 13, 32], False), (40, [2000, 18], True), (12352, [4096 + 5], False)]:
+        a, wa, la = run(False, V, calls, wild=wild)
+        b, wb, lb = run(True, V, calls, wild=wild)
+        assert wa == 0 and wb == lb == la == sum(1 for n in calls if n >= 16), (V, calls, wa, wb, la, lb)
+        for x, y in zip(a, b):
+            np.testing.assert_array_equal(x.view(np.uint32), y.view(np.uint32))
+    for V, calls in [(4096, [4096 + 7, 640]), (1000, [8000])]:
+        a, _, _ = run(False, V, calls, mix=True)
+        b, wb, _ = run(True, V, calls, mix=True)
+        assert wb == len(calls)
+        for x, y in zip(a, b):
+            np.testing.assert_array_equal(x.view(np.uint32), y.view(np.uint32))
+
+
 def test_reset_oscillators(monkeypatch):
     """sawtooth, pulse (with a modulated width) and triangle of lib/v0/std.tuun — a Reset over a tree that is
     closed-form in the run's own clock — as large batches: the lane kernels render the trigger, turn it into a

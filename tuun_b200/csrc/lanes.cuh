@@ -199,9 +199,33 @@ __device__ __forceinline__ double f32_to_f64_alu(float f) {
     const uint32_t hi = (((b >> 3) & 0x0fffffffu) + 0x38000000u) | (b & 0x80000000u);
     return __hiloint2double((int)hi, (int)(b << 29));
 }
+// What the phase warp of lanes_fm_ws.cu hands over for two samples (fm_carrier_tile<.., RAW>): the floats 1.m, or —
+// TB_WS_ARG — the sines' arguments made from them (the FFMA2 of sin_m23x2 moved to the warp with time to spare).
+#ifndef TB_WS_ARG
+#define TB_WS_ARG 0
+#endif
+__device__ __forceinline__ void raw_pair(uint32_t m0, uint32_t m1, float& r0, float& r1) {
+#if TB_WS_ARG
+    unpk2(fma2(pk2(__uint_as_float(m0), __uint_as_float(m1)), pk2(TB_SIN23_A, TB_SIN23_A), pk2(TB_SIN23_B, TB_SIN23_B)), r0, r1);
+#else
+    r0 = __uint_as_float(m0);
+    r1 = __uint_as_float(m1);
+#endif
+}
 // The low word of (f * scale + 1.5 * 2^52): rint(f * scale) mod 2^32.
 #ifndef TB_F2F_ALU
 #define TB_F2F_ALU 0
+#endif
+
+// The carrier frequency as a double in the running-phase DFMA of fm_carrier_tile: the conversion unit, or (TB_WIDEN_ALU) integer
+// instructions.
+#ifndef TB_WIDEN_ALU
+#define TB_WIDEN_ALU 0
+#endif
+#if TB_WIDEN_ALU
+#define TB_WIDEN(x) f32_to_f64_alu(x)
+#else
+#define TB_WIDEN(x) ((double)(x))
 #endif
 
 __device__ __forceinline__ uint32_t magic_lo(float f, double scale) {
@@ -940,7 +964,7 @@ __device__ __forceinline__ void fm_carrier_tile(float (&car)[LS], double& S, dou
             p += freq_to_inc(f[j + 1], sk) >> 20;
             if (CAP && j == cap) *p_cap = t0;
             if (CAP && j + 1 == cap) *p_cap = t1;
-            if (RAW) { car[j] = __uint_as_float(p44_m23(t0)); car[j + 1] = __uint_as_float(p44_m23(t1)); }
+            if (RAW) raw_pair(p44_m23(t0), p44_m23(t1), car[j], car[j + 1]);
             else if (!PHASE_ONLY) sin_m23x2(p44_m23(t0), p44_m23(t1), car[j], car[j + 1]);
         }
         return;
@@ -961,15 +985,15 @@ __device__ __forceinline__ void fm_carrier_tile(float (&car)[LS], double& S, dou
     double Pd = pd_make(p);
     UNROLL for (int j = 0; j < LS; j += 2) {
         const double T0 = Pd;
-        Pd = fma((double)f[j], sk.kscale, Pd);
+        Pd = fma(TB_WIDEN(f[j]), sk.kscale, Pd);
         const double T1 = Pd;
-        Pd = fma((double)f[j + 1], sk.kscale, Pd);
+        Pd = fma(TB_WIDEN(f[j + 1]), sk.kscale, Pd);
         if (CAP && j == cap) *p_cap = pd_bits(T0);
         if (CAP && j + 1 == cap) *p_cap = pd_bits(T1);
 #if TB_ABL == 2
         car[j] = __uint_as_float(pd_m23(T0)); car[j + 1] = __uint_as_float(pd_m23(T1));
 #else
-        if (RAW) { car[j] = __uint_as_float(pd_m23(T0, sk.one23)); car[j + 1] = __uint_as_float(pd_m23(T1, sk.one23)); }
+        if (RAW) raw_pair(pd_m23(T0, sk.one23), pd_m23(T1, sk.one23), car[j], car[j + 1]);
         else if (!PHASE_ONLY) sin_m23x2(pd_m23(T0, sk.one23), pd_m23(T1, sk.one23), car[j], car[j + 1]);
 #endif
     }

@@ -18,6 +18,17 @@
 // State blocks, stream position, rows and partial mix rows are those of lanes_fm.cu: results are
 // bit-identical (tests/test_gpu_lanes.py::test_fm_ws_matches_single_thread_kernel).
 #define TB_LANE_THREADS 32
+// Measured on 65,536 voices x 2 s (this kernel 6.00 ms as first written): the conversion / special-function unit is the
+// busy one (56 % of its instruction rate, in bursts), so the carrier frequency becomes a double by integer
+// instructions here (lanes.cuh f32_to_f64_alu: 4.5 instructions instead of one F2F.F64.F32; 5.90 ms) — a trade the
+// one-thread form loses (32.3 against 31.1 ms there) — and with that the phase warp also makes the sines' arguments
+// (the FFMA2 of sin_m23x2: 5.85 ms; without the integer widening that move costs 0.05 ms).
+#ifndef TB_WIDEN_ALU
+#define TB_WIDEN_ALU 1
+#endif
+#ifndef TB_WS_ARG
+#define TB_WS_ARG 1
+#endif
 #include "lanes.cuh"
 
 namespace {
@@ -39,12 +50,6 @@ __device__ __forceinline__ void ring_put(uint4* ring, const float (&v)[LS]) {
         ring[q * LT] = make_uint4(__float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]), __float_as_uint(v[4 * q + 2]),
                                   __float_as_uint(v[4 * q + 3]));
 }
-__device__ __forceinline__ void ring_get(const uint4* ring, uint32_t (&m)[LS]) {
-    UNROLL for (int q = 0; q < 4; q++) {
-        const uint4 t = ring[q * LT];
-        m[4 * q] = t.x; m[4 * q + 1] = t.y; m[4 * q + 2] = t.z; m[4 * q + 3] = t.w;
-    }
-}
 
 // Barrier numbers are immediates (a register operand makes ptxas reserve all 16 barriers for the CTA, which costs
 // resident CTAs), so the loops below take tiles in pairs: buffer 0, then buffer 1.
@@ -65,10 +70,12 @@ struct PhaseRegs {
     FmRot rr;
 };
 // One tile of the phase warp into buffer B.  CAP: the tile of which only the first `rem` samples count.
-template <bool SLOW, uint32_t B, bool CAP>
+//   ALL: every lane has a live voice (the flag would otherwise sit in a register this warp does not have: measured,
+//   18 % of the kernel's stall samples were the two warps waiting for it to come back from local memory).
+template <bool SLOW, uint32_t B, bool CAP, bool ALL = false>
 __device__ __forceinline__ void phase_step(PhaseRegs& G, const double2* rot, const SineK& sk, uint4* ring, bool active, int rem) {
     nb_sync<Bar<B>::empty>();
-    if (active) {
+    if (ALL || active) {
         float raw[LS];
         if (CAP) {
             u64 p_rem = G.p;
@@ -102,9 +109,16 @@ __device__ __forceinline__ void ws_phase(const tb_insn* code, LaneMem& M, const 
         G.rr = fm_rot_load(rot);
     }
     __syncwarp();  // the ring lies over the rotation table: every lane has read its entries
-    for (uint32_t left = (uint32_t)(n_tiles >> 1); left != 0; left--) {
-        phase_step<SLOW, 0, false>(G, rot, sk, ring, active, 0);
-        phase_step<SLOW, 1, false>(G, rot, sk, ring, active, 0);
+    if (__all_sync(FULL, active)) {
+        for (uint32_t left = (uint32_t)(n_tiles >> 1); left != 0; left--) {
+            phase_step<SLOW, 0, false, true>(G, rot, sk, ring, true, 0);
+            phase_step<SLOW, 1, false, true>(G, rot, sk, ring, true, 0);
+        }
+    } else {
+        for (uint32_t left = (uint32_t)(n_tiles >> 1); left != 0; left--) {
+            phase_step<SLOW, 0, false>(G, rot, sk, ring, active, 0);
+            phase_step<SLOW, 1, false>(G, rot, sk, ring, active, 0);
+        }
     }
     if (n_tiles & 1) {
         phase_step<SLOW, 0, false>(G, rot, sk, ring, active, 0);
@@ -140,7 +154,12 @@ __device__ __forceinline__ void tone_tile(const uint4* ring, float4* dst, ToneRe
         float yq[4];
         UNROLL for (int h = 0; h < 2; h++) {
             float x0, x1;
+#if TB_WS_ARG
+            x0 = __sinf(__uint_as_float(mq[2 * h]));
+            x1 = __sinf(__uint_as_float(mq[2 * h + 1]));
+#else
             sin_m23x2(mq[2 * h], mq[2 * h + 1], x0, x1);
+#endif
             const u64 xx = pk2(x0, x1);
             float s0, s1, q0, q1;
             unpk2(mul2(xx, bb0), s0, s1);
@@ -174,10 +193,10 @@ __device__ __forceinline__ void tone_tile(const uint4* ring, float4* dst, ToneRe
 
 // One tile of the tone warp out of buffer B: sines, filter, into half B of the row buffer.
 //   refill: the phase warp has a tile to put into this buffer again.
-template <uint32_t B>
+template <uint32_t B, bool ALL = false>
 __device__ __forceinline__ void tone_step(ToneRegs& F, float4* abase, const uint4* ring, bool active, bool refill) {
     nb_sync<Bar<B>::full>();
-    if (active) tone_tile<false>(ring + B * 4 * LT, abase + B * 4 * AS, F, nullptr, nullptr);
+    if (ALL || active) tone_tile<false>(ring + B * 4 * LT, abase + B * 4 * AS, F, nullptr, nullptr);
     // (handed back after the tile, not after its loads: sixteen words waiting in registers do not fit next to the filter,
     // and the phase warp is the one with time to spare)
     if (refill) nb_arrive<Bar<B>::empty>();  // (the whole warp, once)
@@ -206,7 +225,7 @@ __device__ __forceinline__ void ws_tone(const tb_insn* code, LaneMem& M, RowStor
     if (slots > 1) nb_arrive<BAR_EMPTY1>();
     const uint32_t pairs = (uint32_t)(n_tiles >> 1);
     // (every pair but the last is followed by at least two more tiles)
-    if (!MIX && R.fast && pairs > 1) {
+    if (!MIX && R.fast && pairs > 1 && __all_sync(FULL, active)) {
         // All 32 rows exist and are 16-byte aligned: lanes.cuh store_pair with nothing but a pointer and the row step
         // alive across the tiles (the general form's bookkeeping does not fit this warp's 64 registers next to the
         // filter), and the 32 x 128 bytes leaving as two batches of four rows per lane.
@@ -214,8 +233,8 @@ __device__ __forceinline__ void ws_tone(const tb_insn* code, LaneMem& M, RowStor
         const size_t step4 = R.step4;
         const float4* src = R.tbase + (l & 7) * AS + (l >> 3);
         for (uint32_t left = pairs; left > 1; left--) {
-            tone_step<0>(F, abase, ring, active, true);
-            tone_step<1>(F, abase, ring, active, true);
+            tone_step<0, true>(F, abase, ring, true, true);
+            tone_step<1, true>(F, abase, ring, true, true);
             __syncwarp();
             float* q = d;
             UNROLL for (int h = 0; h < 2; h++) {
