@@ -505,6 +505,7 @@ def test_fm_ws_matches_single_thread_kernel(monkeypatch):
             if mix:
                 m = torch.zeros((n,), dtype=torch.float32, device="cuda")
                 p.render_mix(m, V, params=params)
+                torch.cuda.synchronize()  # (the program renders on its own stream; no host lengths were asked for)
                 outs.append(m.cpu().numpy())
             else:
                 out = torch.full((V, n), float("inf"), dtype=torch.float32, device="cuda")

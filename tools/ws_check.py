@@ -26,6 +26,7 @@ def render(ws, V, calls, mix=False):
         if mix:
             m = torch.zeros((n,), dtype=torch.float32, device="cuda")
             p.render_mix(m, V, params=params)
+            torch.cuda.synchronize()
             outs.append(m.cpu().numpy())
         else:
             lens = p.render(out, params=params, out_len=np.zeros(V, dtype=np.uint64))

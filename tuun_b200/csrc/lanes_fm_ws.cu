@@ -74,6 +74,8 @@ struct PhaseRegs {
 //   18 % of the kernel's stall samples were the two warps waiting for it to come back from local memory).
 template <bool SLOW, uint32_t B, bool CAP, bool ALL = false>
 __device__ __forceinline__ void phase_step(PhaseRegs& G, const double2* rot, const SineK& sk, uint4* ring, bool active, int rem) {
+    // (Making the tile in registers first and asking for the buffer only then — a tile further ahead of the tone warp —
+    // was tried: sixteen values alive across the barrier spill, 5.59 -> 5.84 ms.)
     nb_sync<Bar<B>::empty>();
     if (ALL || active) {
         float raw[LS];
@@ -137,58 +139,72 @@ struct ToneRegs {
     float y1, y2;      // y[-1], y[-2]
     float p1, p2, q2;  // a1 y[-1], a2 y[-2], a2 y[-1]
 };
-// generator.rs:496-507 for K = 3, J = 2 over one tile: the operations and roundings of lanes.cuh biquad_tile (bit-identical
-// results), in an order that keeps few values alive, because this warp lives on 64 registers: chunk by chunk of four
-// samples — the sines' arguments (1.m floats, pd_m23) come out of the ring, the sines, two sample pairs through the
-// filter, the four outputs into the row buffer.
-// x_out / y_out (the tile's inputs and outputs in registers) only for the tile a call ends in.
-template <bool KEEP>
-__device__ __forceinline__ void tone_tile(const uint4* ring, float4* dst, ToneRegs& F, float* x_out, float* y_out) {
+// The four sines of one chunk from what the phase warp handed over (TB_WS_ARG: their arguments; else the floats 1.m).
+__device__ __forceinline__ void tone_sines(const uint4 mv, float (&x)[4]) {
+#if TB_WS_ARG
+    x[0] = __sinf(__uint_as_float(mv.x));
+    x[1] = __sinf(__uint_as_float(mv.y));
+    x[2] = __sinf(__uint_as_float(mv.z));
+    x[3] = __sinf(__uint_as_float(mv.w));
+#else
+    sin_m23x2(mv.x, mv.y, x[0], x[1]);
+    sin_m23x2(mv.z, mv.w, x[2], x[3]);
+#endif
+}
+// Four samples through the filter: generator.rs:496-507 for K = 3, J = 2, the operations and roundings of lanes.cuh
+// biquad_tile (bit-identical results) in an order that keeps few values alive — this warp lives on 64 registers.
+//   b1p: b1 x[i - 1]; b2p: (b2 x[i - 2], b2 x[i - 1]) on entry, the same one chunk on when it returns.
+__device__ __forceinline__ void tone_chunk(const float (&xq)[4], float (&yq)[4], ToneRegs& F, float& b1p, u64& b2p) {
     const u64 bb0 = pk2(F.b0, F.b0), bb1 = pk2(F.b1, F.b1), bb2 = pk2(F.b2, F.b2), aa = pk2(F.a1, F.a2);
+    UNROLL for (int h = 0; h < 2; h++) {
+        const u64 xx = pk2(xq[2 * h], xq[2 * h + 1]);
+        float s0, s1, q0, q1;
+        unpk2(mul2(xx, bb0), s0, s1);
+        unpk2(mul2(xx, bb1), q0, q1);
+        s0 = __fadd_rn(s0, b1p);
+        s1 = __fadd_rn(s1, q0);
+        b1p = q1;
+        unpk2(add2(pk2(s0, s1), b2p), s0, s1);
+        b2p = mul2(xx, bb2);
+        const float y0 = __fsub_rn(__fsub_rn(s0, F.p1), F.p2);
+        float n1, n2;
+        unpk2(mul2(aa, pk2(y0, y0)), n1, n2);        // a1 y0, a2 y0
+        const float y1 = __fsub_rn(__fsub_rn(s1, n1), F.q2);
+        F.p2 = n2;
+        unpk2(mul2(aa, pk2(y1, y1)), F.p1, F.q2);    // a1 y1, a2 y1
+        yq[2 * h] = y0;
+        yq[2 * h + 1] = y1;
+    }
+}
+// One tile, chunk by chunk of four samples: what the phase warp handed over comes out of the ring, the sines, the
+// filter, the four outputs into the row buffer.  The sines of chunk q + 1 are under way (ring load, range multiply, MUFU)
+// before the serial part of chunk q starts: written out, because the compiler will not move a shared-memory load above
+// the store of the chunk before it (5.85 -> 5.59 ms on 65,536 voices x 2 s).
+//   xn: the sines of the tile's first chunk when PRIMED (the caller, or the tile before, started them), and on return
+//   whatever `next` left there: next() runs where chunk 3 would start its successor — the tile loop of ws_tone waits for
+//   the other buffer there and starts the first sines of the next tile.
+// x_out / y_out (the tile's inputs and outputs in registers) only for the tile a call ends in.
+template <bool KEEP, bool PRIMED, typename Next>
+__device__ __forceinline__ void tone_tile(const uint4* ring, float4* dst, ToneRegs& F, float (&xn)[4], Next next, float* x_out,
+                                          float* y_out) {
     float b1p = __fmul_rn(F.b1, F.x1);                                   // b1 x[i - 1]
     u64 b2p = pk2(__fmul_rn(F.b2, F.x2), __fmul_rn(F.b2, F.x1));         // b2 x[i - 2], b2 x[i - 1]
-    float xl0 = 0.f, xl1 = 0.f, yl0 = 0.f, yl1 = 0.f;
+    if (!PRIMED) tone_sines(ring[0], xn);
+    float xq[4], yq[4];
     UNROLL for (int q = 0; q < 4; q++) {
-        const uint4 mv = ring[q * LT];
-        const uint32_t mq[4] = {mv.x, mv.y, mv.z, mv.w};
-        float yq[4];
-        UNROLL for (int h = 0; h < 2; h++) {
-            float x0, x1;
-#if TB_WS_ARG
-            x0 = __sinf(__uint_as_float(mq[2 * h]));
-            x1 = __sinf(__uint_as_float(mq[2 * h + 1]));
-#else
-            sin_m23x2(mq[2 * h], mq[2 * h + 1], x0, x1);
-#endif
-            const u64 xx = pk2(x0, x1);
-            float s0, s1, q0, q1;
-            unpk2(mul2(xx, bb0), s0, s1);
-            unpk2(mul2(xx, bb1), q0, q1);
-            s0 = __fadd_rn(s0, b1p);
-            s1 = __fadd_rn(s1, q0);
-            b1p = q1;
-            unpk2(add2(pk2(s0, s1), b2p), s0, s1);
-            b2p = mul2(xx, bb2);
-            const float y0 = __fsub_rn(__fsub_rn(s0, F.p1), F.p2);
-            float n1, n2;
-            unpk2(mul2(aa, pk2(y0, y0)), n1, n2);        // a1 y0, a2 y0
-            const float y1 = __fsub_rn(__fsub_rn(s1, n1), F.q2);
-            F.p2 = n2;
-            unpk2(mul2(aa, pk2(y1, y1)), F.p1, F.q2);    // a1 y1, a2 y1
-            yq[2 * h] = y0;
-            yq[2 * h + 1] = y1;
-            if (KEEP) {
-                x_out[4 * q + 2 * h] = x0; x_out[4 * q + 2 * h + 1] = x1;
-                y_out[4 * q + 2 * h] = y0; y_out[4 * q + 2 * h + 1] = y1;
-            }
-            xl0 = x0; xl1 = x1; yl0 = y0; yl1 = y1;
+        UNROLL for (int k = 0; k < 4; k++) xq[k] = xn[k];
+        if (q + 1 < 4) tone_sines(ring[(q + 1) * LT], xn);
+        else next();
+        tone_chunk(xq, yq, F, b1p, b2p);
+        if (KEEP) {
+            UNROLL for (int k = 0; k < 4; k++) { x_out[4 * q + k] = xq[k]; y_out[4 * q + k] = yq[k]; }
         }
         dst[q * AS] = make_float4(yq[0], yq[1], yq[2], yq[3]);
     }
-    F.x1 = xl1;
-    F.x2 = xl0;
-    F.y1 = yl1;
-    F.y2 = yl0;
+    F.x1 = xq[3];
+    F.x2 = xq[2];
+    F.y1 = yq[3];
+    F.y2 = yq[2];
 }
 
 // One tile of the tone warp out of buffer B: sines, filter, into half B of the row buffer.
@@ -196,7 +212,8 @@ __device__ __forceinline__ void tone_tile(const uint4* ring, float4* dst, ToneRe
 template <uint32_t B, bool ALL = false>
 __device__ __forceinline__ void tone_step(ToneRegs& F, float4* abase, const uint4* ring, bool active, bool refill) {
     nb_sync<Bar<B>::full>();
-    if (ALL || active) tone_tile<false>(ring + B * 4 * LT, abase + B * 4 * AS, F, nullptr, nullptr);
+    float xn[4];
+    if (ALL || active) tone_tile<false, false>(ring + B * 4 * LT, abase + B * 4 * AS, F, xn, [] {}, nullptr, nullptr);
     // (handed back after the tile, not after its loads: sixteen words waiting in registers do not fit next to the filter,
     // and the phase warp is the one with time to spare)
     if (refill) nb_arrive<Bar<B>::empty>();  // (the whole warp, once)
@@ -232,9 +249,10 @@ __device__ __forceinline__ void ws_tone(const tb_insn* code, LaneMem& M, RowStor
         float* d = R.dfast;
         const size_t step4 = R.step4;
         const float4* src = R.tbase + (l & 7) * AS + (l >> 3);
-        for (uint32_t left = pairs; left > 1; left--) {
-            tone_step<0, true>(F, abase, ring, true, true);
-            tone_step<1, true>(F, abase, ring, true, true);
+        // (Tried on this loop, 65,536 voices x 2 s, 5.59 ms as it stands: the buffer handed back right after its last chunk
+        // is read instead of after the tile, 5.62 ms; tiles chained — the next tile's buffer waited for and its first sines
+        // started while chunk 3 is in the filter — 5.64 ms, 5.79 ms when the buffer is handed back after that wait.)
+        auto leave = [&] {
             __syncwarp();
             float* q = d;
             UNROLL for (int h = 0; h < 2; h++) {
@@ -247,6 +265,11 @@ __device__ __forceinline__ void ws_tone(const tb_insn* code, LaneMem& M, RowStor
             }
             __syncwarp();
             d += 2 * LS;
+        };
+        for (uint32_t left = pairs; left > 1; left--) {
+            tone_step<0, true>(F, abase, ring, true, true);
+            tone_step<1, true>(F, abase, ring, true, true);
+            leave();
         }
         R.dfast = d;
         R.off = (size_t)(pairs - 1) * 2 * LS;
@@ -279,7 +302,8 @@ __device__ __forceinline__ void ws_tone(const tb_insn* code, LaneMem& M, RowStor
             float ex[LS + 2], ey[LS + 2];  // history ++ tile
             ex[0] = F.x2; ex[1] = F.x1;
             ey[0] = F.y2; ey[1] = F.y1;
-            tone_tile<true>(ring + half * 4 * LT, abase + half * 4 * AS, F, car, y);
+            float xn[4];
+            tone_tile<true, false>(ring + half * 4 * LT, abase + half * 4 * AS, F, xn, [] {}, car, y);
             UNROLL for (int j = 0; j < LS; j++) { ex[2 + j] = car[j]; ey[2 + j] = y[j]; }
             UNROLL for (int j = 0; j < LS; j++) {
                 if (j == rem) { F.x2 = ex[j]; F.x1 = ex[j + 1]; F.y2 = ey[j]; F.y1 = ey[j + 1]; }
