@@ -195,9 +195,13 @@ __device__ __forceinline__ void sin_m23x2(uint32_t m0, uint32_t m1, float& s0, f
 // increments still round to zero); infinities and NaNs are excluded by the range test that guards
 // the magic-number conversion.
 __device__ __forceinline__ double f32_to_f64_alu(float f) {
+    // |f| x 2^29 as a 64-bit product is (|f| >> 3, |f| << 29) in one IMAD.WIDE, whose addend rebiases the exponent:
+    // three instructions with the two sign operations.
     const uint32_t b = __float_as_uint(f);
-    const uint32_t hi = (((b >> 3) & 0x0fffffffu) + 0x38000000u) | (b & 0x80000000u);
-    return __hiloint2double((int)hi, (int)(b << 29));
+    unsigned long long w;  // (as PTX: the compiler takes a multiplication by 2^29 apart into shifts)
+    asm("mad.wide.u32 %0, %1, 0x20000000, %2;" : "=l"(w) : "r"(b & 0x7fffffffu), "l"(0x3800000000000000ull));
+    const uint32_t hi = (uint32_t)(w >> 32) | (b & 0x80000000u);
+    return __hiloint2double((int)hi, (int)(uint32_t)w);
 }
 // What the phase warp of lanes_fm_ws.cu hands over for two samples (fm_carrier_tile<.., RAW>): the floats 1.m, or —
 // TB_WS_ARG — the sines' arguments made from them (the FFMA2 of sin_m23x2 moved to the warp with time to spare).
