@@ -28,7 +28,8 @@
 extern "C" {
 #endif
 
-#define TB_ABI_VERSION 2u
+/* 3: tb_program_info grew (lane_fm_ws_capacity, fm_ws_launches); sample rates must be below 2^31 */
+#define TB_ABI_VERSION 3u
 
 /* enum Waveform variants, src/lib/waveform.rs:23-100 (same order). */
 typedef enum tb_kind {

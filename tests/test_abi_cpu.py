@@ -22,7 +22,7 @@ def test_exports_match_header():
     L = _abi.lib()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.tb_abi_version() == 2
+    assert L.tb_abi_version() == 3
 
 
 def test_node_layout():
