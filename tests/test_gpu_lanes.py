@@ -521,6 +521,19 @@ def test_fm_ws_matches_single_thread_kernel(monkeypatch):
         assert wa == 0 and wb == lb == la == sum(1 for n in calls if n >= 16), (V, calls, wa, wb, la, lb)
         for x, y in zip(a, b):
             np.testing.assert_array_equal(x.view(np.uint32), y.view(np.uint32))
+    # the whole 65,536-voice batch, every SM holding its 14 CTAs: compared on the device
+    def whole(ws):
+        monkeypatch.setenv("TUUN_B200_FM_WS", "1" if ws else "0")
+        p = program(w, monkeypatch)
+        params = torch.from_numpy(fm_filter_params(np.arange(65536))).cuda()
+        out = torch.empty((65536, 8192 + 16), dtype=torch.float32, device="cuda")
+        lens = p.render(out, params=params, out_len=np.zeros(65536, dtype=np.uint64))
+        assert (lens == out.shape[1]).all() and p.info.fm_ws_launches == (1 if ws else 0)
+        return out
+    a = whole(False)
+    b = whole(True)
+    assert torch.equal(a.view(torch.int32), b.view(torch.int32))
+    del a, b
     for V, calls in [(4096, [4096 + 7, 640]), (1000, [8000])]:
         a, _, _ = run(False, V, calls, mix=True)
         b, wb, _ = run(True, V, calls, mix=True)
