@@ -279,6 +279,35 @@ def time_shard_record(args, world, rank, local, barrier, peak):
             "sharding": "time: rank r renders segments [r S/N, (r+1) S/N) of every voice; states all-gathered per pass"}
 
 
+def streaming_record(args, local, n_local, n_samples, params_d):
+    """The reference's own calling pattern (main.rs:42-43, tracker.rs:597-642: generate() once per block of 1024
+    samples): the same batch rendered block by block into one reused [voices, 1024] device buffer, state carried by
+    the program from call to call; CUDA events around the whole stream of calls."""
+    import torch
+    from tuun_b200.generator import Program
+    from tuun_b200.workloads import fm_filter_voice
+    block = 1024
+    n = n_samples // block * block
+    prog = Program(fm_filter_voice(), SAMPLE_RATE, device=local)
+    stream = torch.cuda.ExternalStream(prog.stream, device=local)
+    buf = torch.empty((n_local, block), dtype=torch.float32, device=f"cuda:{local}")
+    best = None
+    for _ in range(2):
+        prog.reset()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record(stream)
+        for _ in range(n // block):
+            prog.render(buf, params=params_d)
+        b.record(stream)
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+        best = ms if best is None else min(best, ms)
+    return {"value": n_local * n / (best * 1e-3), "unit": UNIT, "block_samples": block, "calls": n // block,
+            "us_per_call": best * 1e3 / (n // block), "voices": n_local, "samples_per_voice": n,
+            "note": "one tb_render per 1024-sample block (the reference's block size), one launch a call, rows in HBM"}
+
+
 def exact_sines_record(args, local, n_local, n_samples, params_d, out, peak):
     """The same batch with every sine in the EXACT class (TUUN_B200_FAST_SINES=0: f64 polynomial on the 64-bit
     phase, the f32 the reference's libm sin rounds to on 99.98 % of samples) — what the FAST-class carrier
@@ -592,6 +621,7 @@ def main():
     if not args.no_extras:
         if world == 1:
             extras["exact_sines"] = exact_sines_record(args, local, n_local, n_samples, params_d, out, peak)
+            extras["streaming_1024"] = streaming_record(args, local, n_local, n_samples, params_d)
         del out
         torch.cuda.empty_cache()
         if world > 1 and args.scaling == "weak":

@@ -27,6 +27,8 @@ extern "C" cudaError_t tb_lanes_occupancy(size_t smem, int kind, int* blocks_per
 extern "C" size_t tb_lanes_fm_ws_smem_bytes(uint32_t n_lane_code, uint32_t w_words, uint32_t q_units, uint32_t slots);
 extern "C" void tb_lanes_fm_ws_run(const tb_launch* P, size_t smem, cudaStream_t stream);
 extern "C" cudaError_t tb_lanes_fm_ws_occupancy(size_t smem, int* blocks_per_sm);
+extern "C" void tb_lanes_fm_ws_split_run(const tb_launch* P, size_t smem, cudaStream_t stream);  // lanes_fm_ws_split.cu
+extern "C" cudaError_t tb_lanes_fm_ws_split_occupancy(size_t smem, int* blocks_per_sm);
 extern "C" cudaError_t tb_len_set(unsigned long long* out_len, uint32_t n, unsigned long long add, int accumulate,
                                   cudaStream_t stream);
 extern "C" cudaError_t tb_mix_launch(const float* rows, uint64_t stride, const unsigned long long* lens,
@@ -86,6 +88,7 @@ struct tb_program {
     uint32_t lane_fm_capacity = 0;  // same for the fused-FM-voice kernel; 0: the program is not one fused FM voice
     uint32_t lane_fm_ws_capacity = 0;  // 32-voice CTAs of its two-warps-a-voice form (lanes_fm_ws.cu) the device holds; 0: not applicable
     size_t lane_fm_ws_smem = 0;
+    uint32_t lane_fm_ws_split_capacity = 0;  // the same for virtual voices (lanes_fm_ws_split.cu)
     uint32_t lane_fm_ws_min_voices = 0;
     uint64_t fm_ws_launches = 0;
     uint32_t* d_lane_queue = nullptr;  // work queue of the persistent form (program.h tb_launch::lane_queue)
@@ -320,8 +323,11 @@ int launch_lanes(tb_program* p, tb_launch& B) {
     const uint32_t groups = (B.n_voices + TB_LANE_THREADS - 1) / TB_LANE_THREADS;
     const bool fm = fm_kernel_applies(p, B.n_voices);
     // ... as a phase warp and a tone warp per 32 voices when the device holds all those CTAs at once (lanes_fm_ws.cu)
-    const bool fm_ws = fm && p->lane_fm_ws_capacity != 0 && (B.n_voices + 31u) / 32u <= p->lane_fm_ws_capacity &&
-                       B.vsplit_total <= 1 && B.n_voices >= p->lane_fm_ws_min_voices;
+    // (virtual voices — the segments of a time-axis split — too: lanes_fm_ws_split.cu; the phase-sum pass has its own kernel)
+    const bool vs = B.vsplit_total > 1;
+    const uint32_t ws_cap = vs ? p->lane_fm_ws_split_capacity : p->lane_fm_ws_capacity;
+    const bool fm_ws = fm && ws_cap != 0 && (B.n_voices + 31u) / 32u <= ws_cap && !(vs && (B.fm_sums || B.mix_partial)) &&
+                       B.n_voices >= p->lane_fm_ws_min_voices;
     const char* qe = std::getenv("TUUN_B200_LANE_QUEUE");  // diagnostics: "0" never, "1" always
     const bool want = !fm && B.vsplit_total <= 1 && (qe ? qe[0] == '1' : groups > p->lane_capacity);
     B.lane_queue = nullptr;
@@ -354,7 +360,8 @@ int launch_lanes(tb_program* p, tb_launch& B) {
     CU(cudaEventRecord(ev[0], p->stream));
     cudaError_t e = cudaSuccess;
     if (fm_ws) {
-        tb_lanes_fm_ws_run(&B, p->lane_fm_ws_smem, p->stream);
+        if (vs) tb_lanes_fm_ws_split_run(&B, p->lane_fm_ws_smem, p->stream);
+        else tb_lanes_fm_ws_run(&B, p->lane_fm_ws_smem, p->stream);
         e = cudaGetLastError();
         p->fm_ws_launches++;
     } else {
@@ -1105,6 +1112,9 @@ static int create_program(const tb_node* nodes, uint32_t n_nodes, const int32_t*
                     tb_lanes_fm_ws_occupancy(ws, &wb) == cudaSuccess && wb > 0) {
                     p->lane_fm_ws_capacity = (uint32_t)(wb * fs);
                     p->lane_fm_ws_smem = ws;
+                    int sb = 0;
+                    if (tb_lanes_fm_ws_split_occupancy(ws, &sb) == cudaSuccess && sb > 0)
+                        p->lane_fm_ws_split_capacity = (uint32_t)(sb * fs);
                     const char* wm = std::getenv("TUUN_B200_FM_WS_MIN_VOICES");
                     p->lane_fm_ws_min_voices = wm ? (uint32_t)std::strtoul(wm, nullptr, 10) : 0u;
                 }
