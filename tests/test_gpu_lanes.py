@@ -534,6 +534,22 @@ def test_fm_ws_matches_single_thread_kernel(monkeypatch):
     b = whole(True)
     assert torch.equal(a.view(torch.int32), b.view(torch.int32))
     del a, b
+    # a batch cut in time (abi.cpp render_split_fm): the warm-up and the samples pass run on the two-warp kernel over
+    # virtual voices (lanes_fm_ws_split.cu), the phase-sum pass keeps its own kernel
+    def cut(ws):
+        monkeypatch.setenv("TUUN_B200_FM_WS", "1" if ws else "0")
+        monkeypatch.setenv("TUUN_B200_SPLIT_FM", "4")  # (read when a call is planned)
+        p = program(w, monkeypatch)
+        params = torch.from_numpy(fm_filter_params(fm_filter_sample_ids(4096))).cuda()
+        out = torch.empty((4096, 4 * 32768 + 24), dtype=torch.float32, device="cuda")
+        lens = p.render(out, params=params, out_len=np.zeros(4096, dtype=np.uint64))
+        monkeypatch.delenv("TUUN_B200_SPLIT_FM")
+        assert (lens == out.shape[1]).all() and p.info.split_fm_rounds == 1
+        return out, int(p.info.fm_ws_launches)
+    a, wa = cut(False)
+    b, wb = cut(True)
+    assert wa == 0 and wb >= 2 and torch.equal(a.view(torch.int32), b.view(torch.int32))
+    del a, b
     for V, calls in [(4096, [4096 + 7, 640]), (1000, [8000])]:
         a, _, _ = run(False, V, calls, mix=True)
         b, wb, _ = run(True, V, calls, mix=True)
