@@ -55,14 +55,16 @@ __device__ __forceinline__ void ring_put(uint4* ring, const float (&v)[LS]) {
 
 // Barrier numbers are immediates (a register operand makes ptxas reserve all 16 barriers for the CTA, which costs
 // resident CTAs), so the loops below take tiles in pairs: buffer 0, then buffer 1.
-template <uint32_t ID>
+//   CONV: the warp is converged by construction (the loops compiled for "every lane live" have no branch around the
+//   tile's arithmetic), so the __syncwarp() in front of the barrier is left out.
+template <uint32_t ID, bool CONV = false>
 __device__ __forceinline__ void nb_sync() {
-    __syncwarp();
+    if (!CONV) __syncwarp();
     asm volatile("bar.sync %0, 64;" ::"n"(ID) : "memory");
 }
-template <uint32_t ID>
+template <uint32_t ID, bool CONV = false>
 __device__ __forceinline__ void nb_arrive() {
-    __syncwarp();
+    if (!CONV) __syncwarp();
     asm volatile("bar.arrive %0, 64;" ::"n"(ID) : "memory");
 }
 
@@ -78,7 +80,7 @@ template <bool SLOW, uint32_t B, bool CAP, bool ALL = false>
 __device__ __forceinline__ void phase_step(PhaseRegs& G, const double2* rot, const SineK& sk, uint4* ring, bool active, int rem) {
     // (Making the tile in registers first and asking for the buffer only then — a tile further ahead of the tone warp —
     // was tried: sixteen values alive across the barrier spill, 5.59 -> 5.84 ms.)
-    nb_sync<Bar<B>::empty>();
+    nb_sync<Bar<B>::empty, ALL>();
     if (ALL || active) {
         float raw[LS];
         if (CAP) {
@@ -90,7 +92,7 @@ __device__ __forceinline__ void phase_step(PhaseRegs& G, const double2* rot, con
         }
         ring_put(ring + B * 4 * LT, raw);
     }
-    nb_arrive<Bar<B>::full>();
+    nb_arrive<Bar<B>::full, ALL>();
 }
 
 // The phase warp: n_tiles tiles into the ring (tile i into buffer i & 1), then — when `rem` > 0 — the tile of which
@@ -213,12 +215,12 @@ __device__ __forceinline__ void tone_tile(const uint4* ring, float4* dst, ToneRe
 //   refill: the phase warp has a tile to put into this buffer again.
 template <uint32_t B, bool ALL = false>
 __device__ __forceinline__ void tone_step(ToneRegs& F, float4* abase, const uint4* ring, bool active, bool refill) {
-    nb_sync<Bar<B>::full>();
+    nb_sync<Bar<B>::full, ALL>();
     float xn[4];
     if (ALL || active) tone_tile<false, false>(ring + B * 4 * LT, abase + B * 4 * AS, F, xn, [] {}, nullptr, nullptr);
     // (handed back after the tile, not after its loads: sixteen words waiting in registers do not fit next to the filter,
     // and the phase warp is the one with time to spare)
-    if (refill) nb_arrive<Bar<B>::empty>();  // (the whole warp, once)
+    if (refill) nb_arrive<Bar<B>::empty, ALL>();  // (the whole warp, once)
 }
 
 // The tone warp: sines, filter, rows.
