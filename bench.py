@@ -209,7 +209,8 @@ def strong_record(args, world, rank, local, n_samples, barrier, peak):
     ms = timed_steps(step, steps, stream, barrier, world)
     info = prog.info
     value = args.voices * n_samples * steps / (ms * 1e-3)
-    kernel = ("tb_render_lanes_fm_split_kernel after tb_render_lanes_fm_sums_kernel (every voice cut in time: phase-sum pass, "
+    kernel = (("tb_render_lanes_fm_ws_split_kernel" if info.fm_ws_launches else "tb_render_lanes_fm_split_kernel") +
+              " after tb_render_lanes_fm_sums_kernel (every voice cut in time: phase-sum pass, "
               "filter warm-up, samples)" if info.lane_launches and info.lane_fm_capacity and info.split_rounds
               else "tb_render_lanes_fm_ws_kernel" if info.lane_launches and info.fm_ws_launches
               else "tb_render_lanes_fm_kernel" if info.lane_launches and info.lane_fm_capacity
