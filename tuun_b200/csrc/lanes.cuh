@@ -978,10 +978,18 @@ __device__ __forceinline__ void fm_carrier_tile(float (&car)[LS], double& S, dou
         // integers the running DFMA below adds: the sum of an integer and f * kscale rounds to that integer plus
         // rint(f * kscale); a tie would need f * kscale to be a half-integer exactly, which its 77-bit product with
         // 2^44 / (2 pi sample_rate) never is) and added as integers — no serial chain of 16 DFMAs.
-        u64 sum = 0;
+        // Four running sums in the mantissas of doubles at 1.5 * 2^52 (pd_make), four increments each: a DFMA adds
+        // rint(f * kscale) to an integer-valued sum whatever the order, so the tile costs 16 DFMAs and a handful of
+        // integer adds instead of 16 DFMAs and 16 64-bit adds.
         // (f as a double by integer instructions: this pass is bound by the conversion unit, the ALU is idle)
-        UNROLL for (int j = 0; j < LS; j++)
-            sum += (u64)__double_as_longlong(fma(f32_to_f64_alu(f[j]), sk.kscale, 6755399441055744.0));
+        double a0 = pd_make(0), a1 = a0, a2 = a0, a3 = a0;
+        UNROLL for (int j = 0; j < LS; j += 4) {
+            a0 = fma(f32_to_f64_alu(f[j]), sk.kscale, a0);
+            a1 = fma(f32_to_f64_alu(f[j + 1]), sk.kscale, a1);
+            a2 = fma(f32_to_f64_alu(f[j + 2]), sk.kscale, a2);
+            a3 = fma(f32_to_f64_alu(f[j + 3]), sk.kscale, a3);
+        }
+        const u64 sum = (pd_bits(a0) + pd_bits(a1)) + (pd_bits(a2) + pd_bits(a3));
         p += sum;  // the magic bits above the 44 phase bits are dropped by whoever reads p
         return;
     }
