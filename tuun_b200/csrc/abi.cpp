@@ -1102,12 +1102,12 @@ static int create_program(const tb_node* nodes, uint32_t n_nodes, const int32_t*
                 (lc[0].op >> 24) == TB_SINE_FAST && p->fast_mode == 2 && !(fe && fe[0] == '0')) {
                 int fb = 0, fs = 0;
                 if (tb_lanes_occupancy(ls, 2, &fb, &fs) == cudaSuccess && fb > 0) p->lane_fm_capacity = (uint32_t)(fb * fs);
-                // Two warps a voice (lanes_fm_ws.cu): a filter tail, no root Fin; its ring lies over 8 Q units.
+                // Two warps a voice (lanes_fm_ws.cu): a filter tail; its ring lies over 8 Q units.
                 const char* we = std::getenv("TUUN_B200_FM_WS");  // diagnostics: "0" keeps one thread a voice
                 const size_t ws = tb_lanes_fm_ws_smem_bytes((uint32_t)lc.size(), p->low.lane_w_words, p->low.lane_q_units,
                                                             p->low.lane_slots);
                 int wb = 0;
-                if (p->lane_fm_capacity != 0 && lc[1].c >= 0 && p->low.lane_fin_goe < 0 && p->low.filt.size() == 1 &&
+                if (p->lane_fm_capacity != 0 && lc[1].c >= 0 && p->low.filt.size() == 1 &&
                     p->low.lane_q_units + 4 * p->low.lane_slots >= 8 && ws <= 48 * 1024 && !(we && we[0] == '0') &&
                     tb_lanes_fm_ws_occupancy(ws, &wb) == cudaSuccess && wb > 0) {
                     p->lane_fm_ws_capacity = (uint32_t)(wb * fs);

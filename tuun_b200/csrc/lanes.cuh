@@ -299,7 +299,7 @@ __device__ __forceinline__ void lane_sine_var(const LaneMem& M, float (&acc)[LS]
                 Pd = fma((double)f[i], sk.kscale, Pd);
                 const double T1 = UNIFORM_PH ? Pd : fma((double)acc[i + 1], sk.pscale, Pd);
                 Pd = fma((double)f[i + 1], sk.kscale, Pd);
-                sin_m23x2(pd_m23(T0), pd_m23(T1), acc[i], acc[i + 1]);
+                sin_m23x2(pd_m23(T0, sk.one23), pd_m23(T1, sk.one23), acc[i], acc[i + 1]);
             }
             p = pd_bits(Pd);
         }

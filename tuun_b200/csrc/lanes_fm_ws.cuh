@@ -340,7 +340,7 @@ __device__ __forceinline__ void ws_tone(const tb_insn* code, LaneMem& M, RowStor
 }
 
 // One CTA: voices [32 blockIdx.x, +32), the whole launch.  The host (lanes.cu tb_lanes_launch) sends only
-// programs that are one LN_FM with a filter tail and no root Fin, never virtual voices.
+// programs that are one LN_FM with a filter tail (under a root Fin of analytic length or not).
 template <bool MIX>
 __device__ __forceinline__ void fm_ws_body(const tb_launch& P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -480,8 +480,33 @@ __device__ __forceinline__ void fm_ws_body(const tb_launch& P) {
         finish_lane(P, M, ns);
         const bool accumulate = P.accumulate != 0;
         const u64 before = (accumulate && P.out_len) ? __ldcg(P.out_len + vidx) : 0ull;
+        u64 mine = ns;  // samples of this launch that belong to the voice
+        if (P.lane_fin_goe >= 0) {
+            // Root Fin (generator.rs:133-168), as in lanes.cuh lanes_body: the inner tree was rendered for the whole launch
+            // (the tail of a finished voice's row is undefined by contract, generator.rs:76-95); what counts is how far
+            // the analytic length reaches (greater_or_equals_at, :787-862, the arithmetic of goe_eval in render.cu).
+            const tb_goe g = P.goe[P.lane_fin_goe];
+            float value = 0.0f;
+            for (uint32_t k = 0; k < g.n_steps; k++) {
+                const int sign = P.goe_steps[g.step_off + 2 * k];
+                const float c = ldf(M, P.goe_steps[g.step_off + 2 * k + 1]);
+                value = sign > 0 ? __fadd_rn(value, c) : __fsub_rn(value, c);
+            }
+            u64 left = ~0ull;
+            if (g.term == GOE_TIME) {
+                const int wt = (int)P.n_cval + g.term_arg;
+                const u64 pos = ld64(M, wt);
+                const u64 target = f32_as_usize(ceilf(__fmul_rn(value, (float)P.sample_rate)));
+                left = target > pos ? target - pos : 0ull;
+                st64(M, wt, pos + ns);  // Fin advances both children to the end of the block (:141-167)
+            } else if (ldf(M, g.term_arg) >= value) {
+                left = 0ull;
+            }
+            if (before < P.call_pos) left = 0ull;  // returned short earlier in this call
+            mine = left < ns ? left : ns;
+        }
         for (uint32_t k = 0; k < P.state_words; k++) gstate[k] = ldw(M, (int)(P.n_cval + k));
-        if (P.out_len) P.out_len[vidx] = before + ns;
+        if (P.out_len) P.out_len[vidx] = before + mine;
     }
 }
 
