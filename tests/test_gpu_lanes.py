@@ -123,6 +123,7 @@ def test_partition_invariance_and_device_rows(monkeypatch):
     within(parts, one, params)
     assert np.median(per_voice) <= 5e-6
     dev = torch.zeros((V, N + 8), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()  # (the fill runs on torch's stream, the renders on the program's own)
     q = program(w, monkeypatch)
     q.render(dev[:, :N], params=torch.from_numpy(params).cuda())
     torch.cuda.synchronize()
@@ -242,6 +243,7 @@ def test_mixdown_on_chip(monkeypatch):
     N2 = N + 5
     q = program(w, monkeypatch)
     dmix = torch.zeros(N2, dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()  # (the fill runs on torch's stream, the renders on the program's own)
     q.render_mix(dmix, V, params=torch.from_numpy(params).cuda())
     torch.cuda.synchronize()
     _, _, omix, _ = OracleProgram(w, SR).render_batch(params, V, N2, mix=True, threads=1)
@@ -416,6 +418,7 @@ def test_full_batch_of_65536_voices():
     p = Program(w, SR)
     assert p.info.lane_min_voices <= V and p.info.lane_fm_capacity * 64 >= V
     out = torch.zeros((V, 2 * N), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()  # (the fill runs on torch's stream, the renders on the program's own)
     lens = np.zeros(V, dtype=np.uint64)
     p.render(out[:, :N], params=pd, out_len=lens)
     assert (lens == N).all() and p.info.lane_launches == 1
@@ -426,12 +429,14 @@ def test_full_batch_of_65536_voices():
     ref, _, _, _ = OracleProgram(w, SR).render_batch(params[pick], len(pick), 2 * N, threads=4)
     within(got, ref, params[pick])
     one = torch.zeros((V, 2 * N), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()  # (the fill runs on torch's stream, the renders on the program's own)
     Program(w, SR).render(one, params=pd)
     d = (one - out).abs().amax(dim=1)
     from tuun_b200.workloads import fm_filter_tolerance
     assert bool((d.cpu().numpy() <= fm_filter_tolerance(params, TOL)).all()) and float(d.median()) <= 5e-6
     assert bool(torch.isfinite(out).all())
     mix = torch.zeros(2 * N, dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()  # (the fill runs on torch's stream, the renders on the program's own)
     Program(w, SR).render_mix(mix, V, params=pd)
     want = one.sum(dim=0, dtype=torch.float64)
     # 65,536 f32 terms summed in blocks against an f64 sum (the voices start in phase: |mix| reaches thousands)
@@ -504,11 +509,13 @@ def test_fm_ws_matches_single_thread_kernel(monkeypatch):
         for n in calls:
             if mix:
                 m = torch.zeros((n,), dtype=torch.float32, device="cuda")
+                torch.cuda.synchronize()  # (the fill runs on torch's stream, the renders on the program's own)
                 p.render_mix(m, V, params=params)
                 torch.cuda.synchronize()  # (the program renders on its own stream; no host lengths were asked for)
                 outs.append(m.cpu().numpy())
             else:
                 out = torch.full((V, n), float("inf"), dtype=torch.float32, device="cuda")
+                torch.cuda.synchronize()  # (the fill runs on torch's stream, the render on the program's own)
                 lens = p.render(out, params=params, out_len=np.zeros(V, dtype=np.uint64))
                 assert (lens == n).all()
                 outs.append(out.cpu().numpy())

@@ -36,6 +36,7 @@ def two_rank_render(w, params, V, S, seg, monkeypatch, tail=1000, fm_form=False)
         p.render(h, params=params)
         heads.append(h)
     outs = [torch.zeros((V, S // 2 * seg), dtype=torch.float32, device="cuda") for _ in ranks]
+    torch.cuda.synchronize()  # (the fill runs on torch's stream, the renders on the program's own)
     if fm_form:
         monkeypatch.setenv("TUUN_B200_SPLIT_FM", "1")
     shards = [TimeShard(p, V, S, seg, *segment_range(S, r, 2), params=params) for r, p in enumerate(ranks)]

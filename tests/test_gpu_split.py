@@ -217,6 +217,7 @@ def test_fm_batch_split_with_filter_warm_up(monkeypatch):
     monkeypatch.setenv("TUUN_B200_SPLIT_FM", "4")
     p = Program(w, SR)
     got = torch.zeros((V, n), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()  # (the fill runs on torch's stream, the renders on the program's own)
     lens = np.zeros(V, dtype=np.uint64)
     p.render(got, params=params, out_len=lens)
     info = p.info

@@ -23,6 +23,7 @@ def render(ws, V, calls, mix=False):
     outs = []
     for n in calls:
         out = torch.zeros((V, n), dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()  # (the fills run on torch's stream, the renders on the program's own)
         if mix:
             m = torch.zeros((n,), dtype=torch.float32, device="cuda")
             p.render_mix(m, V, params=params)
@@ -67,6 +68,7 @@ for V, n in [(8192, 176400 + 40), (300, 441000)]:
         p = Program(w, 44100)
         params = torch.from_numpy(fm_filter_params(fm_filter_sample_ids(V))).cuda()
         out = torch.zeros((V, n), dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()
         lens = p.render(out, params=params, out_len=np.zeros(V, dtype=np.uint64))
         assert (np.asarray(lens) == n).all()
         res.append((out, int(p.info.fm_ws_launches), int(p.info.lane_launches), int(p.info.split_fm_rounds), int(p.info.split_segments)))
@@ -74,6 +76,14 @@ for V, n in [(8192, 176400 + 40), (300, 441000)]:
     print(f"split V={V} n={n}: ws launches {res[1][1]}/{res[1][2]} (off {res[0][1]}/{res[0][2]}), split-fm rounds {res[1][3]}, "
           f"segments {res[1][4]}, bit-identical rows: {same}")
     bad += 0 if same else 1
+    if not same:
+        d = (res[0][0] - res[1][0]).abs()
+        rows = torch.nonzero(d.amax(dim=1) > 0).flatten().cpu().numpy()
+        prm = fm_filter_params(fm_filter_sample_ids(V))
+        print(f"   {len(rows)} rows differ, max diff {float(d.max()):.3e}; first rows {rows[:12]}")
+        for r in rows[:6]:
+            first = int(torch.nonzero(d[r] > 0).flatten()[0])
+            print(f"   row {r}: m={prm[r, 1]:.6g} c={prm[r, 2]:.6g} first differing sample {first}, max {float(d[r].max()):.3e}")
     del res, out
 os.environ["TUUN_B200_LANE_MIN_VOICES"] = "1"
 print("PARITY", "OK" if bad == 0 else f"FAILED ({bad})")

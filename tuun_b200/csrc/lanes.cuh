@@ -203,6 +203,12 @@ __device__ __forceinline__ double f32_to_f64_alu(float f) {
     const uint32_t hi = (uint32_t)(w >> 32) | (b & 0x80000000u);
     return __hiloint2double((int)hi, (int)(uint32_t)w);
 }
+// The same for f >= 0 (sign bit clear): the multiply-add alone.
+__device__ __forceinline__ double f32_to_f64_pos(float f) {
+    unsigned long long w;
+    asm("mad.wide.u32 %0, %1, 0x20000000, %2;" : "=l"(w) : "r"(__float_as_uint(f)), "l"(0x3800000000000000ull));
+    return __longlong_as_double((long long)w);
+}
 // What the phase warp of lanes_fm_ws.cu hands over for two samples (fm_carrier_tile<.., RAW>): the floats 1.m, or —
 // TB_WS_ARG — the sines' arguments made from them (the FFMA2 of sin_m23x2 moved to the warp with time to spare).
 #ifndef TB_WS_ARG
@@ -912,10 +918,19 @@ __device__ __forceinline__ FmRot fm_rot_load(const double2* rot) {
 //   PHASE_ONLY: the summary pass of a time-axis split (run_fm_sums) wants the phase after the tile, not its sines.
 //   RAW: car[] receives the bit patterns 1.m of the sines' arguments (pd_m23) instead of the sines — the producer
 //   warp of the warp-specialised kernel (lanes_fm_ws.cu) hands those to the warp that owns MUFU and the filter.
-template <bool SLOW, bool CAP = false, bool PHASE_ONLY = false, bool RAW = false>
+//   FMODE (what the whole warp's voices allow, lanes_fm_ws.cuh): 1 = the carrier frequency is never negative
+//   (c >= |m|: any FM patch of moderate index), so its widening to f64 by integer instructions drops the two sign
+//   operations; 2 = no modulation at all (m == 0: the frequency IS c, whatever the modulator does), so the tile needs
+//   neither the modulator nor the affine map.  Same bits as FMODE 0 in both cases.
+template <bool SLOW, bool CAP = false, bool PHASE_ONLY = false, bool RAW = false, int FMODE = 0>
 __device__ __forceinline__ void fm_carrier_tile(float (&car)[LS], double& S, double& Cq, const double2* rot, const FmRot& rr,
                                                 u64 mm, u64 cc, u64& p, const SineK& sk, int cap = 0, u64* p_cap = nullptr) {
     float f[LS];
+    if (FMODE == 2) {
+        float c0, c1;
+        unpk2(cc, c0, c1);
+        UNROLL for (int j = 0; j < LS; j++) f[j] = c0;  // fl(fl(s * 0) + c) = c for every finite s
+    } else {
 #if TB_ABL == 4
     UNROLL for (int j = 0; j < LS; j++) f[j] = TB_D2F(S) + j;
 #elif TB_FM_ROT_REGS
@@ -960,6 +975,7 @@ __device__ __forceinline__ void fm_carrier_tile(float (&car)[LS], double& S, dou
 #endif
     S = S2;
     UNROLL for (int j = 0; j < LS; j += 2) unpk2(add2(mul2(pk2(f[j], f[j + 1]), mm), cc), f[j], f[j + 1]);
+    }
     if (SLOW) {
         UNROLL for (int j = 0; j < LS; j += 2) {
             const u64 t0 = p;
@@ -997,9 +1013,9 @@ __device__ __forceinline__ void fm_carrier_tile(float (&car)[LS], double& S, dou
     double Pd = pd_make(p);
     UNROLL for (int j = 0; j < LS; j += 2) {
         const double T0 = Pd;
-        Pd = fma(TB_WIDEN(f[j]), sk.kscale, Pd);
+        Pd = fma(FMODE == 1 ? f32_to_f64_pos(f[j]) : TB_WIDEN(f[j]), sk.kscale, Pd);
         const double T1 = Pd;
-        Pd = fma(TB_WIDEN(f[j + 1]), sk.kscale, Pd);
+        Pd = fma(FMODE == 1 ? f32_to_f64_pos(f[j + 1]) : TB_WIDEN(f[j + 1]), sk.kscale, Pd);
         if (CAP && j == cap) *p_cap = pd_bits(T0);
         if (CAP && j + 1 == cap) *p_cap = pd_bits(T1);
 #if TB_ABL == 2

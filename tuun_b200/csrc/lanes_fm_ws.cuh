@@ -76,7 +76,8 @@ struct PhaseRegs {
 // One tile of the phase warp into buffer B.  CAP: the tile of which only the first `rem` samples count.
 //   ALL: every lane has a live voice (the flag would otherwise sit in a register this warp does not have: measured,
 //   18 % of the kernel's stall samples were the two warps waiting for it to come back from local memory).
-template <bool SLOW, uint32_t B, bool CAP, bool ALL = false>
+//   FMODE: what the warp's voices allow (lanes.cuh fm_carrier_tile): 1 = no negative carrier frequency, 2 = no modulation.
+template <bool SLOW, uint32_t B, bool CAP, bool ALL = false, int FMODE = 0>
 __device__ __forceinline__ void phase_step(PhaseRegs& G, const double2* rot, const SineK& sk, uint4* ring, bool active, int rem) {
     // (Making the tile in registers first and asking for the buffer only then — a tile further ahead of the tone warp —
     // was tried: sixteen values alive across the barrier spill, 5.59 -> 5.84 ms.)
@@ -88,7 +89,7 @@ __device__ __forceinline__ void phase_step(PhaseRegs& G, const double2* rot, con
             fm_carrier_tile<SLOW, true, false, true>(raw, G.S, G.Cq, rot, G.rr, G.mm, G.cc, G.p, sk, rem, &p_rem);
             G.p = p_rem;
         } else {
-            fm_carrier_tile<SLOW, false, false, true>(raw, G.S, G.Cq, rot, G.rr, G.mm, G.cc, G.p, sk);
+            fm_carrier_tile<SLOW, false, false, true, FMODE>(raw, G.S, G.Cq, rot, G.rr, G.mm, G.cc, G.p, sk);
         }
         ring_put(ring + B * 4 * LT, raw);
     }
@@ -116,9 +117,28 @@ __device__ __forceinline__ void ws_phase(const tb_insn* code, LaneMem& M, const 
     }
     __syncwarp();  // the ring lies over the rotation table: every lane has read its entries
     if (__all_sync(FULL, active)) {
-        for (uint32_t left = (uint32_t)(n_tiles >> 1); left != 0; left--) {
-            phase_step<SLOW, 0, false, true>(G, rot, sk, ring, true, 0);
-            phase_step<SLOW, 1, false, true>(G, rot, sk, ring, true, 0);
+        // What the 32 voices have in common decides how much of the tile is needed (same bits either way): no
+        // modulation (m == 0: a plain filtered sine), or a carrier frequency that never turns negative (c >= |m|).
+        float m = 0.0f, c = 0.0f, dummy;
+        unpk2(G.mm, m, dummy);
+        unpk2(G.cc, c, dummy);
+        const bool flat = !SLOW && __all_sync(FULL, m == 0.0f);
+        const bool pos = !SLOW && __all_sync(FULL, c >= fabsf(m));
+        if (flat) {
+            for (uint32_t left = (uint32_t)(n_tiles >> 1); left != 0; left--) {
+                phase_step<SLOW, 0, false, true, 2>(G, rot, sk, ring, true, 0);
+                phase_step<SLOW, 1, false, true, 2>(G, rot, sk, ring, true, 0);
+            }
+        } else if (pos) {
+            for (uint32_t left = (uint32_t)(n_tiles >> 1); left != 0; left--) {
+                phase_step<SLOW, 0, false, true, 1>(G, rot, sk, ring, true, 0);
+                phase_step<SLOW, 1, false, true, 1>(G, rot, sk, ring, true, 0);
+            }
+        } else {
+            for (uint32_t left = (uint32_t)(n_tiles >> 1); left != 0; left--) {
+                phase_step<SLOW, 0, false, true>(G, rot, sk, ring, true, 0);
+                phase_step<SLOW, 1, false, true>(G, rot, sk, ring, true, 0);
+            }
         }
     } else {
         for (uint32_t left = (uint32_t)(n_tiles >> 1); left != 0; left--) {

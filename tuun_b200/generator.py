@@ -98,6 +98,12 @@ class Program:
         `out`: 2-D float32, numpy (host) or torch.cuda tensor (device).  `params`: [n_voices,
         n_params] float32 (numpy or torch.cuda) or None.  Returns out_len (uint64 per voice) when
         `out_len` is given or out is a numpy array.
+
+        Device tensors: the program renders on its OWN (non-blocking) CUDA stream, which is not ordered
+        against torch's.  Work queued on torch's stream that touches `out` or `params` (a `torch.zeros`
+        fill, a copy) must have finished — torch.cuda.synchronize(), or an event — before this call, or
+        the program must be put on torch's stream with set_stream(); without host lengths the call
+        returns before the samples exist, and a reader on torch's stream has to wait for `stream` too.
         """
         flags = 0
         is_torch = hasattr(out, "data_ptr")
