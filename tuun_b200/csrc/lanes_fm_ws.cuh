@@ -460,6 +460,9 @@ __device__ __forceinline__ void fm_ws_body(const tb_launch& P) {
             // scheduler (and its share of the conversion unit) sees both kinds of warp.
             uint32_t slot;
             asm("mov.u32 %0, %%warpid;" : "=r"(slot));
+            // (The two warps of a CTA swapping roles every 256 or 2,048 tiles — state through the voice's column of shared
+            // memory, the ring's second buffer moved off the rotation table so that the new phase warp can load it —
+            // was tried: the swap itself buys 1 %, the layout and the outer loop it needs cost 6 %.)
             // (Measured on the 65,536-voice batch, 5.38 ms with this rule: roles fixed by warp number 6.08 ms — every
             // phase warp on schedulers 0 and 2; other rules that give every scheduler four warps of one kind and three
             // of the other 5.28 - 5.46 ms, depending on which voices meet on a scheduler.  This one balances from four
