@@ -214,7 +214,13 @@ int tb_segments_states(tb_program* p, void** states, uint64_t* bytes_per_segment
 int tb_segments_fix(tb_program* p, uint32_t pass);
 int tb_segments_end(tb_program* p);
 
-/* Stream the render is enqueued on (a cudaStream_t), for callers that time with events. */
+/*
+ * Stream the render is enqueued on (a cudaStream_t).  A program creates its own NON-BLOCKING stream: device-side work
+ * of the caller that touches `out` / `params` / `mix` (a fill, a copy, a consumer kernel) is not ordered against a
+ * render unless the caller orders it — wait for this stream (or an event on it), or hand the program the caller's own
+ * stream with tb_set_stream.  Calls that return host data (out_len, host rows, tb_length) synchronize before returning;
+ * with TB_OUT_DEVICE and no out_len a call returns as soon as its launches are queued.
+ */
 void* tb_stream(tb_program* p);
 /* Run subsequent renders of this program on a caller-owned cudaStream_t. */
 int tb_set_stream(tb_program* p, void* cuda_stream);
