@@ -902,6 +902,9 @@ __device__ __forceinline__ void tile_done(RowStore& R, int l, u64 t, u64 n_tiles
 #ifndef TB_FM_ROT_REGS
 #define TB_FM_ROT_REGS 1
 #endif
+#ifndef TB_FM_CHEB
+#define TB_FM_CHEB 1
+#endif
 struct FmRot {
     double c1, s1, c2, s2, c3, s3, c4, s4, c16, s16;
 };
@@ -933,6 +936,33 @@ __device__ __forceinline__ void fm_carrier_tile(float (&car)[LS], double& S, dou
     } else {
 #if TB_ABL == 4
     UNROLL for (int j = 0; j < LS; j++) f[j] = TB_D2F(S) + j;
+#elif TB_FM_ROT_REGS && TB_FM_CHEB
+    (void)rot;
+    {
+        // The tile from its centre outwards by the three-term recurrence s[k + 1] = 2 cos(d) s[k] - s[k - 1], both ways:
+        // sin at +-1 by angle addition (3 operations), then one DFMA a sample — 16 f64 operations a tile against 30 for
+        // the two-level angle additions, and 3 entries of the rotation table in registers against 5.  Rounding errors
+        // grow like k^2 ulp over the k <= 8 steps of a chain (the recurrence is a double integrator at worst, for a
+        // modulator near 0 Hz): 1e-14, against the 6e-8 of the f32 the value is rounded to; the centre itself moves by
+        // an angle addition as before, so nothing carries from tile to tile.
+        f[8] = TB_D2F(S);
+        const double k2 = rr.c1 + rr.c1;
+        const double b = Cq * rr.s1;
+        double up1 = fma(S, rr.c1, b), dn1 = fma(S, rr.c1, -b);   // sin at samples 9 and 7
+        f[9] = TB_D2F(up1);
+        f[7] = TB_D2F(dn1);
+        double up0 = S, dn0 = S;
+        UNROLL for (int k = 2; k <= 7; k++) {
+            const double u = fma(k2, up1, -up0);
+            up0 = up1; up1 = u;
+            f[8 + k] = TB_D2F(u);
+        }
+        UNROLL for (int k = 2; k <= 8; k++) {
+            const double v = fma(k2, dn1, -dn0);
+            dn0 = dn1; dn1 = v;
+            f[8 - k] = TB_D2F(v);
+        }
+    }
 #elif TB_FM_ROT_REGS
     (void)rot;
     {
