@@ -162,6 +162,8 @@ struct ToneRegs {
     float x1, x2;      // x[-1], x[-2]
     float y1, y2;      // y[-1], y[-2]
     float p1, p2, q2;  // a1 y[-1], a2 y[-2], a2 y[-1]
+    float b1p;         // b1 x[-1]
+    u64 b2p;           // (b2 x[-2], b2 x[-1]): the feed-forward products that reach into the next tile
 };
 // The four sines of one chunk from what the phase warp handed over (TB_WS_ARG: their arguments; else the floats 1.m).
 __device__ __forceinline__ void tone_sines(const uint4 mv, float (&x)[4]) {
@@ -211,8 +213,8 @@ __device__ __forceinline__ void tone_chunk(const float (&xq)[4], float (&yq)[4],
 template <bool KEEP, bool PRIMED, typename Next>
 __device__ __forceinline__ void tone_tile(const uint4* ring, float4* dst, ToneRegs& F, float (&xn)[4], Next next, float* x_out,
                                           float* y_out) {
-    float b1p = __fmul_rn(F.b1, F.x1);                                   // b1 x[i - 1]
-    u64 b2p = pk2(__fmul_rn(F.b2, F.x2), __fmul_rn(F.b2, F.x1));         // b2 x[i - 2], b2 x[i - 1]
+    float b1p = F.b1p;  // b1 x[i - 1]
+    u64 b2p = F.b2p;    // b2 x[i - 2], b2 x[i - 1]
     if (!PRIMED) tone_sines(ring[0], xn);
     float xq[4], yq[4];
     UNROLL for (int q = 0; q < 4; q++) {
@@ -229,6 +231,8 @@ __device__ __forceinline__ void tone_tile(const uint4* ring, float4* dst, ToneRe
     F.x2 = xq[2];
     F.y1 = yq[3];
     F.y2 = yq[2];
+    F.b1p = b1p;
+    F.b2p = b2p;
 }
 
 // One tile of the tone warp out of buffer B: sines, filter, into half B of the row buffer.
@@ -259,6 +263,8 @@ __device__ __forceinline__ void ws_tone(const tb_insn* code, LaneMem& M, RowStor
         F.p1 = __fmul_rn(F.a1, F.y1);
         F.q2 = __fmul_rn(F.a2, F.y1);
         F.p2 = __fmul_rn(F.a2, F.y2);
+        F.b1p = __fmul_rn(F.b1, F.x1);
+        F.b2p = pk2(__fmul_rn(F.b2, F.x2), __fmul_rn(F.b2, F.x1));
     }
     const u64 slots = n_tiles + (rem > 0 ? 1u : 0u);  // tiles the phase warp makes
     // both buffers start empty
