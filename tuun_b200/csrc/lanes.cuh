@@ -214,6 +214,10 @@ __device__ __forceinline__ double f32_to_f64_pos(float f) {
 #ifndef TB_WS_ARG
 #define TB_WS_ARG 0
 #endif
+// TB_WS_SINES: the first TB_WS_SINES chunks of four samples leave as finished sines.
+#ifndef TB_WS_SINES
+#define TB_WS_SINES 0
+#endif
 __device__ __forceinline__ void raw_pair(uint32_t m0, uint32_t m1, float& r0, float& r1) {
 #if TB_WS_ARG
     unpk2(fma2(pk2(__uint_as_float(m0), __uint_as_float(m1)), pk2(TB_SIN23_A, TB_SIN23_A), pk2(TB_SIN23_B, TB_SIN23_B)), r0, r1);
@@ -1014,7 +1018,7 @@ __device__ __forceinline__ void fm_carrier_tile(float (&car)[LS], double& S, dou
             p += freq_to_inc(f[j + 1], sk) >> 20;
             if (CAP && j == cap) *p_cap = t0;
             if (CAP && j + 1 == cap) *p_cap = t1;
-            if (RAW) raw_pair(p44_m23(t0), p44_m23(t1), car[j], car[j + 1]);
+            if (RAW && j >= 4 * TB_WS_SINES) raw_pair(p44_m23(t0), p44_m23(t1), car[j], car[j + 1]);
             else if (!PHASE_ONLY) sin_m23x2(p44_m23(t0), p44_m23(t1), car[j], car[j + 1]);
         }
         return;
@@ -1051,7 +1055,7 @@ __device__ __forceinline__ void fm_carrier_tile(float (&car)[LS], double& S, dou
 #if TB_ABL == 2
         car[j] = __uint_as_float(pd_m23(T0)); car[j + 1] = __uint_as_float(pd_m23(T1));
 #else
-        if (RAW) raw_pair(pd_m23(T0, sk.one23), pd_m23(T1, sk.one23), car[j], car[j + 1]);
+        if (RAW && j >= 4 * TB_WS_SINES) raw_pair(pd_m23(T0, sk.one23), pd_m23(T1, sk.one23), car[j], car[j + 1]);
         else if (!PHASE_ONLY) sin_m23x2(pd_m23(T0, sk.one23), pd_m23(T1, sk.one23), car[j], car[j + 1]);
 #endif
     }

@@ -31,6 +31,12 @@
 #ifndef TB_WS_ARG
 #define TB_WS_ARG 1
 #endif
+// ... and the sines themselves of a tile's first TB_WS_SINES chunks of four samples: with one, the tone warp's filter
+// starts on a tile without waiting for a sine (5.29 -> 5.20 ms; two: 5.30; while the phase warp was the slower one —
+// before the integer widening, the recurrence and the loops by voice class — one cost 0.10 ms).
+#ifndef TB_WS_SINES
+#define TB_WS_SINES 1
+#endif
 #include "lanes.cuh"
 
 namespace {
@@ -165,8 +171,13 @@ struct ToneRegs {
     float b1p;         // b1 x[-1]
     u64 b2p;           // (b2 x[-2], b2 x[-1]): the feed-forward products that reach into the next tile
 };
-// The four sines of one chunk from what the phase warp handed over (TB_WS_ARG: their arguments; else the floats 1.m).
-__device__ __forceinline__ void tone_sines(const uint4 mv, float (&x)[4]) {
+// The four sines of chunk Q from what the phase warp handed over: the sines themselves (Q < TB_WS_SINES), their arguments
+// (TB_WS_ARG), or the floats 1.m.
+__device__ __forceinline__ void tone_sines(const uint4 mv, float (&x)[4], int Q = 3) {
+    if (Q < TB_WS_SINES) {  // (Q is a literal after unrolling)
+        x[0] = __uint_as_float(mv.x); x[1] = __uint_as_float(mv.y); x[2] = __uint_as_float(mv.z); x[3] = __uint_as_float(mv.w);
+        return;
+    }
 #if TB_WS_ARG
     x[0] = __sinf(__uint_as_float(mv.x));
     x[1] = __sinf(__uint_as_float(mv.y));
@@ -215,11 +226,11 @@ __device__ __forceinline__ void tone_tile(const uint4* ring, float4* dst, ToneRe
                                           float* y_out) {
     float b1p = F.b1p;  // b1 x[i - 1]
     u64 b2p = F.b2p;    // b2 x[i - 2], b2 x[i - 1]
-    if (!PRIMED) tone_sines(ring[0], xn);
+    if (!PRIMED) tone_sines(ring[0], xn, 0);
     float xq[4], yq[4];
     UNROLL for (int q = 0; q < 4; q++) {
         UNROLL for (int k = 0; k < 4; k++) xq[k] = xn[k];
-        if (q + 1 < 4) tone_sines(ring[(q + 1) * LT], xn);
+        if (q + 1 < 4) tone_sines(ring[(q + 1) * LT], xn, q + 1);
         else next();
         tone_chunk(xq, yq, F, b1p, b2p);
         if (KEEP) {
