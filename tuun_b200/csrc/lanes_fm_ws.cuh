@@ -5,11 +5,12 @@
 // parallelism the batch has, and the loop is bound by latency (issue slots 54 % used, the conversion /
 // special-function unit 54 %: profiles/r2_*).  Here the voice's work is cut where its data flow is
 // narrowest and the halves run as a producer and a consumer warp, lane l of both owning voice l:
-//   * the PHASE warp: modulator tile by angle addition (f64), the affine map, the running carrier phase
-//     (one DFMA per sample on the 2^-44-turn grid, lanes.cuh pd_make) — it hands over 16 words a tile, the
-//     floats 1.m whose mantissas are the top 23 phase bits (fm_carrier_tile<.., RAW>);
-//   * the TONE warp: the carrier's sines on the special-function unit, the biquad in the reference's
-//     operation order (generator.rs:496-507, lanes.cuh biquad_tile), the row transpose and the stores.
+//   * the PHASE warp: modulator tile (f64, three-term recurrence from the tile's centre), the affine map, the running
+//     carrier phase (one DFMA per sample on the 2^-44-turn grid, lanes.cuh pd_make) — it hands over 16 words a tile
+//     (fm_carrier_tile<.., RAW>): the arguments of the carrier's sines, made from the top 23 phase bits, and for the
+//     tile's first four samples the sines themselves;
+//   * the TONE warp: the other sines on the special-function unit, the biquad in the reference's operation order
+//     (generator.rs:496-507, lanes.cuh biquad_tile), the row transpose and the stores.
 // Twice the warps with the same instructions per sample (+ 8 shared-memory instructions a tile for the
 // hand-over) and about half the registers each: 15 CTAs of 64 threads an SM at <= 64 registers.
 // The hand-over is a two-buffer ring in shared memory guarded by named barriers (bar.sync / bar.arrive
@@ -22,7 +23,7 @@
 #define TB_LANE_THREADS 32
 // Measured on 65,536 voices x 2 s (this kernel 6.00 ms as first written): the conversion / special-function unit is the
 // busy one (56 % of its instruction rate, in bursts), so the carrier frequency becomes a double by integer
-// instructions here (lanes.cuh f32_to_f64_alu: 4.5 instructions instead of one F2F.F64.F32; 5.90 ms) — a trade the
+// instructions here (lanes.cuh f32_to_f64_alu: four instructions instead of one F2F.F64.F32; 5.90 ms) — a trade the
 // one-thread form loses (32.3 against 31.1 ms there) — and with that the phase warp also makes the sines' arguments
 // (the FFMA2 of sin_m23x2: 5.85 ms; without the integer widening that move costs 0.05 ms).
 #ifndef TB_WIDEN_ALU
