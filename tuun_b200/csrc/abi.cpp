@@ -358,7 +358,12 @@ int launch_lanes(tb_program* p, tb_launch& B) {
         CU(cudaEventCreate(&ev[1]));
     }
     CU(cudaEventRecord(ev[0], p->stream));
-    cudaError_t e = cudaSuccess;
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "before the lane kernel launch");
+    if (std::getenv("TUUN_B200_DEBUG"))
+        std::fprintf(stderr, "[tuun_b200] lane launch: voices %u samples %llu smem %zu groups %u queue %d fm %d out %p stride %llu\n",
+                     B.n_voices, (unsigned long long)B.n_samples, p->lane_smem, groups, B.lane_queue != nullptr, (int)fm,
+                     (void*)B.out, (unsigned long long)B.out_stride);
     if (fm_ws) {
         if (vs) tb_lanes_fm_ws_split_run(&B, p->lane_fm_ws_smem, p->stream);
         else tb_lanes_fm_ws_run(&B, p->lane_fm_ws_smem, p->stream);
@@ -992,7 +997,7 @@ static int create_program(const tb_node* nodes, uint32_t n_nodes, const int32_t*
     if (!p) return set_error(TB_ERR_NOMEM, "out of host memory");
     const char* fs = std::getenv("TUUN_B200_FAST_SINES");
     const bool fast = !(fs && fs[0] == '0');
-    int rc = tb::lower(nodes, n_nodes, lists, n_lists, fixed_len, fast, p->low, noise_ids);
+    int rc = tb::lower(nodes, n_nodes, lists, n_lists, fixed_len, fast, p->low, noise_ids, sample_rate);
     std::string whole_error;
     if (rc == TB_ERR_UNSUPPORTED && allow_sequence) {
         // A long tune nests deeper than the interpreter's control stack as ONE program, but lowers part by part: the
@@ -1184,7 +1189,9 @@ int tb_lower_check(const tb_node* nodes, uint32_t n_nodes, const int32_t* lists,
     if (!nodes || n_nodes == 0) return set_error(TB_ERR_INVALID, "empty op list");
     tb::Lowered low;
     const char* fs = std::getenv("TUUN_B200_FAST_SINES");
-    int rc = tb::lower(nodes, n_nodes, lists, n_lists, fixed_len, !(fs && fs[0] == '0'), low);
+    // (lengths in samples — a timeline in the steady stream, lower.cpp — are decided at the default rate of the
+    //  reference's tracker, 44,100 Hz: this entry point has no rate argument)
+    int rc = tb::lower(nodes, n_nodes, lists, n_lists, fixed_len, !(fs && fs[0] == '0'), low, nullptr, 44100u);
     if (rc == TB_ERR_UNSUPPORTED) {
         // part by part (create_program): every part must lower; the geometry reported is that of the largest one
         std::vector<tb::SeqPart> parts;
@@ -1202,7 +1209,7 @@ int tb_lower_check(const tb_node* nodes, uint32_t n_nodes, const int32_t* lists,
                 extract_subtree(all, all_lists, sp.root, sub, sub_lists, ids);
                 tb::Lowered one;
                 if (tb::lower(sub.data(), (uint32_t)sub.size(), sub_lists.data(), (uint32_t)sub_lists.size(), fixed_len,
-                              !(fs && fs[0] == '0'), one, ids.data()) != TB_OK) {
+                              !(fs && fs[0] == '0'), one, ids.data(), 44100u) != TB_OK) {
                     ok = false;
                     break;
                 }
@@ -1333,7 +1340,7 @@ int tb_substitute(tb_program* p, uint32_t mark_id, float value, uint32_t* n_repl
     // (a literal can decide the lowering only through is_const's Append(c, c) arm, generator.rs:597-603).
     tb::Lowered low;
     int rc = tb::lower(nodes.data(), (uint32_t)nodes.size(), p->lists.data(), (uint32_t)p->lists.size(), p->fixed_len,
-                       p->fast_sines, low, p->noise_ids.empty() ? nullptr : p->noise_ids.data());
+                       p->fast_sines, low, p->noise_ids.empty() ? nullptr : p->noise_ids.data(), p->sample_rate);
     if (rc != TB_OK) return set_error(rc, low.error);
     const tb::Lowered& o = p->low;
     const bool same = low.code.size() == o.code.size() && low.cexpr.size() == o.cexpr.size() &&

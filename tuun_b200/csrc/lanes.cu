@@ -2,6 +2,7 @@
 // entry points of the lane path.
 #include <algorithm>
 
+#include <cstdio>
 #include "lanes.cuh"
 
 // grid = ceil(n_voices / LT) CTAs of LT voices; P.n_samples is a multiple of TB_LS; P.out points at the
@@ -28,20 +29,32 @@ extern "C" size_t tb_lanes_smem_bytes(uint32_t n_lane_code, uint32_t w_words, ui
 
 // kind: 0 = interpreter kernels, one unit per CTA; 1 = the same behind the work queue (tb_launch::lane_queue);
 //       2 = the fused-FM-voice kernels (lanes_fm.cu).
-extern "C" cudaError_t tb_lanes_launch(const tb_launch* P, size_t smem, int kind, cudaStream_t stream) {
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        const void* ks[9] = {(const void*)tb_render_lanes_kernel, (const void*)tb_render_lanes_mix_kernel};
-        tb_lanes_queue_kernels(&ks[2], &ks[3]);
-        tb_lanes_fm_kernels(&ks[4], &ks[5]);
-        tb_lanes_split_kernels(&ks[6]);
-        tb_lanes_fm_split_kernels(&ks[7], &ks[8]);
-        for (const void* k : ks) {
-            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-        }
-        configured = smem;
+// Every kernel that may take a lane program is opted in to the largest shared-memory size any program of this
+// process has needed on the device (never lowered: a program created later with a smaller footprint must not
+// take the opt-in away from one that is still rendering).
+static cudaError_t ensure_lane_smem(size_t smem) {
+    static size_t configured[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    size_t& have = configured[dev & 63];
+    if (smem <= 48 * 1024 || smem <= have) return cudaSuccess;
+    const void* ks[9] = {(const void*)tb_render_lanes_kernel, (const void*)tb_render_lanes_mix_kernel};
+    tb_lanes_queue_kernels(&ks[2], &ks[3]);
+    tb_lanes_fm_kernels(&ks[4], &ks[5]);
+    tb_lanes_split_kernels(&ks[6]);
+    tb_lanes_fm_split_kernels(&ks[7], &ks[8]);
+    for (const void* k : ks) {
+        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
     }
+    have = smem;
+    return cudaSuccess;
+}
+
+extern "C" cudaError_t tb_lanes_launch(const tb_launch* P, size_t smem, int kind, cudaStream_t stream) {
+    cudaError_t se = ensure_lane_smem(smem);
+    if (se != cudaSuccess) return se;
     const uint32_t groups = (P->n_voices + LT - 1) / LT;
     const bool vsplit = P->vsplit_total > 1;  // virtual voices (time-axis split): the kernels of lanes_*split.cu; no mixdown
     if (vsplit && P->mix_partial) return cudaErrorInvalidValue;
@@ -60,8 +73,7 @@ extern "C" cudaError_t tb_lanes_occupancy(size_t smem, int kind, int* blocks_per
     const void* dummy = nullptr;
     if (kind == 1) tb_lanes_queue_kernels(&k, &dummy);
     if (kind == 2) tb_lanes_fm_kernels(&k, &dummy);
-    cudaError_t e = cudaSuccess;
-    if (smem > 48 * 1024) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = ensure_lane_smem(smem);
     if (e != cudaSuccess) return e;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, LT, smem);
     if (e != cudaSuccess) return e;

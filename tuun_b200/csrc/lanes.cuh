@@ -536,14 +536,23 @@ __device__ __forceinline__ void run_lane_tile(const tb_launch& P, uint32_t code_
                 // last sample; -0.0 counts as non-negative but re-arms).  What the inner tree needs is each
                 // sample's local time: j - o behind a restart at o, else "j samples into a run that began
                 // before this tile", encoded -1 - j, which every clocked node adds to its own carried position.
+                // Nested in another Reset (in.c = its clock slot): where that one restarts, this one is Initial again —
+                // "previously negative" (:276-279) — and so is everything under it (set_state, :311-313).
                 lacc_load(M, acc);
                 bool neg = ldw(M, in.a) == 0u;
                 // second state word: the class of the first sample seen since it was last cleared (split.cu SP_CLK)
                 if (ldw(M, in.a + 1) == 0u) stw(M, in.a + 1, acc[0] >= 0.0f ? 2u : 1u);
                 int o = -1;
                 float clk[LS];
+                float oclk[LS];
+                const bool nested = in.c >= 0;
+                if (nested) lslot_load(M, in.c, oclk);
                 UNROLL for (int j = 0; j < LS; j++) {
                     const float x = acc[j];
+                    if (nested && __float_as_int(oclk[j]) == 0) {
+                        neg = true;
+                        o = j;
+                    }
                     if (neg && x >= 0.0f) {
                         o = j;
                         neg = signbit(x);
@@ -555,6 +564,26 @@ __device__ __forceinline__ void run_lane_tile(const tb_launch& P, uint32_t code_
                 lslot_store(M, in.b, clk);
                 stw(M, in.a, neg ? 0u : 1u);
                 continue;
+            }
+            case ST_SEG_CLK: {  // a piece of a timeline: samples since it began (program.h)
+                const u64 p0 = ld64(M, in.a);
+                float clk[LS];
+                UNROLL for (int j = 0; j < LS; j++) {
+                    const u64 at = p0 + (u64)j, c0 = (u64)(uint32_t)in.c;
+                    const u64 d = at > c0 ? at - c0 : 0ull;
+                    clk[j] = __int_as_float((int)(d < 0x7fffffffull ? d : 0x7fffffffull));
+                }
+                lslot_store(M, in.b, clk);
+                continue;
+            }
+            case ST_SEG_SEL: {  // the running result is this piece; before its first sample the pieces before it hold
+                const u64 p0 = ld64(M, in.a);
+                float before[LS];
+                lslot_load(M, in.b, before);
+                lacc_load(M, acc);
+                UNROLL for (int j = 0; j < LS; j++) acc[j] = p0 + (u64)j >= (u64)(uint32_t)in.c ? acc[j] : before[j];
+                if (in.op & 0x100u) st64(M, in.a, p0 + (u64)LS);
+                break;
             }
             case ST_TIME_CLK: {  // Time under a Reset: (local time) as f32 / sample_rate (generator.rs:101-111)
                 const TimeDiv td = time_div_setup(P.sample_rate);
@@ -732,6 +761,9 @@ __device__ void setup_lane(const tb_launch& P, const LaneMem& M, const float* pr
             }
         } else if (a.kind == LA_PHASE) {
             st64(M, (int)a.w_off, turns_to_fx_slow((double)ldf(M, a.a) / TB_TAU));
+        } else if (a.kind == LA_TL_POS) {  // a timeline starts with the root Fin: its position is that clock's
+            st64(M, (int)a.w_off, ld64(M, a.a));
+        } else if (a.kind == LA_TL_PIECE || a.kind == LA_TL_ZERO) {
         } else {  // LA_COEF
             const tb_filter_tab* ft = &P.filt[a.a];
             for (uint32_t e = 0; e < ft->K + ft->J; e++) stw(M, (int)(a.w_off + e), ldw(M, ~ft->coef[e]));
@@ -743,6 +775,20 @@ __device__ void finish_lane(const tb_launch& P, const LaneMem& M, u64 n_samples)
     for (uint32_t t = 0; t < P.n_lane_aux; t++) {
         const tb_lane_aux a = P.lane_aux[t];
         if (a.kind == LA_ROT) st64(M, a.b, ld64(M, a.b) + ld64(M, (int)a.w_off) * n_samples);
+        // A timeline (ST_SEG_*): the state the general interpreter would hold at this position (generator.rs:133-188).
+        // A piece that has begun: its Fin's clock counts from its first sample (the clocked words of the piece left
+        // theirs), the Append in front of the next piece says whether that one has begun; a piece that has rendered
+        // no sample yet is Initial (its clocked words ran on a clock held at 0).
+        if (a.kind == LA_TL_PIECE) {
+            const u64 pos = ld64(M, (int)a.w_off), c0 = (u64)(uint32_t)a.a;
+            if (pos >= c0) {
+                if (a.b >= 0) st64(M, a.b, pos - c0);
+                if (a.c >= 0) stw(M, a.c, pos >= (u64)a.q_off ? 1u : 0u);
+            }
+        } else if (a.kind == LA_TL_ZERO) {
+            if (ld64(M, (int)a.w_off) <= (u64)(uint32_t)a.a)
+                for (int k = 0; k < a.c; k++) stw(M, a.b + k, 0u);
+        }
     }
 }
 

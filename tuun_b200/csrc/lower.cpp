@@ -32,6 +32,7 @@ struct Lowerer {
     const uint32_t* noise_ids = nullptr;  // node -> number of its Noise stream (a part of a sequence keeps the numbers
                                           // its nodes have in the whole tree, lower.h sequence_parts); NULL: the index
     int noise_id(int i) const { return noise_ids ? (int)noise_ids[i] : i; }
+    uint32_t sample_rate = 0;  // 0: not known (no timeline in the steady stream)
 
     std::vector<int> const_memo;   // node -> cval index, -2 = not computed, -1 = not const
     std::vector<int> state_off;    // node -> offset of its state block (or -1)
@@ -882,7 +883,7 @@ struct Lowerer {
             negzero_idx = literal_cexpr(-0.0f);
         }
         tb_insn& prod = out.code[s_last];
-        const int npost = (int)(prod.op >> 16);
+        const int npost = (int)((prod.op >> 16) & 0xffu);
         if (op == TB_MERGE) op = TB_ADD;  // infinite operands: Merge is Add (generator.rs:263)
         if (op == TB_ADD || op == TB_SUBTRACT) {
             const int addend = op == TB_ADD ? cidx : new_cexpr(tb_cexpr{CE_NEG, 0, cidx, 0, 0.f});
@@ -910,6 +911,91 @@ struct Lowerer {
     // triangle of lib/v0/std.tuun (Appendix B of SURVEY.md); anything else keeps the general interpreter.
     int clk_slot = -1;
     bool lane_steady_root = false;  // the steady stream renders the whole (infinite) tree
+    bool steady_nested_clk = false; // a Reset inside a Reset: no time-axis split
+    // greater_or_equals_at (generator.rs:787-862) of a chain of literals against a clock: the sample the Fin ends at
+    // (the arithmetic of the kernels' goe_eval); false when a step is a per-voice parameter.
+    bool literal_target(const tb_goe& g, uint64_t* target) const {
+        float value = 0.0f;
+        for (uint32_t k = 0; k < g.n_steps; k++) {
+            const tb_cexpr& e = out.cexpr[out.goe_steps[g.step_off + 2 * k + 1]];
+            if (e.kind != CE_LIT) return false;
+            value = out.goe_steps[g.step_off + 2 * k] > 0 ? value + e.value : value - e.value;
+        }
+        const float t = std::ceil(value * (float)sample_rate);
+        if (!(t >= 1.0f) || t >= 2.0e9f) return false;
+        *target = (uint64_t)t;
+        return true;
+    }
+    // A timeline (program.h ST_SEG_*): Append(Fin{T - c0, e0}, Append(Fin{T - c1, e1}, .. last)) where `last` is one more
+    // such Fin or a tree that never ends, under a root Fin that ends no later than the timeline does (so neither the
+    // timeline's own end nor the zero-extension of a Merge around it is ever rendered: generator.rs:169-188, :520-570).
+    // Every e_k must be closed-form in the clock of its piece, like the inner tree of a Reset.
+    uint64_t steady_limit = 0;  // samples the root Fin lets through when that is a literal, else 0
+    int tl_root_time = -1;      // state offset of the root Fin's Time
+    bool in_piece = false;
+    bool have_timeline = false;
+    struct TlPiece {
+        uint32_t start, next;                        // first sample of the piece and of the one behind it
+        int fin_time, app;                           // state offsets or -1
+        std::vector<std::pair<int, int>> ranges;     // its state ranges
+    };
+    std::vector<TlPiece> tl_pieces;
+    bool emit_timeline(int i) {
+        if (clk_slot >= 0 || in_piece || have_timeline || steady_limit == 0 || sample_rate == 0) return false;
+        struct Piece { int tree, fin, fin_time, app; uint64_t start; };
+        std::vector<Piece> pieces;
+        uint64_t start = 0;
+        for (int cur = i;;) {
+            const tb_node& n = nodes[cur];
+            const bool app = n.kind == TB_APPEND;
+            const int f = app ? n.a : cur;
+            if (nodes[f].kind == TB_FIN) {
+                const tb_goe g = out.goe[build_goe(nodes[f].a)];
+                uint64_t len = 0;
+                if (g.term != GOE_TIME || g.through_append || !literal_target(g, &len)) return false;
+                pieces.push_back(Piece{nodes[f].b, f, g.term_arg, app ? state_of(cur, 1) : -1, start});
+                start += len;
+            } else if (!app && never_ends(cur)) {
+                pieces.push_back(Piece{cur, -1, -1, -1, start});
+                start = ~0ull;
+            } else {
+                return false;
+            }
+            if (!app) break;
+            cur = n.b;
+            if (pieces.size() > 64) return false;
+        }
+        if (start < steady_limit) return false;  // the timeline would end inside the note
+        while (pieces.back().start >= steady_limit) pieces.pop_back();  // never begun
+        const int cs = s_alloc(), vs = s_alloc();
+        if (vs > 0xff) return false;
+        have_timeline = true;
+        out.lane_clk = 1;
+        for (size_t k = 0; k < pieces.size(); k++) {
+            const Piece& pc = pieces[k];
+            const bool last = k + 1 == pieces.size();
+            emit(ST_SEG_CLK, 0, cs, (int)pc.start);
+            s_last = -1;
+            in_piece = true;
+            clk_slot = cs;
+            const bool ok = emit_steady(pc.tree);
+            clk_slot = -1;
+            in_piece = false;
+            if (!ok) return false;
+            if (k > 0) s_produced(emit(ST_SEG_SEL | (last ? 0x100u : 0u), 0, vs, (int)pc.start));
+            else if (last) return false;  // (an Append has two parts)
+            if (!last) emit(ST_SAVE, vs);
+            TlPiece t;
+            t.start = (uint32_t)pc.start;
+            t.next = last ? 0xffffffffu : (uint32_t)pieces[k + 1].start;
+            t.fin_time = pc.fin_time;
+            t.app = pc.app;
+            collect_state(pc.fin >= 0 ? pc.fin : pc.tree, t.ranges);
+            tl_pieces.push_back(t);
+        }
+        s_slots -= 2;
+        return true;
+    }
     bool emit_steady(int i) {
         const tb_node& n = nodes[i];
         switch (n.kind) {
@@ -919,19 +1005,25 @@ struct Lowerer {
                 else s_produced(emit(ST_TIME, state_of(i, 2)));
                 return true;
             case TB_RESET: {
-                if (clk_slot >= 0) return false;  // nested
+                // Nested (hard sync: a pulse restarted by another oscillator): the trigger is rendered against the
+                // enclosing clock, and the inner clock restarts with it as well — set_state(inner, Initial) of the
+                // enclosing Reset (generator.rs:311-313) makes this one "previously negative" again (:276-279).
+                if (in_piece) return false;
+                const int outer = clk_slot;
                 if (!emit_steady(n.a)) return false;
                 const int s = s_alloc();
                 if (s > 0xff) return false;
-                emit(ST_RESET_CLK, state_of(i, 2), s);
+                emit(ST_RESET_CLK, state_of(i, 2), s, outer);
                 s_last = -1;
                 clk_slot = s;
                 const bool ok = emit_steady(n.b);
-                clk_slot = -1;
+                clk_slot = outer;
                 s_slots--;
                 out.lane_clk = 1;
+                if (outer >= 0) steady_nested_clk = true;
                 return ok;
             }
+            case TB_APPEND: return emit_timeline(i);
             case TB_NOISE: s_produced(emit(ST_NOISE, state_of(i, 2), noise_id(i))); return true;
             case TB_MARKED:
             case TB_CAPTURED: return emit_steady(n.a);
@@ -939,7 +1031,7 @@ struct Lowerer {
                 const int cb = const_of(n.b);
                 if (!emit_steady(n.a)) return false;
                 if (cb >= 0) {
-                    if ((out.code[s_last].op >> 16) >= 15) return false;
+                    if (s_last < 0 || ((out.code[s_last].op >> 16) & 0xffu) >= 15) return false;
                     s_postop(n.op, cb);
                 } else {
                     const int s = s_alloc();
@@ -1126,7 +1218,17 @@ struct Lowerer {
             switch (op) {
                 case ST_END: case ST_CONST: case ST_ALT_CC: case ST_AFFINE: case ST_OPC: break;
                 case ST_TIME: case ST_NOISE: in.a += st0; break;
-                case ST_RESET_CLK: case ST_TIME_CLK: in.a += st0; slot(in.b); break;
+                case ST_TIME_CLK: in.a += st0; slot(in.b); break;
+                case ST_RESET_CLK:
+                    in.a += st0;
+                    slot(in.b);
+                    if (in.c >= 0) slot(in.c);
+                    break;
+                case ST_SEG_CLK: case ST_SEG_SEL:
+                    if (tl_root_time < 0) return false;
+                    in.a = lane_new_aux(LA_TL_POS, st0 + tl_root_time, 2, 0, nullptr);
+                    slot(in.b);
+                    break;
                 case ST_SINE_CLK: {
                     const tb_aux* inc = aux_at(in.b);
                     const tb_aux* ph = aux_at(in.c);
@@ -1184,6 +1286,16 @@ struct Lowerer {
             if (op == ST_END) break;
         }
         out.lane_slots = (uint32_t)(max_slot + 1);
+        if (!tl_pieces.empty()) {  // what finish_lane leaves for the general interpreter (lanes.cuh)
+            const uint32_t pos_w = (uint32_t)lane_new_aux(LA_TL_POS, st0 + tl_root_time, 2, 0, nullptr);
+            for (const TlPiece& t : tl_pieces) {
+                out.lane_aux.push_back(tb_lane_aux{LA_TL_PIECE, (int32_t)t.start, t.fin_time >= 0 ? st0 + t.fin_time : -1,
+                                                   t.app >= 0 ? st0 + t.app : -1, pos_w, t.next});
+                for (const auto& r : t.ranges)
+                    if (r.second > 0)
+                        out.lane_aux.push_back(tb_lane_aux{LA_TL_ZERO, (int32_t)t.start, st0 + r.first, r.second, pos_w, 0u});
+            }
+        }
         const char* fe = std::getenv("TUUN_B200_LANE_FUSE");  // diagnostics: "0" keeps the plain ST_* words
         if (!(fe && fe[0] == '0')) {
             fuse_lane_fm();
@@ -1210,7 +1322,7 @@ struct Lowerer {
                 res.push_back(w);
                 for (uint32_t k = 0; k < np; k++) res.push_back(in[i + 1 + k]);
             } else {
-                last = (op == ST_SAVE || op == ST_RESET_CLK || op == ST_END) ? -1 : (long)res.size();
+                last = (op == ST_SAVE || op == ST_RESET_CLK || op == ST_SEG_CLK || op == ST_END) ? -1 : (long)res.size();
                 for (size_t k = 0; k < words + np && i + k < in.size(); k++) res.push_back(in[i + k]);
             }
             i += words + np;
@@ -1231,7 +1343,7 @@ struct Lowerer {
                               ((in[i + 2].op & 0xffu) == ST_SINE_AC || (in[i + 2].op & 0xffu) == ST_SINE_CA);
             if (!cand) {
                 // copy the instruction with its post-op words
-                const size_t n = 1 + (((cc.op & 0xffu) == ST_END) ? 0 : (cc.op >> 16));
+                const size_t n = 1 + (((cc.op & 0xffu) == ST_END) ? 0 : ((cc.op >> 16) & 0xffu));
                 for (size_t k = 0; k < n && i + k < in.size(); k++) res.push_back(in[i + k]);
                 i += n;
                 continue;
@@ -1300,6 +1412,9 @@ struct Lowerer {
                 const size_t goe0 = out.goe.size(), steps0 = out.goe_steps.size();
                 const int gi = build_goe(nodes[sroot].a);
                 const tb_goe g = out.goe[gi];
+                uint64_t target = 0;
+                steady_limit = (g.term == GOE_TIME && !g.through_append && sample_rate != 0 && literal_target(g, &target)) ? target : 0;
+                tl_root_time = g.term == GOE_TIME ? g.term_arg : -1;
                 if ((g.term == GOE_TIME || g.term == GOE_CONST) && !g.through_append && emit_steady(nodes[sroot].b)) {
                     emit(ST_END);
                     out.lane_fin_goe = gi;
@@ -1307,7 +1422,10 @@ struct Lowerer {
                 } else {
                     out.goe.resize(goe0);
                     out.goe_steps.resize(steps0);
+                    tl_pieces.clear();
+                    have_timeline = false;
                 }
+                steady_limit = 0;
             }
             if (fin_ok) {
                 out.steady_ok = 0;
@@ -1317,13 +1435,15 @@ struct Lowerer {
                 lane_steady_root = true;
                 {   // clocked words run on the lane kernels only: lane_ok decides below whether the plan stands
                     const int passes = split_level(root);
-                    bool ok = passes <= 8;
+                    bool ok = passes <= 8 && !steady_nested_clk;
                     for (const tb_split_entry& e : out.split) ok = ok && (int)e.state_off >= 0;
                     if (ok) out.split_passes = (uint32_t)passes;
                     else out.split.clear();
                 }
             } else {
                 out.lane_clk = 0;
+                tl_pieces.clear();
+                have_timeline = false;
                 out.code.resize(code0);
                 out.cexpr.resize(cexpr0);
                 for (int& m : const_memo)
@@ -1411,10 +1531,11 @@ bool sequence_parts(const tb_node* nodes, uint32_t n_nodes, const int32_t* lists
 }
 
 int lower(const tb_node* nodes, uint32_t n_nodes, const int32_t* lists, uint32_t n_lists,
-          uint64_t pool_len, bool fast_sines, Lowered& out, const uint32_t* noise_ids) {
+          uint64_t pool_len, bool fast_sines, Lowered& out, const uint32_t* noise_ids, uint32_t sample_rate) {
     out = Lowered();
     Lowerer L(nodes, n_nodes, lists, n_lists, pool_len, out, fast_sines);
     L.noise_ids = noise_ids;
+    L.sample_rate = sample_rate;
     try {
         L.run();
     } catch (int status) {

@@ -40,7 +40,8 @@ struct Lowered {
 // Returns TB_OK or a negative tb_status (out.error holds the reason).  noise_ids (may be NULL): node -> number of
 // its Noise stream, for an op list that is a part of a larger tree.
 int lower(const tb_node* nodes, uint32_t n_nodes, const int32_t* lists, uint32_t n_lists,
-          uint64_t pool_len, bool fast_sines, Lowered& out, const uint32_t* noise_ids = nullptr);
+          uint64_t pool_len, bool fast_sines, Lowered& out, const uint32_t* noise_ids = nullptr,
+          uint32_t sample_rate = 0);  // sample_rate 0: not known (lengths in samples are not decided while lowering)
 
 // A root SEQUENCE — a tree of Appends (nested either way, under Marked / Captured wrappers) whose leaves are
 // Fin{len_0, a_0}, Fin{len_1, a_1}, ..., rest: what `<[a, b, c]>`, `a \ b` and Player::beats_waveform evaluate to

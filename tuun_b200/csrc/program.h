@@ -136,9 +136,17 @@ enum tb_op : uint32_t {
     ST_OPC,        // post-op word: acc = acc (operator a) cval[b]
     // ---- steady words only the lane kernels run (a Reset over a tree whose nodes are closed-form in the run's
     //      own time: the sawtooth / pulse / triangle oscillators of lib/v0/std.tuun) ----
-    ST_RESET_CLK,  // a = state (sign word), b = slot: acc = trigger -> slot = per-sample local clock, see lanes.cuh
+    ST_RESET_CLK,  // a = state (sign word), b = slot: acc = trigger -> slot = per-sample local clock, see lanes.cuh;
+                   // c = clock slot of the Reset it is nested in (restarts with it), or -1
     ST_TIME_CLK,   // a = state, b = clock slot
     ST_SINE_CLK,   // a = state, b = aux of increment, c = aux of phase; clock slot in op bits 24-31; class in op >> 8
+    // ---- a timeline in the steady stream (lane kernels only): Append(Fin{c0, e0}, Append(Fin{c1, e1}, ..)) under a
+    //      root Fin, every length a literal and every e_k closed-form in its own clock — the envelopes of
+    //      lib/v0/std.tuun (ADSR: four linear ramps).  All pieces are evaluated, the one a sample lies in is kept ----
+    ST_SEG_CLK,    // a = W of the timeline's position, b = clock slot, c = first sample of the piece:
+                   // slot = samples since the piece began (0 before it begins)
+    ST_SEG_SEL,    // a = W of the position, b = slot (the pieces before), c = first sample of the piece:
+                   // acc = at or after c ? acc : slot; op bit 8: the last piece (the position advances by a tile)
     // ---- lane program only (lanes.cuh; fused by lower.cpp build_lane_plan) ----
     LN_FM,         // ST_SINE_CC + one ST_AFFINE + ST_SINE_AC (or ST_SINE_CA) [+ ST_FILT K=3 J=2], two words:
                    //   word 0: a = W of the carried (sin, cos), b = W of the carrier's accumulator,
@@ -196,7 +204,14 @@ enum tb_lane_aux_kind : uint32_t {
                    // centre of the coming tile as two doubles (4 W words; b = W index of the node's
                    // accumulator, c = cval of its phase offset), + the rotations (cos, sin)(2 pi k inc / 2^64),
                    // k = 1..TB_LS/2 and k = TB_LS, as double2 in TB_LS/2 + 1 Q units
-    LA_COEF = 3    // filter table a: K feed-forward then J feedback coefficient values, K + J W words
+    LA_COEF = 3,   // filter table a: K feed-forward then J feedback coefficient values, K + J W words
+    // a timeline (ST_SEG_*): its position is that of the root Fin's clock when a launch begins; when it ends the
+    // nodes of the pieces get the state the general interpreter would have left (they share state blocks)
+    LA_TL_POS = 4,   // a = W of the root Fin's Time: position -> 2 W words at w_off
+    LA_TL_PIECE = 5, // a = first sample of the piece, b = W of its Fin's Time or -1, c = W of its Append's word or
+                     // -1, q_off = first sample of the next piece, w_off = W of the position
+    LA_TL_ZERO = 6   // a = first sample of the piece, b = W of a state range of it, c = words: cleared while the
+                     // piece has not begun; w_off = W of the position
 };
 struct tb_lane_aux {
     uint32_t kind;

@@ -1715,7 +1715,10 @@ extern "C" size_t tb_kernel_smem_bytes(uint32_t n_code, uint32_t n_slots, uint32
 }
 
 extern "C" cudaError_t tb_kernel_launch(const tb_launch* P, size_t smem, uint32_t warps, cudaStream_t stream) {
-    static size_t configured = 0;
+    static size_t configured_on[64] = {};  // per device; raised, never lowered
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    size_t& configured = configured_on[dev & 63];
     if (smem > 48 * 1024 && smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(tb_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
