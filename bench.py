@@ -632,6 +632,10 @@ def main():
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             import config_bench
             extras["configs"] = config_bench.run(reps=3, hbm_gbs=peak)
+            try:
+                extras["config_batches"] = config_bench.run_batches(reps=2, hbm_gbs=peak)
+            except Exception as e:  # a secondary record must not cost the line
+                extras["config_batches"] = {"error": str(e)[:200]}
             extras["configs_note"] = ("one voice each (the reference's own bench shape), wall clock of tb_render with device rows "
                                       "against the CPU port on one core in 1024-sample blocks; see tools/config_bench.py")
     if rank == 0:

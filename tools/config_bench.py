@@ -90,6 +90,50 @@ def run(reps=5, hbm_gbs=None, names=None):
     return rows
 
 
+def run_batches(reps=3, hbm_gbs=None, voices=16384):
+    """Config 2 as a batch (the four-note harmonica sequence, every voice the same tree): the default kernel
+    selection — from 10,656 voices the lane-per-voice kernels, which take the notes' nested Resets and ADSR timeline
+    (lanes.cuh ST_RESET_CLK / ST_SEG_*) — next to the general interpreter alone (TUUN_B200_LANES=0)."""
+    import torch
+    from tuun_b200 import workloads as W
+    from tuun_b200.generator import Program
+    w, n = W.cfg2_harmonica(4), 88200
+    out = torch.empty((voices, n), dtype=torch.float32, device="cuda")
+    rows = []
+    keep = os.environ.get("TUUN_B200_LANES")
+    try:
+        for name, lanes in (("general interpreter", "0"), ("default selection", None)):
+            if lanes is None:
+                os.environ.pop("TUUN_B200_LANES", None)
+            else:
+                os.environ["TUUN_B200_LANES"] = lanes
+            p = Program(w, SR)
+            best = float("inf")
+            for _ in range(reps + 1):
+                p.reset()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                p.render(out)
+                torch.cuda.synchronize()
+                best = min(best, time.perf_counter() - t0)
+            info = p.info
+            row = {"config": "cfg2 harmonica x4", "voices": voices, "samples_per_voice": n, "kernels": name,
+                   "gpu_ms": best * 1e3, "gpu_value": voices * n / best, "kernel_launches_per_render": int(info.kernel_launches) // (reps + 1),
+                   "lane_launches_per_render": int(info.lane_launches) // (reps + 1)}
+            if hbm_gbs:
+                row["hbm_frac"] = 4.0 * voices * n / best / 1e9 / hbm_gbs
+            rows.append(row)
+            del p
+    finally:
+        if keep is None:
+            os.environ.pop("TUUN_B200_LANES", None)
+        else:
+            os.environ["TUUN_B200_LANES"] = keep
+    del out
+    torch.cuda.empty_cache()
+    return rows
+
+
 def main():
     import argparse
     ap = argparse.ArgumentParser()
@@ -106,8 +150,12 @@ def main():
     for r in rows:
         print(f"{r['config']:34s} {r['samples']:9d} {r['gpu_ms']:9.3f} {r['gpu_value']:11.3e} {r['cpu_1core_value']:11.3e} "
               f"{r['gpu_over_cpu_1core']:8.1f} {r['split_segments']:6d}" + ("" if r["length_matches_cpu"] else "  LENGTH MISMATCH"))
+    batches = run_batches(args.reps, peak)
+    for r in batches:
+        print(f"{r['config']} x {r['voices']} voices, {r['kernels']}: {r['gpu_ms']:.2f} ms, {r['gpu_value']:.3e} voice-samples/s "
+              f"({r['lane_launches_per_render']} lane launches of {r['kernel_launches_per_render']})")
     if args.json:
-        print(json.dumps(rows))
+        print(json.dumps(rows + batches))
 
 
 if __name__ == "__main__":

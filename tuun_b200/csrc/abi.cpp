@@ -1348,7 +1348,11 @@ int tb_substitute(tb_program* p, uint32_t mark_id, float value, uint32_t* n_repl
                       low.lane_code.size() == o.lane_code.size() && low.lane_aux.size() == o.lane_aux.size() &&
                       low.split.size() == o.split.size() && low.goe.size() == o.goe.size() &&
                       low.goe_steps.size() == o.goe_steps.size() && low.filt.size() == o.filt.size() &&
-                      (low.code.empty() || std::memcmp(low.code.data(), o.code.data(), low.code.size() * sizeof(tb_insn)) == 0);
+                      (low.code.empty() || std::memcmp(low.code.data(), o.code.data(), low.code.size() * sizeof(tb_insn)) == 0) &&
+                      (low.lane_code.empty() ||
+                       std::memcmp(low.lane_code.data(), o.lane_code.data(), low.lane_code.size() * sizeof(tb_insn)) == 0) &&
+                      (low.lane_aux.empty() ||
+                       std::memcmp(low.lane_aux.data(), o.lane_aux.data(), low.lane_aux.size() * sizeof(tb_lane_aux)) == 0);
     if (!same) return set_error(TB_ERR_UNSUPPORTED, "tb_substitute: the new value changes how the tree lowers");
     CU(cudaSetDevice(p->device));
     // Renders enqueued so far read the old table: the copy is ordered behind them on the program's stream.

@@ -162,13 +162,21 @@ struct Lowerer {
                     r = a;
                 break;
             }
-            case TB_MARKED: r = const_of(n.a); break;
+            case TB_MARKED:
+                r = const_of(n.a);
+                if (r >= 0) {  // tb_substitute may give this constant another value later
+                    if (cexpr_marked.size() <= (size_t)r) cexpr_marked.resize((size_t)r + 1, 0);
+                    cexpr_marked[r] = 1;
+                }
+                break;
             default: break;
         }
         const_memo[i] = r;
         return r;
     }
     int literal_cexpr(float v) { return new_cexpr(tb_cexpr{CE_LIT, 0, 0, 0, v}); }
+    std::vector<char> cexpr_marked;  // cval index -> the constant of a Marked node
+    bool is_marked_cexpr(int i) const { return (size_t)i < cexpr_marked.size() && cexpr_marked[i] != 0; }
 
     int new_aux(uint32_t kind, int a, int b, uint32_t words) {
         for (const tb_aux& e : out.aux)  // a node emitted twice (Filter pre-read, Fin) shares its constants
@@ -1197,6 +1205,24 @@ struct Lowerer {
                 return (int)e.w_off;
             }
         tb_lane_aux x{kind, a, b, c, out.lane_w_words, out.lane_q_units};
+        if (kind == LA_ROT) {
+            // The rotation table depends on the frequency alone: sines of one frequency (the same constant, the
+            // same literal, the same parameter column) share it; each keeps its own increment and carried pair.
+            // (Shared memory per voice decides how many voices an SM holds: 144 bytes a table.)
+            auto same = [&](int i, int j) {
+                if (i == j) return true;
+                const tb_cexpr &p = out.cexpr[i], &q = out.cexpr[j];
+                if (p.kind == CE_LIT && q.kind == CE_LIT)  // (not a literal tb_substitute may replace)
+                    return !is_marked_cexpr(i) && !is_marked_cexpr(j) && std::memcmp(&p.value, &q.value, sizeof(float)) == 0;
+                return p.kind == CE_PARAM && q.kind == CE_PARAM && p.a == q.a;
+            };
+            for (const tb_lane_aux& e : out.lane_aux)
+                if (e.kind == LA_ROT && same(e.a, a)) {
+                    x.q_off = e.q_off;
+                    q_units = 0;
+                    break;
+                }
+        }
         out.lane_aux.push_back(x);
         out.lane_w_words += w_words;
         out.lane_q_units += q_units;
