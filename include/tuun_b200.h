@@ -271,7 +271,9 @@ int tb_lane_kernel_times(tb_program* p, float* ms, uint32_t cap, uint32_t* n);
  * tb_last_error(), else TB_OK), and the launch geometry it would use.  The reference's analogue is
  * the panics of initialize_state / generate on a malformed tree (generator.rs:112,132,189,...),
  * surfaced before any sample is produced.  `tile` reports 512 when the tree qualifies for the
- * steady-state interpreter, else 256.
+ * steady-state interpreter, else 256.  (This entry point has no sample rate: where a length in
+ * samples decides the lowering — an envelope timeline under a note, see DESIGN.md section 2c — it is
+ * taken at 44,100 Hz, the rate of the reference's tracker.)
  */
 int tb_lower_check(const tb_node* nodes, uint32_t n_nodes, const int32_t* lists, uint32_t n_lists,
                    uint64_t fixed_len, tb_program_info* info);
