@@ -1130,6 +1130,10 @@ static int create_program(const tb_node* nodes, uint32_t n_nodes, const int32_t*
             const char* mv = std::getenv("TUUN_B200_LANE_MIN_VOICES");
             p->lane_min_voices = mv ? (uint32_t)std::strtoul(mv, nullptr, 10)
                                     : (uint32_t)std::max(1, n_sm * TB_LANE_THREADS * 9 / 8);
+            // Clocked words (a Reset or a timeline in the steady stream) run on the lane kernels only: the other
+            // choice is the general interpreter.  Measured on config 2 (harmonica notes): level at 4,096 voices
+            // (23.7 against 25.7 ms), the lane kernels ahead from there on (profiles/r2c_cfg2_lanes.txt).
+            if (!mv && p->low.lane_clk) p->lane_min_voices = 4096;
         } else {
             cudaGetLastError();
         }

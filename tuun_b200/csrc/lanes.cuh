@@ -568,20 +568,29 @@ __device__ __forceinline__ void run_lane_tile(const tb_launch& P, uint32_t code_
             case ST_SEG_CLK: {  // a piece of a timeline: samples since it began (program.h)
                 const u64 p0 = ld64(M, in.a);
                 float clk[LS];
-                UNROLL for (int j = 0; j < LS; j++) {
-                    const u64 at = p0 + (u64)j, c0 = (u64)(uint32_t)in.c;
-                    const u64 d = at > c0 ? at - c0 : 0ull;
-                    clk[j] = __int_as_float((int)(d < 0x7fffffffull ? d : 0x7fffffffull));
+                if (p0 < 0x7fff0000ull) {  // (pieces begin below 2^31: lower.cpp literal_target) 32-bit arithmetic
+                    const int d0 = (int)(uint32_t)p0 - in.c;
+                    UNROLL for (int j = 0; j < LS; j++) clk[j] = __int_as_float(max(d0 + j, 0));
+                } else {
+                    UNROLL for (int j = 0; j < LS; j++) {
+                        const u64 at = p0 + (u64)j, c0 = (u64)(uint32_t)in.c;
+                        const u64 d = at > c0 ? at - c0 : 0ull;
+                        clk[j] = __int_as_float((int)(d < 0x7fffffffull ? d : 0x7fffffffull));
+                    }
                 }
                 lslot_store(M, in.b, clk);
                 continue;
             }
             case ST_SEG_SEL: {  // the running result is this piece; before its first sample the pieces before it hold
                 const u64 p0 = ld64(M, in.a);
-                float before[LS];
-                lslot_load(M, in.b, before);
+                const u64 c0 = (u64)(uint32_t)in.c;
                 lacc_load(M, acc);
-                UNROLL for (int j = 0; j < LS; j++) acc[j] = p0 + (u64)j >= (u64)(uint32_t)in.c ? acc[j] : before[j];
+                if (p0 < c0) {  // (a tile wholly inside the piece keeps the running result as it is)
+                    float before[LS];
+                    lslot_load(M, in.b, before);
+                    const int k = (int)(c0 - p0 < (u64)LS ? c0 - p0 : (u64)LS);  // samples of this tile in front of the piece
+                    UNROLL for (int j = 0; j < LS; j++) acc[j] = j >= k ? acc[j] : before[j];
+                }
                 if (in.op & 0x100u) st64(M, in.a, p0 + (u64)LS);
                 break;
             }
@@ -590,10 +599,28 @@ __device__ __forceinline__ void run_lane_tile(const tb_launch& P, uint32_t code_
                 float clk[LS];
                 lslot_load(M, in.b, clk);
                 const u64 pos = ld64(M, in.a);
-                UNROLL for (int j = 0; j < LS; j++) {
-                    const int c = __float_as_int(clk[j]);
-                    const u64 nloc = c >= 0 ? (u64)c : pos + (u64)(-1 - c);
-                    acc[j] = time_div(nloc, td);
+                // Every local time of the tile below 2^24 (any run younger than 6 minutes): the short division of
+                // time_div for all sixteen, the range looked at once instead of sample by sample.
+                bool done = false;
+                if (td.ok && pos < 16777216ull - (u64)LS) {
+                    const uint32_t p32 = (uint32_t)pos;
+                    uint32_t any = 0u;
+                    UNROLL for (int j = 0; j < LS; j++) {
+                        const int c = __float_as_int(clk[j]);
+                        const uint32_t nloc = c >= 0 ? (uint32_t)c : p32 + (uint32_t)(-1 - c);
+                        any |= nloc;
+                        const float a = (float)nloc;
+                        const float q0 = __fmul_rn(a, td.r);
+                        acc[j] = fmaf(fmaf(-q0, td.b, a), td.r, q0);
+                    }
+                    done = any < 16777216u;
+                }
+                if (!done) {
+                    UNROLL for (int j = 0; j < LS; j++) {
+                        const int c = __float_as_int(clk[j]);
+                        const u64 nloc = c >= 0 ? (u64)c : pos + (u64)(-1 - c);
+                        acc[j] = time_div(nloc, td);
+                    }
                 }
                 const int cl = __float_as_int(clk[LS - 1]);
                 st64(M, in.a, cl >= 0 ? (u64)cl + 1ull : pos + (u64)LS);
