@@ -547,19 +547,26 @@ __device__ __forceinline__ void run_lane_tile(const tb_launch& P, uint32_t code_
                 float oclk[LS];
                 const bool nested = in.c >= 0;
                 if (nested) lslot_load(M, in.c, oclk);
-                UNROLL for (int j = 0; j < LS; j++) {
-                    const float x = acc[j];
-                    if (nested && __float_as_int(oclk[j]) == 0) {
-                        neg = true;
-                        o = j;
+                // (selects, not branches: the state machine runs once a sample; a NaN changes nothing)
+                if (nested) {
+                    UNROLL for (int j = 0; j < LS; j++) {
+                        const float x = acc[j];
+                        const bool r = __float_as_int(oclk[j]) == 0;
+                        neg = neg || r;
+                        o = r ? j : o;
+                        const bool fire = neg && x >= 0.0f;
+                        o = fire ? j : o;
+                        neg = fire ? (__float_as_int(x) < 0) : (neg || x < 0.0f);
+                        clk[j] = __int_as_float(o >= 0 ? j - o : -1 - j);
                     }
-                    if (neg && x >= 0.0f) {
-                        o = j;
-                        neg = signbit(x);
-                    } else if (!neg && x < 0.0f) {
-                        neg = true;
+                } else {
+                    UNROLL for (int j = 0; j < LS; j++) {
+                        const float x = acc[j];
+                        const bool fire = neg && x >= 0.0f;
+                        o = fire ? j : o;
+                        neg = fire ? (__float_as_int(x) < 0) : (neg || x < 0.0f);
+                        clk[j] = __int_as_float(o >= 0 ? j - o : -1 - j);
                     }
-                    clk[j] = __int_as_float(o >= 0 ? j - o : -1 - j);
                 }
                 lslot_store(M, in.b, clk);
                 stw(M, in.a, neg ? 0u : 1u);
@@ -630,9 +637,10 @@ __device__ __forceinline__ void run_lane_tile(const tb_launch& P, uint32_t code_
                 float clk[LS];
                 lslot_load(M, (int)(in.op >> 24), clk);
                 const u64 a0 = ld64(M, in.a), inc = ld64(M, in.b), ph0 = ld64(M, in.c);
+                const u64 a1 = a0 + ph0;
                 UNROLL for (int j = 0; j < LS; j++) {
                     const int c = __float_as_int(clk[j]);
-                    const u64 ph = (c >= 0 ? inc * (u64)c : a0 + inc * (u64)(-1 - c)) + ph0;
+                    const u64 ph = inc * (u64)(uint32_t)(c >= 0 ? c : -1 - c) + (c >= 0 ? ph0 : a1);
                     acc[j] = !fast ? sin_turns_exact(ph) : (FASTMODE == 2 ? sin_p32((uint32_t)(ph >> 32)) : sin_hi<1>((int)(ph >> 32)));
                 }
                 const int cl = __float_as_int(clk[LS - 1]);
