@@ -573,7 +573,18 @@ __device__ __forceinline__ void run_lane_tile(const tb_launch& P, uint32_t code_
                 continue;
             }
             case ST_SEG_CLK: {  // a piece of a timeline: samples since it began (program.h)
+                const tb_insn ex = nxt;  // second word: a = where the piece ends, b = words to its ST_SEG_SEL
+                ip += sizeof(tb_insn);
                 const u64 p0 = ld64(M, in.a);
+                // A tile that lies wholly in front of the piece or behind it: nothing of the piece is kept (ST_SEG_SEL
+                // takes the pieces before it, or a later piece takes over), so its words are not run.  (Positions are
+                // the same for every voice of a launch: no divergence.)
+                if (p0 + (u64)LS <= (u64)(uint32_t)in.c || p0 >= (u64)(uint32_t)ex.a) {
+                    ip += (uint32_t)ex.b * (uint32_t)sizeof(tb_insn);
+                    nxt = lds_insn(ip);
+                    continue;
+                }
+                nxt = lds_insn(ip);
                 float clk[LS];
                 if (p0 < 0x7fff0000ull) {  // (pieces begin below 2^31: lower.cpp literal_target) 32-bit arithmetic
                     const int d0 = (int)(uint32_t)p0 - in.c;

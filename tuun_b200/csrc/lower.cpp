@@ -983,6 +983,9 @@ struct Lowerer {
             const Piece& pc = pieces[k];
             const bool last = k + 1 == pieces.size();
             emit(ST_SEG_CLK, 0, cs, (int)pc.start);
+            // its second word (never run: ST_SEG_CLK takes it): a = where the piece ends, b = words from here to its
+            // ST_SEG_SEL (build_lane_plan) — a tile that lies wholly outside the piece jumps there
+            emit(ST_SEG_CLK | 0x200u, last ? 0x7fffffff : (int)pieces[k + 1].start, 0, 0);
             s_last = -1;
             in_piece = true;
             clk_slot = cs;
@@ -990,8 +993,8 @@ struct Lowerer {
             clk_slot = -1;
             in_piece = false;
             if (!ok) return false;
-            if (k > 0) s_produced(emit(ST_SEG_SEL | (last ? 0x100u : 0u), 0, vs, (int)pc.start));
-            else if (last) return false;  // (an Append has two parts)
+            if (k == 0 && last) return false;  // (an Append has two parts)
+            s_produced(emit(ST_SEG_SEL | (last ? 0x100u : 0u), 0, vs, (int)pc.start));
             if (!last) emit(ST_SAVE, vs);
             TlPiece t;
             t.start = (uint32_t)pc.start;
@@ -1251,6 +1254,7 @@ struct Lowerer {
                     if (in.c >= 0) slot(in.c);
                     break;
                 case ST_SEG_CLK: case ST_SEG_SEL:
+                    if (in.op & 0x200u) break;  // second word of ST_SEG_CLK
                     if (tl_root_time < 0) return false;
                     in.a = lane_new_aux(LA_TL_POS, st0 + tl_root_time, 2, 0, nullptr);
                     slot(in.b);
@@ -1326,6 +1330,18 @@ struct Lowerer {
         if (!(fe && fe[0] == '0')) {
             fuse_lane_fm();
             fold_lane_postops();
+        }
+        // ST_SEG_CLK: distance to the piece's ST_SEG_SEL, in words of the program as it now stands
+        auto width = [&](size_t i) {
+            const uint32_t op = out.lane_code[i].op & 0xffu;
+            return (size_t)1 + (op == ST_END ? 0u : ((out.lane_code[i].op >> 16) & 0xffu)) + (op == LN_FM ? 1u : 0u);
+        };
+        for (size_t i = 0; i < out.lane_code.size(); i += width(i)) {
+            if ((out.lane_code[i].op & 0xffu) != ST_SEG_CLK || (out.lane_code[i].op & 0x200u)) continue;
+            size_t j = i + 2;
+            while (j < out.lane_code.size() && (out.lane_code[j].op & 0xffu) != ST_SEG_SEL) j += width(j);
+            if (j >= out.lane_code.size()) return false;
+            out.lane_code[i + 1].b = (int32_t)(j - (i + 2));
         }
         return true;
     }
