@@ -765,6 +765,12 @@ __device__ __forceinline__ void run_lane_tile(const tb_launch& P, uint32_t code_
                 UNROLL for (int j = 0; j < LS; j++) acc[j] = acc[j] >= 0.0f ? cp : cn;
             } else if (pk == ST_FILT) {    // folded biquad
                 lane_filter<3, 2>(M, acc, po.a, po.b, 3, 2);
+            } else if (pk == ST_SAVE) {    // folded: the running result into a slot
+                lslot_store(M, po.a, acc);
+            } else if (pk == ST_BIN) {     // folded: slot (operator) running result
+                float av[LS];
+                lslot_load(M, po.a, av);
+                APPLY_OP_L((uint32_t)po.b, acc, av[j], acc[j])
             } else {
                 const float c = ldf(M, po.b);
                 APPLY_OP_L((uint32_t)po.a, acc, acc[j], c)

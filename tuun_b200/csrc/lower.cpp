@@ -1356,7 +1356,10 @@ struct Lowerer {
             const uint32_t op = in[i].op & 0xffu;
             const size_t words = (op == LN_FM ? 2 : 1);
             const uint32_t np = op == ST_END ? 0 : ((in[i].op >> 16) & 0xffu);
-            const bool foldable = op == ST_ALT_CC || (in[i].op & 0xffffu) == (ST_FILT | (3u << 8) | (2u << 12));
+            // (ST_SAVE — the running result into a slot — and ST_BIN — slot (op) running result — ride along too: what
+            //  they need is in registers where the producer ends, and every word that is not a dispatch saves one)
+            const bool foldable = op == ST_ALT_CC || (in[i].op & 0xffffu) == (ST_FILT | (3u << 8) | (2u << 12)) ||
+                                  op == ST_SAVE || op == ST_BIN;
             if (foldable && last >= 0 && ((res[last].op >> 16) & 0xffu) + 1 + np <= 0xffu) {
                 res[last].op += (1u + np) << 16;
                 tb_insn w = in[i];
