@@ -118,6 +118,37 @@ def test_lane_plan_of_the_headline_voice():
     assert lower_check(Fin(Sine(Const(1.0), Const(0.0)), Sine(Const(440.0), Const(0.0)))).lane_smem_bytes == 0
 
 
+def test_lane_plan_of_instruments():
+    """Host half only: a Reset nested in a Reset (hard sync) and a timeline of literal-length pieces under a root Fin
+    (an ADSR over a note) lower into the lane program (lower.cpp emit_steady / emit_timeline); so does a note of config
+    2's harmonica, with one rotation table for each of its two frequencies.  A timeline that ends inside its note, a
+    piece of per-voice length and a Filter under a piece's clock keep the general interpreter."""
+    from tuun_b200.generator import lower_check
+    from tuun_b200.waveform import Alt, Append, Const, Filter, Fin, Reset, Sine, Time, add, mul
+    from tuun_b200.workloads import cfg2_harmonica
+    saw = lambda f: mul(add(Reset(Sine(Const(6.2831855 * f), Const(0.0)), mul(Time(), Const(-f))), Const(0.5)), Const(2.0))
+    pulse = lambda f, w: Alt(add(saw(f), Const(w)), Const(1.0), Const(-1.0))
+    sync = Reset(pulse(440.0, -0.93), pulse(701.0, 0.3))
+    assert lower_check(sync).lane_smem_bytes > 0 and lower_check(sync).split_passes == 0  # no time-axis split
+    assert lower_check(pulse(440.0, -0.93)).split_passes > 0                              # (one clock level: split)
+    def adsr(c0, c1, c2=None, sustain=None):
+        last = Const(sustain) if sustain is not None else Fin(add(Time(), Const(-0.3)), add(mul(Time(), Const(-1.0)), Const(0.8)))
+        return Append(Fin(add(Time(), c0), mul(Time(), Const(20.0))),
+                      Append(Fin(add(Time(), c1), add(mul(Time(), Const(-1.0)), Const(1.0))), last))
+    tone = lambda: Sine(Const(1.0, param=0), Const(0.0))
+    note = lambda dur, env: Fin(add(Time(), Const(-dur)), mul(tone(), env))
+    assert lower_check(note(0.4, adsr(Const(-0.05), Const(-0.2)))).lane_smem_bytes > 0
+    assert lower_check(note(5.0, adsr(Const(-0.05), Const(-0.2), sustain=0.7))).lane_smem_bytes > 0   # held level: never ends
+    assert lower_check(note(1.5, adsr(Const(-0.05), Const(-0.2)))).lane_smem_bytes == 0               # ends at 0.55 s
+    assert lower_check(note(0.4, adsr(Const(-0.05, param=1), Const(-0.2)))).lane_smem_bytes == 0      # per-voice length
+    lp = Filter(mul(Time(), Const(20.0)), [Const(0.5), Const(0.5)], [])
+    filtered = Append(Fin(add(Time(), Const(-0.05)), lp), Const(1.0))
+    assert lower_check(note(0.4, filtered)).lane_smem_bytes == 0
+    h = lower_check(cfg2_harmonica(2).a)
+    # 18 Q units: two rotation tables of nine for four constant-rate sines (440 Hz twice, the 1.6 Hz vibrato twice)
+    assert h.lane_smem_bytes > 0 and h.lane_smem_bytes < 76 * 1024 and h.tile == 256
+
+
 def test_nesting_is_checked_against_the_kernel_control_stack():
     """A sequence is a right-nested Append chain (optimizer.rs:212-229): two control-stack words per note when it has to
     be ONE program — per-voice note lengths here (a root sequence of voice-independent lengths lowers part by part and
