@@ -144,6 +144,9 @@ def test_lane_plan_of_instruments():
     lp = Filter(mul(Time(), Const(20.0)), [Const(0.5), Const(0.5)], [])
     filtered = Append(Fin(add(Time(), Const(-0.05)), lp), Const(1.0))
     assert lower_check(note(0.4, filtered)).lane_smem_bytes == 0
+    from tuun_b200.waveform import Noise
+    breath = Append(Fin(add(Time(), Const(-0.05)), mul(Noise(), Const(0.1))), Const(1.0))  # a draw count is no clock
+    assert lower_check(note(0.4, breath)).lane_smem_bytes == 0
     h = lower_check(cfg2_harmonica(2).a)
     # 18 Q units: two rotation tables of nine for four constant-rate sines (440 Hz twice, the 1.6 Hz vibrato twice)
     assert h.lane_smem_bytes > 0 and h.lane_smem_bytes < 76 * 1024 and h.tile == 256

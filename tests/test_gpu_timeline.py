@@ -177,3 +177,65 @@ def test_harmonica_note_and_sequence(monkeypatch):
     slens = np.asarray(s.render(sout))
     assert (slens == 88200).all() and s.info.sequence_parts == 4 and s.info.lane_launches >= 4
     assert float(np.max(np.abs(sout[:, :88200] - sref[None, :]))) <= TOL
+
+
+def test_random_timelines_streamed(monkeypatch):
+    """Seeded random timelines — 2 to 5 pieces of random literal lengths, each a ramp, a level, a tremolo or a square
+    LFO, the last one a Fin or a held level — over a per-voice tone that a hard-synced pulse may replace, under a note
+    that ends inside the timeline; rendered whole and in random block sizes (blocks end inside pieces, on their first
+    samples and past the note's end) against the oracle."""
+    from tuun_b200.generator import lower_check
+    rng = np.random.default_rng(20261019)
+    V = 70
+    f = rng.uniform(80.0, 1500.0, V).astype(np.float32)
+    g = (f * rng.uniform(1.3, 2.9, V).astype(np.float32)).astype(np.float32)
+    params = np.stack([TAU * f, -f, TAU * g, -g], axis=1).astype(np.float32)
+
+    def piece_tree(kind, level):
+        if kind == 0:
+            return add(mul(Time(), Const(f32(rng.uniform(-3.0, 3.0)))), Const(f32(level)))
+        if kind == 1:
+            return Const(f32(level))
+        if kind == 2:
+            return add(mul(Sine(Const(f32(TAU * rng.uniform(3.0, 9.0))), Const(f32(rng.uniform(0.0, 1.0)))), Const(0.2)), Const(f32(level)))
+        return Alt(Sine(Const(f32(TAU * rng.uniform(4.0, 12.0))), Const(0.0)), Const(f32(level)), mul(Time(), Const(2.0)))
+
+    taken = 0
+    for case in range(14):
+        n_pieces = int(rng.integers(2, 6))
+        lens = [float(np.float32(rng.uniform(0.004, 0.09))) for _ in range(n_pieces)]
+        held = bool(rng.integers(0, 2))
+        parts = [Fin(add(Time(), Const(-f32(d))), piece_tree(int(rng.integers(0, 4)), rng.uniform(0.2, 1.0))) for d in lens]
+        env = Const(f32(0.6)) if held else parts.pop()
+        for p in reversed(parts):
+            env = Append(p, env)
+        total = sum(lens[:len(parts)]) + (10.0 if held else lens[-1])
+        dur = float(np.float32(rng.uniform(0.3, 0.95) * min(total, 0.3)))
+        if rng.integers(0, 2):
+            tone = Sine(Const(1.0, param=0), Const(0.0))
+        else:
+            tone = Reset(Alt(add(saw(0, 1), Const(-0.9)), Const(1.0), Const(-1.0)), mul(saw(2, 3), Const(0.5)))
+        w = Fin(add(Time(), Const(-f32(dur))), mul(tone, env))
+        N = int(dur * SR) + 700
+        ref, rlens = oracle_rows(w, params, V, N)
+        if lower_check(w).lane_smem_bytes == 0:
+            continue  # (a note rounded past the end of its timeline)
+        taken += 1
+        p = program(w, monkeypatch)
+        out = np.zeros((V, N), dtype=np.float32)
+        got = np.asarray(p.render(out, params=params)).astype(np.int64)
+        assert (got == rlens).all(), (case, got[:3], rlens[:3])
+        assert p.info.lane_launches >= 1 or N < 272 + 16, case
+        blocks = []
+        while sum(blocks) < N:
+            blocks.append(int(rng.choice([16, 100, 256, 272, 300, 1024, 1500, 4000])))
+        q = program(w, monkeypatch)
+        rows, slens = streamed(q, V, N, blocks, params)
+        assert (slens == rlens).all(), (case, blocks[:4], slens[:3], rlens[:3])
+        for name, x, xl in (("whole", out, got), ("streamed", rows, slens)):
+            bad = 0
+            for v in range(V):
+                bad += int((np.abs(x[v, :xl[v]] - ref[v, :xl[v]]) > TOL).any())
+            # an edge of a pulse or of a square LFO within rounding of zero moves by a sample (SURVEY 7, hard part 1)
+            assert bad <= 1, (case, name, bad, blocks[:4])
+    assert taken >= 10

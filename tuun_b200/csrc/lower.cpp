@@ -1035,7 +1035,11 @@ struct Lowerer {
                 return ok;
             }
             case TB_APPEND: return emit_timeline(i);
-            case TB_NOISE: s_produced(emit(ST_NOISE, state_of(i, 2), noise_id(i))); return true;
+            case TB_NOISE:
+                // (in a piece of a timeline its draw count would have to start with the piece: not closed-form in a clock)
+                if (in_piece) return false;
+                s_produced(emit(ST_NOISE, state_of(i, 2), noise_id(i)));
+                return true;
             case TB_MARKED:
             case TB_CAPTURED: return emit_steady(n.a);
             case TB_BINARY: {
