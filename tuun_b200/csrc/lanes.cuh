@@ -751,16 +751,24 @@ __device__ __forceinline__ void run_lane_tile(const tb_launch& P, uint32_t code_
             }
             default: return;  // unreachable: lower.cpp emits only the words above
         }
-        for (uint32_t np = (in.op >> 16) & 0xffu; np > 0; np--) {  // constant point operators (generator.rs:541-548)
+        // Post-op words: constant point operators (generator.rs:541-548) and what lower.cpp folded behind the
+        // producer.  Runs of ST_AFFINE — most of them — have a loop of their own: with one path through its body the
+        // sixteen values stay where they are (in one loop over all kinds every word cost sixteen register moves).
+        for (uint32_t np = (in.op >> 16) & 0xffu; np > 0; np--) {
+            while ((nxt.op & 0xffu) == ST_AFFINE) {  // (acc * m) + a, both rounded
+                const float m = ldf(M, nxt.b), a = ldf(M, nxt.c);
+                ip += sizeof(tb_insn);
+                nxt = lds_insn(ip);
+                const u64 mm = pk2(m, m), aa = pk2(a, a);
+                UNROLL for (int j = 0; j < LS; j += 2) unpk2(add2(mul2(pk2(acc[j], acc[j + 1]), mm), aa), acc[j], acc[j + 1]);
+                if (--np == 0) break;
+            }
+            if (np == 0) break;
             const tb_insn po = nxt;
             ip += sizeof(tb_insn);
             nxt = lds_insn(ip);
             const uint32_t pk = po.op & 0xffu;
-            if (pk == ST_AFFINE) {  // (acc * m) + a, both rounded
-                const float m = ldf(M, po.b), a = ldf(M, po.c);
-                const u64 mm = pk2(m, m), aa = pk2(a, a);
-                UNROLL for (int j = 0; j < LS; j += 2) unpk2(add2(mul2(pk2(acc[j], acc[j + 1]), mm), aa), acc[j], acc[j + 1]);
-            } else if (pk == ST_ALT_CC) {  // folded by lower.cpp fold_lane_postops (generator.rs:335-341)
+            if (pk == ST_ALT_CC) {  // folded by lower.cpp fold_lane_postops (generator.rs:335-341)
                 const float cp = ldf(M, po.a), cn = ldf(M, po.b);
                 UNROLL for (int j = 0; j < LS; j++) acc[j] = acc[j] >= 0.0f ? cp : cn;
             } else if (pk == ST_FILT) {    // folded biquad
