@@ -22,6 +22,13 @@ _trig = lambda: Sine(Const(1.0, param=0), Const(0.0))
 saw = mul(add(Reset(_trig(), mul(Time(), Const(1.0, param=1))), Const(0.5)), Const(2.0))      # std.tuun:19
 tri = Alt(_trig(), Reset(_trig(), add(mul(Time(), Const(1.0, param=2)), Const(-1.0))),
           Reset(_trig(), add(mul(Time(), Const(1.0, param=3)), Const(3.0))))                  # std.tuun:23-28
+def _adsr(dur):
+    """attack / decay / sustain ramp / release, each a Fin of literal length; longer than the note."""
+    from tuun_b200.waveform import Append
+    ramp = lambda d, m, a: Fin(sub(Time(), Const(f32(d))), add(mul(Time(), Const(f32(m))), Const(f32(a))))
+    return Append(ramp(0.02, 50.0, 0.0), Append(ramp(0.1, -3.0, 1.0), Append(ramp(dur, -0.1 / dur, 0.7), ramp(0.5, -1.2, 0.6))))
+
+
 shapes = [
     ("sine", Sine(Const(1.0, param=0), Const(0.0)), fr),
     ("pm", Sine(Const(1.0, param=0), mul(Sine(Const(1.0, param=1), Const(0.0)), Const(6.0))), fr),
@@ -35,6 +42,11 @@ shapes = [
     ("sawtooth(f)", saw, osc),
     ("pulse(0.3,f)|lpf", lpf(Alt(sub(saw, Const(0.3)), Const(1.0), Const(-1.0)), 0.707, 2000), osc),
     ("triangle(f)", tri, osc),
+    # hard sync (a Reset nested in a Reset) and a note under an ADSR of literal-length pieces (a timeline): lanes.cuh
+    # ST_RESET_CLK with an enclosing clock, ST_SEG_CLK / ST_SEG_SEL
+    ("sync(pulse f, saw 4f)", Reset(Alt(sub(saw, Const(0.9)), Const(1.0), Const(-1.0)),
+                                    mul(add(Reset(Sine(Const(1.0, param=2), Const(0.0)), mul(Time(), Const(1.0, param=3))), Const(0.125)), Const(2.0))), osc),
+    ("(fm|lpf) * adsr note(N)", Fin(sub(Time(), Const(f32(N / SR))), mul(fm_filter_voice(), _adsr(N / SR))), p5),
 ]
 out = torch.empty((V, N), dtype=torch.float32, device="cuda")
 

@@ -573,12 +573,13 @@ __device__ __forceinline__ void run_lane_tile(const tb_launch& P, uint32_t code_
                 continue;
             }
             case ST_SEG_CLK: {  // a piece of a timeline: samples since it began (program.h)
-                const tb_insn ex = nxt;  // second word: a = where the piece ends, b = words to its ST_SEG_SEL
+                const tb_insn ex = nxt;  // second word: a = where the piece ends, b = words to jump (lower.cpp)
                 ip += sizeof(tb_insn);
                 const u64 p0 = ld64(M, in.a);
-                // A tile that lies wholly in front of the piece or behind it: nothing of the piece is kept (ST_SEG_SEL
-                // takes the pieces before it, or a later piece takes over), so its words are not run.  (Positions are
-                // the same for every voice of a launch: no divergence.)
+                // A tile that lies wholly in front of the piece or behind it: nothing of the piece is kept (the running
+                // result stays what the pieces before it made it, or a later piece takes over), so its words are not
+                // run — nor its ST_SEG_SEL, unless it is the last one.  (Positions are the same for every voice of a
+                // launch: no divergence.)
                 if (p0 + (u64)LS <= (u64)(uint32_t)in.c || p0 >= (u64)(uint32_t)ex.a) {
                     ip += (uint32_t)ex.b * (uint32_t)sizeof(tb_insn);
                     nxt = lds_insn(ip);

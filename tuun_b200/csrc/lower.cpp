@@ -1345,6 +1345,10 @@ struct Lowerer {
             size_t j = i + 2;
             while (j < out.lane_code.size() && (out.lane_code[j].op & 0xffu) != ST_SEG_SEL) j += width(j);
             if (j >= out.lane_code.size()) return false;
+            // Not the last piece: past its ST_SEG_SEL (and the ST_SAVE folded behind it) as well — a tile in front of
+            // the piece keeps the running result (the pieces before it, already saved), a tile behind it keeps nothing.
+            // The last piece's ST_SEG_SEL runs every tile: it advances the position.
+            if (!(out.lane_code[j].op & 0x100u)) j += width(j);
             out.lane_code[i + 1].b = (int32_t)(j - (i + 2));
         }
         return true;

@@ -145,7 +145,7 @@ enum tb_op : uint32_t {
     //      lib/v0/std.tuun (ADSR: four linear ramps).  All pieces are evaluated, the one a sample lies in is kept ----
     ST_SEG_CLK,    // a = W of the timeline's position, b = clock slot, c = first sample of the piece:
                    // slot = samples since the piece began (0 before it begins); two words: the second (op bit 9) holds
-                   // a = first sample behind the piece, b = words to its ST_SEG_SEL (tiles outside the piece jump there)
+                   // a = first sample behind the piece, b = words to jump for a tile outside the piece (past its ST_SEG_SEL; to it for the last piece)
     ST_SEG_SEL,    // a = W of the position, b = slot (the pieces before), c = first sample of the piece:
                    // acc = at or after c ? acc : slot; op bit 8: the last piece (the position advances by a tile)
     // ---- lane program only (lanes.cuh; fused by lower.cpp build_lane_plan) ----
