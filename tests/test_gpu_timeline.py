@@ -239,3 +239,38 @@ def test_random_timelines_streamed(monkeypatch):
             # an edge of a pulse or of a square LFO within rounding of zero moves by a sample (hard part 1)
             assert bad <= 1, (case, name, bad, blocks[:4])
     assert taken >= 10
+
+
+def test_clocked_batch_at_the_default_threshold(monkeypatch):
+    """Programs with clocked words take the lane kernels from 4,096 voices by default (no environment switches here):
+    rows, and the mixdown without rows (tb_render_mix on the chip), of a pulse | lpf batch of 4,200 voices against the
+    rows the general interpreter renders."""
+    import os
+    from tuun_b200.generator import Program
+    from tuun_b200.workloads import lpf
+    for k in ("TUUN_B200_LANE_MIN_VOICES", "TUUN_B200_LANES", "TUUN_B200_STEADY", "TUUN_B200_SPLIT"):
+        monkeypatch.delenv(k, raising=False)
+    V, N = 4200, 256 + 16 * 120 + 3
+    rng = np.random.default_rng(11)
+    f = rng.uniform(40.0, 1500.0, V).astype(np.float32)
+    params = np.stack([TAU * f, -f], axis=1).astype(np.float32)
+    w = lpf(Alt(sub(saw(0, 1), Const(0.3)), Const(1.0), Const(-1.0)), 0.707, 2000)
+    p = Program(w, SR)
+    assert p.info.lane_min_voices == 4096
+    rows = np.zeros((V, N), dtype=np.float32)
+    p.render(rows, params=params)
+    assert p.info.lane_launches == 1
+    monkeypatch.setenv("TUUN_B200_LANES", "0")
+    g = Program(w, SR)
+    monkeypatch.delenv("TUUN_B200_LANES")
+    gen = np.zeros((V, N), dtype=np.float32)
+    g.render(gen, params=params)
+    assert g.info.lane_launches == 0
+    bad = int(np.count_nonzero((np.abs(rows - gen) > TOL).any(axis=1)))
+    assert bad <= 2, bad  # (an edge within rounding of zero may move by a sample on one of the two kernels)
+    q = Program(w, SR)
+    mix = np.zeros(N, dtype=np.float32)
+    q.render_mix(mix, V, params=params)
+    assert q.info.lane_launches >= 1
+    want = rows.astype(np.float64).sum(axis=0)
+    assert np.max(np.abs(mix - want)) <= 2e-3 * max(1.0, float(np.max(np.abs(want))))
